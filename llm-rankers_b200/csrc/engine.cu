@@ -1,0 +1,1028 @@
+// Host side of libb200rank.so: weight arena + layout conversion, workspaces, the Flan-T5
+// encoder/decoder pass as a sequence of sm_100a kernel launches on one stream, and the C-ABI
+// declared in include/b200rank.h. No torch, no cuBLAS, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/b200rank.h"
+#include "attention_enc.cuh"
+#include "gemm_tcgen05.cuh"
+#include "kernels_misc.cuh"
+
+using namespace b200;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+static int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CU_OK(expr)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return set_error(B200RANK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                                     \
+    } while (0)
+#define RET_IF(expr)              \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != B200RANK_OK) return _r; \
+    } while (0)
+
+// -------------------------------------------------- driver entry point (TMA descriptors)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode_tiled = nullptr;
+static int get_encode_tiled() {
+    if (g_encode_tiled) return B200RANK_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn)
+        return set_error(B200RANK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    return B200RANK_OK;
+}
+
+// 2-D bf16 K-major tensor map: dims {cols (contiguous), rows}, box {64, box_rows}, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+    RET_IF(get_encode_tiled());
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * sizeof(bf16)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(B200RANK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%u",
+                         (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ GEMM launch
+template <int BN, int EPI>
+static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args) {
+    static bool attr_set = false;
+    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    if (!attr_set) {
+        CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = ((args.M + kGemmBlockM - 1) / kGemmBlockM) * ((args.N + BN - 1) / BN);
+    const int grid = std::min(tiles, num_sms);
+    kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, args);
+    CU_OK(cudaGetLastError());
+    return B200RANK_OK;
+}
+
+static int pick_block_n(int M, int N, int epi, int num_sms) {
+    if (epi == EPI_GATED_BF16) return 256;  // weight packing fixes the tile (HALF = 128)
+    const int tiles_m = (M + kGemmBlockM - 1) / kGemmBlockM;
+    const int cands[4] = {256, 128, 64, 32};
+    for (int i = 0; i < 4; ++i) {
+        const int bn = cands[i];
+        if (tiles_m * ((N + bn - 1) / bn) >= num_sms) return bn;
+    }
+    return 32;
+}
+
+static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
+                          int epi, int bn) {
+#define GEMM_CASE(BN, EPI) \
+    if (bn == BN && epi == EPI) return launch_gemm_inst<BN, EPI>(st, num_sms, ta, tb, a);
+    GEMM_CASE(256, EPI_BF16) GEMM_CASE(128, EPI_BF16) GEMM_CASE(64, EPI_BF16) GEMM_CASE(32, EPI_BF16)
+    GEMM_CASE(256, EPI_RESID_F32) GEMM_CASE(128, EPI_RESID_F32) GEMM_CASE(64, EPI_RESID_F32) GEMM_CASE(32, EPI_RESID_F32)
+    GEMM_CASE(256, EPI_GATED_BF16)
+    GEMM_CASE(256, EPI_F32) GEMM_CASE(128, EPI_F32) GEMM_CASE(64, EPI_F32) GEMM_CASE(32, EPI_F32)
+#undef GEMM_CASE
+    return set_error(B200RANK_ERR_ARG, "no GEMM instantiation for block_n=%d epi=%d", bn, epi);
+}
+
+// ------------------------------------------------------------------ model
+struct LayerW {
+    // encoder: ln1, wqkv, wo, ln2, wi, wff     decoder: + ln_c, wq_c, wo_c
+    float *ln1 = nullptr, *ln2 = nullptr, *ln_c = nullptr;
+    bf16 *wqkv = nullptr, *wo = nullptr, *wi = nullptr, *wff = nullptr, *wq_c = nullptr, *wo_c = nullptr;
+};
+
+struct b200rank_engine {
+    b200rank_config cfg;
+    int device = 0, num_sms = 0;
+    int d = 0, inner = 0, H = 0, F = 0, V = 0, Le = 0, Ld = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool debug_simt = false, debug_sync = false;
+    uint64_t launches = 0;
+
+    // weight arena
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    float* emb = nullptr;        // [V, d] fp32
+    bf16* lm_head = nullptr;     // [V, d]
+    float *enc_final_ln = nullptr, *dec_final_ln = nullptr;
+    float *bias_enc = nullptr;   // [H][257]
+    float *bias_dec = nullptr;   // [H][129]
+    bf16* wckv = nullptr;        // [Ld * 2 * inner, d]  (k rows then v rows per decoder layer)
+    std::vector<LayerW> enc, dec;
+    std::map<std::string, bool> loaded;  // expected tensor names -> loaded?
+    bool weights_ready = false;
+
+    // workspaces
+    int cap_tokens = 0, cap_docs = 0, cap_T = 0, cap_rows = 0, cap_logit_rows = 0;
+    float* x = nullptr; bf16 *h = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr, *ckv = nullptr;
+    float* xd = nullptr; bf16 *hd = nullptr, *qkvd = nullptr, *aod = nullptr, *qd = nullptr, *gd = nullptr, *hlast = nullptr;
+    float* logits = nullptr;       // [cap_logit_rows, V]
+    float* small_out = nullptr;    // [cap_rows * 32] generic fp32 results
+    float* small_out2 = nullptr;   // [cap_docs * 32]
+    int* d_ids = nullptr;          // [cap_tokens]
+    int* d_cu = nullptr;           // [cap_docs + 1]
+    int* d_dec_ids = nullptr;      // [cap_rows]
+    int* d_cols = nullptr;         // [64]
+    int* d_labels = nullptr;       // [cap_rows]
+    int* d_int_out = nullptr;      // [cap_docs * 16]: new ids | argmax scratch
+    int* d_finished = nullptr;     // [cap_docs]
+    uint8_t* l2_scratch = nullptr; size_t l2_scratch_bytes = 0;
+    size_t workspace_bytes = 0;
+
+    // pinned host staging
+    int* h_ids = nullptr; int* h_cu = nullptr; float* h_out = nullptr; int* h_int = nullptr;
+    int* h_small = nullptr; size_t h_small_cap = 0, h_small_off = 0;  // pinned bump buffer for small async uploads
+    int staged_docs = 0, staged_tokens = 0, staged_maxlen = 0;
+
+    std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+};
+
+static int engine_tmap(b200rank_engine* e, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                       const CUtensorMap** out) {
+    auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+    auto it = e->tmaps.find(key);
+    if (it == e->tmaps.end()) {
+        CUtensorMap m;
+        RET_IF(make_tmap(&m, ptr, rows, cols, ld, box_rows));
+        it = e->tmaps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return B200RANK_OK;
+}
+
+static int post_launch(b200rank_engine* e, const char* what) {
+    e->launches++;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return set_error(B200RANK_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(err));
+    if (e->debug_sync) {
+        err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess) return set_error(B200RANK_ERR_CUDA, "kernel %s: %s", what, cudaGetErrorString(err));
+    }
+    return B200RANK_OK;
+}
+
+// acc[M,N] = A[M,K] . W[N,K]^T with fused epilogue. a_rows/w_rows: row capacity of the operands (TMA bounds).
+static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
+                int K, int epi, void* out, int ldo, int force_bn = 0) {
+    if (M <= 0) return B200RANK_OK;
+    if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
+        return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
+    const int bn = force_bn ? force_bn : pick_block_n(M, N, epi, e->num_sms);
+    if (e->debug_simt) {
+        const int n_out = epi == EPI_GATED_BF16 ? N / 2 : N;
+        dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
+        gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi, 256, out, ldo);
+        return post_launch(e, "gemm_simt_debug");
+    }
+    const CUtensorMap *ta, *tb;
+    RET_IF(engine_tmap(e, A, a_rows, K, lda, kGemmBlockM, &ta));
+    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn, &tb));
+    GemmArgs args{M, N, K, out, ldo};
+    RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, args, epi, bn));
+    return post_launch(e, "gemm_tcgen05");
+}
+
+// ------------------------------------------------------------------ relative position buckets
+// modeling_t5.py:189-234. The "large" branch is max_exact + trunc(log(n/max_exact)/log(max_distance/max_exact)
+// * (num_buckets - max_exact)); values that are mathematically integers (n = max_exact * ratio^(k/steps)) are snapped
+// so that float rounding cannot move a bucket boundary (checked against the HF function in tests/).
+extern "C" int b200rank_rel_bucket(int relative_position, int bidirectional, int num_buckets, int max_distance) {
+    int ret = 0, n;
+    if (bidirectional) {
+        num_buckets /= 2;
+        if (relative_position > 0) ret += num_buckets;
+        n = std::abs(relative_position);
+    } else {
+        n = relative_position < 0 ? -relative_position : 0;
+    }
+    const int max_exact = num_buckets / 2;
+    if (n < max_exact) return ret + n;
+    double v = std::log(static_cast<double>(n) / max_exact) / std::log(static_cast<double>(max_distance) / max_exact) *
+               (num_buckets - max_exact);
+    const double rv = std::round(v);
+    if (std::fabs(v - rv) < 1e-6) v = rv;
+    int b = max_exact + static_cast<int>(v);
+    b = std::min(b, num_buckets - 1);
+    return ret + b;
+}
+
+// ------------------------------------------------------------------ create / destroy
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+static int dev_alloc(b200rank_engine* e, T** p, size_t n) {
+    const size_t bytes = align_up(std::max<size_t>(n, 1) * sizeof(T), 256);
+    CU_OK(cudaMalloc(reinterpret_cast<void**>(p), bytes));
+    CU_OK(cudaMemsetAsync(*p, 0, bytes, e->stream));
+    e->workspace_bytes += bytes;
+    return B200RANK_OK;
+}
+
+static void expect(b200rank_engine* e, const std::string& name) { e->loaded[name] = false; }
+
+extern "C" const char* b200rank_version(void) { return "b200rank 0.1.0 (sm_100a, tcgen05/TMA)"; }
+extern "C" const char* b200rank_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" void b200rank_destroy(b200rank_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
+                     e->logits, e->small_out, e->small_out2, e->d_ids, e->d_cu, e->d_dec_ids, e->d_cols, e->d_labels,
+                     e->d_int_out, e->d_finished, e->l2_scratch};
+    for (void* p : frees)
+        if (p) cudaFree(p);
+    if (e->h_ids) cudaFreeHost(e->h_ids);
+    if (e->h_cu) cudaFreeHost(e->h_cu);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->h_int) cudaFreeHost(e->h_int);
+    if (e->h_small) cudaFreeHost(e->h_small);
+    for (int i = 0; i < 2; ++i)
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int create_impl(b200rank_engine* e) {
+    const b200rank_config& c = e->cfg;
+    CU_OK(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    CU_OK(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major != 10)
+        return set_error(B200RANK_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", e->device, prop.major,
+                         prop.minor);
+    e->num_sms = prop.multiProcessorCount;
+    CU_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU_OK(cudaEventCreate(&e->ev[0]));
+    CU_OK(cudaEventCreate(&e->ev[1]));
+    e->debug_simt = getenv("B200RANK_DEBUG_SIMT_GEMM") && atoi(getenv("B200RANK_DEBUG_SIMT_GEMM")) != 0;
+    e->debug_sync = getenv("B200RANK_DEBUG_SYNC") && atoi(getenv("B200RANK_DEBUG_SYNC")) != 0;
+
+    const size_t d = e->d, I = e->inner, F = e->F, V = e->V;
+    // ---- weight arena layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    std::vector<std::pair<void**, size_t>> fix;  // (pointer slot, offset)
+    auto reserve = [&](void** slot, size_t bytes) { fix.emplace_back(slot, take(bytes)); };
+    reserve((void**)&e->emb, V * d * 4);
+    reserve((void**)&e->lm_head, V * d * 2);
+    reserve((void**)&e->enc_final_ln, d * 4);
+    reserve((void**)&e->dec_final_ln, d * 4);
+    reserve((void**)&e->bias_enc, (size_t)e->H * kAttnBiasLen * 4);
+    reserve((void**)&e->bias_dec, (size_t)e->H * (kAttnRelClamp + 1) * 4);
+    reserve((void**)&e->wckv, (size_t)e->Ld * 2 * I * d * 2);
+    e->enc.resize(e->Le);
+    e->dec.resize(e->Ld);
+    for (int l = 0; l < e->Le; ++l) {
+        LayerW& w = e->enc[l];
+        reserve((void**)&w.ln1, d * 4); reserve((void**)&w.ln2, d * 4);
+        reserve((void**)&w.wqkv, 3 * I * d * 2); reserve((void**)&w.wo, d * I * 2);
+        reserve((void**)&w.wi, 2 * F * d * 2); reserve((void**)&w.wff, d * F * 2);
+    }
+    for (int l = 0; l < e->Ld; ++l) {
+        LayerW& w = e->dec[l];
+        reserve((void**)&w.ln1, d * 4); reserve((void**)&w.ln_c, d * 4); reserve((void**)&w.ln2, d * 4);
+        reserve((void**)&w.wqkv, 3 * I * d * 2); reserve((void**)&w.wo, d * I * 2);
+        reserve((void**)&w.wq_c, I * d * 2); reserve((void**)&w.wo_c, d * I * 2);
+        reserve((void**)&w.wi, 2 * F * d * 2); reserve((void**)&w.wff, d * F * 2);
+    }
+    e->arena_bytes = off;
+    CU_OK(cudaMalloc(reinterpret_cast<void**>(&e->arena), e->arena_bytes));
+    CU_OK(cudaMemsetAsync(e->arena, 0, e->arena_bytes, e->stream));
+    for (auto& f : fix) *f.first = e->arena + f.second;
+
+    // ---- expected tensors
+    expect(e, "shared.weight"); expect(e, "lm_head.weight");
+    expect(e, "encoder.final_layer_norm.weight"); expect(e, "decoder.final_layer_norm.weight");
+    expect(e, "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight");
+    expect(e, "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight");
+    char nm[256];
+    for (int l = 0; l < e->Le; ++l) {
+        for (const char* m : {"q", "k", "v", "o"}) { snprintf(nm, sizeof nm, "encoder.block.%d.layer.0.SelfAttention.%s.weight", l, m); expect(e, nm); }
+        snprintf(nm, sizeof nm, "encoder.block.%d.layer.0.layer_norm.weight", l); expect(e, nm);
+        for (const char* m : {"wi_0", "wi_1", "wo"}) { snprintf(nm, sizeof nm, "encoder.block.%d.layer.1.DenseReluDense.%s.weight", l, m); expect(e, nm); }
+        snprintf(nm, sizeof nm, "encoder.block.%d.layer.1.layer_norm.weight", l); expect(e, nm);
+    }
+    for (int l = 0; l < e->Ld; ++l) {
+        for (const char* m : {"q", "k", "v", "o"}) {
+            snprintf(nm, sizeof nm, "decoder.block.%d.layer.0.SelfAttention.%s.weight", l, m); expect(e, nm);
+            snprintf(nm, sizeof nm, "decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, m); expect(e, nm);
+        }
+        for (int j = 0; j < 3; ++j) { snprintf(nm, sizeof nm, "decoder.block.%d.layer.%d.layer_norm.weight", l, j); expect(e, nm); }
+        for (const char* m : {"wi_0", "wi_1", "wo"}) { snprintf(nm, sizeof nm, "decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, m); expect(e, nm); }
+    }
+
+    // ---- workspaces (row capacities rounded to the 128-row GEMM tile)
+    e->cap_tokens = (int)align_up(c.max_tokens > 0 ? c.max_tokens : 32768, 128);
+    e->cap_docs = c.max_docs > 0 ? c.max_docs : 1024;
+    e->cap_T = c.max_dec_len > 0 ? c.max_dec_len : 64;
+    if (e->cap_T > 64) return set_error(B200RANK_ERR_ARG, "max_dec_len %d > 64 unsupported", e->cap_T);
+    e->cap_logit_rows = (int)align_up(c.max_logit_rows > 0 ? c.max_logit_rows : 4096, 128);
+    e->cap_rows = (int)align_up(std::max(e->cap_docs, e->cap_logit_rows), 128);
+    const size_t Tk = e->cap_tokens, R = e->cap_rows;
+    RET_IF(dev_alloc(e, &e->x, Tk * d)); RET_IF(dev_alloc(e, &e->h, Tk * d));
+    RET_IF(dev_alloc(e, &e->qkv, Tk * 3 * I)); RET_IF(dev_alloc(e, &e->ao, Tk * I));
+    RET_IF(dev_alloc(e, &e->g, Tk * F)); RET_IF(dev_alloc(e, &e->ckv, Tk * (size_t)e->Ld * 2 * I));
+    RET_IF(dev_alloc(e, &e->xd, R * d)); RET_IF(dev_alloc(e, &e->hd, R * d));
+    RET_IF(dev_alloc(e, &e->qkvd, R * 3 * I)); RET_IF(dev_alloc(e, &e->aod, R * I));
+    RET_IF(dev_alloc(e, &e->qd, R * I)); RET_IF(dev_alloc(e, &e->gd, R * F)); RET_IF(dev_alloc(e, &e->hlast, R * d));
+    RET_IF(dev_alloc(e, &e->logits, (size_t)e->cap_logit_rows * V));
+    RET_IF(dev_alloc(e, &e->small_out, R * 32)); RET_IF(dev_alloc(e, &e->small_out2, (size_t)e->cap_docs * 32));
+    RET_IF(dev_alloc(e, &e->d_ids, Tk)); RET_IF(dev_alloc(e, &e->d_cu, (size_t)e->cap_docs + 1));
+    RET_IF(dev_alloc(e, &e->d_dec_ids, R)); RET_IF(dev_alloc(e, &e->d_cols, 64)); RET_IF(dev_alloc(e, &e->d_labels, R));
+    RET_IF(dev_alloc(e, &e->d_int_out, (size_t)e->cap_docs * 16)); RET_IF(dev_alloc(e, &e->d_finished, (size_t)e->cap_docs));
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ids), Tk * sizeof(int), cudaHostAllocDefault));
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_cu), ((size_t)e->cap_docs + 1) * sizeof(int), cudaHostAllocDefault));
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_out), (size_t)e->cap_docs * 64 * sizeof(float), cudaHostAllocDefault));
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_int), (size_t)e->cap_docs * 8 * sizeof(int), cudaHostAllocDefault));
+    e->h_small_cap = 4 * R + 4096;
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_small), e->h_small_cap * sizeof(int), cudaHostAllocDefault));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_engine** out) {
+    if (!cfg || !out) return set_error(B200RANK_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->d_kv != 64) return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (kernels are specialised for 64)", cfg->d_kv);
+    if (!cfg->gated_gelu) return set_error(B200RANK_ERR_ARG, "only gated-gelu feed-forward (Flan-T5) is supported");
+    if (cfg->d_model % 64 || cfg->d_ff % 128 || cfg->d_model > 4096 || cfg->vocab_size % 8)
+        return set_error(B200RANK_ERR_ARG, "unsupported dims d_model=%d d_ff=%d vocab=%d", cfg->d_model, cfg->d_ff, cfg->vocab_size);
+    if (cfg->num_heads <= 0 || cfg->num_layers <= 0 || cfg->num_decoder_layers <= 0)
+        return set_error(B200RANK_ERR_ARG, "bad layer/head counts");
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev <= 0)
+        return set_error(B200RANK_ERR_CUDA, "no CUDA device available (%s); b200rank has no CPU fallback",
+                         err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+    if (device < 0 || device >= ndev) return set_error(B200RANK_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    b200rank_engine* e = new b200rank_engine();
+    e->cfg = *cfg;
+    e->device = device;
+    e->d = cfg->d_model; e->H = cfg->num_heads; e->inner = cfg->num_heads * cfg->d_kv; e->F = cfg->d_ff; e->V = cfg->vocab_size;
+    e->Le = cfg->num_layers; e->Ld = cfg->num_decoder_layers;
+    int r = create_impl(e);
+    if (r != B200RANK_OK) { std::string keep = g_last_error; b200rank_destroy(e); g_last_error = keep; return r; }
+    *out = e;
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ weight loading
+static inline bf16 to_bf16(float f) { return __float2bfloat16_rn(f); }
+static inline float src_at(const void* data, int dtype, size_t i) {
+    if (dtype == B200RANK_DTYPE_F32) return reinterpret_cast<const float*>(data)[i];
+    return __bfloat162float(reinterpret_cast<const bf16*>(data)[i]);
+}
+
+// copy a [rows, cols] host matrix as bf16 into dst rows given by row_map(r)
+template <typename RowMap>
+static int put_bf16_rows(b200rank_engine* e, bf16* dst, size_t dst_ld, const void* data, int dtype, int64_t rows, int64_t cols,
+                         RowMap row_map) {
+    std::vector<bf16> tmp(static_cast<size_t>(rows) * cols);
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = to_bf16(src_at(data, dtype, i));
+    // contiguous destination runs are common (identity map): detect and use one 2-D copy
+    bool contiguous = true;
+    const int64_t r0 = row_map(0);
+    for (int64_t r = 1; r < rows && contiguous; ++r) contiguous = (row_map(r) == r0 + r);
+    if (contiguous) {
+        CU_OK(cudaMemcpy2D(dst + r0 * dst_ld, dst_ld * 2, tmp.data(), cols * 2, cols * 2, rows, cudaMemcpyHostToDevice));
+    } else {
+        // runs of consecutive rows
+        int64_t r = 0;
+        while (r < rows) {
+            int64_t r1 = r + 1;
+            while (r1 < rows && row_map(r1) == row_map(r) + (r1 - r)) ++r1;
+            CU_OK(cudaMemcpy2D(dst + row_map(r) * dst_ld, dst_ld * 2, tmp.data() + r * cols, cols * 2, cols * 2, r1 - r,
+                               cudaMemcpyHostToDevice));
+            r = r1;
+        }
+    }
+    return B200RANK_OK;
+}
+static int put_f32(float* dst, const void* data, int dtype, size_t n) {
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = src_at(data, dtype, i);
+    CU_OK(cudaMemcpy(dst, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+    return B200RANK_OK;
+}
+
+static int shape_check(const char* name, int64_t rows, int64_t cols, int64_t er, int64_t ec) {
+    if (rows != er || cols != ec)
+        return set_error(B200RANK_ERR_ARG, "tensor %s has shape [%lld, %lld], expected [%lld, %lld]", name, (long long)rows,
+                         (long long)cols, (long long)er, (long long)ec);
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, const void* data, int dtype, int64_t rows,
+                                    int64_t cols) {
+    if (!e || !hf_name || !data) return set_error(B200RANK_ERR_ARG, "null argument");
+    if (dtype != B200RANK_DTYPE_F32 && dtype != B200RANK_DTYPE_BF16) return set_error(B200RANK_ERR_ARG, "bad dtype %d", dtype);
+    CU_OK(cudaSetDevice(e->device));
+    std::string name(hf_name);
+    const int64_t d = e->d, I = e->inner, F = e->F, V = e->V;
+    auto ident = [](int64_t r) { return r; };
+    if (name == "encoder.embed_tokens.weight" || name == "decoder.embed_tokens.weight") return B200RANK_OK;  // aliases of shared.weight
+    if (e->loaded.find(name) == e->loaded.end()) return set_error(B200RANK_ERR_ARG, "unexpected tensor name %s", hf_name);
+
+    int r = B200RANK_OK;
+    if (name == "shared.weight") {
+        RET_IF(shape_check(hf_name, rows, cols, V, d));
+        r = put_f32(e->emb, data, dtype, (size_t)V * d);
+    } else if (name == "lm_head.weight") {
+        RET_IF(shape_check(hf_name, rows, cols, V, d));
+        r = put_bf16_rows(e, e->lm_head, d, data, dtype, rows, cols, ident);
+    } else if (name == "encoder.final_layer_norm.weight") {
+        RET_IF(shape_check(hf_name, rows * cols, 1, d, 1));
+        r = put_f32(e->enc_final_ln, data, dtype, d);
+    } else if (name == "decoder.final_layer_norm.weight") {
+        RET_IF(shape_check(hf_name, rows * cols, 1, d, 1));
+        r = put_f32(e->dec_final_ln, data, dtype, d);
+    } else {
+        int l = -1, sub = -1;
+        char stack[16] = {0}, rest[160] = {0};
+        if (sscanf(hf_name, "%7[a-z].block.%d.layer.%d.%159s", stack, &l, &sub, rest) != 4)
+            return set_error(B200RANK_ERR_ARG, "cannot parse tensor name %s", hf_name);
+        const bool is_dec = strcmp(stack, "decoder") == 0;
+        if (l < 0 || l >= (is_dec ? e->Ld : e->Le)) return set_error(B200RANK_ERR_ARG, "layer index out of range in %s", hf_name);
+        LayerW& w = is_dec ? e->dec[l] : e->enc[l];
+        std::string rs(rest);
+        const int ff_sub = is_dec ? 2 : 1;
+        if (rs == "layer_norm.weight") {
+            RET_IF(shape_check(hf_name, rows * cols, 1, d, 1));
+            float* dst = (sub == 0) ? w.ln1 : (sub == ff_sub ? w.ln2 : w.ln_c);
+            r = put_f32(dst, data, dtype, d);
+        } else if (rs == "SelfAttention.relative_attention_bias.weight") {
+            RET_IF(shape_check(hf_name, rows, cols, e->cfg.rel_buckets, e->H));
+            const int nb = e->cfg.rel_buckets, md = e->cfg.rel_max_distance;
+            if (md > kAttnRelClamp) return set_error(B200RANK_ERR_ARG, "rel_max_distance %d > %d unsupported", md, kAttnRelClamp);
+            if (!is_dec) {
+                std::vector<float> t((size_t)e->H * kAttnBiasLen);
+                for (int h = 0; h < e->H; ++h)
+                    for (int dlt = -kAttnRelClamp; dlt <= kAttnRelClamp; ++dlt)
+                        t[(size_t)h * kAttnBiasLen + dlt + kAttnRelClamp] =
+                            src_at(data, dtype, (size_t)b200rank_rel_bucket(dlt, 1, nb, md) * e->H + h);
+                CU_OK(cudaMemcpy(e->bias_enc, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+            } else {
+                const int len = kAttnRelClamp + 1;
+                std::vector<float> t((size_t)e->H * len);
+                for (int h = 0; h < e->H; ++h)
+                    for (int n = 0; n < len; ++n)
+                        t[(size_t)h * len + n] = src_at(data, dtype, (size_t)b200rank_rel_bucket(-n, 0, nb, md) * e->H + h);
+                CU_OK(cudaMemcpy(e->bias_dec, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+            }
+        } else if (rs.rfind("SelfAttention.", 0) == 0 && sub == 0) {
+            const char m = rs[14];
+            if (m == 'o') { RET_IF(shape_check(hf_name, rows, cols, d, I)); r = put_bf16_rows(e, w.wo, I, data, dtype, rows, cols, ident); }
+            else {
+                RET_IF(shape_check(hf_name, rows, cols, I, d));
+                const int64_t base = (m == 'q') ? 0 : (m == 'k' ? I : 2 * I);
+                r = put_bf16_rows(e, w.wqkv, d, data, dtype, rows, cols, [base](int64_t rr) { return base + rr; });
+            }
+        } else if (rs.rfind("EncDecAttention.", 0) == 0 && is_dec && sub == 1) {
+            const char m = rs[16];
+            if (m == 'o') { RET_IF(shape_check(hf_name, rows, cols, d, I)); r = put_bf16_rows(e, w.wo_c, I, data, dtype, rows, cols, ident); }
+            else if (m == 'q') { RET_IF(shape_check(hf_name, rows, cols, I, d)); r = put_bf16_rows(e, w.wq_c, d, data, dtype, rows, cols, ident); }
+            else {
+                RET_IF(shape_check(hf_name, rows, cols, I, d));
+                const int64_t base = (int64_t)l * 2 * I + (m == 'k' ? 0 : I);
+                r = put_bf16_rows(e, e->wckv, d, data, dtype, rows, cols, [base](int64_t rr) { return base + rr; });
+            }
+        } else if (rs.rfind("DenseReluDense.", 0) == 0 && sub == ff_sub) {
+            std::string m = rs.substr(15);
+            if (m == "wo.weight") { RET_IF(shape_check(hf_name, rows, cols, d, F)); r = put_bf16_rows(e, w.wff, F, data, dtype, rows, cols, ident); }
+            else if (m == "wi_0.weight" || m == "wi_1.weight") {
+                RET_IF(shape_check(hf_name, rows, cols, F, d));
+                // tile interleave for the gated epilogue: N-tile nb of 256 accumulator columns =
+                // [wi_0 rows nb*128 .. +128 | wi_1 rows nb*128 .. +128]
+                const int64_t add = (m == "wi_1.weight") ? 128 : 0;
+                r = put_bf16_rows(e, w.wi, d, data, dtype, rows, cols, [add](int64_t f) { return (f / 128) * 256 + add + (f % 128); });
+            } else return set_error(B200RANK_ERR_ARG, "unknown feed-forward tensor %s", hf_name);
+        } else {
+            return set_error(B200RANK_ERR_ARG, "unknown tensor %s", hf_name);
+        }
+    }
+    if (r != B200RANK_OK) return r;
+    e->loaded[name] = true;
+    bool all = true;
+    for (auto& kv : e->loaded) all = all && kv.second;
+    e->weights_ready = all;
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_missing_tensors(b200rank_engine* e, char* buf, int buflen) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    int n = 0;
+    std::string s;
+    for (auto& kv : e->loaded)
+        if (!kv.second) { if (n++) s += ","; s += kv.first; }
+    if (buf && buflen > 0) { strncpy(buf, s.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+    return n;
+}
+extern "C" int b200rank_weights_blob(b200rank_engine* e, void** device_ptr, size_t* nbytes) {
+    if (!e || !device_ptr || !nbytes) return set_error(B200RANK_ERR_ARG, "null argument");
+    *device_ptr = e->arena; *nbytes = e->arena_bytes;
+    return B200RANK_OK;
+}
+extern "C" int b200rank_mark_weights_loaded(b200rank_engine* e) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    for (auto& kv : e->loaded) kv.second = true;
+    e->weights_ready = true;
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ forward pieces
+static int k_embed(b200rank_engine* e, const int* ids, float* x, int n) {
+    if (n <= 0) return B200RANK_OK;
+    embed_kernel<<<(n + 7) / 8, 256, 0, e->stream>>>(ids, e->emb, x, n, e->d, e->V);
+    return post_launch(e, "embed");
+}
+static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n) {
+    if (n <= 0) return B200RANK_OK;
+    const int grid = (n + 7) / 8;
+    if (e->d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
+    else if (e->d <= 2048) rmsnorm_kernel<16><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
+    else rmsnorm_kernel<32><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
+    return post_launch(e, "rmsnorm");
+}
+
+// Encoder over the staged batch + stacked cross-attention K|V projection of its output.
+static int run_encoder(b200rank_engine* e) {
+    const int n = e->staged_tokens, nd = e->staged_docs;
+    const int d = e->d, I = e->inner, F = e->F, Tk = e->cap_tokens;
+    RET_IF(k_embed(e, e->d_ids, e->x, n));
+    const int q_tiles = (e->staged_maxlen + 63) / 64;
+    for (int l = 0; l < e->Le; ++l) {
+        const LayerW& w = e->enc[l];
+        RET_IF(k_rmsnorm(e, e->x, w.ln1, e->h, n));
+        RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
+        enc_attention_kernel<<<dim3(q_tiles, e->H, nd), 128, 0, e->stream>>>(e->qkv, 3 * I, I, e->d_cu, e->bias_enc, e->ao, I);
+        RET_IF(post_launch(e, "enc_attention"));
+        RET_IF(gemm(e, e->ao, I, Tk, w.wo, I, d, n, d, I, EPI_RESID_F32, e->x, d));
+        RET_IF(k_rmsnorm(e, e->x, w.ln2, e->h, n));
+        RET_IF(gemm(e, e->h, d, Tk, w.wi, d, 2 * F, n, 2 * F, d, EPI_GATED_BF16, e->g, F));
+        RET_IF(gemm(e, e->g, F, Tk, w.wff, F, d, n, d, F, EPI_RESID_F32, e->x, d));
+    }
+    RET_IF(k_rmsnorm(e, e->x, e->enc_final_ln, e->h, n));
+    const int NC = e->Ld * 2 * I;
+    RET_IF(gemm(e, e->h, d, Tk, e->wckv, d, NC, n, NC, d, EPI_BF16, e->ckv, NC));
+    return B200RANK_OK;
+}
+
+// Decoder over documents [doc0, doc0+nd) with T positions each; dec ids in d_dec_ids[nd*T].
+// Leaves the final-normed hidden states in hd[nd*T, d].
+static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
+    const int R = nd * T;
+    const int d = e->d, I = e->inner, F = e->F, cap = e->cap_rows;
+    if (R > cap) return set_error(B200RANK_ERR_CAPACITY, "decoder rows %d exceed capacity %d", R, cap);
+    if (T > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "decoder length %d exceeds max_dec_len %d", T, e->cap_T);
+    RET_IF(k_embed(e, e->d_dec_ids, e->xd, R));
+    const size_t ldkv = (size_t)e->Ld * 2 * I;
+    for (int l = 0; l < e->Ld; ++l) {
+        const LayerW& w = e->dec[l];
+        RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
+        RET_IF(gemm(e, e->hd, d, cap, w.wqkv, d, 3 * I, R, 3 * I, d, EPI_BF16, e->qkvd, 3 * I));
+        dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+        RET_IF(post_launch(e, "dec_self_attention"));
+        RET_IF(gemm(e, e->aod, I, cap, w.wo, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+        RET_IF(k_rmsnorm(e, e->xd, w.ln_c, e->hd, R));
+        RET_IF(gemm(e, e->hd, d, cap, w.wq_c, d, I, R, I, d, EPI_BF16, e->qd, I));
+        const int k_off = l * 2 * I, v_off = l * 2 * I + I;
+        if (T <= 4)
+            cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+        else
+            cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+        RET_IF(post_launch(e, "cross_attention"));
+        RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+        RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
+        RET_IF(gemm(e, e->hd, d, cap, w.wi, d, 2 * F, R, 2 * F, d, EPI_GATED_BF16, e->gd, F));
+        RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
+    }
+    RET_IF(k_rmsnorm(e, e->xd, e->dec_final_ln, e->hd, R));
+    return B200RANK_OK;
+}
+
+static float logit_scale(const b200rank_engine* e) {
+    return e->cfg.scale_decoder_outputs ? 1.0f / std::sqrt(static_cast<float>(e->d)) : 1.0f;
+}
+
+// ------------------------------------------------------------------ staging
+static int check_ready(b200rank_engine* e) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    if (!e->weights_ready) return set_error(B200RANK_ERR_STATE, "weights are not fully loaded (%d tensors missing)", b200rank_missing_tensors(e, nullptr, 0));
+    CU_OK(cudaSetDevice(e->device));
+    e->h_small_off = 0;
+    return B200RANK_OK;
+}
+
+// Pack documents [d0, d1) into the pinned staging buffers and copy to the device (async on the stream).
+static int stage_range(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int stride, int d0, int d1) {
+    int tok = 0, maxlen = 0;
+    e->h_cu[0] = 0;
+    for (int i = d0; i < d1; ++i) {
+        const int len = lengths[i];
+        memcpy(e->h_ids + tok, ids + (size_t)i * stride, (size_t)len * sizeof(int));
+        tok += len;
+        maxlen = std::max(maxlen, len);
+        e->h_cu[i - d0 + 1] = tok;
+    }
+    e->staged_docs = d1 - d0; e->staged_tokens = tok; e->staged_maxlen = maxlen;
+    CU_OK(cudaMemcpyAsync(e->d_ids, e->h_ids, (size_t)tok * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU_OK(cudaMemcpyAsync(e->d_cu, e->h_cu, (size_t)(d1 - d0 + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    return B200RANK_OK;
+}
+
+// Greedy split of documents into device passes that respect max_tokens / max_docs / doc_limit.
+static int next_group(b200rank_engine* e, const int32_t* lengths, int n_docs, int stride, int d0, int doc_limit, int* d1_out) {
+    int tok = 0, d1 = d0;
+    while (d1 < n_docs && (d1 - d0) < doc_limit) {
+        const int len = lengths[d1];
+        if (len <= 0 || len > stride) return set_error(B200RANK_ERR_ARG, "lengths[%d]=%d out of range (stride %d)", d1, len, stride);
+        if (len > e->cap_tokens) return set_error(B200RANK_ERR_CAPACITY, "document %d has %d tokens > max_tokens %d", d1, len, e->cap_tokens);
+        if (tok + len > e->cap_tokens) break;
+        tok += len; ++d1;
+    }
+    *d1_out = d1;
+    return B200RANK_OK;
+}
+
+// Small async upload through a pinned bump buffer (reset at the start of every API call) so the host never
+// blocks behind queued kernels the way a pageable cudaMemcpyAsync would.
+static int upload_ints(b200rank_engine* e, int* dst, const std::vector<int>& v) {
+    if (e->h_small_off + v.size() > e->h_small_cap) {
+        CU_OK(cudaStreamSynchronize(e->stream));
+        e->h_small_off = 0;
+        if (v.size() > e->h_small_cap) return set_error(B200RANK_ERR_CAPACITY, "upload of %zu ints exceeds staging", v.size());
+    }
+    int* src = e->h_small + e->h_small_off;
+    memcpy(src, v.data(), v.size() * sizeof(int));
+    e->h_small_off += v.size();
+    CU_OK(cudaMemcpyAsync(dst, src, v.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ yes/no
+static int yes_no_device(b200rank_engine* e, int yes_id, int no_id) {
+    const int nd = e->staged_docs;
+    if (yes_id < 0 || yes_id >= e->V || no_id < 0 || no_id >= e->V) return set_error(B200RANK_ERR_ARG, "yes/no ids out of vocabulary");
+    RET_IF(run_encoder(e));
+    std::vector<int> dec(nd, e->cfg.pad_id);  // decoder_input_ids = [[pad]] per row, pointwise.py:102
+    RET_IF(upload_ints(e, e->d_dec_ids, dec));
+    RET_IF(upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id}));
+    RET_IF(run_decoder(e, 0, nd, 1));
+    lm_head_cols_kernel<<<nd, 64, 0, e->stream>>>(e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
+    RET_IF(post_launch(e, "lm_head_cols"));
+    yes_no_score_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, e->small_out2, nd);
+    RET_IF(post_launch(e, "yes_no_score"));
+    return B200RANK_OK;
+}
+
+static int fetch_yes_no(b200rank_engine* e, float* logits2, float* scores) {
+    const int nd = e->staged_docs;
+    CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * 2 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU_OK(cudaMemcpyAsync(e->h_out + 2 * (size_t)nd, e->small_out2, (size_t)nd * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    if (logits2) memcpy(logits2, e->h_out, (size_t)nd * 2 * sizeof(float));
+    if (scores) memcpy(scores, e->h_out + 2 * (size_t)nd, (size_t)nd * sizeof(float));
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_score_yes_no(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
+                                     int yes_id, int no_id, float* logits2, float* scores) {
+    RET_IF(check_ready(e));
+    if (!ids || !lengths || n_docs < 0 || stride <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    int d0 = 0;
+    while (d0 < n_docs) {
+        int d1 = 0;
+        RET_IF(next_group(e, lengths, n_docs, stride, d0, e->cap_docs, &d1));
+        RET_IF(stage_range(e, ids, lengths, stride, d0, d1));
+        RET_IF(yes_no_device(e, yes_id, no_id));
+        RET_IF(fetch_yes_no(e, logits2 ? logits2 + 2 * (size_t)d0 : nullptr, scores ? scores + d0 : nullptr));
+        d0 = d1;
+    }
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_stage(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride) {
+    RET_IF(check_ready(e));
+    if (!ids || !lengths || n_docs <= 0 || stride <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    int d1 = 0;
+    RET_IF(next_group(e, lengths, n_docs, stride, 0, e->cap_docs, &d1));
+    if (d1 != n_docs) return set_error(B200RANK_ERR_CAPACITY, "staged batch does not fit one device pass (%d of %d docs)", d1, n_docs);
+    RET_IF(stage_range(e, ids, lengths, stride, 0, n_docs));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    return B200RANK_OK;
+}
+extern "C" int b200rank_run_yes_no_staged(b200rank_engine* e, int yes_id, int no_id) {
+    RET_IF(check_ready(e));
+    if (e->staged_docs <= 0) return set_error(B200RANK_ERR_STATE, "nothing staged");
+    return yes_no_device(e, yes_id, no_id);
+}
+extern "C" int b200rank_fetch_yes_no(b200rank_engine* e, float* logits2, float* scores) {
+    RET_IF(check_ready(e));
+    if (e->staged_docs <= 0) return set_error(B200RANK_ERR_STATE, "nothing staged");
+    return fetch_yes_no(e, logits2, scores);
+}
+extern "C" int b200rank_sync(b200rank_engine* e) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    CU_OK(cudaSetDevice(e->device));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ qlm
+extern "C" int b200rank_score_qlm(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
+                                  const int32_t* labels, int T, float* scores) {
+    RET_IF(check_ready(e));
+    if (!ids || !lengths || !labels || !scores || n_docs < 0 || stride <= 0 || T <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    if (T > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "label length %d exceeds max_dec_len %d", T, e->cap_T);
+    for (int t = 0; t < T; ++t)
+        if (labels[t] < 0 || labels[t] >= e->V) return set_error(B200RANK_ERR_ARG, "label id out of vocabulary");
+    const int doc_limit = std::min(e->cap_docs, e->cap_logit_rows / T);
+    if (doc_limit <= 0) return set_error(B200RANK_ERR_CAPACITY, "max_logit_rows %d < T %d", e->cap_logit_rows, T);
+    // decoder inputs = shift_right(labels): [decoder_start(=pad), labels[0..T-2]]  (modeling_t5.py:595-614)
+    std::vector<int> dec_row(T), lab_row(labels, labels + T);
+    dec_row[0] = e->cfg.pad_id;
+    for (int t = 1; t < T; ++t) dec_row[t] = labels[t - 1];
+    int d0 = 0;
+    while (d0 < n_docs) {
+        int d1 = 0;
+        RET_IF(next_group(e, lengths, n_docs, stride, d0, doc_limit, &d1));
+        const int nd = d1 - d0, R = nd * T;
+        RET_IF(stage_range(e, ids, lengths, stride, d0, d1));
+        RET_IF(run_encoder(e));
+        std::vector<int> dec((size_t)R), lab((size_t)R);
+        for (int i = 0; i < nd; ++i) { std::copy(dec_row.begin(), dec_row.end(), dec.begin() + (size_t)i * T); std::copy(lab_row.begin(), lab_row.end(), lab.begin() + (size_t)i * T); }
+        RET_IF(upload_ints(e, e->d_dec_ids, dec));
+        RET_IF(upload_ints(e, e->d_labels, lab));
+        RET_IF(run_decoder(e, 0, nd, T));
+        RET_IF(gemm(e, e->hd, e->d, e->cap_rows, e->lm_head, e->d, e->V, R, e->V, e->d, EPI_F32, e->logits, e->V));
+        vocab_row_kernel<<<R, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 0, logit_scale(e), e->d_labels, nullptr, 0, e->small_out, nullptr);
+        RET_IF(post_launch(e, "vocab_row_logprob"));
+        sum_rows_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, T, e->small_out2, nd);
+        RET_IF(post_launch(e, "sum_rows"));
+        CU_OK(cudaMemcpyAsync(e->h_out, e->small_out2, (size_t)nd * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CU_OK(cudaStreamSynchronize(e->stream));
+        memcpy(scores + d0, e->h_out, (size_t)nd * sizeof(float));
+        d0 = d1;
+    }
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ logits_at
+extern "C" int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
+                                  const int32_t* dec_prefix, int prefix_len, const int32_t* cols, int ncols, int normalize,
+                                  float* out) {
+    RET_IF(check_ready(e));
+    if (!ids || !lengths || !dec_prefix || !cols || !out || n_docs < 0 || stride <= 0 || prefix_len <= 0 || ncols <= 0 || ncols > 32)
+        return set_error(B200RANK_ERR_ARG, "bad arguments (ncols must be 1..32)");
+    const int T = prefix_len;
+    if (T > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "prefix length %d exceeds max_dec_len %d", T, e->cap_T);
+    for (int c = 0; c < ncols; ++c)
+        if (cols[c] < 0 || cols[c] >= e->V) return set_error(B200RANK_ERR_ARG, "column id out of vocabulary");
+    const int doc_limit = std::min(std::min(e->cap_docs, e->cap_rows / T), normalize ? e->cap_logit_rows : e->cap_docs);
+    int d0 = 0;
+    while (d0 < n_docs) {
+        int d1 = 0;
+        RET_IF(next_group(e, lengths, n_docs, stride, d0, doc_limit, &d1));
+        const int nd = d1 - d0;
+        RET_IF(stage_range(e, ids, lengths, stride, d0, d1));
+        RET_IF(run_encoder(e));
+        std::vector<int> dec((size_t)nd * T);
+        for (int i = 0; i < nd; ++i) std::copy(dec_prefix, dec_prefix + T, dec.begin() + (size_t)i * T);
+        RET_IF(upload_ints(e, e->d_dec_ids, dec));
+        RET_IF(upload_ints(e, e->d_cols, std::vector<int>(cols, cols + ncols)));
+        RET_IF(run_decoder(e, 0, nd, T));
+        if (!normalize) {
+            lm_head_cols_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
+            RET_IF(post_launch(e, "lm_head_cols"));
+        } else {
+            gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
+            RET_IF(post_launch(e, "gather_rows"));
+            RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
+            vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 2, logit_scale(e), nullptr, e->d_cols, ncols, e->small_out, nullptr);
+            RET_IF(post_launch(e, "vocab_row_softmax_gather"));
+        }
+        CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * ncols * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        CU_OK(cudaStreamSynchronize(e->stream));
+        memcpy(out + (size_t)d0 * ncols, e->h_out, (size_t)nd * ncols * sizeof(float));
+        d0 = d1;
+    }
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ greedy
+// dec_ids[doc, T_cap] updated on device: write argmax (or pad once finished) at position t.
+__global__ void greedy_update_kernel(const int* __restrict__ argmax, int* __restrict__ dec_rows, int* __restrict__ finished,
+                                     int* __restrict__ new_ids, int nd, int t_write, int t_stride, int step, int max_new,
+                                     int eos, int pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    int tok = argmax[i];
+    if (finished[i]) tok = pad;            // generation/utils.py:2797: next_tokens * unfinished + pad * (1 - unfinished)
+    if (tok == eos) finished[i] = 1;
+    new_ids[i * max_new + step] = tok;
+    if (t_write < t_stride) dec_rows[i * t_stride + t_write] = tok;
+}
+// expand dec rows [nd, t_stride] -> contiguous [nd, T] ids for this step
+__global__ void dec_rows_to_ids_kernel(const int* __restrict__ dec_rows, int t_stride, int T, int* __restrict__ dec_ids, int nd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd * T) return;
+    dec_ids[i] = dec_rows[(i / T) * t_stride + (i % T)];
+}
+
+extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
+                               const int32_t* dec_prefix, int prefix_len, int max_new, int32_t* new_ids) {
+    RET_IF(check_ready(e));
+    if (!ids || !lengths || !dec_prefix || !new_ids || n_docs < 0 || stride <= 0 || prefix_len <= 0 || max_new <= 0 || max_new > 8)
+        return set_error(B200RANK_ERR_ARG, "bad arguments (max_new must be 1..8)");
+    const int Tmax = prefix_len + max_new - 1;  // longest decoder input actually run
+    if (Tmax > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "prefix+new %d exceeds max_dec_len %d", Tmax, e->cap_T);
+    const int t_stride = prefix_len + max_new;
+    const int doc_limit = std::min(std::min(e->cap_docs, e->cap_rows / t_stride), e->cap_logit_rows);
+    int d0 = 0;
+    while (d0 < n_docs) {
+        int d1 = 0;
+        RET_IF(next_group(e, lengths, n_docs, stride, d0, doc_limit, &d1));
+        const int nd = d1 - d0;
+        RET_IF(stage_range(e, ids, lengths, stride, d0, d1));
+        RET_IF(run_encoder(e));
+        // decoder token rows live in d_labels ([nd, t_stride]); finished flags in d_finished; new ids in d_int_out
+        std::vector<int> rows((size_t)nd * t_stride, e->cfg.pad_id);
+        for (int i = 0; i < nd; ++i) std::copy(dec_prefix, dec_prefix + prefix_len, rows.begin() + (size_t)i * t_stride);
+        RET_IF(upload_ints(e, e->d_labels, rows));
+        CU_OK(cudaMemsetAsync(e->d_finished, 0, (size_t)nd * sizeof(int), e->stream));
+        for (int step = 0; step < max_new; ++step) {
+            const int T = prefix_len + step;
+            // No KV cache: the decoder prefix is re-run (<= prefix_len + max_new - 1 positions; negligible next to
+            // the encoder pass) — token-for-token the same greedy choice as the cached loop in generation/utils.py:2762-2804.
+            dec_rows_to_ids_kernel<<<(nd * T + 255) / 256, 256, 0, e->stream>>>(e->d_labels, t_stride, T, e->d_dec_ids, nd);
+            RET_IF(post_launch(e, "dec_rows_to_ids"));
+            RET_IF(run_decoder(e, 0, nd, T));
+            gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
+            RET_IF(post_launch(e, "gather_rows"));
+            RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
+            int* d_argmax = e->d_int_out + (size_t)e->cap_docs * 8;  // second half of the int scratch
+            vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 1, logit_scale(e), nullptr, nullptr, 0, nullptr, d_argmax);
+            RET_IF(post_launch(e, "vocab_row_argmax"));
+            greedy_update_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
+                                                                          t_stride, step, max_new, e->cfg.eos_id, e->cfg.pad_id);
+            RET_IF(post_launch(e, "greedy_update"));
+        }
+        CU_OK(cudaMemcpyAsync(e->h_int, e->d_int_out, (size_t)nd * max_new * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        CU_OK(cudaStreamSynchronize(e->stream));
+        memcpy(new_ids + (size_t)d0 * max_new, e->h_int, (size_t)nd * max_new * sizeof(int));
+        d0 = d1;
+    }
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ measurement plumbing
+extern "C" int b200rank_event_record(b200rank_engine* e, int which) {
+    if (!e || which < 0 || which > 1) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    CU_OK(cudaSetDevice(e->device));
+    CU_OK(cudaEventRecord(e->ev[which], e->stream));
+    return B200RANK_OK;
+}
+extern "C" int b200rank_event_elapsed_ms(b200rank_engine* e, float* ms) {
+    if (!e || !ms) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    CU_OK(cudaSetDevice(e->device));
+    CU_OK(cudaEventSynchronize(e->ev[1]));
+    CU_OK(cudaEventElapsedTime(ms, e->ev[0], e->ev[1]));
+    return B200RANK_OK;
+}
+extern "C" int b200rank_launch_count(b200rank_engine* e, uint64_t* n) {
+    if (!e || !n) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    *n = e->launches;
+    return B200RANK_OK;
+}
+__global__ void fill_kernel(uint4* p, size_t n, uint32_t v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(v, v, v, v);
+}
+extern "C" int b200rank_flush_l2(b200rank_engine* e) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    CU_OK(cudaSetDevice(e->device));
+    if (!e->l2_scratch) {
+        e->l2_scratch_bytes = 256ull << 20;
+        CU_OK(cudaMalloc(reinterpret_cast<void**>(&e->l2_scratch), e->l2_scratch_bytes));
+    }
+    fill_kernel<<<e->num_sms * 8, 256, 0, e->stream>>>(reinterpret_cast<uint4*>(e->l2_scratch), e->l2_scratch_bytes / 16, (uint32_t)e->launches);
+    CU_OK(cudaGetLastError());
+    return B200RANK_OK;
+}
+extern "C" int b200rank_device_info(b200rank_engine* e, int* sm_count, size_t* weight_bytes, size_t* workspace_bytes) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    if (sm_count) *sm_count = e->num_sms;
+    if (weight_bytes) *weight_bytes = e->arena_bytes;
+    if (workspace_bytes) *workspace_bytes = e->workspace_bytes;
+    return B200RANK_OK;
+}
+
+// ------------------------------------------------------------------ kernel-level test hooks
+extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_bf16, int M, int N, int K, int epi, int block_n,
+                                  int use_simt, void* out, float* elapsed_ms) {
+    if (!a_bf16 || !w_bf16 || !out || M <= 0 || N <= 0 || K <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(B200RANK_ERR_CUDA, "no CUDA device available; b200rank has no CPU fallback");
+    CU_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_OK(cudaGetDeviceProperties(&prop, device));
+    const int n_out = epi == EPI_GATED_BF16 ? N / 2 : N;
+    const size_t out_elem = (epi == EPI_BF16 || epi == EPI_GATED_BF16) ? 2 : 4;
+    bf16 *dA = nullptr, *dW = nullptr; void* dO = nullptr;
+    const size_t Mp = align_up(M, 128), Np = align_up(N, 256);
+    CU_OK(cudaMalloc((void**)&dA, Mp * K * 2)); CU_OK(cudaMalloc((void**)&dW, Np * K * 2)); CU_OK(cudaMalloc(&dO, (size_t)M * n_out * out_elem));
+    CU_OK(cudaMemset(dA, 0, Mp * K * 2)); CU_OK(cudaMemset(dW, 0, Np * K * 2));
+    CU_OK(cudaMemcpy(dA, a_bf16, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(dW, w_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(dO, out, (size_t)M * n_out * out_elem, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CU_OK(cudaEventCreate(&e0)); CU_OK(cudaEventCreate(&e1));
+    int rc = B200RANK_OK;
+    CU_OK(cudaEventRecord(e0, 0));
+    if (use_simt) {
+        dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
+        gemm_simt_debug_kernel<<<grd, blk>>>(dA, K, dW, K, M, N, K, epi, 256, dO, n_out);
+    } else {
+        const int bn = block_n ? block_n : pick_block_n(M, N, epi, prop.multiProcessorCount);
+        CUtensorMap ta, tb;
+        rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
+        if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn);
+        GemmArgs args{M, N, K, dO, n_out};
+        if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, args, epi, bn);
+    }
+    if (rc == B200RANK_OK) {
+        cudaEventRecord(e1, 0);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "test_gemm kernel failed: %s", cudaGetErrorString(err));
+        else {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (elapsed_ms) *elapsed_ms = ms;
+            cudaMemcpy(out, dO, (size_t)M * n_out * out_elem, cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dW); cudaFree(dO);
+    return rc;
+}
+
+extern "C" int b200rank_test_enc_attention(int device, const void* qkv_bf16, const int32_t* cu_seqlens, int n_docs, int num_heads,
+                                           const float* bias, void* out_bf16) {
+    if (!qkv_bf16 || !cu_seqlens || !bias || !out_bf16 || n_docs <= 0 || num_heads <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(B200RANK_ERR_CUDA, "no CUDA device available; b200rank has no CPU fallback");
+    CU_OK(cudaSetDevice(device));
+    const int inner = num_heads * 64, tokens = cu_seqlens[n_docs];
+    int maxlen = 0;
+    for (int i = 0; i < n_docs; ++i) maxlen = std::max(maxlen, cu_seqlens[i + 1] - cu_seqlens[i]);
+    bf16 *dq = nullptr, *dout = nullptr; int* dcu = nullptr; float* dbias = nullptr;
+    CU_OK(cudaMalloc((void**)&dq, (size_t)tokens * 3 * inner * 2)); CU_OK(cudaMalloc((void**)&dout, (size_t)tokens * inner * 2));
+    CU_OK(cudaMalloc((void**)&dcu, (n_docs + 1) * 4)); CU_OK(cudaMalloc((void**)&dbias, (size_t)num_heads * kAttnBiasLen * 4));
+    CU_OK(cudaMemcpy(dq, qkv_bf16, (size_t)tokens * 3 * inner * 2, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(dcu, cu_seqlens, (n_docs + 1) * 4, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(dbias, bias, (size_t)num_heads * kAttnBiasLen * 4, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemset(dout, 0, (size_t)tokens * inner * 2));
+    enc_attention_kernel<<<dim3((maxlen + 63) / 64, num_heads, n_docs), 128>>>(dq, 3 * inner, inner, dcu, dbias, dout, inner);
+    cudaError_t err = cudaDeviceSynchronize();
+    int rc = B200RANK_OK;
+    if (err != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "enc_attention kernel failed: %s", cudaGetErrorString(err));
+    else cudaMemcpy(out_bf16, dout, (size_t)tokens * inner * 2, cudaMemcpyDeviceToHost);
+    cudaFree(dq); cudaFree(dout); cudaFree(dcu); cudaFree(dbias);
+    return rc;
+}
