@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — docs scored/sec for the hot path BASELINE.json names.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1: one rank per GPU)
+
+Workload (BASELINE.json configs[1]): flan-t5-large, pointwise yes_no, 100 hits per query, q_len 32 / p_len 128
+(S = 184 encoder tokens, T = 1 decoder token), synthetic token ids + seeded random-init weights of that architecture.
+A step = one query's 100 candidate documents through the whole hot path (the reference's 4 batches of 32/32/32/4,
+which the engine runs as one device pass — bit-identical, tests/test_engine_gpu.py). With N GPUs every rank scores its
+own query per step (prompts shard embarrassingly; weights are NCCL-broadcast once at load) => weak scaling.
+
+`value`  : device-resident inputs, K steps timed with CUDA events on the engine stream, max over ranks.
+`e2e`    : the same K steps through the C-ABI call a host makes (b200rank_score_yes_no: HOST token ids in, HOST scores
+           out; packing, H2D, compute, D2H and the sync inside the timed region), wall clock, max over ranks.
+`roofline`: GEMM kernel (gemm_tcgen05_kernel, all launches of a step): algorithmic GEMM FLOPs / summed launch time,
+           measured live with per-launch CUDA events in a separate profiled pass; peak from MEASURED_PEAKS.json.
+`cpu_baseline`: the numpy oracle (a port of the transformers fp32 path the reference runs on CPU) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "llm-rankers_b200"))
+
+MODEL = "flan-t5-large"
+HITS, Q_LEN, P_LEN = 100, 32, 128
+SEED = 929
+# SURVEY.md §8d / BASELINE.md §2: algorithmic FLOPs per document of the reference's arithmetic at S=184, T=1
+GF_PER_DOC = 136.10
+FALLBACK_PEAK_TFLOPS = 1400.0  # B200_PROFILING.md: sustained bf16 cuBLAS figure on this pool, used only if MEASURED_PEAKS.json is absent
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def gemm_gflop_per_doc(cfg, S):
+    """Algorithmic FLOPs (2*MAC) of the GEMM launches per document: encoder QKVO + gated FFN, stacked cross-K|V
+    projection, decoder (T=1) projections/FFN — i.e. §8d's formula without the attention-core and lm_head terms."""
+    d, I, F = cfg["d_model"], cfg["num_heads"] * 64, cfg["d_ff"]
+    Le, Ld = cfg["num_layers"], cfg["num_decoder_layers"]
+    enc = Le * (8 * d * I * S + 6 * d * F * S)
+    ckv = Ld * 4 * d * I * S
+    dec = Ld * (8 * d * I + 4 * d * I + 6 * d * F)
+    return (enc + ckv + dec) / 1e9
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+        except Exception:  # noqa: BLE001 - clocks are best effort
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9][-3:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][2]) if rows[0][2].replace(".", "").isdigit() else None,
+                "power_w_max": max(float(r[3]) for r in rows if r[3].replace(".", "").isdigit()) if rows else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, seconds-long loop)"
+    return FALLBACK_PEAK_TFLOPS, "fallback (B200_PROFILING.md sustained figure; MEASURED_PEAKS.json absent)"
+
+
+def cpu_oracle_docs_per_s(n_docs, repeats=1):
+    """Times the CPU oracle (numpy fp32 port of the transformers path the reference runs) on n_docs of the workload."""
+    from b200rank.synthetic import NO_ID, YES_ID, model_cfg, synthetic_prompt_ids, synthetic_weights
+    from oracle.t5_oracle import T5Oracle
+    cfg = model_cfg(MODEL)
+    orc = T5Oracle(cfg, synthetic_weights(cfg, SEED))
+    ids, lengths = synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED)
+    ids = ids[:n_docs].astype(np.int64)
+    mask = np.ones_like(ids)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.score_yes_no(ids, mask, YES_ID, NO_ID)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_docs / best, best
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count()
+    sample = 8
+    from b200rank.synthetic import NO_ID, YES_ID, model_cfg, synthetic_prompt_ids, synthetic_weights
+    from oracle.t5_oracle import T5Oracle
+    cfg = model_cfg(MODEL)
+    orc = T5Oracle(cfg, synthetic_weights(cfg, SEED))
+    ids, _ = synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED)
+    ids = ids[:sample].astype(np.int64)
+    mask = np.ones_like(ids)
+    for _ in range(args.warmup):
+        orc.score_yes_no(ids, mask, YES_ID, NO_ID)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.score_yes_no(ids, mask, YES_ID, NO_ID)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = f"{sample} of the {HITS} documents of one query per step (S={Q_LEN + P_LEN + 24}, fp32, numpy/OpenBLAS on all host threads)"
+    line = {
+        "impl": "reference", "metric": "docs scored/sec (flan-t5-large q32/p128, pointwise yes_no)", "value": value, "unit": "docs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, sample_docs=sample),
+        "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(world, sample_docs=None):
+    return {
+        "workload": f"{MODEL} pointwise yes_no, {HITS} hits/query, batch_size 32 (one device pass), q_len {Q_LEN} p_len {P_LEN} -> S {Q_LEN + P_LEN + 24}, T 1 (BASELINE configs[1])",
+        "docs_per_step_per_gpu": HITS if sample_docs is None else sample_docs,
+        "global_docs_per_step": (HITS if sample_docs is None else sample_docs) * world,
+        "parallelism": f"dp{world} (queries sharded across ranks, weights NCCL-broadcast once at load, no collective in the loop)",
+        "weights": f"seeded random init (numpy PCG64 seed {SEED}), bf16 on device",
+        "l2": "no explicit flush: each step streams 1.6 GB of weights + ~3.5 GB of activations, far beyond the 126 MB L2",
+        "algorithmic_gflop_per_doc": GF_PER_DOC,
+    }
+
+
+def run_engine(args):
+    rank, world, local = dist_env()
+    import b200rank as br
+    from b200rank.synthetic import NO_ID, YES_ID, model_cfg, synthetic_prompt_ids, synthetic_weights
+
+    use_dist = world > 1
+    if use_dist:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = model_cfg(MODEL)
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                       max_tokens=HITS * (Q_LEN + P_LEN + 24) + 256, max_docs=128, max_logit_rows=256)
+    eng = br.Engine(c, local)
+    t_load = time.time()
+    if rank == 0:
+        eng.load_state_dict(synthetic_weights(cfg, SEED).items())
+    if use_dist:
+        # the ONE collective of the whole system: broadcast the device weight arena from rank 0 over NCCL/NVLink
+        import torch
+        import torch.distributed as dist
+        ptr, nbytes = eng.weights_blob()
+
+        class _Arena:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        arena = torch.as_tensor(_Arena(), device=torch.device("cuda", local))
+        dist.broadcast(arena, src=0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            eng.mark_weights_loaded()
+    t_load = time.time() - t_load
+
+    # every rank scores its own query (different seed => different token ids), 100 hits each
+    ids, lengths = synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED + rank)
+    n_tok = int(lengths.sum())
+
+    def barrier():
+        eng.sync()
+        if use_dist:
+            import torch.distributed as dist
+            dist.barrier()
+        eng.sync()
+
+    def max_over_ranks(x):
+        if not use_dist:
+            return x
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM, CUDA events on the engine stream
+    eng.stage(ids, lengths)
+    for _ in range(max(args.warmup, 3)):
+        eng.run_yes_no_staged(YES_ID, NO_ID)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    l0 = eng.launch_count()
+    t0 = time.time()
+    eng.event_record(0)
+    for _ in range(args.steps):
+        eng.run_yes_no_staged(YES_ID, NO_ID)
+    eng.event_record(1)
+    ms = eng.event_elapsed_ms()
+    barrier()
+    t1 = time.time()
+    launches = eng.launch_count() - l0
+    sampler.stop()
+    clocks = sampler.summary(t0, t1)
+    ms = max_over_ranks(ms)
+    value = world * HITS * args.steps / (ms * 1e-3)
+    logits_dev, scores_dev = eng.fetch_yes_no()
+
+    # ---- e2e: host buffers through the C-ABI call, wall clock
+    for _ in range(max(args.warmup, 3)):
+        eng.score_yes_no(ids, lengths, YES_ID, NO_ID)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        lg, sc = eng.score_yes_no(ids, lengths, YES_ID, NO_ID)
+    eng.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - w0)
+    e2e_value = world * HITS * args.steps / e2e_s
+    assert np.array_equal(lg, logits_dev), "e2e and device-resident passes disagree"
+    h2d = n_tok * 4 + (HITS + 1) * 4 + HITS * 4 + 2 * 4  # packed ids + cu_seqlens + decoder ids + (yes,no) ids
+    d2h = HITS * 3 * 4                                   # (yes, no) logits + P(yes) per document
+
+    # ---- roofline for the dominant kernel: per-launch CUDA events in a separate profiled pass
+    roofline = None
+    cpu_baseline = None
+    if rank == 0:
+        prof_steps = min(args.steps, 10)
+        eng.profile(True)
+        for _ in range(prof_steps):
+            eng.run_yes_no_staged(YES_ID, NO_ID)
+        rep = eng.profile_report()
+        eng.profile(False)
+        gemm_ms = sum(v["ms"] for k, v in rep.items() if k.startswith("gemm_tcgen05")) / prof_steps
+        gemm_n = sum(v["n"] for k, v in rep.items() if k.startswith("gemm_tcgen05")) / prof_steps
+        all_ms = sum(v["ms"] for v in rep.values()) / prof_steps
+        peak, peak_src = load_peaks()
+        flops = gemm_gflop_per_doc(cfg, Q_LEN + P_LEN + 24) * 1e9 * HITS
+        achieved = flops / (gemm_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of one step)", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+            "gemm_share_of_step": gemm_ms / all_ms if all_ms else None,
+            "step_frac": (value / world) * GF_PER_DOC * 1e9 / (peak * 1e12),
+            "by_kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:14]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample = 8
+            cb, secs = cpu_oracle_docs_per_s(n_sample, repeats=2)
+            cpu_baseline = {"value": cb, "unit": "docs/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"{n_sample} of the {HITS} documents of one query (S={Q_LEN + P_LEN + 24}), best of 2, {secs:.1f} s, numpy fp32 oracle on all host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": "docs scored/sec (flan-t5-large q32/p128, pointwise yes_no)", "value": value, "unit": "docs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "weights_load_s": round(t_load, 2), "sample_scores": [float(x) for x in scores_dev[:4]],
+        }
+        print(json.dumps(line))
+    barrier()
+    eng.close()
+    if use_dist:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    rank, world, _ = dist_env()
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when asked for N > 1 directly
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        return subprocess.call(cmd)
+    return run_engine(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

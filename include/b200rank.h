@@ -125,6 +125,10 @@ int b200rank_sync(b200rank_engine* e);
 int b200rank_event_record(b200rank_engine* e, int which /* 0 = start, 1 = stop */);
 int b200rank_event_elapsed_ms(b200rank_engine* e, float* ms); /* synchronises on the stop event */
 int b200rank_launch_count(b200rank_engine* e, uint64_t* n);  /* kernels launched by this engine so far */
+/* Per-launch timing: enable=1 brackets every kernel launch with CUDA events on the engine stream (labelled by kernel
+ * and GEMM shape); report writes {"label": {"ms": total, "n": launches}, ...} as JSON. Used for roofline.achieved. */
+int b200rank_profile(b200rank_engine* e, int enable);
+int b200rank_profile_report(b200rank_engine* e, char* buf, int buflen);
 int b200rank_flush_l2(b200rank_engine* e);                   /* overwrite a 256 MiB scratch (> 126 MB L2) */
 int b200rank_device_info(b200rank_engine* e, int* sm_count, size_t* weight_bytes, size_t* workspace_bytes);
 

@@ -90,6 +90,8 @@ def load_library() -> C.CDLL:
         "b200rank_event_elapsed_ms": [vp, f32p],
         "b200rank_launch_count": [vp, C.POINTER(C.c_uint64)],
         "b200rank_flush_l2": [vp],
+        "b200rank_profile": [vp, C.c_int],
+        "b200rank_profile_report": [vp, C.c_char_p, C.c_int],
         "b200rank_device_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
         "b200rank_test_gemm": [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p],
         "b200rank_test_enc_attention": [C.c_int, vp, i32p, C.c_int, C.c_int, f32p, vp],
@@ -110,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "b200rank_missing_tensors", "b200rank_weights_blob", "b200rank_mark_weights_loaded", "b200rank_score_yes_no",
     "b200rank_score_qlm", "b200rank_logits_at", "b200rank_greedy", "b200rank_stage", "b200rank_run_yes_no_staged",
     "b200rank_fetch_yes_no", "b200rank_sync", "b200rank_event_record", "b200rank_event_elapsed_ms",
-    "b200rank_launch_count", "b200rank_flush_l2", "b200rank_device_info", "b200rank_test_gemm",
+    "b200rank_launch_count", "b200rank_flush_l2", "b200rank_profile", "b200rank_profile_report", "b200rank_device_info", "b200rank_test_gemm",
     "b200rank_test_enc_attention", "b200rank_rel_bucket",
 ]
 
@@ -276,6 +278,15 @@ class Engine:
         n = C.c_uint64()
         _check(self.lib.b200rank_launch_count(self._h, C.byref(n)))
         return int(n.value)
+
+    def profile(self, enable: bool) -> None:
+        _check(self.lib.b200rank_profile(self._h, int(enable)))
+
+    def profile_report(self) -> Dict[str, Dict[str, float]]:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        _check(self.lib.b200rank_profile_report(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def flush_l2(self) -> None:
         _check(self.lib.b200rank_flush_l2(self._h))

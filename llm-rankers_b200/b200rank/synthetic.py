@@ -42,7 +42,7 @@ def synthetic_tokenizer(n_words: int = N_FILLER_WORDS):
 def synthetic_weights(cfg: Dict, seed: int, lm_head_std: float = 0.05) -> Dict[str, np.ndarray]:
     """Seeded random weights in HF state_dict naming. Scales follow T5's fan-in init
     (transformers/models/t5/modeling_t5.py:520-575) except lm_head, which is scaled down so logits are O(1) and
-    softmaxes are not saturated (SURVEY.md §7 'random-init degeneracy'); q gets a x4 so attention is not uniform."""
+    softmaxes are not saturated (SURVEY.md §7 'random-init degeneracy'); q gets a x2 so attention is moderately peaked without making the random network chaotic under bf16 rounding."""
     rng = np.random.default_rng(seed)
     d, H, dk, F, V = cfg["d_model"], cfg["num_heads"], cfg.get("d_kv", 64), cfg["d_ff"], cfg["vocab_size"]
     I = H * dk
@@ -61,7 +61,7 @@ def synthetic_weights(cfg: Dict, seed: int, lm_head_std: float = 0.05) -> Dict[s
             p = f"{stack}.block.{l}"
             atts = ["layer.0.SelfAttention"] + (["layer.1.EncDecAttention"] if stack == "decoder" else [])
             for att in atts:
-                w[f"{p}.{att}.q.weight"] = n((I, d), (d * dk) ** -0.5 * 4.0)
+                w[f"{p}.{att}.q.weight"] = n((I, d), (d * dk) ** -0.5 * 2.0)
                 w[f"{p}.{att}.k.weight"] = n((I, d), d ** -0.5)
                 w[f"{p}.{att}.v.weight"] = n((I, d), d ** -0.5)
                 w[f"{p}.{att}.o.weight"] = n((d, I), I ** -0.5)

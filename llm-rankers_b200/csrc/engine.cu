@@ -171,7 +171,43 @@ struct b200rank_engine {
     int staged_docs = 0, staged_tokens = 0, staged_maxlen = 0;
 
     std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+
+    // optional per-launch timing (b200rank_profile): event pairs around every kernel, keyed by a label
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;                        // pool, 2 per recorded launch
+    std::vector<std::pair<std::string, size_t>> prof_records;    // (label, index of the start event)
+    size_t prof_used = 0;
+    std::map<std::string, std::pair<double, uint64_t>> prof_acc;  // label -> (total ms, launches)
 };
+
+static void prof_begin(b200rank_engine* e, const char* label) {
+    if (!e->profiling) return;
+    if (e->prof_used + 2 > e->prof_events.size()) {
+        const size_t old = e->prof_events.size();
+        e->prof_events.resize(old + 1024);
+        for (size_t i = old; i < e->prof_events.size(); ++i) cudaEventCreate(&e->prof_events[i]);
+    }
+    e->prof_records.emplace_back(label, e->prof_used);
+    cudaEventRecord(e->prof_events[e->prof_used], e->stream);
+}
+static void prof_end(b200rank_engine* e) {
+    if (!e->profiling) return;
+    cudaEventRecord(e->prof_events[e->prof_used + 1], e->stream);
+    e->prof_used += 2;
+}
+static void prof_collect(b200rank_engine* e) {
+    if (e->prof_records.empty()) return;
+    cudaStreamSynchronize(e->stream);
+    for (auto& r : e->prof_records) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e->prof_events[r.second], e->prof_events[r.second + 1]);
+        auto& acc = e->prof_acc[r.first];
+        acc.first += ms;
+        acc.second += 1;
+    }
+    e->prof_records.clear();
+    e->prof_used = 0;
+}
 
 static int engine_tmap(b200rank_engine* e, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                        const CUtensorMap** out) {
@@ -188,6 +224,7 @@ static int engine_tmap(b200rank_engine* e, const void* ptr, uint64_t rows, uint6
 
 static int post_launch(b200rank_engine* e, const char* what) {
     e->launches++;
+    if (strncmp(what, "gemm", 4) != 0) prof_end(e);  // gemm() closes its own interval
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return set_error(B200RANK_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(err));
     if (e->debug_sync) {
@@ -204,6 +241,10 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     const int bn = force_bn ? force_bn : pick_block_n(M, N, epi, e->num_sms);
+    char label[96];
+    if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);
+    prof_begin(e, label);
+    struct ProfEnd { b200rank_engine* e; ~ProfEnd() { prof_end(e); } } prof_end_guard{e};
     if (e->debug_simt) {
         const int n_out = epi == EPI_GATED_BF16 ? N / 2 : N;
         dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
@@ -275,6 +316,7 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     if (e->h_small) cudaFreeHost(e->h_small);
     for (int i = 0; i < 2; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -569,12 +611,13 @@ extern "C" int b200rank_mark_weights_loaded(b200rank_engine* e) {
 // ------------------------------------------------------------------ forward pieces
 static int k_embed(b200rank_engine* e, const int* ids, float* x, int n) {
     if (n <= 0) return B200RANK_OK;
-    embed_kernel<<<(n + 7) / 8, 256, 0, e->stream>>>(ids, e->emb, x, n, e->d, e->V);
+    prof_begin(e, "embed"); embed_kernel<<<(n + 7) / 8, 256, 0, e->stream>>>(ids, e->emb, x, n, e->d, e->V);
     return post_launch(e, "embed");
 }
 static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n) {
     if (n <= 0) return B200RANK_OK;
     const int grid = (n + 7) / 8;
+    prof_begin(e, "rmsnorm");
     if (e->d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
     else if (e->d <= 2048) rmsnorm_kernel<16><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
     else rmsnorm_kernel<32><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
@@ -591,7 +634,7 @@ static int run_encoder(b200rank_engine* e) {
         const LayerW& w = e->enc[l];
         RET_IF(k_rmsnorm(e, e->x, w.ln1, e->h, n));
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
-        enc_attention_kernel<<<dim3(q_tiles, e->H, nd), 128, 0, e->stream>>>(e->qkv, 3 * I, I, e->d_cu, e->bias_enc, e->ao, I);
+        prof_begin(e, "enc_attention"); enc_attention_kernel<<<dim3(q_tiles, e->H, nd), 128, 0, e->stream>>>(e->qkv, 3 * I, I, e->d_cu, e->bias_enc, e->ao, I);
         RET_IF(post_launch(e, "enc_attention"));
         RET_IF(gemm(e, e->ao, I, Tk, w.wo, I, d, n, d, I, EPI_RESID_F32, e->x, d));
         RET_IF(k_rmsnorm(e, e->x, w.ln2, e->h, n));
@@ -617,12 +660,13 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         const LayerW& w = e->dec[l];
         RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
         RET_IF(gemm(e, e->hd, d, cap, w.wqkv, d, 3 * I, R, 3 * I, d, EPI_BF16, e->qkvd, 3 * I));
-        dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+        prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
         RET_IF(post_launch(e, "dec_self_attention"));
         RET_IF(gemm(e, e->aod, I, cap, w.wo, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
         RET_IF(k_rmsnorm(e, e->xd, w.ln_c, e->hd, R));
         RET_IF(gemm(e, e->hd, d, cap, w.wq_c, d, I, R, I, d, EPI_BF16, e->qd, I));
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
+        prof_begin(e, "cross_attention");
         if (T <= 4)
             cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
         else
@@ -705,9 +749,9 @@ static int yes_no_device(b200rank_engine* e, int yes_id, int no_id) {
     RET_IF(upload_ints(e, e->d_dec_ids, dec));
     RET_IF(upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id}));
     RET_IF(run_decoder(e, 0, nd, 1));
-    lm_head_cols_kernel<<<nd, 64, 0, e->stream>>>(e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
+    prof_begin(e, "lm_head_cols"); lm_head_cols_kernel<<<nd, 64, 0, e->stream>>>(e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
     RET_IF(post_launch(e, "lm_head_cols"));
-    yes_no_score_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, e->small_out2, nd);
+    prof_begin(e, "yes_no_score"); yes_no_score_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, e->small_out2, nd);
     RET_IF(post_launch(e, "yes_no_score"));
     return B200RANK_OK;
 }
@@ -792,9 +836,9 @@ extern "C" int b200rank_score_qlm(b200rank_engine* e, const int32_t* ids, const 
         RET_IF(upload_ints(e, e->d_labels, lab));
         RET_IF(run_decoder(e, 0, nd, T));
         RET_IF(gemm(e, e->hd, e->d, e->cap_rows, e->lm_head, e->d, e->V, R, e->V, e->d, EPI_F32, e->logits, e->V));
-        vocab_row_kernel<<<R, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 0, logit_scale(e), e->d_labels, nullptr, 0, e->small_out, nullptr);
+        prof_begin(e, "vocab_row"); vocab_row_kernel<<<R, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 0, logit_scale(e), e->d_labels, nullptr, 0, e->small_out, nullptr);
         RET_IF(post_launch(e, "vocab_row_logprob"));
-        sum_rows_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, T, e->small_out2, nd);
+        prof_begin(e, "sum_rows"); sum_rows_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, T, e->small_out2, nd);
         RET_IF(post_launch(e, "sum_rows"));
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out2, (size_t)nd * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
         CU_OK(cudaStreamSynchronize(e->stream));
@@ -829,13 +873,13 @@ extern "C" int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const 
         RET_IF(upload_ints(e, e->d_cols, std::vector<int>(cols, cols + ncols)));
         RET_IF(run_decoder(e, 0, nd, T));
         if (!normalize) {
-            lm_head_cols_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
+            prof_begin(e, "lm_head_cols"); lm_head_cols_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
             RET_IF(post_launch(e, "lm_head_cols"));
         } else {
-            gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
+            prof_begin(e, "gather_rows"); gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
             RET_IF(post_launch(e, "gather_rows"));
             RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
-            vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 2, logit_scale(e), nullptr, e->d_cols, ncols, e->small_out, nullptr);
+            prof_begin(e, "vocab_row"); vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 2, logit_scale(e), nullptr, e->d_cols, ncols, e->small_out, nullptr);
             RET_IF(post_launch(e, "vocab_row_softmax_gather"));
         }
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * ncols * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -891,16 +935,16 @@ extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int
             const int T = prefix_len + step;
             // No KV cache: the decoder prefix is re-run (<= prefix_len + max_new - 1 positions; negligible next to
             // the encoder pass) — token-for-token the same greedy choice as the cached loop in generation/utils.py:2762-2804.
-            dec_rows_to_ids_kernel<<<(nd * T + 255) / 256, 256, 0, e->stream>>>(e->d_labels, t_stride, T, e->d_dec_ids, nd);
+            prof_begin(e, "dec_rows_to_ids"); dec_rows_to_ids_kernel<<<(nd * T + 255) / 256, 256, 0, e->stream>>>(e->d_labels, t_stride, T, e->d_dec_ids, nd);
             RET_IF(post_launch(e, "dec_rows_to_ids"));
             RET_IF(run_decoder(e, 0, nd, T));
-            gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
+            prof_begin(e, "gather_rows"); gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
             RET_IF(post_launch(e, "gather_rows"));
             RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
             int* d_argmax = e->d_int_out + (size_t)e->cap_docs * 8;  // second half of the int scratch
-            vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 1, logit_scale(e), nullptr, nullptr, 0, nullptr, d_argmax);
+            prof_begin(e, "vocab_row"); vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 1, logit_scale(e), nullptr, nullptr, 0, nullptr, d_argmax);
             RET_IF(post_launch(e, "vocab_row_argmax"));
-            greedy_update_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
+            prof_begin(e, "greedy_update"); greedy_update_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
                                                                           t_stride, step, max_new, e->cfg.eos_id, e->cfg.pad_id);
             RET_IF(post_launch(e, "greedy_update"));
         }
@@ -929,6 +973,32 @@ extern "C" int b200rank_event_elapsed_ms(b200rank_engine* e, float* ms) {
 extern "C" int b200rank_launch_count(b200rank_engine* e, uint64_t* n) {
     if (!e || !n) return set_error(B200RANK_ERR_ARG, "bad arguments");
     *n = e->launches;
+    return B200RANK_OK;
+}
+extern "C" int b200rank_profile(b200rank_engine* e, int enable) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    CU_OK(cudaSetDevice(e->device));
+    prof_collect(e);
+    e->profiling = enable != 0;
+    if (enable) e->prof_acc.clear();
+    return B200RANK_OK;
+}
+extern "C" int b200rank_profile_report(b200rank_engine* e, char* buf, int buflen) {
+    if (!e || !buf || buflen <= 2) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    CU_OK(cudaSetDevice(e->device));
+    prof_collect(e);
+    std::string js = "{";
+    bool first = true;
+    for (auto& kv : e->prof_acc) {
+        char line[256];
+        snprintf(line, sizeof line, "%s\"%s\": {\"ms\": %.6f, \"n\": %llu}", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+                 (unsigned long long)kv.second.second);
+        js += line;
+        first = false;
+    }
+    js += "}";
+    if ((int)js.size() + 1 > buflen) return set_error(B200RANK_ERR_ARG, "profile report needs %zu bytes", js.size() + 1);
+    memcpy(buf, js.c_str(), js.size() + 1);
     return B200RANK_OK;
 }
 __global__ void fill_kernel(uint4* p, size_t n, uint32_t v) {

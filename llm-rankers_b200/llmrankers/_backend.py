@@ -1,0 +1,170 @@
+"""What `self.llm` + `self.tokenizer` are to the reference rankers, re-based on the B200 engine.
+
+A T5Backend owns (a) a tokenizer (transformers.T5Tokenizer — tokenisation is not on the device path) and (b) a
+b200rank.Engine holding the model on one GPU. Model sources:
+  * "synthetic:<shape>[:seed=N]"  seeded random weights of a Flan-T5 shape + the in-memory synthetic tokenizer
+                                   (benchmarks/tests on a box with no checkpoints),
+  * a local directory with config.json + model.safetensors | pytorch_model.bin (real Flan-T5 checkpoints),
+  * anything else is handed to transformers' from_pretrained (hub cache) to obtain the state dict on the CPU.
+There is no CPU execution path: device must be 'cuda' / 'cuda:N' (the reference's device='cpu' raises here).
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_ENGINE_CACHE: Dict[Tuple[str, int], "T5Backend"] = {}
+
+
+def _device_index(device) -> int:
+    d = str(device)
+    if d == "cuda":
+        return int(os.environ.get("LOCAL_RANK", "0"))
+    if d.startswith("cuda:"):
+        return int(d.split(":", 1)[1])
+    raise RuntimeError(f"device={device!r}: the B200 engine has no CPU path (use device='cuda')")
+
+
+def generate_mask_mode() -> str:
+    """How generate() calls WITHOUT attention_mask treat pad tokens inside a padded batch (pairwise.py:97-99,196-200):
+    'ones'  — pads are ordinary tokens and are attended: transformers >= 5 for encoder-decoder models
+              (generation/utils.py:2429: mask inference is skipped when config.is_encoder_decoder); the default,
+              because it is what the reference does on this image and what the golden fixtures pin;
+    'infer' — attention_mask = ids != pad: transformers 4.31.0, the reference's README-tested pin."""
+    m = os.environ.get("B200RANK_GENERATE_MASK", "ones")
+    if m not in ("ones", "infer"):
+        raise ValueError("B200RANK_GENERATE_MASK must be 'ones' or 'infer'")
+    return m
+
+
+class T5Backend:
+    def __init__(self, engine, tokenizer, cfg: Dict):
+        self.engine = engine
+        self.tokenizer = tokenizer
+        self.cfg = cfg
+        self.pad_id = cfg.get("pad_id", 0)
+        self.eos_id = cfg.get("eos_id", 1)
+
+    # ---------------------------------------------------------------- construction
+    @classmethod
+    def load(cls, model_name_or_path: str, tokenizer_name_or_path: Optional[str], device, cache_dir=None,
+             max_tokens: int = 0, max_docs: int = 0) -> "T5Backend":
+        import b200rank as br
+        dev = _device_index(device)
+        key = (f"{model_name_or_path}|{tokenizer_name_or_path}|{max_tokens}|{max_docs}", dev)
+        if key in _ENGINE_CACHE:
+            return _ENGINE_CACHE[key]
+        if model_name_or_path.startswith("synthetic:"):
+            from b200rank.synthetic import model_cfg, synthetic_tokenizer, synthetic_weights
+            parts = model_name_or_path.split(":")
+            shape = parts[1]
+            opts = dict(p.split("=", 1) for p in parts[2:])
+            cfg = model_cfg(shape, int(opts.get("vocab", 32128)))
+            tensors: Iterable = synthetic_weights(cfg, int(opts.get("seed", 929)), float(opts.get("lm_head_std", 0.05))).items()
+            tokenizer = synthetic_tokenizer()
+        else:
+            cfg, tensors = _load_checkpoint(model_name_or_path, cache_dir)
+            from transformers import T5Tokenizer
+            tokenizer = T5Tokenizer.from_pretrained(tokenizer_name_or_path or model_name_or_path, cache_dir=cache_dir)
+        c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                           vocab_size=cfg["vocab_size"], d_kv=cfg.get("d_kv", 64), rel_buckets=cfg.get("rel_buckets", 32),
+                           rel_max_distance=cfg.get("rel_max_distance", 128), layer_norm_eps=cfg.get("layer_norm_eps", 1e-6),
+                           gated_gelu=cfg.get("gated_gelu", True), scale_decoder_outputs=cfg.get("scale_decoder_outputs", False),
+                           pad_id=cfg.get("pad_id", 0), eos_id=cfg.get("eos_id", 1), max_tokens=max_tokens, max_docs=max_docs)
+        engine = br.Engine(c, dev)
+        engine.load_state_dict(tensors)
+        be = cls(engine, tokenizer, cfg)
+        _ENGINE_CACHE[key] = be
+        return be
+
+    # ---------------------------------------------------------------- host-side token plumbing
+    def tokenize_prompts(self, prompts: Sequence[str]) -> List[List[int]]:
+        """`tokenizer(data)` of Text2TextGenerationDataset (pairwise.py:17-26): appends </s>, no padding, no truncation."""
+        prompts = list(prompts)
+        return self.tokenizer(prompts)["input_ids"] if prompts else []
+
+    @staticmethod
+    def pad_rows(rows: Sequence[Sequence[int]], pad_id: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        n = len(rows)
+        lengths = np.fromiter((len(r) for r in rows), dtype=np.int32, count=n)
+        ids = np.full((n, int(lengths.max()) if n else 1), pad_id, dtype=np.int32)
+        for i, r in enumerate(rows):
+            ids[i, : len(r)] = r
+        return ids, lengths
+
+    # ---------------------------------------------------------------- the four uses of the forward
+    def score_yes_no(self, rows, yes_id: int, no_id: int):
+        ids, lengths = self.pad_rows(rows, self.pad_id)
+        return self.engine.score_yes_no(ids, lengths, yes_id, no_id)
+
+    def score_qlm(self, rows, labels: Sequence[int]) -> np.ndarray:
+        ids, lengths = self.pad_rows(rows, self.pad_id)
+        return self.engine.score_qlm(ids, lengths, labels)
+
+    def label_probs(self, rows, dec_prefix: Sequence[int], cols: Sequence[int]) -> np.ndarray:
+        ids, lengths = self.pad_rows(rows, self.pad_id)
+        return self.engine.logits_at(ids, lengths, dec_prefix, cols, normalize=True)
+
+    def generate(self, padded_ids: np.ndarray, dec_prefix: Sequence[int], max_new: int) -> np.ndarray:
+        """`self.llm.generate(input_ids, decoder_input_ids=prefix, max_new_tokens=max_new)` for one padded batch; returns the
+        HF-shaped output [B, len(prefix) + steps] where steps stops early once every row has emitted eos."""
+        ids = np.ascontiguousarray(padded_ids, dtype=np.int32)
+        if generate_mask_mode() == "infer" and (ids == self.pad_id).any():
+            lengths = (ids != self.pad_id).sum(axis=1).astype(np.int32)
+            # right padding only (T5Tokenizer pads right): the non-pad prefix is the real row
+        else:
+            lengths = np.full((ids.shape[0],), ids.shape[1], np.int32)
+        new = self.engine.greedy(ids, lengths, dec_prefix, max_new)
+        finished = np.zeros(ids.shape[0], bool)
+        steps = max_new
+        for s in range(max_new):
+            finished |= new[:, s] == self.eos_id
+            if finished.all():
+                steps = s + 1
+                break
+        prefix = np.tile(np.asarray(dec_prefix, np.int64)[None], (ids.shape[0], 1))
+        return np.concatenate([prefix, new[:, :steps].astype(np.int64)], axis=1)
+
+
+def _load_checkpoint(path: str, cache_dir=None):
+    """(cfg dict, iterable of (name, fp32 ndarray)) from a local HF checkpoint dir, else via transformers on the CPU."""
+    if os.path.isdir(path) and os.path.exists(os.path.join(path, "config.json")):
+        with open(os.path.join(path, "config.json")) as f:
+            hf = json.load(f)
+        cfg = _cfg_from_hf(hf)
+        st = os.path.join(path, "model.safetensors")
+        if os.path.exists(st):
+            from safetensors import safe_open
+
+            def gen():
+                with safe_open(st, framework="np") as f:
+                    for name in f.keys():
+                        yield name, np.asarray(f.get_tensor(name), dtype=np.float32)
+            return cfg, gen()
+        import torch
+        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        return cfg, ((k, v.float().numpy()) for k, v in sd.items())
+    from transformers import AutoConfig, T5ForConditionalGeneration
+    hf_cfg = AutoConfig.from_pretrained(path, cache_dir=cache_dir)
+    if hf_cfg.model_type != "t5":
+        raise NotImplementedError(f"Model type {hf_cfg.model_type} is not supported by the B200 engine (Flan-T5 only)")
+    model = T5ForConditionalGeneration.from_pretrained(path, cache_dir=cache_dir)
+    cfg = _cfg_from_hf(hf_cfg.to_dict())
+    return cfg, ((k, v.float().numpy()) for k, v in model.state_dict().items())
+
+
+def _cfg_from_hf(hf: Dict) -> Dict:
+    if hf.get("model_type", "t5") != "t5":
+        raise NotImplementedError(f"Model type {hf.get('model_type')} is not supported by the B200 engine (Flan-T5 only)")
+    proj = hf.get("feed_forward_proj", "relu")
+    if proj != "gated-gelu":
+        raise NotImplementedError(f"feed_forward_proj={proj!r}: only gated-gelu (Flan-T5 / T5 v1.1) is implemented")
+    return dict(vocab_size=hf["vocab_size"], d_model=hf["d_model"], d_kv=hf["d_kv"], num_heads=hf["num_heads"], d_ff=hf["d_ff"],
+                num_layers=hf["num_layers"], num_decoder_layers=hf.get("num_decoder_layers") or hf["num_layers"],
+                rel_buckets=hf.get("relative_attention_num_buckets", 32), rel_max_distance=hf.get("relative_attention_max_distance", 128),
+                layer_norm_eps=hf.get("layer_norm_epsilon", 1e-6), gated_gelu=True,
+                scale_decoder_outputs=bool(hf.get("tie_word_embeddings", True)), pad_id=hf.get("pad_token_id", 0),
+                eos_id=hf.get("eos_token_id", 1))

@@ -1,0 +1,127 @@
+"""Pairwise ranker on the B200 engine — drop-in for the T5 branch of the reference's llmrankers/pairwise.py.
+
+Keeps the prompt, the `<pad> Passage` decoder prefix, both-orders comparison, exact-string win/conflict scoring,
+counters and output assembly (pairwise.py:30-63, 84-103, 164-290). allpair sends all 2*C(n,2) prompts through the
+engine in the reference's batch order (batch composition matters here: generate() is called without an attention
+mask, so how pads are treated follows B200RANK_GENERATE_MASK, see _backend.generate_mask_mode).
+"""
+import copy
+from collections import defaultdict
+from itertools import combinations
+from typing import List, Optional
+
+from ._backend import T5Backend
+from ._sorting import binary_heap_top_k, pairwise_bubble_top_k
+from .rankers import LlmRanker, SearchResult
+from .setwise import _assemble
+
+PAIRWISE_PROMPT = """Given a query "{query}", which of the following two passages is more relevant to the query?
+
+Passage A: "{doc1}"
+
+Passage B: "{doc2}"
+
+Output Passage A or Passage B:"""
+
+
+class Text2TextGenerationDataset:
+    """pairwise.py:17-26 — tokenises all prompts up front (appends </s>, no padding, no truncation)."""
+
+    def __init__(self, data: List[str], tokenizer):
+        self.data = tokenizer(list(data))
+
+    def __len__(self):
+        return len(self.data['input_ids'])
+
+    def __getitem__(self, item):
+        return {'input_ids': self.data['input_ids'][item], 'attention_mask': self.data['attention_mask'][item]}
+
+
+class PairwiseLlmRanker(LlmRanker):
+    def __init__(self, model_name_or_path, tokenizer_name_or_path, device, method="allpair", batch_size=2, k=10, cache_dir=None,
+                 *, backend: Optional[T5Backend] = None):
+        self.device = device
+        self.method = method
+        self.batch_size = batch_size
+        self.k = k
+        self.prompt = PAIRWISE_PROMPT
+        self.backend = backend or T5Backend.load(model_name_or_path, tokenizer_name_or_path, device, cache_dir)
+        self.tokenizer = self.backend.tokenizer
+        self.llm = self.backend.engine
+        self.config = self.backend.cfg
+        self.decoder_input_ids = self.tokenizer.encode("<pad> Passage", add_special_tokens=False)
+        self.total_compare = 0
+        self.total_completion_tokens = 0
+        self.total_prompt_tokens = 0
+
+    def compare(self, query: str, docs: List):
+        """Both presentation orders of (doc1, doc2) in one padded batch of 2 -> two decoded strings (pairwise.py:84-103)."""
+        self.total_compare += 1
+        doc1, doc2 = docs[0], docs[1]
+        rows = self.backend.tokenize_prompts([self.prompt.format(query=query, doc1=doc1, doc2=doc2),
+                                              self.prompt.format(query=query, doc1=doc2, doc2=doc1)])
+        ids, _ = self.backend.pad_rows(rows, self.backend.pad_id)
+        self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
+        out = self.backend.generate(ids, self.decoder_input_ids, 2)
+        self.total_completion_tokens += out.shape[0] * out.shape[1]
+        return self.tokenizer.batch_decode(out.tolist(), skip_special_tokens=True)
+
+    def _first_wins(self, query: str, a, b) -> bool:
+        out = self.compare(query, [a.text, b.text])
+        return out[0] == "Passage A" and out[1] == "Passage B"
+
+    def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
+        original_ranking = copy.deepcopy(ranking)
+        self.total_compare = 0
+        self.total_completion_tokens = 0
+        self.total_prompt_tokens = 0
+        if self.method == "allpair":
+            doc_pairs = list(combinations(ranking, 2))
+            prompts = []
+            for d1, d2 in doc_pairs:
+                prompts.append(self.prompt.format(query=query, doc1=d1.text, doc2=d2.text))
+                prompts.append(self.prompt.format(query=query, doc1=d2.text, doc2=d1.text))
+            rows = self.backend.tokenize_prompts(prompts) if prompts else []
+            outputs = []
+            for i in range(0, len(rows), self.batch_size):
+                ids, _ = self.backend.pad_rows(rows[i:i + self.batch_size], self.backend.pad_id)
+                self.total_compare += 1
+                self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
+                out = self.backend.generate(ids, self.decoder_input_ids, 2)
+                self.total_completion_tokens += out.shape[0] * out.shape[1]
+                outputs.extend(out.tolist())
+            outputs = self.tokenizer.batch_decode(outputs, skip_special_tokens=True)
+            scores = defaultdict(float)
+            for i in range(0, len(outputs), 2):
+                d1, d2 = doc_pairs[i // 2]
+                if outputs[i] == "Passage A" and outputs[i + 1] == "Passage B":
+                    scores[d1.docid] += 1
+                elif outputs[i] == "Passage B" and outputs[i + 1] == "Passage A":
+                    scores[d2.docid] += 1
+                else:  # conflict
+                    scores[d1.docid] += 0.5
+                    scores[d2.docid] += 0.5
+            ranking = sorted([SearchResult(docid=docid, score=score, text=None) for docid, score in scores.items()],
+                             key=lambda x: x.score, reverse=True)
+        elif self.method == "heapsort":
+            arr = list(ranking)
+            binary_heap_top_k(arr, self.k, lambda a, b: self._first_wins(query, a, b))
+            ranking = [SearchResult(docid=doc.docid, score=-i, text=None) for i, doc in enumerate(reversed(arr))]
+        elif self.method == "bubblesort":
+            pairwise_bubble_top_k(ranking, self.k, lambda a, b: self._first_wins(query, a, b))
+        else:
+            raise NotImplementedError(f'Method {self.method} is not implemented.')
+        return _assemble(ranking, original_ranking, self.k)
+
+    def truncate(self, text, length):
+        return self.tokenizer.convert_tokens_to_string(self.tokenizer.tokenize(text)[:length])
+
+
+class DuoT5LlmRanker(PairwiseLlmRanker):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("duoT5 (T5 v1.0 relu feed-forward) is not implemented by the B200 engine yet (SURVEY.md §8f)")
+
+
+class OpenAiPairwiseLlmRanker(PairwiseLlmRanker):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("OpenAI-backed rankers are a remote API, outside the B200 engine's scope (SURVEY.md §2.1)")

@@ -1,0 +1,154 @@
+"""Setwise ranker on the B200 engine — drop-in for the T5 branch of the reference's llmrankers/setwise.py.
+
+compare() keeps the reference's prompt, decoder prefix `<pad> Passage`, label extraction (last character of the decoded
+generation, or arg-max label probability under scoring='likelihood'), fallbacks and counters (setwise.py:79-198); the
+sort drivers reproduce the reference's compare sequence (setwise.py:200-313) via llmrankers/_sorting.py.
+The llama / OpenAI / Rank-R1(vLLM) variants of the reference are different model families and out of scope.
+"""
+import copy
+import random
+from collections import Counter
+from typing import List, Optional
+
+import numpy as np
+
+from ._backend import T5Backend
+from ._sorting import heap_top_k, setwise_bubble_top_k
+from .rankers import LlmRanker, SearchResult
+
+random.seed(929)  # setwise.py:18
+
+
+class SetwiseLlmRanker(LlmRanker):
+    CHARACTERS = ["A", "B", "C", "D", "E", "F", "G", "H", "I", "J", "K", "L",
+                  "M", "N", "O", "P", "Q", "R", "S", "T", "U", "V", "W"]
+
+    def __init__(self, model_name_or_path, tokenizer_name_or_path, device, num_child=3, k=10, scoring='generation',
+                 method="heapsort", num_permutation=1, cache_dir=None, *, backend: Optional[T5Backend] = None):
+        self.device = device
+        self.num_child = num_child
+        self.num_permutation = num_permutation
+        self.k = k
+        self.backend = backend or T5Backend.load(model_name_or_path, tokenizer_name_or_path, device, cache_dir)
+        self.tokenizer = self.backend.tokenizer
+        self.llm = self.backend.engine
+        self.config = self.backend.cfg
+        # setwise.py:51-59 — the reference's batch_encode_plus call no longer exists in transformers 5; same ids
+        self.decoder_input_ids = self.tokenizer.encode("<pad> Passage", add_special_tokens=False)
+        self.target_token_ids = [self.tokenizer.encode(f"<pad> Passage {c}", add_special_tokens=False)[-1] for c in self.CHARACTERS]
+        self.scoring = scoring
+        self.method = method
+        self.total_compare = 0
+        self.total_completion_tokens = 0
+        self.total_prompt_tokens = 0
+
+    @staticmethod
+    def _prompt(query: str, texts: List[str], labels: List[str]) -> str:
+        passages = "\n\n".join(f'Passage {labels[i]}: "{t}"' for i, t in enumerate(texts))
+        return (f'Given a query "{query}", which of the following passages is the most relevant one to the query?\n\n'
+                + passages + '\n\nOutput only the passage label of the most relevant passage:')
+
+    def compare(self, query: str, docs: List):
+        self.total_compare += 1 if self.num_permutation == 1 else self.num_permutation
+        if self.scoring == 'generation':
+            if self.num_permutation == 1:
+                row = self.backend.tokenize_prompts([self._prompt(query, [d.text for d in docs], self.CHARACTERS)])[0]
+                self.total_prompt_tokens += len(row)
+                out = self.backend.generate(np.asarray([row], np.int32), self.decoder_input_ids, 2)[0]
+                self.total_completion_tokens += int(out.shape[0])
+                output = self.tokenizer.decode(out.tolist(), skip_special_tokens=True).strip()
+                output = output[-1]
+            else:
+                output = self._compare_permutations(query, docs)
+        elif self.scoring == 'likelihood':
+            row = self.backend.tokenize_prompts([self._prompt(query, [d.text for d in docs], self.CHARACTERS)])[0]
+            self.total_prompt_tokens += len(row)
+            probs = self.backend.label_probs([row], self.decoder_input_ids, self.target_token_ids[:len(docs)])[0]
+            ranked = sorted(zip(self.CHARACTERS[:len(docs)], probs), key=lambda x: x[1], reverse=True)
+            output = ranked[0][0]
+        else:
+            raise NotImplementedError
+        if not (len(output) == 1 and output in self.CHARACTERS):
+            print(f"Unexpected output: {output}")
+        return output
+
+    def _compare_permutations(self, query: str, docs: List) -> str:
+        """setwise.py:102-157 — vote over num_permutation shuffles of passages and labels (module RNG, seed 929)."""
+        id_passage = list(enumerate(docs))
+        labels = [self.CHARACTERS[i] for i in range(len(docs))]
+        refs, prompts = [], []
+        for _ in range(self.num_permutation):
+            perm = random.sample(id_passage, len(id_passage))
+            chars = random.sample(labels, len(labels))
+            refs.append(([p[0] for p in perm], chars))
+            prompts.append(self._prompt(query, [p[1].text for p in perm], chars))
+        rows = self.backend.tokenize_prompts(prompts)
+        ids, _ = self.backend.pad_rows(rows, self.backend.pad_id)
+        self.total_prompt_tokens += ids.shape[1] * ids.shape[0]
+        out = self.backend.generate(ids, self.decoder_input_ids, 2)
+        texts = self.tokenizer.batch_decode(out[:, len(self.decoder_input_ids):].tolist(), skip_special_tokens=True)
+        candidates = []
+        for (docids, chars), result in zip(refs, texts):
+            result = result.strip().upper()
+            if len(result) != 1 or result not in chars:
+                print(f"Unexpected output: {result}")
+                continue
+            candidates.append(docids[chars.index(result)])
+        if not candidates:
+            print(f"Unexpected voting: {texts}")
+            return "Unexpected voting."
+        counts = Counter(candidates)
+        top = max(counts.values())
+        best = [c for c, n in counts.items() if n == top]
+        return self.CHARACTERS[best[0] if len(best) == 1 else random.choice(best)]
+
+    def _best_index(self, query: str, docs: List) -> int:
+        """Label -> position in the compared set; an unknown label keeps the head (setwise.py:206-209, 252-255)."""
+        try:
+            return self.CHARACTERS.index(self.compare(query, docs))
+        except ValueError:
+            return 0
+
+    def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
+        original_ranking = copy.deepcopy(ranking)
+        self.total_compare = 0
+        self.total_completion_tokens = 0
+        self.total_prompt_tokens = 0
+        if self.method == "heapsort":
+            def pick(docs, inds):
+                b = self._best_index(query, docs)
+                return inds[b] if b < len(inds) else inds[0]  # a label beyond the set keeps the parent (setwise.py:210-213)
+            heap_top_k(ranking, self.num_child, self.k, pick)
+            ranking = list(reversed(ranking))
+        elif self.method == "bubblesort":
+            setwise_bubble_top_k(ranking, self.num_child, self.k, lambda window: self._best_index(query, window))
+        else:
+            raise NotImplementedError(f'Method {self.method} is not implemented.')
+        return _assemble(ranking, original_ranking, self.k)
+
+    def truncate(self, text, length):
+        return self.tokenizer.convert_tokens_to_string(self.tokenizer.tokenize(text)[:length])
+
+
+def _assemble(ranking: List[SearchResult], original: List[SearchResult], k: int) -> List[SearchResult]:
+    """setwise.py:300-311 / pairwise.py:279-290: top-k get score -rank; the rest follow in their ORIGINAL order."""
+    results, top, rank = [], set(), 1
+    for doc in ranking[:k]:
+        top.add(doc.docid)
+        results.append(SearchResult(docid=doc.docid, score=-rank, text=None))
+        rank += 1
+    for doc in original:
+        if doc.docid not in top:
+            results.append(SearchResult(docid=doc.docid, score=-rank, text=None))
+            rank += 1
+    return results
+
+
+class OpenAiSetwiseLlmRanker(SetwiseLlmRanker):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("OpenAI-backed rankers are a remote API, outside the B200 engine's scope (SURVEY.md §2.1)")
+
+
+class RankR1SetwiseLlmRanker(SetwiseLlmRanker):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("Rank-R1 (vLLM decoder-only models) is outside the B200 engine's scope (SURVEY.md §2.1)")

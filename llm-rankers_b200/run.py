@@ -1,0 +1,222 @@
+"""CLI with the reference's grammar (run.py:206-258): `python run.py run <run flags> {pointwise|pairwise|setwise} <flags>`,
+same flags and defaults, same four summary prints and the same TREC output line (run.py:41-49, 198-201).
+
+Differences, all additive: ir_datasets / pyserini are imported lazily (absent on an offline box), and two extra
+`run` flags name plain-text sources so the CLI is usable without them:
+    --queries_tsv  qid<TAB>text         --collection_tsv  docid<TAB>text
+`--model_name_or_path synthetic:flan-t5-large` selects seeded random weights + the synthetic tokenizer.
+"""
+import argparse
+import json
+import logging
+import random
+import sys
+import time
+
+from llmrankers.pairwise import DuoT5LlmRanker, OpenAiPairwiseLlmRanker, PairwiseLlmRanker
+from llmrankers.pointwise import MonoT5LlmRanker, PointwiseLlmRanker
+from llmrankers.rankers import SearchResult
+from llmrankers.setwise import OpenAiSetwiseLlmRanker, SetwiseLlmRanker
+from llmrankers.listwise import ListwiseLlmRanker, OpenAiListwiseLlmRanker
+
+random.seed(929)
+logger = logging.getLogger(__name__)
+
+
+def parse_args(parser, commands, argv=None):
+    """Split argv at sub-command names and parse each slice into its own namespace (run.py:20-38)."""
+    argv = sys.argv[1:] if argv is None else argv
+    groups = [[]]
+    for tok in argv:
+        if tok in commands.choices:
+            groups.append([tok])
+        else:
+            groups[-1].append(tok)
+    args = argparse.Namespace(**{c: None for c in commands.choices})
+    parser.parse_args(groups[0], namespace=args)
+    for g in groups[1:]:
+        ns = argparse.Namespace()
+        setattr(args, g[0], ns)
+        parser.parse_args(g, namespace=ns)
+    return args
+
+
+def write_run_file(path, results, tag):
+    with open(path, 'w') as f:
+        for qid, _, ranking in results:
+            for rank, doc in enumerate(ranking, start=1):
+                f.write(f"{qid}\tQ0\t{doc.docid}\t{rank}\t{doc.score}\t{tag}\n")
+
+
+def build_ranker(args):
+    run = args.run
+    common = dict(model_name_or_path=run.model_name_or_path, tokenizer_name_or_path=run.tokenizer_name_or_path,
+                  device=run.device, cache_dir=run.cache_dir)
+    if args.pointwise:
+        cls = MonoT5LlmRanker if 'monot5' in run.model_name_or_path else PointwiseLlmRanker
+        return cls(method=args.pointwise.method, batch_size=args.pointwise.batch_size, **common)
+    if args.setwise:
+        if run.openai_key:
+            return OpenAiSetwiseLlmRanker(model_name_or_path=run.model_name_or_path, api_key=run.openai_key,
+                                          num_child=args.setwise.num_child, method=args.setwise.method, k=args.setwise.k)
+        return SetwiseLlmRanker(num_child=args.setwise.num_child, scoring=run.scoring, method=args.setwise.method,
+                                num_permutation=args.setwise.num_permutation, k=args.setwise.k, **common)
+    if args.pairwise:
+        if args.pairwise.method != 'allpair':
+            args.pairwise.batch_size = 2
+            logger.info('Setting batch_size to 2.')
+        if run.openai_key:
+            return OpenAiPairwiseLlmRanker(model_name_or_path=run.model_name_or_path, api_key=run.openai_key,
+                                           method=args.pairwise.method, k=args.pairwise.k)
+        cls = DuoT5LlmRanker if 'duot5' in run.model_name_or_path else PairwiseLlmRanker
+        return cls(method=args.pairwise.method, batch_size=args.pairwise.batch_size, k=args.pairwise.k, **common)
+    if args.listwise:
+        cls = OpenAiListwiseLlmRanker if run.openai_key else ListwiseLlmRanker
+        return cls(model_name_or_path=run.model_name_or_path)
+    raise ValueError('Must specify either --pointwise, --setwise, --pairwise or --listwise.')
+
+
+def _read_tsv(path):
+    out = {}
+    with open(path) as f:
+        for line in f:
+            key, _, text = line.rstrip("\n").partition("\t")
+            out[key] = text
+    return out
+
+
+def load_sources(run, ranker):
+    """query_map (truncated queries) and a docid -> text getter, from TSV files, ir_datasets or pyserini (run.py:135-149)."""
+    query_map = {}
+    if run.queries_tsv is not None or run.collection_tsv is not None:
+        if run.queries_tsv is None or run.collection_tsv is None:
+            raise ValueError('--queries_tsv and --collection_tsv must be given together.')
+        for qid, text in _read_tsv(run.queries_tsv).items():
+            query_map[qid] = ranker.truncate(text, run.query_length)
+        docs = _read_tsv(run.collection_tsv)
+        return query_map, docs.__getitem__
+    if run.ir_dataset_name is not None:
+        import ir_datasets
+        dataset = ir_datasets.load(run.ir_dataset_name)
+        for q in dataset.queries_iter():
+            query_map[q.query_id] = ranker.truncate(q.text, run.query_length)
+        store = dataset.docs_store()
+
+        def get(docid):
+            d = store.get(docid)
+            return f'{d.title} {d.text}' if 'title' in dir(d) else d.text
+        return query_map, get
+    from pyserini.search._base import get_topics
+    from pyserini.search.lucene import LuceneSearcher
+    topics = get_topics(run.pyserini_index + '-test')
+    for tid in list(topics.keys()):
+        query_map[str(tid)] = ranker.truncate(topics[tid]['title'], run.query_length)
+    searcher = LuceneSearcher.from_prebuilt_index(run.pyserini_index + '.flat')
+
+    def get(docid):
+        data = json.loads(searcher.doc(docid).raw())
+        return f'{data["title"]} {data["text"]}' if 'title' in data else data['text']
+    return query_map, get
+
+
+def read_first_stage(run, ranker, query_map, get_text):
+    """6-column TREC run -> [(qid, query, [SearchResult] capped at --hits)] in file order (run.py:151-176)."""
+    rankings, cur_qid, cur = [], None, []
+    with open(run.run_path) as f:
+        for line in f:
+            qid, _, docid, _, score, _ = line.strip().split()
+            if qid != cur_qid:
+                if cur_qid is not None:
+                    rankings.append((cur_qid, query_map[cur_qid], cur[:run.hits]))
+                cur, cur_qid = [], qid
+            if len(cur) >= run.hits:
+                continue
+            cur.append(SearchResult(docid=docid, score=float(score), text=ranker.truncate(get_text(docid), run.passage_length)))
+    rankings.append((cur_qid, query_map[cur_qid], cur[:run.hits]))
+    return rankings
+
+
+def main(args):
+    ranker = build_ranker(args)
+    query_map, get_text = load_sources(args.run, ranker)
+    logger.info(f'Loading first stage run from {args.run.run_path}.')
+    first_stage = read_first_stage(args.run, ranker, query_map, get_text)
+
+    reranked, n_cmp, n_prompt, n_completion = [], 0, 0, 0
+    tic = time.time()
+    for qid, query, ranking in first_stage:
+        if args.run.shuffle_ranking is not None:
+            if args.run.shuffle_ranking == 'random':
+                random.shuffle(ranking)
+            elif args.run.shuffle_ranking == 'inverse':
+                ranking = ranking[::-1]
+            else:
+                raise ValueError(f'Invalid shuffle ranking method: {args.run.shuffle_ranking}.')
+        reranked.append((qid, query, ranker.rerank(query, ranking)))
+        n_cmp += ranker.total_compare
+        n_prompt += ranker.total_prompt_tokens
+        n_completion += ranker.total_completion_tokens
+    toc = time.time()
+    print(f'Avg comparisons: {n_cmp / len(reranked)}')
+    print(f'Avg prompt tokens: {n_prompt / len(reranked)}')
+    print(f'Avg completion tokens: {n_completion / len(reranked)}')
+    print(f'Avg time per query: {(toc - tic) / len(reranked)}')
+    write_run_file(args.run.save_path, reranked, 'LLMRankers')
+
+
+def make_parser():
+    parser = argparse.ArgumentParser()
+    commands = parser.add_subparsers(title='sub-commands')
+    run = commands.add_parser('run')
+    run.add_argument('--run_path', type=str, help='Path to the first stage run file (TREC format) to rerank.')
+    run.add_argument('--save_path', type=str, help='Path to save the reranked run file (TREC format).')
+    run.add_argument('--model_name_or_path', type=str, help='Checkpoint directory / hub id, or synthetic:<flan-t5-size>')
+    run.add_argument('--tokenizer_name_or_path', type=str, default=None)
+    run.add_argument('--ir_dataset_name', type=str, default=None)
+    run.add_argument('--pyserini_index', type=str, default=None)
+    run.add_argument('--hits', type=int, default=100)
+    run.add_argument('--query_length', type=int, default=128)
+    run.add_argument('--passage_length', type=int, default=128)
+    run.add_argument('--device', type=str, default='cuda')
+    run.add_argument('--cache_dir', type=str, default=None)
+    run.add_argument('--openai_key', type=str, default=None)
+    run.add_argument('--scoring', type=str, default='generation', choices=['generation', 'likelihood'])
+    run.add_argument('--shuffle_ranking', type=str, default=None, choices=['inverse', 'random'])
+    run.add_argument('--queries_tsv', type=str, default=None, help='(extension) qid<TAB>text')
+    run.add_argument('--collection_tsv', type=str, default=None, help='(extension) docid<TAB>text')
+
+    pointwise = commands.add_parser('pointwise')
+    pointwise.add_argument('--method', type=str, default='yes_no', choices=['qlm', 'yes_no'])
+    pointwise.add_argument('--batch_size', type=int, default=2)
+
+    pairwise = commands.add_parser('pairwise')
+    pairwise.add_argument('--method', type=str, default='allpair', choices=['allpair', 'heapsort', 'bubblesort'])
+    pairwise.add_argument('--batch_size', type=int, default=2)
+    pairwise.add_argument('--k', type=int, default=10)
+
+    setwise = commands.add_parser('setwise')
+    setwise.add_argument('--num_child', type=int, default=3)
+    setwise.add_argument('--method', type=str, default='heapsort', choices=['heapsort', 'bubblesort'])
+    setwise.add_argument('--k', type=int, default=10)
+    setwise.add_argument('--num_permutation', type=int, default=1)
+
+    listwise = commands.add_parser('listwise')
+    listwise.add_argument('--window_size', type=int, default=3)
+    listwise.add_argument('--step_size', type=int, default=1)
+    listwise.add_argument('--num_repeat', type=int, default=1)
+    return parser, commands
+
+
+def cli(argv=None):
+    parser, commands = make_parser()
+    args = parse_args(parser, commands, argv)
+    if args.run is not None and args.run.ir_dataset_name is not None and args.run.pyserini_index is not None:
+        raise ValueError('Must specify either --ir_dataset_name or --pyserini_index, not both.')
+    chosen = vars(args)
+    if chosen['run'] is None or sum(v is not None for v in chosen.values()) != 2:
+        raise ValueError('Need to set --run and can only set one of --pointwise, --pairwise, --setwise, --listwise')
+    main(args)
+
+
+if __name__ == '__main__':
+    cli()

@@ -26,6 +26,12 @@ import numpy as np
 F32_MIN = np.finfo(np.float32).min
 
 
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 -> fp32, round-to-nearest-even (what the engine's bf16 stores do)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
 # ------------------------------------------------------------------------------------------------ pieces
 def relative_position_bucket(relative_position: np.ndarray, bidirectional: bool, num_buckets: int = 32,
                              max_distance: int = 128) -> np.ndarray:
@@ -97,16 +103,31 @@ class T5Oracle:
     """cfg keys: vocab_size d_model d_kv num_heads d_ff num_layers num_decoder_layers rel_buckets rel_max_distance
     layer_norm_eps scale_decoder_outputs pad_id eos_id. weights: HF state_dict names -> fp32 arrays."""
 
-    def __init__(self, cfg: Dict, weights: Dict[str, np.ndarray]):
+    def __init__(self, cfg: Dict, weights: Dict[str, np.ndarray], emulate_bf16: bool = False):
+        """emulate_bf16=True rounds to bf16 at exactly the points where the CUDA engine stores bf16 (GEMM weights, normed
+        activations, q/k/v, attention outputs, gated activations, encoder output, cross K/V, final hidden) while keeping
+        fp32 accumulation, fp32 residual stream, fp32 softmax statistics and the fp32 embedding table. It separates
+        'inherent bf16 error' from 'kernel bug' in the GPU tests; the fp32 mode is the reference-pinned oracle."""
         self.cfg = dict(cfg)
+        self.bf16 = bool(emulate_bf16)
         self.w = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
+        if self.bf16:
+            for k in list(self.w):
+                if k.endswith((".q.weight", ".k.weight", ".v.weight", ".o.weight", ".wi_0.weight", ".wi_1.weight", ".wo.weight")) or k == "lm_head.weight":
+                    self.w[k] = round_bf16(self.w[k])
         if "lm_head.weight" not in self.w:
-            self.w["lm_head.weight"] = self.w["shared.weight"]
+            self.w["lm_head.weight"] = round_bf16(self.w["shared.weight"]) if self.bf16 else self.w["shared.weight"]
         self.H = cfg["num_heads"]
         self.dk = cfg.get("d_kv", 64)
         self.eps = cfg.get("layer_norm_eps", 1e-6)
         self.nb = cfg.get("rel_buckets", 32)
         self.md = cfg.get("rel_max_distance", 128)
+
+    def _r(self, x: np.ndarray) -> np.ndarray:
+        return round_bf16(x) if self.bf16 else x
+
+    def _norm(self, x: np.ndarray, name: str) -> np.ndarray:
+        return self._r(rms_norm(x, self.w[name], self.eps))
 
     # $TF:153-344 T5Attention.forward (eager path): no 1/sqrt(d) scaling (:308), bias+mask added to the scores,
     # softmax in fp32 (:331)
@@ -114,20 +135,20 @@ class T5Oracle:
         B, Tq, _ = x_q.shape
         Tk = x_kv.shape[1]
         H, dk = self.H, self.dk
-        q = (x_q @ self.w[prefix + ".q.weight"].T).reshape(B, Tq, H, dk).transpose(0, 2, 1, 3)
-        k = (x_kv @ self.w[prefix + ".k.weight"].T).reshape(B, Tk, H, dk).transpose(0, 2, 1, 3)
-        v = (x_kv @ self.w[prefix + ".v.weight"].T).reshape(B, Tk, H, dk).transpose(0, 2, 1, 3)
+        q = self._r(x_q @ self.w[prefix + ".q.weight"].T).reshape(B, Tq, H, dk).transpose(0, 2, 1, 3)
+        k = self._r(x_kv @ self.w[prefix + ".k.weight"].T).reshape(B, Tk, H, dk).transpose(0, 2, 1, 3)
+        v = self._r(x_kv @ self.w[prefix + ".v.weight"].T).reshape(B, Tk, H, dk).transpose(0, 2, 1, 3)
         scores = q @ k.transpose(0, 1, 3, 2)
         scores = scores + bias_plus_mask
         p = softmax(scores, axis=-1)
-        o = (p @ v).transpose(0, 2, 1, 3).reshape(B, Tq, H * dk)
+        o = self._r((p @ v).transpose(0, 2, 1, 3).reshape(B, Tq, H * dk))
         return o @ self.w[prefix + ".o.weight"].T
 
     # $TF:115-132 T5DenseGatedActDense
     def _ff(self, prefix: str, x: np.ndarray) -> np.ndarray:
         g = gelu_new(x @ self.w[prefix + ".wi_0.weight"].T)
         l = x @ self.w[prefix + ".wi_1.weight"].T
-        return (g * l) @ self.w[prefix + ".wo.weight"].T
+        return self._r(g * l) @ self.w[prefix + ".wo.weight"].T
 
     # $TF:637-792 T5Stack.forward (encoder), :411-498 T5Block
     def encode(self, input_ids: np.ndarray, attention_mask: Optional[np.ndarray] = None) -> np.ndarray:
@@ -140,10 +161,10 @@ class T5Oracle:
                             self.nb, self.md) + ext  # computed in block 0, reused by all blocks (:625, :758)
         for l in range(self.cfg["num_layers"]):
             p = f"encoder.block.{l}"
-            h = rms_norm(x, self.w[p + ".layer.0.layer_norm.weight"], self.eps)
+            h = self._norm(x, p + ".layer.0.layer_norm.weight")
             x = x + self._attention(p + ".layer.0.SelfAttention", h, h, bias)
-            x = x + self._ff(p + ".layer.1.DenseReluDense", rms_norm(x, self.w[p + ".layer.1.layer_norm.weight"], self.eps))
-        return rms_norm(x, self.w["encoder.final_layer_norm.weight"], self.eps)  # :767
+            x = x + self._ff(p + ".layer.1.DenseReluDense", self._norm(x, p + ".layer.1.layer_norm.weight"))
+        return self._norm(x, "encoder.final_layer_norm.weight")  # :767
 
     # $TF:637-792 T5Stack.forward (decoder): self-attn (causal, unidirectional bias) -> cross-attn (no bias) -> FF
     def decode(self, decoder_input_ids: np.ndarray, enc_out: np.ndarray, attention_mask: Optional[np.ndarray] = None) -> np.ndarray:
@@ -158,12 +179,12 @@ class T5Oracle:
         cross_bias = np.zeros((1, self.H, T, S), np.float32) + ((1.0 - mask) * F32_MIN)[:, None, None, :]  # :313-315 + :720-726
         for l in range(self.cfg["num_decoder_layers"]):
             p = f"decoder.block.{l}"
-            h = rms_norm(x, self.w[p + ".layer.0.layer_norm.weight"], self.eps)
+            h = self._norm(x, p + ".layer.0.layer_norm.weight")
             x = x + self._attention(p + ".layer.0.SelfAttention", h, h, self_bias)
-            h = rms_norm(x, self.w[p + ".layer.1.layer_norm.weight"], self.eps)
+            h = self._norm(x, p + ".layer.1.layer_norm.weight")
             x = x + self._attention(p + ".layer.1.EncDecAttention", h, enc_out, cross_bias)
-            x = x + self._ff(p + ".layer.2.DenseReluDense", rms_norm(x, self.w[p + ".layer.2.layer_norm.weight"], self.eps))
-        return rms_norm(x, self.w["decoder.final_layer_norm.weight"], self.eps)
+            x = x + self._ff(p + ".layer.2.DenseReluDense", self._norm(x, p + ".layer.2.layer_norm.weight"))
+        return self._norm(x, "decoder.final_layer_norm.weight")
 
     # $TF:1064-1110 T5ForConditionalGeneration.forward: encoder -> decoder -> (scale if tied) -> lm_head
     def logits(self, input_ids, attention_mask, decoder_input_ids, cols: Optional[Sequence[int]] = None) -> np.ndarray:

@@ -1,0 +1,43 @@
+"""Test double for llmrankers._backend.T5Backend that routes the four engine calls to the CPU oracle, so the host logic
+of the drop-in rankers (prompts, batching, counters, sort drivers, output assembly, CLI) is testable without a GPU.
+Lives under tests/ — the product never imports it."""
+import numpy as np
+
+from llmrankers._backend import T5Backend, generate_mask_mode
+
+
+class OracleBackend(T5Backend):
+    def __init__(self, oracle, tokenizer, cfg):
+        super().__init__(engine=None, tokenizer=tokenizer, cfg=cfg)
+        self.oracle = oracle
+
+    def _padded(self, rows):
+        ids, lengths = self.pad_rows(rows, self.pad_id)
+        mask = (np.arange(ids.shape[1])[None] < lengths[:, None]).astype(np.int64)
+        return ids.astype(np.int64), mask
+
+    def score_yes_no(self, rows, yes_id, no_id):
+        ids, mask = self._padded(rows)
+        return self.oracle.score_yes_no(ids, mask, yes_id, no_id)
+
+    def score_qlm(self, rows, labels):
+        ids, mask = self._padded(rows)
+        return self.oracle.score_qlm(ids, mask, labels)
+
+    def label_probs(self, rows, dec_prefix, cols):
+        ids, mask = self._padded(rows)
+        return self.oracle.logits_at(ids, mask, dec_prefix, cols, normalize=True)
+
+    def generate(self, padded_ids, dec_prefix, max_new):
+        ids = np.asarray(padded_ids, np.int64)
+        mask = (ids != self.pad_id).astype(np.int64) if generate_mask_mode() == "infer" else np.ones_like(ids)
+        new = self.oracle.greedy(ids, mask, dec_prefix, max_new, self.eos_id, self.pad_id)
+        finished = np.zeros(ids.shape[0], bool)
+        steps = max_new
+        for s in range(max_new):
+            finished |= new[:, s] == self.eos_id
+            if finished.all():
+                steps = s + 1
+                break
+        prefix = np.tile(np.asarray(dec_prefix, np.int64)[None], (ids.shape[0], 1))
+        return np.concatenate([prefix, new[:, :steps]], axis=1)

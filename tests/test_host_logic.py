@@ -1,0 +1,190 @@
+"""CPU tests of the host side: the drop-in `llmrankers` classes (with the oracle standing in for the GPU engine) must
+reproduce what the reference's own rerank() produced in tests/golden (order, scores, counters, truncate), the C-ABI
+library must load and export every symbol of include/b200rank.h, and compute entry points must fail loudly without a GPU."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fake_backend import OracleBackend
+from helpers import ROOT, golden_meta, model_and_weights, oracle_for
+
+_tok = None
+
+
+def tokenizer():
+    global _tok
+    if _tok is None:
+        from b200rank.synthetic import synthetic_tokenizer
+        _tok = synthetic_tokenizer()
+    return _tok
+
+
+def backend(which="tiny", lab=False):
+    cfg, _ = model_and_weights(which, lab)
+    return OracleBackend(oracle_for(which, lab), tokenizer(), cfg)
+
+
+def docs_from(meta_docs):
+    from llmrankers.rankers import SearchResult
+    return [SearchResult(docid=d["docid"], score=d["score"], text=d["text"]) for d in meta_docs]
+
+
+def check_counters(r, c):
+    assert (r.total_compare, r.total_prompt_tokens, r.total_completion_tokens) == \
+           (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+@pytest.mark.parametrize("which,method,case", [("tiny", "yes_no", "yes_no"), ("tiny", "qlm", "qlm"), ("small", "yes_no", "small_yes_no")])
+def test_pointwise_matches_reference(which, method, case):
+    from llmrankers.pointwise import PointwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta[which], meta["cases"][case]
+    r = PointwiseLlmRanker(None, None, "cuda", method=method, batch_size=4, backend=backend(which))
+    docs = docs_from(m["docs"])
+    out = r.rerank(m["query"], docs)
+    assert [d.docid for d in out] == c["order"]
+    for d in out:
+        assert d.score == pytest.approx(c["scores"][d.docid], rel=2e-5, abs=2e-3 if method == "qlm" else 1e-5)
+        assert d.text is not None  # pointwise returns the input objects, text intact
+    check_counters(r, c)
+
+
+@pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik", "setwise_bubble_lik", "setwise_bubble_gen"])
+def test_setwise_matches_reference(case, capsys):
+    from llmrankers.setwise import SetwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"][case]
+    r = SetwiseLlmRanker(None, None, "cuda", num_child=c["num_child"], k=c["k"], scoring=c["scoring"], method=c["method"],
+                         backend=backend("tiny", c["label_favouring"]))
+    assert r.decoder_input_ids == m["decoder_prefix"] and r.target_token_ids == m["target_token_ids"]
+    out = r.rerank(m["query"], docs_from(m["docs12"]))
+    assert [d.docid for d in out] == c["order"]
+    assert [d.score for d in out] == c["scores"]
+    assert all(d.text is None for d in out)
+    check_counters(r, c)
+
+
+@pytest.mark.parametrize("case", ["pairwise_allpair", "pairwise_heap", "pairwise_bubble"])
+def test_pairwise_matches_reference(case):
+    from llmrankers.pairwise import PairwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"][case]
+    r = PairwiseLlmRanker(None, None, "cuda", method=c["method"], batch_size=c["batch_size"], k=c["k"], backend=backend("tiny", True))
+    out = r.rerank(m["query"], docs_from(m["docs12"][:6]))
+    assert [d.docid for d in out] == c["order"]
+    assert [d.score for d in out] == c["scores"]
+    check_counters(r, c)
+
+
+def test_truncate_matches_reference():
+    from llmrankers.pointwise import PointwiseLlmRanker
+    r = PointwiseLlmRanker(None, None, "cuda", backend=backend())
+    for t in golden_meta()["tiny"]["truncate"]:
+        assert r.truncate(t["text"], t["length"]) == t["out"]
+
+
+def test_pointwise_sort_is_stable_and_empty_ok():
+    from llmrankers.pointwise import PointwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=3, backend=backend())
+    assert r.rerank("w1", []) == []
+    same = [SearchResult(f"d{i}", 0.0, "w5 w6 w7") for i in range(5)]  # identical text => identical scores => input order kept
+    assert [d.docid for d in r.rerank("w1 w2", same)] == ["d0", "d1", "d2", "d3", "d4"]
+    assert r.total_compare == 2
+
+
+def test_unsupported_variants_fail_loudly():
+    from llmrankers.listwise import ListwiseLlmRanker
+    from llmrankers.pairwise import DuoT5LlmRanker
+    from llmrankers.setwise import OpenAiSetwiseLlmRanker, SetwiseLlmRanker
+    for cls in (ListwiseLlmRanker, DuoT5LlmRanker, OpenAiSetwiseLlmRanker):
+        with pytest.raises(NotImplementedError):
+            cls("x", "y")
+    r = SetwiseLlmRanker(None, None, "cuda", method="quicksort", backend=backend())
+    with pytest.raises(NotImplementedError):
+        r.rerank("w1", docs_from(golden_meta()["tiny"]["docs12"]))
+
+
+def test_device_cpu_is_refused():
+    from llmrankers.pointwise import PointwiseLlmRanker
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        PointwiseLlmRanker("synthetic:t5-tiny", None, "cpu")
+
+
+# ------------------------------------------------------------------------------------------- CLI
+def test_cli_pointwise_end_to_end(tmp_path, monkeypatch, capsys):
+    import run as cli_mod
+    from llmrankers import _backend
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"]["yes_no"]
+    monkeypatch.setattr(_backend.T5Backend, "load", classmethod(lambda cls, *a, **k: backend("tiny")))
+    (tmp_path / "queries.tsv").write_text(f"q1\t{m['query']}\n")
+    (tmp_path / "docs.tsv").write_text("".join(f"{d['docid']}\t{d['text']}\n" for d in m["docs"]))
+    (tmp_path / "run.txt").write_text("".join(f"q1 Q0 {d['docid']} {i + 1} {d['score']} bm25\n" for i, d in enumerate(m["docs"])))
+    out = tmp_path / "out.txt"
+    cli_mod.cli(["run", "--model_name_or_path", "synthetic:t5-tiny", "--run_path", str(tmp_path / "run.txt"), "--save_path", str(out),
+                 "--queries_tsv", str(tmp_path / "queries.tsv"), "--collection_tsv", str(tmp_path / "docs.tsv"),
+                 "--query_length", "32", "--passage_length", "128", "pointwise", "--method", "yes_no", "--batch_size", "4"])
+    lines = out.read_text().splitlines()
+    assert [l.split("\t")[2] for l in lines] == c["order"]
+    assert all(re.fullmatch(r"q1\tQ0\td\d+\t\d+\t[-0-9.e]+\tLLMRankers", l) for l in lines)
+    printed = capsys.readouterr().out
+    assert f"Avg comparisons: {float(c['total_compare'])}" in printed and "Avg time per query:" in printed
+
+
+def test_cli_grammar_errors():
+    import run as cli_mod
+    with pytest.raises(ValueError):
+        cli_mod.cli(["run", "--model_name_or_path", "x"])                      # no method sub-command
+    with pytest.raises(ValueError):
+        cli_mod.cli(["run", "--model_name_or_path", "x", "pointwise", "setwise"])  # two methods
+    parser, commands = cli_mod.make_parser()
+    args = cli_mod.parse_args(parser, commands, ["run", "--hits", "7", "setwise"])
+    assert args.run.hits == 7 and args.run.query_length == 128 and args.run.device == "cuda" and args.run.scoring == "generation"
+    assert (args.setwise.num_child, args.setwise.method, args.setwise.k, args.setwise.num_permutation) == (3, "heapsort", 10, 1)
+    assert args.pointwise is None and args.pairwise is None
+
+
+# ------------------------------------------------------------------------------------------- C-ABI (no compute without a GPU)
+def test_library_exports_every_declared_symbol():
+    import b200rank as br
+    header = open(os.path.join(ROOT, "include", "b200rank.h")).read()
+    declared = set(re.findall(r"\b(b200rank_[a-z0-9_]+)\s*\(", header))
+    lib = br.load_library()
+    assert declared == set(br.EXPORTED_SYMBOLS), declared ^ set(br.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert b"sm_100a" in lib.b200rank_version()
+    assert ctypes.sizeof(br.Config) == 18 * 4
+
+
+@pytest.mark.skipif(__import__("conftest").HAS_GPU, reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import b200rank as br
+    c = br.make_config(128, 2, 256, 2, 2, vocab_size=2304)
+    with pytest.raises(br.B200RankError, match="no CUDA device|no CPU fallback"):
+        br.Engine(c, 0)
+    with pytest.raises(br.B200RankError):
+        br.test_gemm(np.zeros((128, 64), np.float32), np.zeros((64, 64), np.float32))
+
+
+def test_config_validation_messages():
+    import b200rank as br
+    lib = br.load_library()
+    h = ctypes.c_void_p()
+    bad = br.make_config(128, 2, 256, 2, 2, vocab_size=2304, d_kv=128)
+    assert lib.b200rank_create(ctypes.byref(bad), 0, ctypes.byref(h)) == -1
+    assert b"d_kv" in lib.b200rank_last_error()
+    assert br.rel_bucket(-200, True) == 15 and br.rel_bucket(200, True) == 31 and br.rel_bucket(-16, False) == 16
+
+
+def test_rel_bucket_table_matches_hf_golden():
+    import b200rank as br
+    from helpers import golden_npz
+    g = golden_npz("buckets.npz")
+    assert [br.rel_bucket(int(r), True) for r in g["rel"]] == g["bidirectional"].tolist()
+    assert [br.rel_bucket(int(r), False) for r in g["rel"]] == g["unidirectional"].tolist()
