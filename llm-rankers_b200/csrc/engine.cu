@@ -64,16 +64,21 @@ static int get_encode_tiled() {
     return B200RANK_OK;
 }
 
-// 2-D bf16 K-major tensor map: dims {cols (contiguous), rows}, box {64, box_rows}, 128B swizzle.
-static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+// 2-D row-major tensor map with 128-byte inner boxes and 128B swizzle: dims {cols (contiguous), rows}.
+//   kind 0: bf16 GEMM operand, box {64, box_rows}      kind 1: bf16 epilogue output, box {64, 128}
+//   kind 2: fp32 epilogue output (store or reduce-add), box {32, 128}
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                     int kind = 0) {
     RET_IF(get_encode_tiled());
+    const bool f32 = kind == 2;
+    const size_t esz = f32 ? 4 : 2;
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {ld_elems * sizeof(bf16)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows};
+    cuuint64_t gstride[1] = {ld_elems * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode_tiled(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                                gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(B200RANK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%u",
                          (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
@@ -81,17 +86,18 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 }
 
 // ------------------------------------------------------------------ GEMM launch
-template <int BN, int EPI>
-static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args) {
+template <int BN, int EPI, bool TMA_EPI>
+static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                            const GemmArgs& args) {
     static bool attr_set = false;
-    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, TMA_EPI>;
     if (!attr_set) {
         CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
         attr_set = true;
     }
     const int tiles = ((args.M + kGemmBlockM - 1) / kGemmBlockM) * ((args.N + BN - 1) / BN);
     const int grid = std::min(tiles, num_sms);
-    kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, args);
+    kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, tout, args);
     CU_OK(cudaGetLastError());
     return B200RANK_OK;
 }
@@ -107,10 +113,13 @@ static int pick_block_n(int M, int N, int epi, int num_sms) {
     return 32;
 }
 
-static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a,
-                          int epi, int bn) {
-#define GEMM_CASE(BN, EPI) \
-    if (bn == BN && epi == EPI) return launch_gemm_inst<BN, EPI>(st, num_sms, ta, tb, a);
+static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                          const GemmArgs& a, int epi, int bn, bool tma_epi) {
+    // the staged bf16 epilogue moves 64-column (128 B) tiles; a 32-column accumulator keeps the direct store path
+    if (epi == EPI_BF16 && bn < 64) tma_epi = false;
+#define GEMM_CASE(BN, EPI)                                                                              \
+    if (bn == BN && epi == EPI)                                                                         \
+        return tma_epi ? launch_gemm_inst<BN, EPI, true>(st, num_sms, ta, tb, tout, a) : launch_gemm_inst<BN, EPI, false>(st, num_sms, ta, tb, tout, a);
     GEMM_CASE(256, EPI_BF16) GEMM_CASE(128, EPI_BF16) GEMM_CASE(64, EPI_BF16) GEMM_CASE(32, EPI_BF16)
     GEMM_CASE(256, EPI_RESID_F32) GEMM_CASE(128, EPI_RESID_F32) GEMM_CASE(64, EPI_RESID_F32) GEMM_CASE(32, EPI_RESID_F32)
     GEMM_CASE(256, EPI_GATED_BF16)
@@ -124,6 +133,7 @@ struct LayerW {
     // encoder: ln1, wqkv, wo, ln2, wi, wff     decoder: + ln_c, wq_c, wo_c
     float *ln1 = nullptr, *ln2 = nullptr, *ln_c = nullptr;
     bf16 *wqkv = nullptr, *wo = nullptr, *wi = nullptr, *wff = nullptr, *wq_c = nullptr, *wo_c = nullptr;
+    bf16* wov = nullptr;  // decoder only, derived at load: W_o . W_v (self-attention at T = 1 is exactly o(v(x)))
 };
 
 struct b200rank_engine {
@@ -132,7 +142,7 @@ struct b200rank_engine {
     int d = 0, inner = 0, H = 0, F = 0, V = 0, Le = 0, Ld = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    bool debug_simt = false, debug_sync = false;
+    bool debug_simt = false, debug_sync = false, direct_epi = false;
     uint64_t launches = 0;
 
     // weight arena
@@ -170,7 +180,7 @@ struct b200rank_engine {
     int* h_small = nullptr; size_t h_small_cap = 0, h_small_off = 0;  // pinned bump buffer for small async uploads
     int staged_docs = 0, staged_tokens = 0, staged_maxlen = 0;
 
-    std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+    std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, int>, CUtensorMap> tmaps;
 
     // optional per-launch timing (b200rank_profile): event pairs around every kernel, keyed by a label
     bool profiling = false;
@@ -210,12 +220,13 @@ static void prof_collect(b200rank_engine* e) {
 }
 
 static int engine_tmap(b200rank_engine* e, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                       const CUtensorMap** out) {
-    auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+                       int kind, const CUtensorMap** out) {
+    auto key = std::make_tuple(ptr, rows, cols, ld, box_rows, kind);
     auto it = e->tmaps.find(key);
     if (it == e->tmaps.end()) {
+        if (e->tmaps.size() > 16384) e->tmaps.clear();  // output maps are keyed by the live row count; bound the cache
         CUtensorMap m;
-        RET_IF(make_tmap(&m, ptr, rows, cols, ld, box_rows));
+        RET_IF(make_tmap(&m, ptr, rows, cols, ld, box_rows, kind));
         it = e->tmaps.emplace(key, m).first;
     }
     *out = &it->second;
@@ -236,7 +247,7 @@ static int post_launch(b200rank_engine* e, const char* what) {
 
 // acc[M,N] = A[M,K] . W[N,K]^T with fused epilogue. a_rows/w_rows: row capacity of the operands (TMA bounds).
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn = 0) {
+                int K, int epi, void* out, int ldo, int force_bn) {
     if (M <= 0) return B200RANK_OK;
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
@@ -251,11 +262,15 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
         gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi, 256, out, ldo);
         return post_launch(e, "gemm_simt_debug");
     }
-    const CUtensorMap *ta, *tb;
-    RET_IF(engine_tmap(e, A, a_rows, K, lda, kGemmBlockM, &ta));
-    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn, &tb));
+    const CUtensorMap *ta, *tb, *tout;
+    RET_IF(engine_tmap(e, A, a_rows, K, lda, kGemmBlockM, 0, &ta));
+    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn, 0, &tb));
+    const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32);
+    const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
+    // the output map carries the LIVE row count so TMA clips the ragged last M-tile
+    RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
     GemmArgs args{M, N, K, out, ldo};
-    RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, args, epi, bn));
+    RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi));
     return post_launch(e, "gemm_tcgen05");
 }
 
@@ -335,6 +350,7 @@ static int create_impl(b200rank_engine* e) {
     CU_OK(cudaEventCreate(&e->ev[1]));
     e->debug_simt = getenv("B200RANK_DEBUG_SIMT_GEMM") && atoi(getenv("B200RANK_DEBUG_SIMT_GEMM")) != 0;
     e->debug_sync = getenv("B200RANK_DEBUG_SYNC") && atoi(getenv("B200RANK_DEBUG_SYNC")) != 0;
+    e->direct_epi = getenv("B200RANK_GEMM_DIRECT_EPI") && atoi(getenv("B200RANK_GEMM_DIRECT_EPI")) != 0;
 
     const size_t d = e->d, I = e->inner, F = e->F, V = e->V;
     // ---- weight arena layout
@@ -361,7 +377,7 @@ static int create_impl(b200rank_engine* e) {
         LayerW& w = e->dec[l];
         reserve((void**)&w.ln1, d * 4); reserve((void**)&w.ln_c, d * 4); reserve((void**)&w.ln2, d * 4);
         reserve((void**)&w.wqkv, 3 * I * d * 2); reserve((void**)&w.wo, d * I * 2);
-        reserve((void**)&w.wq_c, I * d * 2); reserve((void**)&w.wo_c, d * I * 2);
+        reserve((void**)&w.wq_c, I * d * 2); reserve((void**)&w.wo_c, d * I * 2); reserve((void**)&w.wov, d * d * 2);
         reserve((void**)&w.wi, 2 * F * d * 2); reserve((void**)&w.wff, d * F * 2);
     }
     e->arena_bytes = off;
@@ -491,6 +507,34 @@ static int shape_check(const char* name, int64_t rows, int64_t cols, int64_t er,
     return B200RANK_OK;
 }
 
+static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
+                int K, int epi, void* out, int ldo, int force_bn = 0);
+
+// Derived weights, computed once on the device when the last tensor arrives (they live in the arena, so the NCCL
+// broadcast carries them): decoder W_ov[l] = W_o[l] . W_v[l]  (bf16 operands, fp32 accumulate, bf16 result).
+// With a single decoder position the causal softmax is over one key and equals 1, so self-attention is o(v(norm(x)))
+// (modeling_t5.py:350-377) and the q/k projections are dead work.
+static int derive_weights(b200rank_engine* e) {
+    const int d = e->d, I = e->inner;
+    bf16* vt = nullptr;  // W_v^T [d, I]
+    CU_OK(cudaMalloc(reinterpret_cast<void**>(&vt), (size_t)align_up(d, 256) * I * sizeof(bf16)));
+    CU_OK(cudaMemsetAsync(vt, 0, (size_t)align_up(d, 256) * I * sizeof(bf16), e->stream));
+    int rc = B200RANK_OK;
+    for (int l = 0; l < e->Ld && rc == B200RANK_OK; ++l) {
+        const LayerW& w = e->dec[l];
+        transpose_bf16_kernel<<<dim3((d + 31) / 32, (I + 31) / 32), dim3(32, 8), 0, e->stream>>>(w.wqkv + (size_t)2 * I * d, I, d, d, vt, I);
+        rc = post_launch(e, "transpose_bf16");
+        // W_ov[i, j] = sum_k W_o[i, k] W_v[k, j]  ==  A[M=d, K=I] . W[N=d, K=I]^T with W = W_v^T
+        if (rc == B200RANK_OK) rc = gemm(e, w.wo, I, d, vt, I, (int)align_up(d, 256), d, d, I, EPI_BF16, w.wov, d, 0);
+    }
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    cudaFree(vt);
+    e->tmaps.clear();  // drop the tensor maps of the temporary
+    if (rc != B200RANK_OK) return rc;
+    if (err != cudaSuccess) return set_error(B200RANK_ERR_CUDA, "derive_weights: %s", cudaGetErrorString(err));
+    return B200RANK_OK;
+}
+
 extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, const void* data, int dtype, int64_t rows,
                                     int64_t cols) {
     if (!e || !hf_name || !data) return set_error(B200RANK_ERR_ARG, "null argument");
@@ -583,6 +627,7 @@ extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, con
     e->loaded[name] = true;
     bool all = true;
     for (auto& kv : e->loaded) all = all && kv.second;
+    if (all && !e->weights_ready) RET_IF(derive_weights(e));
     e->weights_ready = all;
     return B200RANK_OK;
 }
@@ -624,6 +669,27 @@ static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h
     return post_launch(e, "rmsnorm");
 }
 
+// Short documents: whole (doc, head) resident in shared memory; longer ones: 64-query tiles with streamed keys.
+static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, int inner, const int* d_cu, int nd, int maxlen, int H,
+                                const float* bias, bf16* out, int ldo, cudaStream_t st, int q_tiles) {
+    static bool attr_set = false;
+    const bool no_resident = getenv("B200RANK_ATTN_TILED") && atoi(getenv("B200RANK_ATTN_TILED")) != 0;
+    if (maxlen <= 256 && !no_resident) {
+        const int s_pad = (maxlen + 63) & ~63;
+        const int smem = 3 * s_pad * 128;
+        if (!attr_set) {
+            CU_OK(cudaFuncSetAttribute(enc_attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 128));
+            attr_set = true;
+        }
+        if (e) prof_begin(e, "enc_attention_resident");
+        enc_attention_resident_kernel<<<dim3(H, nd), (s_pad / 16) * 32, smem, st>>>(qkv, ld, inner, d_cu, bias, out, ldo, s_pad);
+        return e ? post_launch(e, "enc_attention_resident") : B200RANK_OK;
+    }
+    if (e) prof_begin(e, "enc_attention");
+    enc_attention_kernel<<<dim3(q_tiles, H, nd), 128, 0, st>>>(qkv, ld, inner, d_cu, bias, out, ldo);
+    return e ? post_launch(e, "enc_attention") : B200RANK_OK;
+}
+
 // Encoder over the staged batch + stacked cross-attention K|V projection of its output.
 static int run_encoder(b200rank_engine* e) {
     const int n = e->staged_tokens, nd = e->staged_docs;
@@ -634,8 +700,7 @@ static int run_encoder(b200rank_engine* e) {
         const LayerW& w = e->enc[l];
         RET_IF(k_rmsnorm(e, e->x, w.ln1, e->h, n));
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
-        prof_begin(e, "enc_attention"); enc_attention_kernel<<<dim3(q_tiles, e->H, nd), 128, 0, e->stream>>>(e->qkv, 3 * I, I, e->d_cu, e->bias_enc, e->ao, I);
-        RET_IF(post_launch(e, "enc_attention"));
+        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, I, e->d_cu, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, q_tiles));
         RET_IF(gemm(e, e->ao, I, Tk, w.wo, I, d, n, d, I, EPI_RESID_F32, e->x, d));
         RET_IF(k_rmsnorm(e, e->x, w.ln2, e->h, n));
         RET_IF(gemm(e, e->h, d, Tk, w.wi, d, 2 * F, n, 2 * F, d, EPI_GATED_BF16, e->g, F));
@@ -656,18 +721,28 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
     if (T > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "decoder length %d exceeds max_dec_len %d", T, e->cap_T);
     RET_IF(k_embed(e, e->d_dec_ids, e->xd, R));
     const size_t ldkv = (size_t)e->Ld * 2 * I;
+    const int max_len = e->staged_maxlen;
     for (int l = 0; l < e->Ld; ++l) {
         const LayerW& w = e->dec[l];
         RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
-        RET_IF(gemm(e, e->hd, d, cap, w.wqkv, d, 3 * I, R, 3 * I, d, EPI_BF16, e->qkvd, 3 * I));
-        prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
-        RET_IF(post_launch(e, "dec_self_attention"));
-        RET_IF(gemm(e, e->aod, I, cap, w.wo, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+        if (T == 1) {
+            // one decoder position: softmax over a single key is 1, so the block is x += W_o W_v norm(x) (derive_weights)
+            RET_IF(gemm(e, e->hd, d, cap, w.wov, d, d, R, d, d, EPI_RESID_F32, e->xd, d));
+        } else {
+            RET_IF(gemm(e, e->hd, d, cap, w.wqkv, d, 3 * I, R, 3 * I, d, EPI_BF16, e->qkvd, 3 * I));
+            prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+            RET_IF(post_launch(e, "dec_self_attention"));
+            RET_IF(gemm(e, e->aod, I, cap, w.wo, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+        }
         RET_IF(k_rmsnorm(e, e->xd, w.ln_c, e->hd, R));
         RET_IF(gemm(e, e->hd, d, cap, w.wq_c, d, I, R, I, d, EPI_BF16, e->qd, I));
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
         prof_begin(e, "cross_attention");
-        if (T <= 4)
+        if (T == 1 && e->H % 4 == 0 && max_len <= 256)
+            cross_attention_t1_kernel<8><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+        else if (T == 1 && e->H % 4 == 0 && max_len <= 2048)
+            cross_attention_t1_kernel<64><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+        else if (T <= 4)
             cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
         else
             cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
@@ -1050,11 +1125,13 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         gemm_simt_debug_kernel<<<grd, blk>>>(dA, K, dW, K, M, N, K, epi, 256, dO, n_out);
     } else {
         const int bn = block_n ? block_n : pick_block_n(M, N, epi, prop.multiProcessorCount);
-        CUtensorMap ta, tb;
+        CUtensorMap ta, tb, tout;
+        const bool direct = getenv("B200RANK_GEMM_DIRECT_EPI") && atoi(getenv("B200RANK_GEMM_DIRECT_EPI")) != 0;
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
         if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn);
+        if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
         GemmArgs args{M, N, K, dO, n_out};
-        if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, args, epi, bn);
+        if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct);
     }
     if (rc == B200RANK_OK) {
         cudaEventRecord(e1, 0);
@@ -1088,9 +1165,9 @@ extern "C" int b200rank_test_enc_attention(int device, const void* qkv_bf16, con
     CU_OK(cudaMemcpy(dcu, cu_seqlens, (n_docs + 1) * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(dbias, bias, (size_t)num_heads * kAttnBiasLen * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemset(dout, 0, (size_t)tokens * inner * 2));
-    enc_attention_kernel<<<dim3((maxlen + 63) / 64, num_heads, n_docs), 128>>>(dq, 3 * inner, inner, dcu, dbias, dout, inner);
+    int rc = launch_enc_attention(nullptr, dq, 3 * inner, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, (maxlen + 63) / 64);
     cudaError_t err = cudaDeviceSynchronize();
-    int rc = B200RANK_OK;
+    if (rc != B200RANK_OK) { cudaFree(dq); cudaFree(dout); cudaFree(dcu); cudaFree(dbias); return rc; }
     if (err != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "enc_attention kernel failed: %s", cudaGetErrorString(err));
     else cudaMemcpy(out_bf16, dout, (size_t)tokens * inner * 2, cudaMemcpyDeviceToHost);
     cudaFree(dq); cudaFree(dout); cudaFree(dcu); cudaFree(dbias);

@@ -40,28 +40,44 @@ struct GemmCfg {
     static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     // fill ~192 KB with the ring; at least 3, at most 8 stages
-    static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+    static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;  // BLOCK_N=256: 4 x 48 KB ring + 32 KB staging = 224 KB
     static constexpr int kStages = kStagesRaw > 8 ? 8 : (kStagesRaw < 3 ? 3 : kStagesRaw);
     static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
     static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment slack
+    static constexpr int kStagingBytes = 2 * kGemmBlockM * 128;  // two 128-row x 128-byte epilogue staging tiles (TMA store source)
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024: manual alignment slack
 };
 
-template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// TMA_EPI = true : accumulators leave through shared-memory staging tiles (128 rows x 128 B, 128B swizzle) and
+//                  cp.async.bulk.tensor stores — or cp.reduce.async.bulk.tensor .add for the fp32 residual, which
+//                  performs x += acc inside L2 so the SMs never read the residual stream.
+// TMA_EPI = false: per-thread 16 B global stores straight from registers (round-1 bring-up path, kept for bisecting
+//                  with B200RANK_GEMM_DIRECT_EPI=1).
+template <int BLOCK_N, int EPI, bool TMA_EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmArgs args) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
     using Cfg = GemmCfg<BLOCK_N>;
     constexpr int kStages = Cfg::kStages;
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "bad BLOCK_N");
     static_assert(EPI != EPI_GATED_BF16 || BLOCK_N % 64 == 0, "gated epilogue needs BLOCK_N % 64 == 0");
+    static_assert(!TMA_EPI || EPI != EPI_BF16 || BLOCK_N % 64 == 0 || BLOCK_N == 32, "bf16 staged epilogue moves 64-column tiles");
+    static_assert(!TMA_EPI || EPI != EPI_GATED_BF16 || BLOCK_N % 128 == 0, "gated staged epilogue moves 64 output columns");
 
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA/UMMA tiles need 1024 B alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* smem_stage = smem + kStages * Cfg::kStageBytes;  // 1024 B aligned (stage sizes are multiples of 1024)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStagingBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
@@ -78,6 +94,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if constexpr (TMA_EPI) tma_prefetch_desc(&tmap_out);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -147,6 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ---------------------------------------------------------------- epilogue
         const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
+        int stage_sel = 0;  // which staging tile the next chunk uses (persists across tiles)
         int iter = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
@@ -159,7 +177,93 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
 
-            if constexpr (EPI == EPI_GATED_BF16) {
+            if constexpr (TMA_EPI) {
+                // ---- staged epilogue: registers -> swizzled smem tile -> TMA store / reduce-add
+                const bool issuer = (threadIdx.x == 64);  // warp 2, lane 0
+                uint8_t* my_row = nullptr;
+                auto stage_open = [&]() {
+                    // the store that last read this buffer was committed two groups ago
+                    if (issuer) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    my_row = smem_stage + stage_sel * (kGemmBlockM * 128) + row_in_tile * 128;
+                };
+                auto put16 = [&](int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+                    st_shared_v4(my_row + ((chunk ^ (row_in_tile & 7)) << 4), a, b, c, d);
+                };
+                auto stage_close = [&](int out_col0) {
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (issuer) {
+                        const void* src = smem_stage + stage_sel * (kGemmBlockM * 128);
+                        if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
+                        else tma_store_2d(&tmap_out, src, out_col0, m0);
+                        tma_store_commit();
+                    }
+                    stage_sel ^= 1;
+                };
+                if constexpr (EPI == EPI_BF16) {
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N; c += 64) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(taddr + c, r0);
+                        tmem_ld32(taddr + c + 32, r1);
+                        tmem_ld_wait();
+                        if (c + 64 == BLOCK_N) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); }
+                        stage_open();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            put16(j, pack_bf16(__uint_as_float(r0[8 * j + 0]), __uint_as_float(r0[8 * j + 1])),
+                                  pack_bf16(__uint_as_float(r0[8 * j + 2]), __uint_as_float(r0[8 * j + 3])),
+                                  pack_bf16(__uint_as_float(r0[8 * j + 4]), __uint_as_float(r0[8 * j + 5])),
+                                  pack_bf16(__uint_as_float(r0[8 * j + 6]), __uint_as_float(r0[8 * j + 7])));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            put16(4 + j, pack_bf16(__uint_as_float(r1[8 * j + 0]), __uint_as_float(r1[8 * j + 1])),
+                                  pack_bf16(__uint_as_float(r1[8 * j + 2]), __uint_as_float(r1[8 * j + 3])),
+                                  pack_bf16(__uint_as_float(r1[8 * j + 4]), __uint_as_float(r1[8 * j + 5])),
+                                  pack_bf16(__uint_as_float(r1[8 * j + 6]), __uint_as_float(r1[8 * j + 7])));
+                        stage_close(nb * BLOCK_N + c);
+                    }
+                } else if constexpr (EPI == EPI_GATED_BF16) {
+                    constexpr int HALF = BLOCK_N / 2;
+#pragma unroll 1
+                    for (int c = 0; c < HALF; c += 64) {
+                        stage_open();
+#pragma unroll 1
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t g[32], l[32];
+                            tmem_ld32(taddr + c + 32 * hh, g);
+                            tmem_ld32(taddr + HALF + c + 32 * hh, l);
+                            tmem_ld_wait();
+                            if (c + 64 == HALF && hh == 1) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t v[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float a0 = gelu_new(__uint_as_float(g[8 * j + 2 * e])) * __uint_as_float(l[8 * j + 2 * e]);
+                                    const float a1 = gelu_new(__uint_as_float(g[8 * j + 2 * e + 1])) * __uint_as_float(l[8 * j + 2 * e + 1]);
+                                    v[e] = pack_bf16(a0, a1);
+                                }
+                                put16(4 * hh + j, v[0], v[1], v[2], v[3]);
+                            }
+                        }
+                        stage_close(nb * HALF + c);
+                    }
+                } else {  // fp32 tiles of 32 columns: plain store (EPI_F32) or in-L2 add (EPI_RESID_F32)
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + c, r);
+                        tmem_ld_wait();
+                        if (c + 32 == BLOCK_N) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); }
+                        stage_open();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) put16(j, r[4 * j + 0], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        stage_close(nb * BLOCK_N + c);
+                    }
+                }
+            } else if constexpr (EPI == EPI_GATED_BF16) {
                 constexpr int HALF = BLOCK_N / 2;
                 __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo;
                 const int n_out_total = args.N / 2;
@@ -249,6 +353,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     }
 
+    if constexpr (TMA_EPI) {
+        if (threadIdx.x == 64) tma_store_wait<0>();  // all bulk stores complete (smem reads and global writes) before exit
+    }
     tc_fence_before();
     __syncthreads();
     if (warp_idx == 1) {

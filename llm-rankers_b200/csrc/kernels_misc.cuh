@@ -232,6 +232,97 @@ __global__ void cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int 
     }
 }
 
+// Cross-attention for a single decoder position (T = 1: pointwise yes_no), the HBM-bound case: one warp per
+// (document, head) streams that head's K rows (one 128 B row per lane: lane j owns keys j, j+32, ...), does the softmax
+// with warp shuffles, then streams the V rows coalesced (lane owns 2 of the 64 dims). grid (H/4, n_docs), 128 threads:
+// the 4 warps of a block take 4 adjacent heads, i.e. 512 contiguous bytes of every K/V row.
+// MAX_ROUNDS * 32 bounds the encoder length handled by this kernel (longer documents take the chunked kernel above).
+template <int MAX_ROUNDS>
+__global__ void __launch_bounds__(128)
+cross_attention_t1_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kv, size_t ldkv,
+                          int k_off, int v_off, const int* __restrict__ cu, __nv_bfloat16* __restrict__ out, int ldo) {
+    __shared__ float sQ[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x * 4 + warp, doc = blockIdx.y;
+    const int tok0 = cu[doc];
+    const int S = cu[doc + 1] - tok0;
+    {
+        const __nv_bfloat162 qv = *reinterpret_cast<const __nv_bfloat162*>(q + static_cast<size_t>(doc) * ldq + h * 64 + 2 * lane);
+        const float2 qf = __bfloat1622float2(qv);
+        sQ[warp][2 * lane] = qf.x;
+        sQ[warp][2 * lane + 1] = qf.y;
+    }
+    __syncwarp();
+    const __nv_bfloat16* kbase = kv + static_cast<size_t>(tok0) * ldkv + k_off + h * 64;
+    const __nv_bfloat16* vbase = kv + static_cast<size_t>(tok0) * ldkv + v_off + h * 64;
+    float s[MAX_ROUNDS];
+    float m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < MAX_ROUNDS; ++r) {
+        const int j = r * 32 + lane;
+        s[r] = -INFINITY;
+        if (j < S) {
+            const uint4* row = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ldkv);
+            uint4 c[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = __ldg(row + i);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&c[i]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 kf = __bfloat1622float2(p2[e]);
+                    acc += sQ[warp][8 * i + 2 * e] * kf.x + sQ[warp][8 * i + 2 * e + 1] * kf.y;
+                }
+            }
+            s[r] = acc;
+        }
+        m = fmaxf(m, s[r]);
+    }
+    m = warp_max(m);
+    float l = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAX_ROUNDS; ++r) {
+        s[r] = (r * 32 + lane < S) ? __expf(s[r] - m) : 0.f;
+        l += s[r];
+    }
+    l = warp_sum(l);
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAX_ROUNDS; ++r) {
+        const int base = r * 32;
+        if (base < S) {  // warp-uniform
+            const int n = min(32, S - base);
+#pragma unroll 8
+            for (int jj = 0; jj < n; ++jj) {
+                const float p = __shfl_sync(0xffffffffu, s[r], jj);
+                const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + static_cast<size_t>(base + jj) * ldkv + 2 * lane));
+                o0 += p * vf.x;
+                o1 += p * vf.y;
+            }
+        }
+    }
+    const float inv = 1.f / l;
+    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(doc) * ldo + h * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+}
+
+// dst[c, r] = src[r, c] for a bf16 matrix (load-time helper: builds W_v^T for the fused decoder W_o.W_v product)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int ld_src,
+                                      __nv_bfloat16* __restrict__ dst, int ld_dst) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[static_cast<size_t>(r) * ld_src + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[static_cast<size_t>(c) * ld_dst + r] = tile[threadIdx.x][i];
+    }
+}
+
 // logits[r, c] = h[row_of(r), :] . lm_head[cols[c], :]  for a short list of vocabulary ids
 // (modeling_t5.py:1110 restricted to the columns pointwise.py:120-121 / setwise.py:186 read).
 // grid = n_rows, one warp per column (strided). row_of(r) = r * row_stride + row_offset.

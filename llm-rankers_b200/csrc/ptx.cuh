@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// 2-D tiled reduction shared -> global: global[tile] += shared[tile], performed by the L2 (dtype from the tensor map).
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
