@@ -354,7 +354,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 
     if constexpr (TMA_EPI) {
-        if (threadIdx.x == 64) tma_store_wait<0>();  // all bulk stores complete (smem reads and global writes) before exit
+        // shared memory must stay alive until the bulk stores have READ it; their global writes complete with the grid
+        if (threadIdx.x == 64) tma_store_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();

@@ -288,23 +288,47 @@ cross_attention_t1_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
         l += s[r];
     }
     l = warp_sum(l);
-    float o0 = 0.f, o1 = 0.f;
+    // V phase: 16 B per lane, 8 lanes per 128 B row, 4 rows per warp-wide load (lane>>3 picks the row, lane&7 the 8-dim chunk)
+    // -> 4x the bytes in flight of a 4 B/lane row walk; partial sums over the 4 row groups are folded with two shuffles.
+    const int chunk = lane & 7, rsub = lane >> 3;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
 #pragma unroll
     for (int r = 0; r < MAX_ROUNDS; ++r) {
         const int base = r * 32;
         if (base < S) {  // warp-uniform
-            const int n = min(32, S - base);
-#pragma unroll 8
-            for (int jj = 0; jj < n; ++jj) {
-                const float p = __shfl_sync(0xffffffffu, s[r], jj);
-                const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + static_cast<size_t>(base + jj) * ldkv + 2 * lane));
-                o0 += p * vf.x;
-                o1 += p * vf.y;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+                const int j = base + jj + rsub;
+                const float p = __shfl_sync(0xffffffffu, s[r], jj + rsub);  // p == 0 for j >= S
+                if (j < S) {
+                    const uint4 c = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(j) * ldkv + chunk * 8));
+                    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 vf = __bfloat1622float2(p2[e]);
+                        o[2 * e] += p * vf.x;
+                        o[2 * e + 1] += p * vf.y;
+                    }
+                }
             }
         }
     }
-    const float inv = 1.f / l;
-    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(doc) * ldo + h * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    }
+    if (rsub == 0) {
+        const float inv = 1.f / l;
+        uint4 v;
+        v.x = pack_bf16(o[0] * inv, o[1] * inv);
+        v.y = pack_bf16(o[2] * inv, o[3] * inv);
+        v.z = pack_bf16(o[4] * inv, o[5] * inv);
+        v.w = pack_bf16(o[6] * inv, o[7] * inv);
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(doc) * ldo + h * 64 + chunk * 8) = v;
+    }
 }
 
 // dst[c, r] = src[r, c] for a bf16 matrix (load-time helper: builds W_v^T for the fused decoder W_o.W_v product)
