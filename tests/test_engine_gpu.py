@@ -168,7 +168,8 @@ def test_yes_no_vs_bf16_emulating_oracle(which):
     got, want = np.concatenate(got).astype(np.float64), np.concatenate(want).astype(np.float64)
     err = np.abs(got - want)
     record(f"{which}/yes_no_vs_bf16_emulation", max_abs_err=err.max(), mean_abs_err=err.mean())
-    assert np.all(err <= 0.02 + 0.01 * np.abs(want)), err.max()
+    # 0.035: includes the T=1 decoder re-association W_o.W_v -> one bf16 matrix (the emulation rounds v, then applies W_o)
+    assert np.all(err <= 0.035 + 0.01 * np.abs(want)), err.max()
 
 
 # ---------------------------------------------------------------------------------------- the drop-in API on the GPU
