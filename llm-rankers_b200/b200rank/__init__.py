@@ -94,7 +94,7 @@ def load_library() -> C.CDLL:
         "b200rank_profile_report": [vp, C.c_char_p, C.c_int],
         "b200rank_device_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
         "b200rank_test_gemm": [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32p],
-        "b200rank_test_enc_attention": [C.c_int, vp, i32p, C.c_int, C.c_int, f32p, vp],
+        "b200rank_test_enc_attention": [C.c_int, vp, i32p, C.c_int, C.c_int, f32p, vp, C.c_int],
         "b200rank_rel_bucket": [C.c_int, C.c_int, C.c_int, C.c_int],
     }
     for name, argtypes in sig.items():
@@ -318,7 +318,7 @@ def test_gemm(a_f32: np.ndarray, w_f32: np.ndarray, epi: int = EPI_BF16, block_n
     return (bf16_bits_to_f32(out) if out.dtype == np.uint16 else out), float(ms.value)
 
 
-def test_enc_attention(qkv_f32: np.ndarray, cu_seqlens, num_heads: int, bias: np.ndarray, device: int = 0) -> np.ndarray:
+def test_enc_attention(qkv_f32: np.ndarray, cu_seqlens, num_heads: int, bias: np.ndarray, device: int = 0, mode: int = 0) -> np.ndarray:
     lib = load_library()
     cu = _i32(cu_seqlens)
     tokens = int(cu[-1])
@@ -329,5 +329,5 @@ def test_enc_attention(qkv_f32: np.ndarray, cu_seqlens, num_heads: int, bias: np
     assert b.shape == (num_heads, ATTN_BIAS_LEN)
     out = np.zeros((tokens, inner), np.uint16)
     _check(lib.b200rank_test_enc_attention(device, q.ctypes.data_as(C.c_void_p), _p(cu, C.c_int32), cu.shape[0] - 1, num_heads,
-                                           _p(b, C.c_float), out.ctypes.data_as(C.c_void_p)))
+                                           _p(b, C.c_float), out.ctypes.data_as(C.c_void_p), mode))
     return bf16_bits_to_f32(out)

@@ -18,6 +18,7 @@
 
 #include "../../include/b200rank.h"
 #include "attention_enc.cuh"
+#include "attention_tc.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels_misc.cuh"
 
@@ -86,20 +87,42 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 }
 
 // ------------------------------------------------------------------ GEMM launch
-template <int BN, int EPI, bool TMA_EPI>
+template <int BN, int EPI, bool TMA_EPI, int CG>
 static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                             const GemmArgs& args) {
     static bool attr_set = false;
-    auto kern = gemm_tcgen05_kernel<BN, EPI, TMA_EPI>;
+    auto kern = gemm_tcgen05_kernel<BN, EPI, TMA_EPI, CG>;
+    using Cfg = GemmCfg<BN, CG>;
     if (!attr_set) {
-        CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+        CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    const int tiles = ((args.M + kGemmBlockM - 1) / kGemmBlockM) * ((args.N + BN - 1) / BN);
-    const int grid = std::min(tiles, num_sms);
-    kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, tout, args);
-    CU_OK(cudaGetLastError());
+    const int tiles = ((args.M + kGemmBlockM * CG - 1) / (kGemmBlockM * CG)) * ((args.N + BN - 1) / BN);
+    const int grid = CG * std::min(tiles, num_sms / CG);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, args));
     return B200RANK_OK;
+}
+
+static int gemm_cta_group_pref() {
+    static int pref = -1;
+    if (pref < 0) {
+        const char* s = getenv("B200RANK_GEMM_CG");
+        pref = s ? atoi(s) : 2;
+        if (pref != 1 && pref != 2) pref = 2;
+    }
+    return pref;
 }
 
 static int pick_block_n(int M, int N, int epi, int num_sms) {
@@ -113,13 +136,27 @@ static int pick_block_n(int M, int N, int epi, int num_sms) {
     return 32;
 }
 
+// CTA pairs (cta_group::2) pay off when there are enough 256-row tiles to keep all 74 pairs busy.
+static int pick_cta_group(int M, int N, int bn, int num_sms) {
+    if (bn != 256 || gemm_cta_group_pref() == 1) return 1;
+    const int pair_tiles = ((M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM)) * ((N + bn - 1) / bn);
+    return pair_tiles >= num_sms / 2 ? 2 : 1;
+}
+
 static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
-                          const GemmArgs& a, int epi, int bn, bool tma_epi) {
+                          const GemmArgs& a, int epi, int bn, bool tma_epi, int cg) {
     // the staged bf16 epilogue moves 64-column (128 B) tiles; a 32-column accumulator keeps the direct store path
     if (epi == EPI_BF16 && bn < 64) tma_epi = false;
+    if (cg == 2) {
+#define GEMM_CG2(EPI) \
+    if (bn == 256 && epi == EPI && tma_epi) return launch_gemm_inst<256, EPI, true, 2>(st, num_sms, ta, tb, tout, a);
+        GEMM_CG2(EPI_BF16) GEMM_CG2(EPI_RESID_F32) GEMM_CG2(EPI_GATED_BF16) GEMM_CG2(EPI_F32)
+#undef GEMM_CG2
+        return set_error(B200RANK_ERR_ARG, "no cta_group::2 GEMM instantiation for block_n=%d epi=%d tma_epi=%d", bn, epi, (int)tma_epi);
+    }
 #define GEMM_CASE(BN, EPI)                                                                              \
     if (bn == BN && epi == EPI)                                                                         \
-        return tma_epi ? launch_gemm_inst<BN, EPI, true>(st, num_sms, ta, tb, tout, a) : launch_gemm_inst<BN, EPI, false>(st, num_sms, ta, tb, tout, a);
+        return tma_epi ? launch_gemm_inst<BN, EPI, true, 1>(st, num_sms, ta, tb, tout, a) : launch_gemm_inst<BN, EPI, false, 1>(st, num_sms, ta, tb, tout, a);
     GEMM_CASE(256, EPI_BF16) GEMM_CASE(128, EPI_BF16) GEMM_CASE(64, EPI_BF16) GEMM_CASE(32, EPI_BF16)
     GEMM_CASE(256, EPI_RESID_F32) GEMM_CASE(128, EPI_RESID_F32) GEMM_CASE(64, EPI_RESID_F32) GEMM_CASE(32, EPI_RESID_F32)
     GEMM_CASE(256, EPI_GATED_BF16)
@@ -253,7 +290,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     const int bn = force_bn ? force_bn : pick_block_n(M, N, epi, e->num_sms);
     char label[96];
-    if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);
+    if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);  // cta group: pick_cta_group
     prof_begin(e, label);
     struct ProfEnd { b200rank_engine* e; ~ProfEnd() { prof_end(e); } } prof_end_guard{e};
     if (e->debug_simt) {
@@ -262,15 +299,16 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
         gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi, 256, out, ldo);
         return post_launch(e, "gemm_simt_debug");
     }
+    const int cg = e->direct_epi ? 1 : pick_cta_group(M, N, bn, e->num_sms);
     const CUtensorMap *ta, *tb, *tout;
     RET_IF(engine_tmap(e, A, a_rows, K, lda, kGemmBlockM, 0, &ta));
-    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn, 0, &tb));
+    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn / cg, 0, &tb));
     const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32);
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
     GemmArgs args{M, N, K, out, ldo};
-    RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi));
+    RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
 }
 
@@ -669,14 +707,44 @@ static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h
     return post_launch(e, "rmsnorm");
 }
 
-// Short documents: whole (doc, head) resident in shared memory; longer ones: 64-query tiles with streamed keys.
-static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, int inner, const int* d_cu, int nd, int maxlen, int H,
-                                const float* bias, bf16* out, int ldo, cudaStream_t st, int q_tiles) {
+// Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length),
+// 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256). B200RANK_ATTN=tiled|resident|tc overrides mode 0.
+static int attn_default_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* s = getenv("B200RANK_ATTN");
+        mode = !s ? 3 : (!strcmp(s, "tiled") ? 1 : (!strcmp(s, "resident") ? 2 : 3));  // default: tcgen05 for len <= 256
+    }
+    return mode;
+}
+template <int NKB>
+static int launch_attn_tc(const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd, int H, const float* bias,
+                          bf16* out, int ldo, cudaStream_t st, const CUtensorMap* tm) {
     static bool attr_set = false;
-    // measured on B200 (profiles/r01_*): the resident variant is ~30 % slower than the tiled one at S = 184 (one 12-warp CTA
-    // per SM by registers); it stays available for experiments behind B200RANK_ATTN_RESIDENT=1.
-    const bool resident = getenv("B200RANK_ATTN_RESIDENT") && atoi(getenv("B200RANK_ATTN_RESIDENT")) != 0;
-    if (maxlen <= 256 && resident) {
+    auto kern = enc_attention_tc_kernel<NKB>;
+    if (!attr_set) {
+        CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<NKB>::kSmemBytes));
+        attr_set = true;
+    }
+    kern<<<dim3(H, nd), kAttnTcThreads, AttnTcCfg<NKB>::kSmemBytes, st>>>(*tm, inner, d_cu, bias, out, ldo);
+    return B200RANK_OK;
+}
+static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
+                                int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode) {
+    static bool attr_set = false;
+    if (mode == 0) mode = attn_default_mode();
+    if (maxlen > 256) mode = 1;
+    if (mode == 3) {
+        CUtensorMap local;
+        const CUtensorMap* tm = &local;
+        if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
+        else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
+        if (e) prof_begin(e, "enc_attention_tc");
+        if (maxlen <= 192) RET_IF(launch_attn_tc<3>(qkv, ld, qkv_rows, inner, d_cu, nd, H, bias, out, ldo, st, tm));
+        else RET_IF(launch_attn_tc<4>(qkv, ld, qkv_rows, inner, d_cu, nd, H, bias, out, ldo, st, tm));
+        return e ? post_launch(e, "enc_attention_tc") : B200RANK_OK;
+    }
+    if (mode == 2) {
         const int s_pad = (maxlen + 63) & ~63;
         const int smem = 3 * s_pad * 128;
         if (!attr_set) {
@@ -688,7 +756,7 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, int
         return e ? post_launch(e, "enc_attention_resident") : B200RANK_OK;
     }
     if (e) prof_begin(e, "enc_attention");
-    enc_attention_kernel<<<dim3(q_tiles, H, nd), 128, 0, st>>>(qkv, ld, inner, d_cu, bias, out, ldo);
+    enc_attention_kernel<<<dim3((maxlen + 63) / 64, H, nd), 128, 0, st>>>(qkv, ld, inner, d_cu, bias, out, ldo);
     return e ? post_launch(e, "enc_attention") : B200RANK_OK;
 }
 
@@ -697,12 +765,11 @@ static int run_encoder(b200rank_engine* e) {
     const int n = e->staged_tokens, nd = e->staged_docs;
     const int d = e->d, I = e->inner, F = e->F, Tk = e->cap_tokens;
     RET_IF(k_embed(e, e->d_ids, e->x, n));
-    const int q_tiles = (e->staged_maxlen + 63) / 64;
     for (int l = 0; l < e->Le; ++l) {
         const LayerW& w = e->enc[l];
         RET_IF(k_rmsnorm(e, e->x, w.ln1, e->h, n));
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
-        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, I, e->d_cu, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, q_tiles));
+        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0));
         RET_IF(gemm(e, e->ao, I, Tk, w.wo, I, d, n, d, I, EPI_RESID_F32, e->x, d));
         RET_IF(k_rmsnorm(e, e->x, w.ln2, e->h, n));
         RET_IF(gemm(e, e->h, d, Tk, w.wi, d, 2 * F, n, 2 * F, d, EPI_GATED_BF16, e->g, F));
@@ -1129,11 +1196,12 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         const int bn = block_n ? block_n : pick_block_n(M, N, epi, prop.multiProcessorCount);
         CUtensorMap ta, tb, tout;
         const bool direct = getenv("B200RANK_GEMM_DIRECT_EPI") && atoi(getenv("B200RANK_GEMM_DIRECT_EPI")) != 0;
+        const int cg = direct ? 1 : pick_cta_group(M, N, bn, prop.multiProcessorCount);
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
-        if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn);
+        if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn / cg);
         if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
         GemmArgs args{M, N, K, dO, n_out};
-        if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct);
+        if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct, cg);
     }
     if (rc == B200RANK_OK) {
         cudaEventRecord(e1, 0);
@@ -1152,7 +1220,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
 }
 
 extern "C" int b200rank_test_enc_attention(int device, const void* qkv_bf16, const int32_t* cu_seqlens, int n_docs, int num_heads,
-                                           const float* bias, void* out_bf16) {
+                                           const float* bias, void* out_bf16, int mode) {
     if (!qkv_bf16 || !cu_seqlens || !bias || !out_bf16 || n_docs <= 0 || num_heads <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(B200RANK_ERR_CUDA, "no CUDA device available; b200rank has no CPU fallback");
@@ -1161,13 +1229,15 @@ extern "C" int b200rank_test_enc_attention(int device, const void* qkv_bf16, con
     int maxlen = 0;
     for (int i = 0; i < n_docs; ++i) maxlen = std::max(maxlen, cu_seqlens[i + 1] - cu_seqlens[i]);
     bf16 *dq = nullptr, *dout = nullptr; int* dcu = nullptr; float* dbias = nullptr;
-    CU_OK(cudaMalloc((void**)&dq, (size_t)tokens * 3 * inner * 2)); CU_OK(cudaMalloc((void**)&dout, (size_t)tokens * inner * 2));
+    const size_t qrows = align_up(tokens, 64) + 256;  // slack rows: tiles may read past the last document (masked)
+    CU_OK(cudaMalloc((void**)&dq, qrows * 3 * inner * 2)); CU_OK(cudaMalloc((void**)&dout, (size_t)tokens * inner * 2));
+    CU_OK(cudaMemset(dq, 0, qrows * 3 * inner * 2));
     CU_OK(cudaMalloc((void**)&dcu, (n_docs + 1) * 4)); CU_OK(cudaMalloc((void**)&dbias, (size_t)num_heads * kAttnBiasLen * 4));
     CU_OK(cudaMemcpy(dq, qkv_bf16, (size_t)tokens * 3 * inner * 2, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(dcu, cu_seqlens, (n_docs + 1) * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(dbias, bias, (size_t)num_heads * kAttnBiasLen * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemset(dout, 0, (size_t)tokens * inner * 2));
-    int rc = launch_enc_attention(nullptr, dq, 3 * inner, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, (maxlen + 63) / 64);
+    int rc = launch_enc_attention(nullptr, dq, 3 * inner, qrows, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, mode);
     cudaError_t err = cudaDeviceSynchronize();
     if (rc != B200RANK_OK) { cudaFree(dq); cudaFree(dout); cudaFree(dcu); cudaFree(dbias); return rc; }
     if (err != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "enc_attention kernel failed: %s", cudaGetErrorString(err));

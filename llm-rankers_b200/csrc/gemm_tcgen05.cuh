@@ -22,25 +22,32 @@ enum EpiMode : int {
     EPI_RESID_F32 = 1,  // out_f32[m, n]            += acc              (residual stream, in place)
     EPI_GATED_BF16 = 2, // out_bf16[m, n/2 ...]      = gelu_new(acc[:, :BN/2]) * acc[:, BN/2:]  per N-tile
     EPI_F32 = 3,        // out_f32[m, n]             = acc
+    EPI_RESID_NORM = 4, // EPI_RESID_F32 with N == row width, plus: every unit owns whole 128-row blocks (all N-tiles), and once a
+                        // block's adds have landed it re-reads those rows from L2 and writes norm_out = bf16(T5LayerNorm(out))
 };
 
 struct GemmArgs {
     int M, N, K;   // N counts accumulator columns (= weight rows); K is the contraction length
     void* out;     // bf16* or float* depending on the epilogue
     int ldo;       // leading dimension of out, in elements
+    // EPI_RESID_NORM only: fused T5LayerNorm (modeling_t5.py:55-68) of the updated residual rows
+    const float* norm_w;        // [N]
+    __nv_bfloat16* norm_out;    // [M, N] bf16, leading dimension N
+    float norm_eps;
 };
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom
 constexpr int kGemmThreads = 192;
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG = 1>
 struct GemmCfg {
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
-    static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
+    static constexpr int kBRows = BLOCK_N / CG;                      // a CTA pair splits the B tile
+    static constexpr int kBBytes = kBRows * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // fill ~192 KB with the ring; at least 3, at most 8 stages
-    static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;  // BLOCK_N=256: 4 x 48 KB ring + 32 KB staging = 224 KB
+    // fill ~192 KB with the ring; at least 3, at most 8 stages (BLOCK_N=256: 4 x 48 KB, or 6 x 32 KB for a CTA pair)
+    static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : (kStagesRaw < 3 ? 3 : kStagesRaw);
     static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
     static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
@@ -48,23 +55,22 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024: manual alignment slack
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 // TMA_EPI = true : accumulators leave through shared-memory staging tiles (128 rows x 128 B, 128B swizzle) and
 //                  cp.async.bulk.tensor stores — or cp.reduce.async.bulk.tensor .add for the fp32 residual, which
 //                  performs x += acc inside L2 so the SMs never read the residual stream.
 // TMA_EPI = false: per-thread 16 B global stores straight from registers (round-1 bring-up path, kept for bisecting
 //                  with B200RANK_GEMM_DIRECT_EPI=1).
-template <int BLOCK_N, int EPI, bool TMA_EPI>
+// CG = 2: the kernel runs as clusters of two CTAs (cta_group::2). One tcgen05.mma then covers 256 x BLOCK_N: each CTA keeps
+//         its own 128 accumulator rows in its own TMEM and stages its own 128 rows of A but only HALF of the B tile — the
+//         tensor core reads the other half from the peer's shared memory. That halves the L2->SM and shared-memory traffic
+//         of the B operand (the 1-CTA 128x256 tile is bound by it: profiles/r01_ncu_summary_v4.txt). Only the leader CTA
+//         issues MMAs; both CTAs run TMA producer and epilogue roles.
+template <int BLOCK_N, int EPI, bool TMA_EPI, int CG = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, CG>;
+    static_assert(CG == 1 || CG == 2, "cta group");
     constexpr int kStages = Cfg::kStages;
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "bad BLOCK_N");
     static_assert(EPI != EPI_GATED_BF16 || BLOCK_N % 64 == 0, "gated epilogue needs BLOCK_N % 64 == 0");
@@ -86,29 +92,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int tiles_m = (args.M + kGemmBlockM - 1) / kGemmBlockM;
+    // a "unit" is one CTA (CG = 1) or one CTA pair (CG = 2); a tile is (128 * CG) x BLOCK_N
+    const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
+    const int tiles_m = (args.M + kGemmBlockM * CG - 1) / (kGemmBlockM * CG);
     const int tiles_n = (args.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (args.K + kGemmBlockK - 1) / kGemmBlockK;
+    constexpr bool kRowOwner = (EPI == EPI_RESID_NORM);
+    constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_NORM);
+    // it-th tile of this unit -> (m-block, n-block). Default: tiles round-robin over units, n fastest. Row-owner mode: a unit
+    // takes whole m-blocks (all n-tiles back to back) so that it alone completes rows.
+    auto get_tile = [&](int it, int& mb, int& nb) -> bool {
+        if constexpr (kRowOwner) {
+            mb = unit + (it / tiles_n) * num_units;
+            nb = it % tiles_n;
+            return mb < tiles_m;
+        } else {
+            const int tile = unit + it * num_units;
+            mb = tile / tiles_n;
+            nb = tile % tiles_n;
+            return tile < num_tiles;
+        }
+    };
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         if constexpr (TMA_EPI) tma_prefetch_desc(&tmap_out);
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], CG);      // CG = 2: leader's arrive.expect_tx + the peer's remote arrive (leader's copy is the live one)
+            mbar_init(&empty_bar[s], 1);      // tcgen05.commit (multicast to both CTAs when CG = 2)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 128);
+            mbar_init(&tmem_empty_bar[a], 128 * CG);  // every epilogue thread of the unit (leader's copy is the live one)
         }
         fence_barrier_init();
     } else if (warp_idx == 1) {
-        tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+        if constexpr (CG == 2) tmem_alloc_cg2(tmem_base_smem, Cfg::kTmemCols);
+        else tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // peer barriers must be initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
@@ -117,28 +144,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * kGemmBlockM;
-                const int n0 = (tile % tiles_n) * BLOCK_N;
+            int mb, nb_;
+            for (int it = 0; get_tile(it, mb, nb_); ++it) {
+                const int m0 = mb * (kGemmBlockM * CG) + cta_rank * kGemmBlockM;
+                const int n0 = nb_ * BLOCK_N + cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0,
-                                kEvictNormal);
-                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n0,
-                                kEvictLast);
+                    if constexpr (CG == 2) {
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        else mbar_arrive_cluster(&full_bar[stage], 0);
+                        tma_load_2d_cg2(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0, kEvictNormal);
+                        tma_load_2d_cg2(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n0, kEvictLast);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0, kEvictNormal);
+                        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n0, kEvictLast);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp_idx == 1) {
         // -------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM * CG, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
-            int iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+            int mb, nb_;
+            for (int iter = 0; get_tile(iter, mb, nb_); ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -152,10 +185,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle atom: +2 in (addr >> 4)
-                        umma_bf16(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CG == 2) umma_bf16_cg2(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+                    if constexpr (CG == 2) {
+                        umma_commit_cg2(&empty_bar[stage], 0b11);
+                        if (kb == num_kb - 1) umma_commit_cg2(&tmem_full_bar[acc], 0b11);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -164,13 +203,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ---------------------------------------------------------------- epilogue
         const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
+        // hand the accumulator buffer back to the MMA issuer (who lives in the leader CTA)
+        auto release_acc = [&](uint64_t* bar) {
+            if constexpr (CG == 2) mbar_arrive_cluster(bar, 0);
+            else mbar_arrive(bar);
+        };
         int stage_sel = 0;  // which staging tile the next chunk uses (persists across tiles)
-        int iter = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        int mb, nb;
+        for (int iter = 0; get_tile(iter, mb, nb); ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
-            const int m0 = (tile / tiles_n) * kGemmBlockM;
-            const int nb = tile % tiles_n;
+            const int m0 = mb * (kGemmBlockM * CG) + cta_rank * kGemmBlockM;
             const int row = m0 + row_in_tile;
             const bool row_ok = row < args.M;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -195,7 +238,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     named_bar_sync(1, 128);
                     if (issuer) {
                         const void* src = smem_stage + stage_sel * (kGemmBlockM * 128);
-                        if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
+                        if constexpr (kResid) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
                         else tma_store_2d(&tmap_out, src, out_col0, m0);
                         tma_store_commit();
                     }
@@ -208,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tmem_ld32(taddr + c, r0);
                         tmem_ld32(taddr + c + 32, r1);
                         tmem_ld_wait();
-                        if (c + 64 == BLOCK_N) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); }
+                        if (c + 64 == BLOCK_N) { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
                         stage_open();
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -235,7 +278,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tmem_ld32(taddr + c + 32 * hh, g);
                             tmem_ld32(taddr + HALF + c + 32 * hh, l);
                             tmem_ld_wait();
-                            if (c + 64 == HALF && hh == 1) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); }
+                            if (c + 64 == HALF && hh == 1) { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 uint32_t v[4];
@@ -256,7 +299,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         uint32_t r[32];
                         tmem_ld32(taddr + c, r);
                         tmem_ld_wait();
-                        if (c + 32 == BLOCK_N) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); }
+                        if (c + 32 == BLOCK_N) { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
                         stage_open();
 #pragma unroll
                         for (int j = 0; j < 8; ++j) put16(j, r[4 * j + 0], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -275,7 +318,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tmem_ld_wait();
                     if (c + 32 == HALF) {
                         tc_fence_before();
-                        mbar_arrive(&tmem_empty_bar[acc]);
+                        release_acc(&tmem_empty_bar[acc]);
                     }
                     const int col0 = nb * HALF + c;
                     if (row_ok) {
@@ -303,7 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tmem_ld_wait();
                     if (c + 32 == BLOCK_N) {
                         tc_fence_before();
-                        mbar_arrive(&tmem_empty_bar[acc]);
+                        release_acc(&tmem_empty_bar[acc]);
                     }
                     const int col0 = nb * BLOCK_N + c;
                     if (row_ok) {
@@ -320,7 +363,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     *reinterpret_cast<uint4*>(out + col0 + j) = v;
                                 }
                             }
-                        } else if constexpr (EPI == EPI_RESID_F32) {
+                        } else if constexpr (kResid) {
                             float* out = reinterpret_cast<float*>(args.out) + static_cast<size_t>(row) * args.ldo;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -350,6 +393,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             }
+            if constexpr (kRowOwner && TMA_EPI) {
+                if (nb == tiles_n - 1) {
+                    // All N-tiles of this unit's rows [m0, m0+128) are issued. Wait until the bulk reduce-adds have been performed
+                    // (wait_group without .read), then normalise the rows straight out of L2: one warp per row, row in registers.
+                    if (threadIdx.x == 64) tma_store_wait<0>();
+                    named_bar_sync(1, 128);
+                    const int d = args.N;
+                    const int nvec = d >> 2;
+                    const int ew = warp_idx - 2;  // 0..3
+                    for (int rr = ew; rr < kGemmBlockM; rr += 4) {
+                        const int row = m0 + rr;
+                        if (row >= args.M) break;
+                        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.out) + static_cast<size_t>(row) * args.ldo);
+                        float4 v[8];
+                        float ss = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = lane + i * 32;
+                            if (idx < nvec) {
+                                v[i] = __ldcg(src + idx);
+                                ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        const float r = rsqrtf(ss / static_cast<float>(d) + args.norm_eps);
+                        const float4* wv = reinterpret_cast<const float4*>(args.norm_w);
+                        uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = lane + i * 32;
+                            if (idx < nvec) {
+                                const float4 gw = __ldg(wv + idx);
+                                uint2 o2;
+                                o2.x = pack_bf16(v[i].x * r * gw.x, v[i].y * r * gw.y);
+                                o2.y = pack_bf16(v[i].z * r * gw.z, v[i].w * r * gw.w);
+                                dst[idx] = o2;
+                            }
+                        }
+                    }
+                }
+            }
         }
     }
 
@@ -358,10 +443,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (threadIdx.x == 64) tma_store_wait_read<0>();
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // no CTA of the pair may exit while its peer can still touch its smem / TMEM
+    else __syncthreads();
     if (warp_idx == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 

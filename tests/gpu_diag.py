@@ -94,7 +94,7 @@ def attention_reference(qkv, cu, H, bias):
     return out
 
 
-def run_attn_case(lens, H):
+def run_attn_case(lens, H, mode=0):
     import b200rank as br
     rng = np.random.default_rng(99 + sum(lens) + H)
     cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
@@ -102,16 +102,23 @@ def run_attn_case(lens, H):
     qkv = rng.standard_normal((tokens, 3 * H * 64)).astype(np.float32)
     qkv[:, : H * 64] *= 0.35  # keep scores O(few) like a trained model (no 1/sqrt(d) in T5)
     bias = rng.standard_normal((H, br.ATTN_BIAS_LEN)).astype(np.float32)
-    out = br.test_enc_attention(qkv, cu, H, bias)
+    out = br.test_enc_attention(qkv, cu, H, bias, mode=mode)
     ref = attention_reference(qkv, cu, H, bias)
     err = np.abs(out - ref)
     tol = 0.03 * np.abs(ref).max()
-    res = dict(kind="attn", lens=list(map(int, lens)), H=H, max_err=float(err.max()), mean_err=float(err.mean()), tol=float(tol),
+    res = dict(kind="attn", lens=list(map(int, lens)), H=H, mode=mode, finite=bool(np.isfinite(out).all()), max_err=float(err.max()), mean_err=float(err.mean()), tol=float(tol),
                ok=bool(err.max() <= tol))
     if not res["ok"]:
         bad = np.argwhere(err > tol)
         res["n_bad"] = int(bad.shape[0])
         res["first_bad"] = bad[:8].tolist()
+        res["bad_rows"] = np.unique(bad[:, 0])[:24].tolist()
+        res["bad_cols"] = np.unique(bad[:, 1])[:24].tolist()
+        os.makedirs(OUT, exist_ok=True)
+        tag = f"attn_m{mode}_{'_'.join(map(str, lens))}_{H}"[:80]
+        if out.size <= 1 << 20:
+            np.save(os.path.join(OUT, tag + "_out.npy"), out)
+            np.save(os.path.join(OUT, tag + "_ref.npy"), ref.astype(np.float32))
     return res
 
 
@@ -135,6 +142,9 @@ def all_cases():
               "gemm:18400:1024:2816:1:256:0:rand", "gemm:18400:1024:1024:1:256:0:rand", "gemm:100:32128:1024:3:256:0:rand",
               "gemm:1000:1152:512:0:0:0:rand"]
     cases += ["attn:64:1", "attn:184:2", "attn:7,64,65,128,129,184,200:3", "attn:1536:1", "attn:184,184,184,184:16"]
+    # tcgen05 attention (mode 3): one tile, two tiles, ragged, 4 key blocks, many heads
+    cases += ["attn:64:1:3", "attn:128:1:3", "attn:184:2:3", "attn:7,64,65,128,129,184,192:3:3", "attn:250,256,130,193:2:3",
+              "attn:184,184,184,184:16:3", "attn:184:2:2"]
     return cases
 
 
@@ -144,7 +154,7 @@ def run_one(spec):
         M, N, K, epi, bn, simt = map(int, parts[1:7])
         return run_gemm_case(M, N, K, epi, bn, simt, parts[7] if len(parts) > 7 else "rand")
     if parts[0] == "attn":
-        return run_attn_case([int(x) for x in parts[1].split(",")], int(parts[2]))
+        return run_attn_case([int(x) for x in parts[1].split(",")], int(parts[2]), int(parts[3]) if len(parts) > 3 else 0)
     raise ValueError(spec)
 
 
@@ -152,6 +162,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case")
     ap.add_argument("--timeout", type=int, default=120)
+    ap.add_argument("--only", default=None, help="substring filter on case specs, e.g. attn")
     args = ap.parse_args()
     if args.case:
         try:
@@ -163,6 +174,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     results = []
     for spec in all_cases():
+        if args.only and args.only not in spec:
+            continue
         t0 = time.time()
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", spec], capture_output=True, text=True,
