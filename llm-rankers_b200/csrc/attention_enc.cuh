@@ -61,7 +61,7 @@ __device__ __forceinline__ void load_tile_64x64(__nv_bfloat16* smem_tile, const 
 // grid (q_tiles, H, n_docs), 128 threads.
 // qkv: packed [tokens, ld] with q | k | v column blocks each `inner` wide; head h at columns h*64.
 // bias: [H][kAttnBiasLen] fp32, index clamp(j - i, -128, 128) + 128  (bidirectional buckets).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, const int* __restrict__ cu,
                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo) {
     __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64];

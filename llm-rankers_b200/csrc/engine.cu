@@ -150,9 +150,13 @@ static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, c
     if (cg == 2) {
 #define GEMM_CG2(EPI) \
     if (bn == 256 && epi == EPI && tma_epi) return launch_gemm_inst<256, EPI, true, 2>(st, num_sms, ta, tb, tout, a);
-        GEMM_CG2(EPI_BF16) GEMM_CG2(EPI_RESID_F32) GEMM_CG2(EPI_GATED_BF16) GEMM_CG2(EPI_F32)
+        GEMM_CG2(EPI_BF16) GEMM_CG2(EPI_RESID_F32) GEMM_CG2(EPI_GATED_BF16) GEMM_CG2(EPI_F32) GEMM_CG2(EPI_RESID_NORM)
 #undef GEMM_CG2
         return set_error(B200RANK_ERR_ARG, "no cta_group::2 GEMM instantiation for block_n=%d epi=%d tma_epi=%d", bn, epi, (int)tma_epi);
+    }
+    if (epi == EPI_RESID_NORM) {
+        if (bn == 256 && tma_epi) return launch_gemm_inst<256, EPI_RESID_NORM, true, 1>(st, num_sms, ta, tb, tout, a);
+        return set_error(B200RANK_ERR_ARG, "fused residual+norm GEMM needs block_n 256 and the staged epilogue");
     }
 #define GEMM_CASE(BN, EPI)                                                                              \
     if (bn == BN && epi == EPI)                                                                         \
@@ -284,11 +288,12 @@ static int post_launch(b200rank_engine* e, const char* what) {
 
 // acc[M,N] = A[M,K] . W[N,K]^T with fused epilogue. a_rows/w_rows: row capacity of the operands (TMA bounds).
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn) {
+                int K, int epi, void* out, int ldo, int force_bn, const float* norm_w, bf16* norm_out) {
     if (M <= 0) return B200RANK_OK;
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
-    const int bn = force_bn ? force_bn : pick_block_n(M, N, epi, e->num_sms);
+    int bn = force_bn ? force_bn : pick_block_n(M, N, epi, e->num_sms);
+    if (epi == EPI_RESID_NORM) bn = 256;
     char label[96];
     if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);  // cta group: pick_cta_group
     prof_begin(e, label);
@@ -296,18 +301,18 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     if (e->debug_simt) {
         const int n_out = epi == EPI_GATED_BF16 ? N / 2 : N;
         dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
-        gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi, 256, out, ldo);
+        gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi == EPI_RESID_NORM ? EPI_RESID_F32 : epi, 256, out, ldo);
         return post_launch(e, "gemm_simt_debug");
     }
     const int cg = e->direct_epi ? 1 : pick_cta_group(M, N, bn, e->num_sms);
     const CUtensorMap *ta, *tb, *tout;
     RET_IF(engine_tmap(e, A, a_rows, K, lda, kGemmBlockM, 0, &ta));
     RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn / cg, 0, &tb));
-    const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32);
+    const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32 || epi == EPI_RESID_NORM);
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
-    GemmArgs args{M, N, K, out, ldo};
+    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps};
     RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
 }
@@ -546,7 +551,7 @@ static int shape_check(const char* name, int64_t rows, int64_t cols, int64_t er,
 }
 
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn = 0);
+                int K, int epi, void* out, int ldo, int force_bn = 0, const float* norm_w = nullptr, bf16* norm_out = nullptr);
 
 // Derived weights, computed once on the device when the last tensor arrives (they live in the arena, so the NCCL
 // broadcast carries them): decoder W_ov[l] = W_o[l] . W_v[l]  (bf16 operands, fp32 accumulate, bf16 result).
@@ -707,13 +712,32 @@ static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h
     return post_launch(e, "rmsnorm");
 }
 
+// x += A.W^T, then h = bf16(T5LayerNorm(x) * norm_w). Fused into one launch (EPI_RESID_NORM: row-block-owning units re-read
+// their finished rows from L2) when there are enough 128*CG-row blocks to occupy the machine; otherwise GEMM + rmsnorm kernel.
+static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n);
+static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int K,
+                                float* x, const float* norm_w, bf16* h) {
+    const int d = e->d;
+    static int fuse_pref = -1;
+    if (fuse_pref < 0) fuse_pref = (getenv("B200RANK_FUSE_NORM") && atoi(getenv("B200RANK_FUSE_NORM")) == 0) ? 0 : 1;
+    const int cg = pick_cta_group(M, d, 256, e->num_sms);
+    const int row_blocks = (M + 128 * cg - 1) / (128 * cg);
+    const int units = e->num_sms / cg;
+    const bool fuse = fuse_pref && !e->direct_epi && !e->debug_simt && d % 256 == 0 && row_blocks * 10 >= units * 6;
+    if (fuse) return gemm(e, A, lda, a_rows, W, ldw, w_rows, M, d, K, EPI_RESID_NORM, x, d, 0, norm_w, h);
+    RET_IF(gemm(e, A, lda, a_rows, W, ldw, w_rows, M, d, K, EPI_RESID_F32, x, d));
+    return k_rmsnorm(e, x, norm_w, h, M);
+}
+
 // Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length),
 // 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256). B200RANK_ATTN=tiled|resident|tc overrides mode 0.
 static int attn_default_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* s = getenv("B200RANK_ATTN");
-        mode = !s ? 3 : (!strcmp(s, "tiled") ? 1 : (!strcmp(s, "resident") ? 2 : 3));  // default: tcgen05 for len <= 256
+        // default: mma.sync tiles. The round-1 tcgen05 kernel is correct but 1.7x slower at S=184 (one 168 KB CTA per SM, phases not
+        // pipelined across work items: profiles/r01_bench_n1_v5*.json); it is opt-in until it is made persistent.
+        mode = !s ? 1 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : 1));
     }
     return mode;
 }
@@ -765,17 +789,17 @@ static int run_encoder(b200rank_engine* e) {
     const int n = e->staged_tokens, nd = e->staged_docs;
     const int d = e->d, I = e->inner, F = e->F, Tk = e->cap_tokens;
     RET_IF(k_embed(e, e->d_ids, e->x, n));
+    RET_IF(k_rmsnorm(e, e->x, e->enc[0].ln1, e->h, n));
     for (int l = 0; l < e->Le; ++l) {
         const LayerW& w = e->enc[l];
-        RET_IF(k_rmsnorm(e, e->x, w.ln1, e->h, n));
+        // h = norm1(x) was produced by the previous layer's last GEMM (or the line above for layer 0)
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
         RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0));
-        RET_IF(gemm(e, e->ao, I, Tk, w.wo, I, d, n, d, I, EPI_RESID_F32, e->x, d));
-        RET_IF(k_rmsnorm(e, e->x, w.ln2, e->h, n));
+        RET_IF(gemm_resid_then_norm(e, e->ao, I, Tk, w.wo, I, d, n, I, e->x, w.ln2, e->h));
         RET_IF(gemm(e, e->h, d, Tk, w.wi, d, 2 * F, n, 2 * F, d, EPI_GATED_BF16, e->g, F));
-        RET_IF(gemm(e, e->g, F, Tk, w.wff, F, d, n, d, F, EPI_RESID_F32, e->x, d));
+        const float* next_ln = (l + 1 < e->Le) ? e->enc[l + 1].ln1 : e->enc_final_ln;
+        RET_IF(gemm_resid_then_norm(e, e->g, F, Tk, w.wff, F, d, n, F, e->x, next_ln, e->h));
     }
-    RET_IF(k_rmsnorm(e, e->x, e->enc_final_ln, e->h, n));
     const int NC = e->Ld * 2 * I;
     RET_IF(gemm(e, e->h, d, Tk, e->wckv, d, NC, n, NC, d, EPI_BF16, e->ckv, NC));
     return B200RANK_OK;
@@ -1200,7 +1224,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
         if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn / cg);
         if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
-        GemmArgs args{M, N, K, dO, n_out};
+        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f};
         if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct, cg);
     }
     if (rc == B200RANK_OK) {

@@ -406,31 +406,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         const int row = m0 + rr;
                         if (row >= args.M) break;
                         const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.out) + static_cast<size_t>(row) * args.ldo);
-                        float4 v[8];
                         float ss = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int idx = lane + i * 32;
-                            if (idx < nvec) {
-                                v[i] = __ldcg(src + idx);
-                                ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-                            }
+#pragma unroll 8
+                        for (int idx = lane; idx < nvec; idx += 32) {   // pass 1: sum of squares (row comes from L2)
+                            const float4 v = __ldcg(src + idx);
+                            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                         const float r = rsqrtf(ss / static_cast<float>(d) + args.norm_eps);
                         const float4* wv = reinterpret_cast<const float4*>(args.norm_w);
                         uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int idx = lane + i * 32;
-                            if (idx < nvec) {
-                                const float4 gw = __ldg(wv + idx);
-                                uint2 o2;
-                                o2.x = pack_bf16(v[i].x * r * gw.x, v[i].y * r * gw.y);
-                                o2.y = pack_bf16(v[i].z * r * gw.z, v[i].w * r * gw.w);
-                                dst[idx] = o2;
-                            }
+#pragma unroll 8
+                        for (int idx = lane; idx < nvec; idx += 32) {   // pass 2: scale, weight, bf16
+                            const float4 v = __ldcg(src + idx);
+                            const float4 gw = __ldg(wv + idx);
+                            uint2 o2;
+                            o2.x = pack_bf16(v.x * r * gw.x, v.y * r * gw.y);
+                            o2.y = pack_bf16(v.z * r * gw.z, v.w * r * gw.w);
+                            dst[idx] = o2;
                         }
                     }
                 }

@@ -296,6 +296,35 @@ def test_greedy_vs_golden(case):
     assert n_skipped <= max(1, n_tok // 20)
 
 
+# ---------------------------------------------------------------------------------------- kernel variants
+def test_kernel_variants_agree(tmp_path):
+    """The optional kernel variants are re-schedulings of the same arithmetic: CTA-pair (cta_group::2) vs single-CTA GEMM
+    tiles, fused residual+RMSNorm epilogue vs separate kernel, TMA-store vs direct-store epilogue must agree BIT-EXACTLY;
+    tcgen05 vs mma.sync attention (different softmax blocking) must agree to bf16 noise."""
+    import subprocess
+    import sys
+    runner = os.path.join(ROOT, "tests", "gpu_variant_runner.py")
+
+    def run(name, **env):
+        out = str(tmp_path / f"{name}.npz")
+        full = dict(os.environ)
+        full.update(env)
+        p = subprocess.run([sys.executable, runner, out], env=full, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        return np.load(out)["logits"]
+
+    base = run("default")
+    assert np.all(np.isfinite(base))
+    for name, env in [("cg1", {"B200RANK_GEMM_CG": "1"}), ("nofuse", {"B200RANK_FUSE_NORM": "0"}),
+                      ("direct_epi", {"B200RANK_GEMM_DIRECT_EPI": "1"})]:
+        got = run(name, **env)
+        record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
+        assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
+    tiled = run("attn_tiled", B200RANK_ATTN="tiled")
+    record("variant/attn_tiled", max_abs_diff=float(np.abs(tiled - base).max()))
+    assert np.abs(tiled - base).max() < 0.05
+
+
 # ---------------------------------------------------------------------------------------- properties at full size
 def large_engine():
     import b200rank as br
