@@ -19,6 +19,7 @@
 #include "../../include/b200rank.h"
 #include "attention_enc.cuh"
 #include "attention_tc.cuh"
+#include "cross_ctx_t1.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels_misc.cuh"
 
@@ -175,6 +176,7 @@ struct LayerW {
     float *ln1 = nullptr, *ln2 = nullptr, *ln_c = nullptr;
     bf16 *wqkv = nullptr, *wo = nullptr, *wi = nullptr, *wff = nullptr, *wq_c = nullptr, *wo_c = nullptr;
     bf16* wov = nullptr;  // decoder only, derived at load: W_o . W_v (self-attention at T = 1 is exactly o(v(x)))
+    bf16* wkT = nullptr;  // decoder only, derived at load: per-head transposed cross W_k, [H*d, 64] (q'_h = W_k,h^T q_h)
 };
 
 struct b200rank_engine {
@@ -203,6 +205,7 @@ struct b200rank_engine {
     int cap_tokens = 0, cap_docs = 0, cap_T = 0, cap_rows = 0, cap_logit_rows = 0;
     float* x = nullptr; bf16 *h = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr, *ckv = nullptr;
     float* xd = nullptr; bf16 *hd = nullptr, *qkvd = nullptr, *aod = nullptr, *qd = nullptr, *gd = nullptr, *hlast = nullptr;
+    bf16 *qp = nullptr, *ctxb = nullptr;  // [cap_docs, H*d]: re-associated T=1 cross-attention (q' and per-head context)
     float* logits = nullptr;       // [cap_logit_rows, V]
     float* small_out = nullptr;    // [cap_rows * 32] generic fp32 results
     float* small_out2 = nullptr;   // [cap_docs * 32]
@@ -288,7 +291,7 @@ static int post_launch(b200rank_engine* e, const char* what) {
 
 // acc[M,N] = A[M,K] . W[N,K]^T with fused epilogue. a_rows/w_rows: row capacity of the operands (TMA bounds).
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn, const float* norm_w, bf16* norm_out) {
+                int K, int epi, void* out, int ldo, int force_bn, const float* norm_w, bf16* norm_out, int n_per_batch, int a_cols) {
     if (M <= 0) return B200RANK_OK;
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
@@ -299,6 +302,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     prof_begin(e, label);
     struct ProfEnd { b200rank_engine* e; ~ProfEnd() { prof_end(e); } } prof_end_guard{e};
     if (e->debug_simt) {
+        if (n_per_batch) return set_error(B200RANK_ERR_ARG, "block-diagonal GEMM has no CUDA-core debug variant");
         const int n_out = epi == EPI_GATED_BF16 ? N / 2 : N;
         dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
         gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi == EPI_RESID_NORM ? EPI_RESID_F32 : epi, 256, out, ldo);
@@ -306,13 +310,13 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     }
     const int cg = e->direct_epi ? 1 : pick_cta_group(M, N, bn, e->num_sms);
     const CUtensorMap *ta, *tb, *tout;
-    RET_IF(engine_tmap(e, A, a_rows, K, lda, kGemmBlockM, 0, &ta));
+    RET_IF(engine_tmap(e, A, a_rows, a_cols > 0 ? a_cols : K, lda, kGemmBlockM, 0, &ta));
     RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn / cg, 0, &tb));
     const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32 || epi == EPI_RESID_NORM);
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
-    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps};
+    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch};
     RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
 }
@@ -363,7 +367,7 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
-                     e->logits, e->small_out, e->small_out2, e->d_ids, e->d_cu, e->d_dec_ids, e->d_cols, e->d_labels,
+                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->d_ids, e->d_cu, e->d_dec_ids, e->d_cols, e->d_labels,
                      e->d_int_out, e->d_finished, e->l2_scratch};
     for (void* p : frees)
         if (p) cudaFree(p);
@@ -420,7 +424,7 @@ static int create_impl(b200rank_engine* e) {
         LayerW& w = e->dec[l];
         reserve((void**)&w.ln1, d * 4); reserve((void**)&w.ln_c, d * 4); reserve((void**)&w.ln2, d * 4);
         reserve((void**)&w.wqkv, 3 * I * d * 2); reserve((void**)&w.wo, d * I * 2);
-        reserve((void**)&w.wq_c, I * d * 2); reserve((void**)&w.wo_c, d * I * 2); reserve((void**)&w.wov, d * d * 2);
+        reserve((void**)&w.wq_c, I * d * 2); reserve((void**)&w.wo_c, d * I * 2); reserve((void**)&w.wov, d * d * 2); reserve((void**)&w.wkT, (size_t)e->H * d * 64 * 2);
         reserve((void**)&w.wi, 2 * F * d * 2); reserve((void**)&w.wff, d * F * 2);
     }
     e->arena_bytes = off;
@@ -464,6 +468,7 @@ static int create_impl(b200rank_engine* e) {
     RET_IF(dev_alloc(e, &e->qkvd, R * 3 * I)); RET_IF(dev_alloc(e, &e->aod, R * I));
     RET_IF(dev_alloc(e, &e->qd, R * I)); RET_IF(dev_alloc(e, &e->gd, R * F)); RET_IF(dev_alloc(e, &e->hlast, R * d));
     RET_IF(dev_alloc(e, &e->logits, (size_t)e->cap_logit_rows * V));
+    RET_IF(dev_alloc(e, &e->qp, (size_t)align_up(e->cap_docs, 128) * e->H * d)); RET_IF(dev_alloc(e, &e->ctxb, (size_t)align_up(e->cap_docs, 128) * e->H * d));
     RET_IF(dev_alloc(e, &e->small_out, R * 32)); RET_IF(dev_alloc(e, &e->small_out2, (size_t)e->cap_docs * 32));
     RET_IF(dev_alloc(e, &e->d_ids, Tk)); RET_IF(dev_alloc(e, &e->d_cu, (size_t)e->cap_docs + 1));
     RET_IF(dev_alloc(e, &e->d_dec_ids, R)); RET_IF(dev_alloc(e, &e->d_cols, 64)); RET_IF(dev_alloc(e, &e->d_labels, R));
@@ -551,7 +556,8 @@ static int shape_check(const char* name, int64_t rows, int64_t cols, int64_t er,
 }
 
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn = 0, const float* norm_w = nullptr, bf16* norm_out = nullptr);
+                int K, int epi, void* out, int ldo, int force_bn = 0, const float* norm_w = nullptr, bf16* norm_out = nullptr,
+                int n_per_batch = 0, int a_cols = 0);
 
 // Derived weights, computed once on the device when the last tensor arrives (they live in the arena, so the NCCL
 // broadcast carries them): decoder W_ov[l] = W_o[l] . W_v[l]  (bf16 operands, fp32 accumulate, bf16 result).
@@ -569,6 +575,12 @@ static int derive_weights(b200rank_engine* e) {
         rc = post_launch(e, "transpose_bf16");
         // W_ov[i, j] = sum_k W_o[i, k] W_v[k, j]  ==  A[M=d, K=I] . W[N=d, K=I]^T with W = W_v^T
         if (rc == B200RANK_OK) rc = gemm(e, w.wo, I, d, vt, I, (int)align_up(d, 256), d, d, I, EPI_BF16, w.wov, d, 0);
+        // per-head transposed cross-attention W_k: wkT[h*d + n, m] = W_k[h*64 + m, n]
+        for (int h = 0; h < e->H && rc == B200RANK_OK; ++h) {
+            const bf16* wk_h = e->wckv + ((size_t)l * 2 * I + (size_t)h * 64) * d;
+            transpose_bf16_kernel<<<dim3((d + 31) / 32, 2), dim3(32, 8), 0, e->stream>>>(wk_h, 64, d, d, w.wkT + (size_t)h * d * 64, 64);
+            rc = post_launch(e, "transpose_bf16");
+        }
     }
     cudaError_t err = cudaStreamSynchronize(e->stream);
     cudaFree(vt);
@@ -705,10 +717,12 @@ static int k_embed(b200rank_engine* e, const int* ids, float* x, int n) {
 static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n) {
     if (n <= 0) return B200RANK_OK;
     const int grid = (n + 7) / 8;
+    static int rev = -1;
+    if (rev < 0) rev = (getenv("B200RANK_RMSNORM_REV") && atoi(getenv("B200RANK_RMSNORM_REV")) == 0) ? 0 : 1;
     prof_begin(e, "rmsnorm");
-    if (e->d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
-    else if (e->d <= 2048) rmsnorm_kernel<16><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
-    else rmsnorm_kernel<32><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps);
+    if (e->d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
+    else if (e->d <= 2048) rmsnorm_kernel<16><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
+    else rmsnorm_kernel<32><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
     return post_launch(e, "rmsnorm");
 }
 
@@ -719,7 +733,8 @@ static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int 
                                 float* x, const float* norm_w, bf16* h) {
     const int d = e->d;
     static int fuse_pref = -1;
-    if (fuse_pref < 0) fuse_pref = (getenv("B200RANK_FUSE_NORM") && atoi(getenv("B200RANK_FUSE_NORM")) == 0) ? 0 : 1;
+    // default OFF: measured slower than GEMM + rmsnorm on B200 in round 1 (profiles/r01_bench_n1_v6*.json); B200RANK_FUSE_NORM=1 enables it
+    if (fuse_pref < 0) fuse_pref = (getenv("B200RANK_FUSE_NORM") && atoi(getenv("B200RANK_FUSE_NORM")) != 0) ? 1 : 0;
     const int cg = pick_cta_group(M, d, 256, e->num_sms);
     const int row_blocks = (M + 128 * cg - 1) / (128 * cg);
     const int units = e->num_sms / cg;
@@ -785,7 +800,7 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
 }
 
 // Encoder over the staged batch + stacked cross-attention K|V projection of its output.
-static int run_encoder(b200rank_engine* e) {
+static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
     const int n = e->staged_tokens, nd = e->staged_docs;
     const int d = e->d, I = e->inner, F = e->F, Tk = e->cap_tokens;
     RET_IF(k_embed(e, e->d_ids, e->x, n));
@@ -800,9 +815,18 @@ static int run_encoder(b200rank_engine* e) {
         const float* next_ln = (l + 1 < e->Le) ? e->enc[l + 1].ln1 : e->enc_final_ln;
         RET_IF(gemm_resid_then_norm(e, e->g, F, Tk, w.wff, F, d, n, F, e->x, next_ln, e->h));
     }
+    if (!need_ckv) return B200RANK_OK;  // re-associated T=1 decoder attends against the encoder output itself
     const int NC = e->Ld * 2 * I;
     RET_IF(gemm(e, e->h, d, Tk, e->wckv, d, NC, n, NC, d, EPI_BF16, e->ckv, NC));
     return B200RANK_OK;
+}
+
+// T = 1 and short documents: the decoder's cross-attention runs in re-associated form (cross_ctx_t1.cuh) and the encoder
+// skips the stacked cross-K|V projection. B200RANK_DEC_REASSOC=0 selects the reference-shaped path (K/V GEMM + attention).
+static bool use_reassoc_t1(const b200rank_engine* e, int T) {
+    static int pref = -1;
+    if (pref < 0) pref = (getenv("B200RANK_DEC_REASSOC") && atoi(getenv("B200RANK_DEC_REASSOC")) == 0) ? 0 : 1;
+    return pref && T == 1 && e->staged_maxlen <= 256 && !e->debug_simt && e->d % kCtxKC == 0;
 }
 
 // Decoder over documents [doc0, doc0+nd) with T positions each; dec ids in d_dec_ids[nd*T].
@@ -815,6 +839,14 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
     RET_IF(k_embed(e, e->d_dec_ids, e->xd, R));
     const size_t ldkv = (size_t)e->Ld * 2 * I;
     const int max_len = e->staged_maxlen;
+    const bool reassoc = use_reassoc_t1(e, T);
+    if (reassoc) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_OK(cudaFuncSetAttribute(cross_ctx_t1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cross_ctx_smem_bytes(256)));
+            attr_set = true;
+        }
+    }
     for (int l = 0; l < e->Ld; ++l) {
         const LayerW& w = e->dec[l];
         RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
@@ -829,6 +861,22 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         }
         RET_IF(k_rmsnorm(e, e->xd, w.ln_c, e->hd, R));
         RET_IF(gemm(e, e->hd, d, cap, w.wq_c, d, I, R, I, d, EPI_BF16, e->qd, I));
+        if (reassoc) {
+            // cross_ctx_t1.cuh: scores = (W_k,h^T q_h) . e_j and out_h = W_v,h (sum_j p_j e_j): no K/V projection of the encoder
+            const int HD = e->H * d, dcap = (int)align_up(e->cap_docs, 128);
+            RET_IF(gemm(e, e->qd, I, cap, w.wkT, 64, HD, R, HD, 64, EPI_BF16, e->qp, HD, 0, nullptr, nullptr, /*n_per_batch=*/d, /*a_cols=*/I));
+            const int s_pad = (max_len + 15) & ~15;
+            prof_begin(e, "cross_ctx_t1");
+            cross_ctx_t1_kernel<<<nd, kCtxThreads, cross_ctx_smem_bytes(s_pad), e->stream>>>(e->qp, e->h, e->d_cu + doc0, e->ctxb, e->H, d, s_pad);
+            RET_IF(post_launch(e, "cross_ctx_t1"));
+            const bf16* wv_l = e->wckv + ((size_t)l * 2 * I + I) * d;
+            RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, nullptr, nullptr, /*n_per_batch=*/64, /*a_cols=*/HD));
+            RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+            RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
+            RET_IF(gemm(e, e->hd, d, cap, w.wi, d, 2 * F, R, 2 * F, d, EPI_GATED_BF16, e->gd, F));
+            RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
+            continue;
+        }
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
         prof_begin(e, "cross_attention");
         if (T == 1 && e->H % 4 == 0 && max_len <= 256)
@@ -912,7 +960,7 @@ static int upload_ints(b200rank_engine* e, int* dst, const std::vector<int>& v) 
 static int yes_no_device(b200rank_engine* e, int yes_id, int no_id) {
     const int nd = e->staged_docs;
     if (yes_id < 0 || yes_id >= e->V || no_id < 0 || no_id >= e->V) return set_error(B200RANK_ERR_ARG, "yes/no ids out of vocabulary");
-    RET_IF(run_encoder(e));
+    RET_IF(run_encoder(e, /*need_ckv=*/!use_reassoc_t1(e, 1)));
     std::vector<int> dec(nd, e->cfg.pad_id);  // decoder_input_ids = [[pad]] per row, pointwise.py:102
     RET_IF(upload_ints(e, e->d_dec_ids, dec));
     RET_IF(upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id}));
@@ -1224,7 +1272,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
         if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn / cg);
         if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
-        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f};
+        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f, 0};
         if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct, cg);
     }
     if (rc == B200RANK_OK) {

@@ -34,6 +34,9 @@ struct GemmArgs {
     const float* norm_w;        // [N]
     __nv_bfloat16* norm_out;    // [M, N] bf16, leading dimension N
     float norm_eps;
+    // Block-diagonal GEMM (n_per_batch > 0): column block b = n / n_per_batch of the output contracts A[:, b*K : (b+1)*K]
+    // with W rows of that block, i.e. out[:, b-th block] = A_b . W_b^T for per-head weight slices (decoder T=1 fast path).
+    int n_per_batch;
 };
 
 constexpr int kGemmBlockM = 128;
@@ -148,16 +151,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int it = 0; get_tile(it, mb, nb_); ++it) {
                 const int m0 = mb * (kGemmBlockM * CG) + cta_rank * kGemmBlockM;
                 const int n0 = nb_ * BLOCK_N + cta_rank * Cfg::kBRows;
+                const int a_k0 = args.n_per_batch > 0 ? ((nb_ * BLOCK_N) / args.n_per_batch) * args.K : 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if constexpr (CG == 2) {
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
                         else mbar_arrive_cluster(&full_bar[stage], 0);
-                        tma_load_2d_cg2(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0, kEvictNormal);
+                        tma_load_2d_cg2(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], a_k0 + kb * kGemmBlockK, m0, kEvictNormal);
                         tma_load_2d_cg2(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n0, kEvictLast);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                        tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0, kEvictNormal);
+                        tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], a_k0 + kb * kGemmBlockK, m0, kEvictNormal);
                         tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n0, kEvictLast);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -401,30 +405,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     named_bar_sync(1, 128);
                     const int d = args.N;
                     const int nvec = d >> 2;
-                    const int ew = warp_idx - 2;  // 0..3
-                    for (int rr = ew; rr < kGemmBlockM; rr += 4) {
-                        const int row = m0 + rr;
-                        if (row >= args.M) break;
-                        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(args.out) + static_cast<size_t>(row) * args.ldo);
-                        float ss = 0.f;
-#pragma unroll 8
-                        for (int idx = lane; idx < nvec; idx += 32) {   // pass 1: sum of squares (row comes from L2)
-                            const float4 v = __ldcg(src + idx);
-                            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-                        }
+                    const int ew = warp_idx - 2;  // 0..3: this warp normalises rows ew*32 .. ew*32+31 of the block
+                    const float4* wv = reinterpret_cast<const float4*>(args.norm_w);
+                    const float* xbase = reinterpret_cast<const float*>(args.out);
+                    if (nvec <= 256) {
+                        // d <= 1024: four rows per step, whole rows held in registers (32 independent 16 B loads per lane in flight)
+                        for (int r4 = 0; r4 < 32; r4 += 4) {
+                            float4 v[4][8];
+                            float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                        const float r = rsqrtf(ss / static_cast<float>(d) + args.norm_eps);
-                        const float4* wv = reinterpret_cast<const float4*>(args.norm_w);
-                        uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
+                            for (int q = 0; q < 4; ++q) {
+                                const int row = m0 + ew * 32 + r4 + q;
+                                const float4* src = reinterpret_cast<const float4*>(xbase + static_cast<size_t>(min(row, args.M - 1)) * args.ldo);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int idx = lane + i * 32;
+                                    v[q][i] = (idx < nvec) ? __ldcg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) ss[q] += v[q][i].x * v[q][i].x + v[q][i].y * v[q][i].y + v[q][i].z * v[q][i].z + v[q][i].w * v[q][i].w;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) ss[q] += __shfl_xor_sync(0xffffffffu, ss[q], o);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int row = m0 + ew * 32 + r4 + q;
+                                if (row < args.M) {
+                                    const float r = rsqrtf(ss[q] / static_cast<float>(d) + args.norm_eps);
+                                    uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const int idx = lane + i * 32;
+                                        if (idx < nvec) {
+                                            const float4 gw = __ldg(wv + idx);
+                                            uint2 o2;
+                                            o2.x = pack_bf16(v[q][i].x * r * gw.x, v[q][i].y * r * gw.y);
+                                            o2.y = pack_bf16(v[q][i].z * r * gw.z, v[q][i].w * r * gw.w);
+                                            dst[idx] = o2;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        for (int rr = ew * 32; rr < ew * 32 + 32; ++rr) {   // wide models: two passes over the L2-resident row
+                            const int row = m0 + rr;
+                            if (row >= args.M) break;
+                            const float4* src = reinterpret_cast<const float4*>(xbase + static_cast<size_t>(row) * args.ldo);
+                            float ss = 0.f;
 #pragma unroll 8
-                        for (int idx = lane; idx < nvec; idx += 32) {   // pass 2: scale, weight, bf16
-                            const float4 v = __ldcg(src + idx);
-                            const float4 gw = __ldg(wv + idx);
-                            uint2 o2;
-                            o2.x = pack_bf16(v.x * r * gw.x, v.y * r * gw.y);
-                            o2.y = pack_bf16(v.z * r * gw.z, v.w * r * gw.w);
-                            dst[idx] = o2;
+                            for (int idx = lane; idx < nvec; idx += 32) {
+                                const float4 v = __ldcg(src + idx);
+                                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                            const float r = rsqrtf(ss / static_cast<float>(d) + args.norm_eps);
+                            uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
+#pragma unroll 8
+                            for (int idx = lane; idx < nvec; idx += 32) {
+                                const float4 v = __ldcg(src + idx);
+                                const float4 gw = __ldg(wv + idx);
+                                uint2 o2;
+                                o2.x = pack_bf16(v.x * r * gw.x, v.y * r * gw.y);
+                                o2.y = pack_bf16(v.z * r * gw.z, v.w * r * gw.w);
+                                dst[idx] = o2;
+                            }
                         }
                     }
                 }

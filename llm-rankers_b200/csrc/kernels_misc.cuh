@@ -36,10 +36,14 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
 // One warp per row; the row is read once (kept in registers for d <= 4096).
 template <int MAX_VEC>  // MAX_VEC float4 per lane: d <= 128 * MAX_VEC
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ h,
-                               int n_rows, int d, float eps) {
+                               int n_rows, int d, float eps, int reverse) {
     const int warps_per_block = blockDim.x >> 5;
-    const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (row >= n_rows) return;
+    // reverse = 1: walk the rows from the end. The residual GEMM that precedes this kernel finished its LAST row blocks most
+    // recently, so those rows are still in the 126 MB L2; and the GEMM that follows starts at row 0, which this kernel then
+    // writes last (L2 ping-pong between memory-bound and compute-bound kernels).
+    if (reverse) row = n_rows - 1 - row;
     const int lane = threadIdx.x & 31;
     const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
     const int nvec = d / 4;

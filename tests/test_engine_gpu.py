@@ -320,9 +320,11 @@ def test_kernel_variants_agree(tmp_path):
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
-    tiled = run("attn_tiled", B200RANK_ATTN="tiled")
-    record("variant/attn_tiled", max_abs_diff=float(np.abs(tiled - base).max()))
-    assert np.abs(tiled - base).max() < 0.05
+    # different arithmetic (re-blocked softmax / re-associated products): agreement to bf16 noise
+    for name, env in [("attn_tc", {"B200RANK_ATTN": "tc"}), ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
+        got = run(name, **env)
+        record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
+        assert np.abs(got - base).max() < 0.05, name
 
 
 # ---------------------------------------------------------------------------------------- properties at full size
