@@ -64,6 +64,8 @@ __device__ __forceinline__ void load_tile_64x64(__nv_bfloat16* smem_tile, const 
 __global__ void __launch_bounds__(128, 4)
 enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, const int* __restrict__ cu,
                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64];
     __shared__ __align__(128) __nv_bfloat16 sK[2][64 * 64];
     __shared__ __align__(128) __nv_bfloat16 sV[2][64 * 64];
@@ -224,6 +226,8 @@ enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, c
 __global__ void __launch_bounds__(512)
 enc_attention_resident_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, const int* __restrict__ cu,
                               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int s_pad) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t attn_smem[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(attn_smem);
     __nv_bfloat16* sK = sQ + s_pad * 64;

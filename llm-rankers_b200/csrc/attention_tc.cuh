@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kAttnTcThreads, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo) {
     using Cfg = AttnTcCfg<NKB>;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -54,10 +55,12 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner,
     float* sBias = reinterpret_cast<float*>(tmem_base_smem + 4);
 
     const int h = blockIdx.x, doc = blockIdx.y;
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp_idx == 1) tmem_alloc(tmem_base_smem, 512);  // prologue work that needs no global data comes before pdl_wait
+    pdl_wait();
     const int tok0 = cu[doc];
     const int len = cu[doc + 1] - tok0;
     const int ntiles = (len + 127) >> 7;
-    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
@@ -69,8 +72,6 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner,
             mbar_init(&bar_o[t], 1);
         }
         fence_barrier_init();
-    } else if (warp_idx == 1) {
-        tmem_alloc(tmem_base_smem, 512);
     }
     for (int i = threadIdx.x; i < kAttnBiasLen; i += kAttnTcThreads) sBias[i] = bias[h * kAttnBiasLen + i];
     tc_fence_before();

@@ -23,10 +23,11 @@ namespace b200 {
 constexpr int kCtxKC = 128;            // columns of E per staged chunk
 constexpr int kCtxLdE = kCtxKC + 8;    // padded smem row (272 B): ldmatrix rows land in different banks
 constexpr int kCtxThreads = 256;
+constexpr int kCtxStages = 3;          // cp.async ring depth: the kernel is L2-latency bound, two chunks stay in flight
 
 __host__ __device__ constexpr int cross_ctx_smem_bytes(int s_pad) {
-    return 2 * s_pad * kCtxLdE * 2      // sE[2][s_pad][kCtxLdE] bf16
-           + 2 * 16 * kCtxLdE * 2       // sQ[2][16][kCtxLdE]   bf16
+    return kCtxStages * s_pad * kCtxLdE * 2      // sE[stages][s_pad][kCtxLdE] bf16
+           + kCtxStages * 16 * kCtxLdE * 2       // sQ[stages][16][kCtxLdE]   bf16
            + 16 * s_pad * 4             // sS[16][s_pad]        fp32 scores
            + 16 * (s_pad + 8) * 2;      // sP[16][s_pad + 8]    bf16 probabilities
 }
@@ -37,10 +38,12 @@ __host__ __device__ constexpr int cross_ctx_smem_bytes(int s_pad) {
 __global__ void __launch_bounds__(kCtxThreads)
 cross_ctx_t1_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* __restrict__ E, const int* __restrict__ cu,
                     __nv_bfloat16* __restrict__ ctx, int H, int d, int s_pad) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t ctx_smem[];
     __nv_bfloat16* sE = reinterpret_cast<__nv_bfloat16*>(ctx_smem);
-    __nv_bfloat16* sQ = sE + 2 * s_pad * kCtxLdE;
-    float* sS = reinterpret_cast<float*>(sQ + 2 * 16 * kCtxLdE);
+    __nv_bfloat16* sQ = sE + kCtxStages * s_pad * kCtxLdE;
+    float* sS = reinterpret_cast<float*>(sQ + kCtxStages * 16 * kCtxLdE);
     __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(sS + 16 * s_pad);
     const int ldP = s_pad + 8;
 
@@ -56,8 +59,12 @@ cross_ctx_t1_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* _
 
     for (int h0 = 0; h0 < H; h0 += 16) {
         const int hn = min(16, H - h0);
-        // stage chunk `c` (columns c*128 ..) of E and of the 16 q' rows into buffer `buf`
-        auto stage = [&](int c, int buf) {
+        // The two passes read the same column chunks of E: chunk id cc in [0, 2*nchunks) maps to columns (cc % nchunks)*128 and
+        // ring slot cc % kCtxStages, so the cp.async pipeline keeps running through the softmax between the passes.
+        const int total = 2 * nchunks;
+        auto stage = [&](int cc) {
+            if (cc >= total) { cp_async_commit(); return; }  // keep the group count uniform
+            const int c = cc % nchunks, buf = cc % kCtxStages;
             __nv_bfloat16* dE = sE + buf * s_pad * kCtxLdE;
             for (int idx = tid; idx < s_pad * 16; idx += kCtxThreads) {
                 const int r = idx >> 4, ch = idx & 15;
@@ -78,10 +85,12 @@ cross_ctx_t1_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* _
         float sc[4][4];  // up to 4 key tiles per warp (s_pad <= 256 -> 32 tiles / 8 warps)
 #pragma unroll
         for (int i = 0; i < 4; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
-        stage(0, 0);
+#pragma unroll
+        for (int i = 0; i < kCtxStages - 1; ++i) stage(i);
         for (int c = 0; c < nchunks; ++c) {
-            const int buf = c & 1;
-            if (c + 1 < nchunks) { stage(c + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            const int buf = c % kCtxStages;
+            stage(c + kCtxStages - 1);          // slot (c-1) % stages: its readers passed the barrier that ended iteration c-1
+            cp_async_wait<kCtxStages - 1>();    // chunk c has landed
             __syncthreads();
             const __nv_bfloat16* bE = sE + buf * s_pad * kCtxLdE;
             const __nv_bfloat16* bQ = sQ + buf * 16 * kCtxLdE;
@@ -117,7 +126,6 @@ cross_ctx_t1_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* _
         }
         __syncthreads();
         // ---------------- softmax over the S keys (fp32), P -> bf16; rows 2*warp and 2*warp+1
-        stage(0, 0);  // prefetch the first chunk of pass 2 underneath the softmax
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int row = 2 * warp + rr;
@@ -137,8 +145,9 @@ cross_ctx_t1_kernel(const __nv_bfloat16* __restrict__ qp, const __nv_bfloat16* _
         __syncthreads();
         // ---------------- pass 2: ctx[16, d] = P E, one 128-column chunk at a time (16 n-tiles, 2 per warp)
         for (int c = 0; c < nchunks; ++c) {
-            const int buf = c & 1;
-            if (c + 1 < nchunks) { stage(c + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            const int cc = nchunks + c, buf = cc % kCtxStages;
+            stage(cc + kCtxStages - 1);
+            cp_async_wait<kCtxStages - 1>();
             __syncthreads();
             const __nv_bfloat16* bE = sE + buf * s_pad * kCtxLdE;
             float o[2][4];

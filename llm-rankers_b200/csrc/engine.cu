@@ -87,6 +87,28 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
     return B200RANK_OK;
 }
 
+// ------------------------------------------------------------------ kernel launch (programmatic dependent launch)
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = (getenv("B200RANK_PDL") && atoi(getenv("B200RANK_PDL")) == 0) ? 0 : 1;
+    return v != 0;
+}
+// All kernels call pdl_trigger()/pdl_wait() (ptx.cuh), so any of them may be launched with the PDL attribute.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI, bool TMA_EPI, int CG>
 static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
@@ -105,13 +127,15 @@ static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta,
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     CU_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, args));
     return B200RANK_OK;
 }
@@ -571,14 +595,14 @@ static int derive_weights(b200rank_engine* e) {
     int rc = B200RANK_OK;
     for (int l = 0; l < e->Ld && rc == B200RANK_OK; ++l) {
         const LayerW& w = e->dec[l];
-        transpose_bf16_kernel<<<dim3((d + 31) / 32, (I + 31) / 32), dim3(32, 8), 0, e->stream>>>(w.wqkv + (size_t)2 * I * d, I, d, d, vt, I);
+        launch_k(transpose_bf16_kernel, dim3(dim3((d + 31) / 32, (I + 31) / 32)), dim3(dim3(32, 8)), 0, e->stream, w.wqkv + (size_t)2 * I * d, I, d, d, vt, I);
         rc = post_launch(e, "transpose_bf16");
         // W_ov[i, j] = sum_k W_o[i, k] W_v[k, j]  ==  A[M=d, K=I] . W[N=d, K=I]^T with W = W_v^T
         if (rc == B200RANK_OK) rc = gemm(e, w.wo, I, d, vt, I, (int)align_up(d, 256), d, d, I, EPI_BF16, w.wov, d, 0);
         // per-head transposed cross-attention W_k: wkT[h*d + n, m] = W_k[h*64 + m, n]
         for (int h = 0; h < e->H && rc == B200RANK_OK; ++h) {
             const bf16* wk_h = e->wckv + ((size_t)l * 2 * I + (size_t)h * 64) * d;
-            transpose_bf16_kernel<<<dim3((d + 31) / 32, 2), dim3(32, 8), 0, e->stream>>>(wk_h, 64, d, d, w.wkT + (size_t)h * d * 64, 64);
+            launch_k(transpose_bf16_kernel, dim3(dim3((d + 31) / 32, 2)), dim3(dim3(32, 8)), 0, e->stream, wk_h, 64, d, d, w.wkT + (size_t)h * d * 64, 64);
             rc = post_launch(e, "transpose_bf16");
         }
     }
@@ -711,7 +735,7 @@ extern "C" int b200rank_mark_weights_loaded(b200rank_engine* e) {
 // ------------------------------------------------------------------ forward pieces
 static int k_embed(b200rank_engine* e, const int* ids, float* x, int n) {
     if (n <= 0) return B200RANK_OK;
-    prof_begin(e, "embed"); embed_kernel<<<(n + 7) / 8, 256, 0, e->stream>>>(ids, e->emb, x, n, e->d, e->V);
+    prof_begin(e, "embed"); launch_k(embed_kernel, dim3((n + 7) / 8), dim3(256), 0, e->stream, ids, e->emb, x, n, e->d, e->V);
     return post_launch(e, "embed");
 }
 static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n) {
@@ -720,9 +744,9 @@ static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h
     static int rev = -1;
     if (rev < 0) rev = (getenv("B200RANK_RMSNORM_REV") && atoi(getenv("B200RANK_RMSNORM_REV")) == 0) ? 0 : 1;
     prof_begin(e, "rmsnorm");
-    if (e->d <= 1024) rmsnorm_kernel<8><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
-    else if (e->d <= 2048) rmsnorm_kernel<16><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
-    else rmsnorm_kernel<32><<<grid, 256, 0, e->stream>>>(x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
+    if (e->d <= 1024) launch_k(rmsnorm_kernel<8>, dim3(grid), dim3(256), 0, e->stream, x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
+    else if (e->d <= 2048) launch_k(rmsnorm_kernel<16>, dim3(grid), dim3(256), 0, e->stream, x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
+    else launch_k(rmsnorm_kernel<32>, dim3(grid), dim3(256), 0, e->stream, x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
     return post_launch(e, "rmsnorm");
 }
 
@@ -765,7 +789,7 @@ static int launch_attn_tc(const bf16* qkv, int ld, uint64_t qkv_rows, int inner,
         CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<NKB>::kSmemBytes));
         attr_set = true;
     }
-    kern<<<dim3(H, nd), kAttnTcThreads, AttnTcCfg<NKB>::kSmemBytes, st>>>(*tm, inner, d_cu, bias, out, ldo);
+    launch_k(kern, dim3(dim3(H, nd)), dim3(kAttnTcThreads), AttnTcCfg<NKB>::kSmemBytes, st, *tm, inner, d_cu, bias, out, ldo);
     return B200RANK_OK;
 }
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
@@ -791,11 +815,11 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
             attr_set = true;
         }
         if (e) prof_begin(e, "enc_attention_resident");
-        enc_attention_resident_kernel<<<dim3(H, nd), (s_pad / 16) * 32, smem, st>>>(qkv, ld, inner, d_cu, bias, out, ldo, s_pad);
+        launch_k(enc_attention_resident_kernel, dim3(dim3(H, nd)), dim3((s_pad / 16) * 32), smem, st, qkv, ld, inner, d_cu, bias, out, ldo, s_pad);
         return e ? post_launch(e, "enc_attention_resident") : B200RANK_OK;
     }
     if (e) prof_begin(e, "enc_attention");
-    enc_attention_kernel<<<dim3((maxlen + 63) / 64, H, nd), 128, 0, st>>>(qkv, ld, inner, d_cu, bias, out, ldo);
+    launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo);
     return e ? post_launch(e, "enc_attention") : B200RANK_OK;
 }
 
@@ -826,7 +850,7 @@ static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
 static bool use_reassoc_t1(const b200rank_engine* e, int T) {
     static int pref = -1;
     if (pref < 0) pref = (getenv("B200RANK_DEC_REASSOC") && atoi(getenv("B200RANK_DEC_REASSOC")) == 0) ? 0 : 1;
-    return pref && T == 1 && e->staged_maxlen <= 256 && !e->debug_simt && e->d % kCtxKC == 0;
+    return pref && T == 1 && e->staged_maxlen <= 240 && !e->debug_simt && e->d % kCtxKC == 0;  // 240: 3-stage ring fits 227 KB
 }
 
 // Decoder over documents [doc0, doc0+nd) with T positions each; dec ids in d_dec_ids[nd*T].
@@ -843,7 +867,7 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
     if (reassoc) {
         static bool attr_set = false;
         if (!attr_set) {
-            CU_OK(cudaFuncSetAttribute(cross_ctx_t1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cross_ctx_smem_bytes(256)));
+            CU_OK(cudaFuncSetAttribute(cross_ctx_t1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cross_ctx_smem_bytes(240)));
             attr_set = true;
         }
     }
@@ -867,7 +891,7 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             RET_IF(gemm(e, e->qd, I, cap, w.wkT, 64, HD, R, HD, 64, EPI_BF16, e->qp, HD, 0, nullptr, nullptr, /*n_per_batch=*/d, /*a_cols=*/I));
             const int s_pad = (max_len + 15) & ~15;
             prof_begin(e, "cross_ctx_t1");
-            cross_ctx_t1_kernel<<<nd, kCtxThreads, cross_ctx_smem_bytes(s_pad), e->stream>>>(e->qp, e->h, e->d_cu + doc0, e->ctxb, e->H, d, s_pad);
+            launch_k(cross_ctx_t1_kernel, dim3(nd), dim3(kCtxThreads), cross_ctx_smem_bytes(s_pad), e->stream, e->qp, e->h, e->d_cu + doc0, e->ctxb, e->H, d, s_pad);
             RET_IF(post_launch(e, "cross_ctx_t1"));
             const bf16* wv_l = e->wckv + ((size_t)l * 2 * I + I) * d;
             RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, nullptr, nullptr, /*n_per_batch=*/64, /*a_cols=*/HD));
@@ -965,9 +989,9 @@ static int yes_no_device(b200rank_engine* e, int yes_id, int no_id) {
     RET_IF(upload_ints(e, e->d_dec_ids, dec));
     RET_IF(upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id}));
     RET_IF(run_decoder(e, 0, nd, 1));
-    prof_begin(e, "lm_head_cols"); lm_head_cols_kernel<<<nd, 64, 0, e->stream>>>(e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
+    prof_begin(e, "lm_head_cols"); launch_k(lm_head_cols_kernel, dim3(nd), dim3(64), 0, e->stream, e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
     RET_IF(post_launch(e, "lm_head_cols"));
-    prof_begin(e, "yes_no_score"); yes_no_score_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, e->small_out2, nd);
+    prof_begin(e, "yes_no_score"); launch_k(yes_no_score_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, e->small_out, e->small_out2, nd);
     RET_IF(post_launch(e, "yes_no_score"));
     return B200RANK_OK;
 }
@@ -1052,9 +1076,9 @@ extern "C" int b200rank_score_qlm(b200rank_engine* e, const int32_t* ids, const 
         RET_IF(upload_ints(e, e->d_labels, lab));
         RET_IF(run_decoder(e, 0, nd, T));
         RET_IF(gemm(e, e->hd, e->d, e->cap_rows, e->lm_head, e->d, e->V, R, e->V, e->d, EPI_F32, e->logits, e->V));
-        prof_begin(e, "vocab_row"); vocab_row_kernel<<<R, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 0, logit_scale(e), e->d_labels, nullptr, 0, e->small_out, nullptr);
+        prof_begin(e, "vocab_row"); launch_k(vocab_row_kernel, dim3(R), dim3(256), 0, e->stream, e->logits, e->V, (size_t)e->V, 0, logit_scale(e), e->d_labels, nullptr, 0, e->small_out, nullptr);
         RET_IF(post_launch(e, "vocab_row_logprob"));
-        prof_begin(e, "sum_rows"); sum_rows_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(e->small_out, T, e->small_out2, nd);
+        prof_begin(e, "sum_rows"); launch_k(sum_rows_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, e->small_out, T, e->small_out2, nd);
         RET_IF(post_launch(e, "sum_rows"));
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out2, (size_t)nd * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
         CU_OK(cudaStreamSynchronize(e->stream));
@@ -1089,13 +1113,13 @@ extern "C" int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const 
         RET_IF(upload_ints(e, e->d_cols, std::vector<int>(cols, cols + ncols)));
         RET_IF(run_decoder(e, 0, nd, T));
         if (!normalize) {
-            prof_begin(e, "lm_head_cols"); lm_head_cols_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
+            prof_begin(e, "lm_head_cols"); launch_k(lm_head_cols_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
             RET_IF(post_launch(e, "lm_head_cols"));
         } else {
-            prof_begin(e, "gather_rows"); gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
+            prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
             RET_IF(post_launch(e, "gather_rows"));
             RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
-            prof_begin(e, "vocab_row"); vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 2, logit_scale(e), nullptr, e->d_cols, ncols, e->small_out, nullptr);
+            prof_begin(e, "vocab_row"); launch_k(vocab_row_kernel, dim3(nd), dim3(256), 0, e->stream, e->logits, e->V, (size_t)e->V, 2, logit_scale(e), nullptr, e->d_cols, ncols, e->small_out, nullptr);
             RET_IF(post_launch(e, "vocab_row_softmax_gather"));
         }
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * ncols * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -1111,6 +1135,8 @@ extern "C" int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const 
 __global__ void greedy_update_kernel(const int* __restrict__ argmax, int* __restrict__ dec_rows, int* __restrict__ finished,
                                      int* __restrict__ new_ids, int nd, int t_write, int t_stride, int step, int max_new,
                                      int eos, int pad) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd) return;
     int tok = argmax[i];
@@ -1121,6 +1147,8 @@ __global__ void greedy_update_kernel(const int* __restrict__ argmax, int* __rest
 }
 // expand dec rows [nd, t_stride] -> contiguous [nd, T] ids for this step
 __global__ void dec_rows_to_ids_kernel(const int* __restrict__ dec_rows, int t_stride, int T, int* __restrict__ dec_ids, int nd) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd * T) return;
     dec_ids[i] = dec_rows[(i / T) * t_stride + (i % T)];
@@ -1151,16 +1179,16 @@ extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int
             const int T = prefix_len + step;
             // No KV cache: the decoder prefix is re-run (<= prefix_len + max_new - 1 positions; negligible next to
             // the encoder pass) — token-for-token the same greedy choice as the cached loop in generation/utils.py:2762-2804.
-            prof_begin(e, "dec_rows_to_ids"); dec_rows_to_ids_kernel<<<(nd * T + 255) / 256, 256, 0, e->stream>>>(e->d_labels, t_stride, T, e->d_dec_ids, nd);
+            prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd * T + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, T, e->d_dec_ids, nd);
             RET_IF(post_launch(e, "dec_rows_to_ids"));
             RET_IF(run_decoder(e, 0, nd, T));
-            prof_begin(e, "gather_rows"); gather_rows_kernel<<<nd, 128, 0, e->stream>>>(e->hd, e->d, T, T - 1, e->hlast, nd);
+            prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
             RET_IF(post_launch(e, "gather_rows"));
             RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
             int* d_argmax = e->d_int_out + (size_t)e->cap_docs * 8;  // second half of the int scratch
-            prof_begin(e, "vocab_row"); vocab_row_kernel<<<nd, 256, 0, e->stream>>>(e->logits, e->V, (size_t)e->V, 1, logit_scale(e), nullptr, nullptr, 0, nullptr, d_argmax);
+            prof_begin(e, "vocab_row"); launch_k(vocab_row_kernel, dim3(nd), dim3(256), 0, e->stream, e->logits, e->V, (size_t)e->V, 1, logit_scale(e), nullptr, nullptr, 0, nullptr, d_argmax);
             RET_IF(post_launch(e, "vocab_row_argmax"));
-            prof_begin(e, "greedy_update"); greedy_update_kernel<<<(nd + 127) / 128, 128, 0, e->stream>>>(d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
+            prof_begin(e, "greedy_update"); launch_k(greedy_update_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
                                                                           t_stride, step, max_new, e->cfg.eos_id, e->cfg.pad_id);
             RET_IF(post_launch(e, "greedy_update"));
         }
@@ -1218,6 +1246,8 @@ extern "C" int b200rank_profile_report(b200rank_engine* e, char* buf, int buflen
     return B200RANK_OK;
 }
 __global__ void fill_kernel(uint4* p, size_t n, uint32_t v) {
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(v, v, v, v);
 }
 extern "C" int b200rank_flush_l2(b200rank_engine* e) {

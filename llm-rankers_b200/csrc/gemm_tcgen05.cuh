@@ -74,6 +74,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
     using Cfg = GemmCfg<BLOCK_N, CG>;
     static_assert(CG == 1 || CG == 2, "cta group");
+    pdl_trigger();
     constexpr int kStages = Cfg::kStages;
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "bad BLOCK_N");
     static_assert(EPI != EPI_GATED_BF16 || BLOCK_N % 64 == 0, "gated epilogue needs BLOCK_N % 64 == 0");
@@ -141,6 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();  // barriers, TMEM and descriptors are set up; from here on we touch global memory written by the previous kernel
 
     if (warp_idx == 0) {
         // ------------------------------------------------------------ TMA producer

@@ -22,6 +22,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // modeling_t5.py:682 (shared embedding, no sqrt(d) scaling)
 __global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ table, float* __restrict__ x,
                              int n_tokens, int d, int vocab) {
+    pdl_trigger();
+    pdl_wait();
     const int warps_per_block = blockDim.x >> 5;
     const int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (t >= n_tokens) return;
@@ -37,6 +39,8 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
 template <int MAX_VEC>  // MAX_VEC float4 per lane: d <= 128 * MAX_VEC
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ h,
                                int n_rows, int d, float eps, int reverse) {
+    pdl_trigger();
+    pdl_wait();
     const int warps_per_block = blockDim.x >> 5;
     int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -81,6 +85,8 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
 __global__ void dec_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, int T,
                                           const float* __restrict__ bias, int bias_len,
                                           __nv_bfloat16* __restrict__ out, int ldo) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int D = 64;
     constexpr int MAXT = 64;
     __shared__ float sK[MAXT][D + 1];
@@ -150,6 +156,8 @@ template <int MAXT, int CH>
 __global__ void cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int T,
                                        const __nv_bfloat16* __restrict__ kv, size_t ldkv, int k_off, int v_off,
                                        const int* __restrict__ cu, __nv_bfloat16* __restrict__ out, int ldo) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int D = 64;
     constexpr int LDS = D + 2;  // bf16 row stride 132 B: conflict-free for row-per-thread dots
     __shared__ __nv_bfloat16 sK[CH * LDS];
@@ -245,6 +253,8 @@ template <int MAX_ROUNDS>
 __global__ void __launch_bounds__(128)
 cross_attention_t1_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kv, size_t ldkv,
                           int k_off, int v_off, const int* __restrict__ cu, __nv_bfloat16* __restrict__ out, int ldo) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sQ[4][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x * 4 + warp, doc = blockIdx.y;
@@ -338,6 +348,8 @@ cross_attention_t1_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __
 // dst[c, r] = src[r, c] for a bf16 matrix (load-time helper: builds W_v^T for the fused decoder W_o.W_v product)
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols, int ld_src,
                                       __nv_bfloat16* __restrict__ dst, int ld_dst) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __nv_bfloat16 tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -357,6 +369,8 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int
 __global__ void lm_head_cols_kernel(const __nv_bfloat16* __restrict__ h, int d, int row_stride, int row_offset,
                                     const __nv_bfloat16* __restrict__ lm_head, const int* __restrict__ cols, int ncols,
                                     float scale, float* __restrict__ logits) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(h + static_cast<size_t>(r * row_stride + row_offset) * d);
@@ -375,6 +389,8 @@ __global__ void lm_head_cols_kernel(const __nv_bfloat16* __restrict__ h, int d, 
 
 // pointwise.py:120-124: softmax over (yes, no) -> P(yes); fp32 like the reference's CPU path.
 __global__ void yes_no_score_kernel(const float* __restrict__ logits2, float* __restrict__ score, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float y = logits2[2 * i], no = logits2[2 * i + 1];
@@ -387,6 +403,8 @@ __global__ void yes_no_score_kernel(const float* __restrict__ logits2, float* __
 // (last decoder position of every document, for the full-vocabulary lm_head GEMM).
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int d, int row_stride, int row_offset,
                                    __nv_bfloat16* __restrict__ dst, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     if (r >= n) return;
     const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<size_t>(r * row_stride + row_offset) * d);
@@ -402,6 +420,8 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int d,
 __global__ void vocab_row_kernel(const float* __restrict__ logits, int V, size_t ld, int mode, float scale,
                                  const int* __restrict__ labels, const int* __restrict__ cols, int ncols,
                                  float* __restrict__ out_f, int* __restrict__ out_i) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_val[32];
     __shared__ int s_idx[32];
     const int r = blockIdx.x;
@@ -461,6 +481,8 @@ __global__ void vocab_row_kernel(const float* __restrict__ logits, int V, size_t
 
 // qlm: score[doc] = sum_t logprob[doc*T + t]   (pointwise.py:79)
 __global__ void sum_rows_kernel(const float* __restrict__ v, int T, float* __restrict__ out, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;

@@ -218,6 +218,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ------------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel calls pdl_trigger() first (the next kernel in the stream may start launching: its CTAs take whatever SMs are
+// idle and run their prologue) and pdl_wait() before its first global-memory access (blocks until the preceding grid has
+// completed and its writes are visible). Launched without the PDL attribute both are no-ops. The decoder is a chain of
+// ~250 small dependent kernels per pass; this hides their launch latency and prologues behind the predecessor.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------- shared memory / named barriers
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

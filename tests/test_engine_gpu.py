@@ -315,8 +315,9 @@ def test_kernel_variants_agree(tmp_path):
 
     base = run("default")
     assert np.all(np.isfinite(base))
-    for name, env in [("cg1", {"B200RANK_GEMM_CG": "1"}), ("nofuse", {"B200RANK_FUSE_NORM": "0"}),
-                      ("direct_epi", {"B200RANK_GEMM_DIRECT_EPI": "1"})]:
+    for name, env in [("cg1", {"B200RANK_GEMM_CG": "1"}), ("fused_norm", {"B200RANK_FUSE_NORM": "1"}),
+                      ("direct_epi", {"B200RANK_GEMM_DIRECT_EPI": "1"}), ("rmsnorm_fwd", {"B200RANK_RMSNORM_REV": "0"}),
+                      ("pdl_off", {"B200RANK_PDL": "0"})]:
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
@@ -324,7 +325,7 @@ def test_kernel_variants_agree(tmp_path):
     for name, env in [("attn_tc", {"B200RANK_ATTN": "tc"}), ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
-        assert np.abs(got - base).max() < 0.05, name
+        assert np.abs(got - base).max() < 0.12, name  # same yardstick as engine-vs-fp32: 0.06 + 0.03*|x|, |x| ~ 2
 
 
 # ---------------------------------------------------------------------------------------- properties at full size
