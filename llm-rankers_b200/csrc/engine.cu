@@ -769,14 +769,15 @@ static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int 
 }
 
 // Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length),
-// 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256). B200RANK_ATTN=tiled|resident|tc overrides mode 0.
+// 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256), 4 = mma.sync scores-in-registers (len <= 256).
+// B200RANK_ATTN=tiled|resident|tc|regs overrides mode 0.
 static int attn_default_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* s = getenv("B200RANK_ATTN");
         // default: mma.sync tiles. The round-1 tcgen05 kernel is correct but 1.7x slower at S=184 (one 168 KB CTA per SM, phases not
         // pipelined across work items: profiles/r01_bench_n1_v5*.json); it is opt-in until it is made persistent.
-        mode = !s ? 1 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : 1));
+        mode = !s ? 1 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : 1)));
     }
     return mode;
 }
@@ -806,6 +807,21 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         if (maxlen <= 192) RET_IF(launch_attn_tc<3>(qkv, ld, qkv_rows, inner, d_cu, nd, H, bias, out, ldo, st, tm));
         else RET_IF(launch_attn_tc<4>(qkv, ld, qkv_rows, inner, d_cu, nd, H, bias, out, ldo, st, tm));
         return e ? post_launch(e, "enc_attention_tc") : B200RANK_OK;
+    }
+    if (mode == 4) {
+        static bool attr3 = false, attr4 = false;
+        const int nkb = maxlen <= 192 ? 3 : 4;
+        const int smem = (64 + 2 * 64 * nkb) * 128 + kAttnWideBias * 4;
+        if (e) prof_begin(e, "enc_attention_regs");
+        const dim3 grid((maxlen + 63) / 64, H, nd);
+        if (nkb == 3) {
+            if (!attr3) { CU_OK(cudaFuncSetAttribute(enc_attention_regs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr3 = true; }
+            CU_OK(launch_k(enc_attention_regs_kernel<3>, grid, dim3(128), smem, st, qkv, ld, inner, d_cu, bias, out, ldo));
+        } else {
+            if (!attr4) { CU_OK(cudaFuncSetAttribute(enc_attention_regs_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr4 = true; }
+            CU_OK(launch_k(enc_attention_regs_kernel<4>, grid, dim3(128), smem, st, qkv, ld, inner, d_cu, bias, out, ldo));
+        }
+        return e ? post_launch(e, "enc_attention_regs") : B200RANK_OK;
     }
     if (mode == 2) {
         const int s_pad = (maxlen + 63) & ~63;

@@ -145,6 +145,9 @@ def all_cases():
     # tcgen05 attention (mode 3): one tile, two tiles, ragged, 4 key blocks, many heads
     cases += ["attn:64:1:3", "attn:128:1:3", "attn:184:2:3", "attn:7,64,65,128,129,184,192:3:3", "attn:250,256,130,193:2:3",
               "attn:184,184,184,184:16:3", "attn:184:2:2"]
+    # scores-in-registers mma.sync attention (mode 4)
+    cases += ["attn:64:1:4", "attn:128:1:4", "attn:184:2:4", "attn:7,64,65,128,129,184,192:3:4", "attn:250,256,130,193:2:4",
+              "attn:184,184,184,184:16:4", "attn:1,2,3,8,9,15,16,17:2:4"]
     return cases
 
 

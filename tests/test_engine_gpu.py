@@ -322,7 +322,8 @@ def test_kernel_variants_agree(tmp_path):
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
     # different arithmetic (re-blocked softmax / re-associated products): agreement to bf16 noise
-    for name, env in [("attn_tc", {"B200RANK_ATTN": "tc"}), ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
+    for name, env in [("attn_tc", {"B200RANK_ATTN": "tc"}), ("attn_regs", {"B200RANK_ATTN": "regs"}),
+                      ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.abs(got - base).max() < 0.12, name  # same yardstick as engine-vs-fp32: 0.06 + 0.03*|x|, |x| ~ 2
