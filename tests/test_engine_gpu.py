@@ -383,3 +383,85 @@ def test_large_ragged_matches_oracle_sample():
     mask = (np.arange(ids.shape[1])[None] < lengths[pick][:, None]).astype(np.int64)
     ref, _ = orc.score_yes_no(ids[pick].astype(np.int64), mask, YES_ID, NO_ID)
     assert_close_logits("large/yes_no_ragged_sample", lg[pick], ref)
+
+
+# ---------------------------------------------------------------------------------------- other BASELINE configs (shapes)
+def _engine_and_oracle(shape, layers, seed, **caps):
+    """Engine + fp32 oracle for a Flan-T5 width (`shape`) truncated to `layers` encoder/decoder blocks (keeps tests fast while
+    exercising every width-dependent code path: rmsnorm vector widths, GEMM tile choices, head-tile loops, block-diagonal GEMMs)."""
+    import b200rank as br
+    from b200rank.synthetic import model_cfg, synthetic_weights
+    from oracle.t5_oracle import T5Oracle
+    cfg = model_cfg(shape)
+    cfg["num_layers"] = cfg["num_decoder_layers"] = layers
+    w = synthetic_weights(cfg, seed)
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], layers, layers, max_tokens=caps.get("max_tokens", 8192),
+                       max_docs=caps.get("max_docs", 64), max_logit_rows=caps.get("max_logit_rows", 512))
+    e = br.Engine(c, 0)
+    e.load_state_dict(w.items())
+    return e, T5Oracle(cfg, w), cfg
+
+
+def test_xl_width_pairwise_generation_and_yes_no():
+    """BASELINE config 4 shape (flan-t5-xl width: d 2048, 32 heads, d_ff 5120), 2+2 layers: batched 2-step greedy on padded
+    pair prompts (S ~ 320, pads attended as transformers 5 does) and pointwise yes_no (T=1 fast path with two 16-head tiles)."""
+    from b200rank.synthetic import NO_ID, YES_ID
+    e, orc, cfg = _engine_and_oracle("flan-t5-xl", 2, 41, max_tokens=4096)
+    rng = np.random.default_rng(3)
+    ids = rng.integers(3, 32000, size=(6, 320)).astype(np.int32)
+    ids[:, -1] = 1
+    ids[1, 300:] = 0  # a padded row inside the batch
+    ids[1, 299] = 1
+    lengths = np.full((6,), 320, np.int32)
+    new = e.greedy(ids, lengths, [0, 5], 2)
+    ref = orc.greedy(ids.astype(np.int64), np.ones_like(ids, dtype=np.int64), [0, 5], 2)
+    lg = orc.logits(ids.astype(np.int64), np.ones_like(ids, dtype=np.int64), np.tile(np.asarray([[0, 5]]), (6, 1)))[:, -1]
+    top2 = np.sort(lg, axis=-1)[:, -2:]
+    for b in range(6):
+        if top2[b, 1] - top2[b, 0] > 0.3:  # outside bf16 noise the first generated token must agree
+            assert new[b, 0] == ref[b, 0], (b, new[b], ref[b])
+    real = np.asarray([320, 300, 320, 320, 320, 320], np.int32)
+    got, _ = e.score_yes_no(ids, real, YES_ID, NO_ID)
+    mask = (np.arange(320)[None] < real[:, None]).astype(np.int64)
+    want, _ = orc.score_yes_no(ids.astype(np.int64), mask, YES_ID, NO_ID)
+    assert_close_logits("xl_width/yes_no", got, want)
+    e.close()
+
+
+def test_xxl_width_qlm():
+    """BASELINE config 5 shape (flan-t5-xxl width: d 4096, 64 heads, d_ff 10240), 1+1 layers: qlm with T = 33 labels over
+    S = 144 prompts (full-vocabulary log-softmax path, reference-shaped decoder with the stacked cross-K|V GEMM)."""
+    e, orc, cfg = _engine_and_oracle("flan-t5-xxl", 1, 43, max_tokens=2048, max_docs=16, max_logit_rows=512)
+    rng = np.random.default_rng(4)
+    ids = rng.integers(3, 32000, size=(5, 144)).astype(np.int32)
+    ids[:, -1] = 1
+    lengths = np.asarray([144, 144, 100, 144, 77], np.int32)
+    labels = [0] + rng.integers(3, 32000, size=32).tolist()
+    got = e.score_qlm(ids, lengths, labels)
+    mask = (np.arange(144)[None] < lengths[:, None]).astype(np.int64)
+    want = orc.score_qlm(ids.astype(np.int64), mask, labels)
+    err = np.abs(got - want)
+    record("xxl_width/qlm", max_abs_err=float(err.max()), max_abs_ref=float(np.abs(want).max()), T=33)
+    assert err.max() <= 33 * 0.05 + 0.01 * np.abs(want).max()
+    e.close()
+
+
+def test_large_setwise_prompt_length():
+    """BASELINE config 3 shape: one setwise compare prompt of 11 passages (S = 1536) on the full flan-t5-large: label
+    probabilities (likelihood scoring) and the first generated token against the fp32 oracle; exercises the long-sequence
+    attention path (64-query tiles with streamed keys) and decoder prefixes of 2 and 3 tokens."""
+    from oracle.t5_oracle import T5Oracle
+    e, cfg, w = large_engine()
+    orc = T5Oracle(cfg, w)
+    rng = np.random.default_rng(6)
+    ids = rng.integers(3, 32000, size=(1, 1536)).astype(np.int32)
+    ids[0, -1] = 1
+    lengths = np.asarray([1536], np.int32)
+    cols = [71, 272, 205, 309, 262, 377, 350, 454, 27, 446, 480]
+    got = e.logits_at(ids, lengths, [0, 5], cols, normalize=False)[0]
+    lg = orc.logits(ids.astype(np.int64), None, np.asarray([[0, 5]]))[0, -1]
+    assert_close_logits("large/setwise_S1536_label_logits", got, lg[cols])
+    new = e.greedy(ids, lengths, [0, 5], 2)[0]
+    top2 = np.sort(lg)[-2:]
+    if top2[1] - top2[0] > 0.3:
+        assert new[0] == int(np.argmax(lg))
