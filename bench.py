@@ -11,9 +11,10 @@ A step = one query's 100 candidate documents through the whole hot path (the ref
 which the engine runs as one device pass — bit-identical, tests/test_engine_gpu.py). With N GPUs every rank scores its
 own query per step (prompts shard embarrassingly; weights are NCCL-broadcast once at load) => weak scaling.
 
-`value`  : device-resident inputs, K steps timed with CUDA events on the engine stream, max over ranks.
-`e2e`    : the same K steps through the C-ABI call a host makes (b200rank_score_yes_no: HOST token ids in, HOST scores
-           out; packing, H2D, compute, D2H and the sync inside the timed region), wall clock, max over ranks.
+`value`  : device-resident inputs, K steps timed with CUDA events on the engine streams, max over ranks.
+`e2e`    : the same K steps through the C-ABI calls a host makes (b200rank_submit_yes_no / _wait_yes_no: HOST token ids in,
+           HOST scores out; packing, H2D, compute, D2H inside the timed region), wall clock, max over ranks.
+Both keep two queries in flight per GPU (--no-pipeline: one), like a host loop `submit(i+1); wait(i)`.
 `roofline`: GEMM kernel (gemm_tcgen05_kernel, all launches of a step): algorithmic GEMM FLOPs / summed launch time,
            measured live with per-launch CUDA events in a separate profiled pass; peak from MEASURED_PEAKS.json.
 `cpu_baseline`: the numpy oracle (a port of the transformers fp32 path the reference runs on CPU) on a bounded sample.
@@ -165,6 +166,7 @@ def workload_config(world, sample_docs=None):
         "docs_per_step_per_gpu": HITS if sample_docs is None else sample_docs,
         "global_docs_per_step": (HITS if sample_docs is None else sample_docs) * world,
         "parallelism": f"dp{world} (queries sharded across ranks, weights NCCL-broadcast once at load, no collective in the loop)",
+        "pipeline": "two queries in flight per GPU (submit/wait): decoder pass of query i on a second stream overlaps the encoder GEMMs of query i+1",
         "weights": f"seeded random init (numpy PCG64 seed {SEED}), bf16 on device",
         "l2": "no explicit flush: each step streams 1.6 GB of weights + ~3.5 GB of activations, far beyond the 126 MB L2",
         "algorithmic_gflop_per_doc": GF_PER_DOC,
@@ -224,10 +226,26 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- value: inputs resident in HBM, CUDA events on the engine stream
+    pipelined = not args.no_pipeline
+
+    def run_steps(n, submit):
+        """n steps, two in flight when pipelined: submit(step i+1) before wait(step i). Returns the last step's (logits, scores)."""
+        out, prev = None, None
+        for _ in range(n):
+            t = submit()
+            if prev is not None:
+                out = eng.wait_yes_no(prev)
+            prev = t
+            if not pipelined:
+                out = eng.wait_yes_no(prev)
+                prev = None
+        if prev is not None:
+            out = eng.wait_yes_no(prev)
+        return out
+
+    # ---- value: inputs resident in HBM (staged once), CUDA events on the engine's streams
     eng.stage(ids, lengths)
-    for _ in range(max(args.warmup, 3)):
-        eng.run_yes_no_staged(YES_ID, NO_ID)
+    run_steps(max(args.warmup, 3), lambda: eng.submit_yes_no_staged(YES_ID, NO_ID))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -235,8 +253,7 @@ def run_engine(args):
     l0 = eng.launch_count()
     t0 = time.time()
     eng.event_record(0)
-    for _ in range(args.steps):
-        eng.run_yes_no_staged(YES_ID, NO_ID)
+    logits_dev, scores_dev = run_steps(args.steps, lambda: eng.submit_yes_no_staged(YES_ID, NO_ID))
     eng.event_record(1)
     ms = eng.event_elapsed_ms()
     barrier()
@@ -246,15 +263,16 @@ def run_engine(args):
     clocks = sampler.summary(t0, t1)
     ms = max_over_ranks(ms)
     value = world * HITS * args.steps / (ms * 1e-3)
-    logits_dev, scores_dev = eng.fetch_yes_no()
+    # the synchronous single-stream path must give the same bits
+    eng.run_yes_no_staged(YES_ID, NO_ID)
+    lg_sync, _ = eng.fetch_yes_no()
+    assert np.array_equal(lg_sync, logits_dev), "pipelined and synchronous passes disagree"
 
-    # ---- e2e: host buffers through the C-ABI call, wall clock
-    for _ in range(max(args.warmup, 3)):
-        eng.score_yes_no(ids, lengths, YES_ID, NO_ID)
+    # ---- e2e: HOST buffers through the C-ABI (submit/wait), wall clock; pack + H2D + compute + D2H inside the timed region
+    run_steps(max(args.warmup, 3), lambda: eng.submit_yes_no(ids, lengths, YES_ID, NO_ID))
     barrier()
     w0 = time.perf_counter()
-    for _ in range(args.steps):
-        lg, sc = eng.score_yes_no(ids, lengths, YES_ID, NO_ID)
+    lg, sc = run_steps(args.steps, lambda: eng.submit_yes_no(ids, lengths, YES_ID, NO_ID))
     eng.sync()
     e2e_s = max_over_ranks(time.perf_counter() - w0)
     e2e_value = world * HITS * args.steps / e2e_s
@@ -327,6 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -121,6 +121,16 @@ int b200rank_run_yes_no_staged(b200rank_engine* e, int yes_id, int no_id);
 int b200rank_fetch_yes_no(b200rank_engine* e, float* logits2, float* scores);
 int b200rank_sync(b200rank_engine* e);
 
+/* Asynchronous form of b200rank_score_yes_no for throughput: at most two batches in flight. submit packs + copies the HOST
+ * token ids and enqueues the encoder pass on the engine's main stream and the decoder pass on a second stream, so the
+ * latency-bound decoder of batch i overlaps the encoder GEMMs of batch i+1 (which leave a few SMs free for it). wait blocks
+ * until that batch's scores are in host memory. Each batch must fit one device pass, documents <= 240 tokens.
+ * (The reference's per-query loop `for qid, query, ranking in ...: ranker.rerank(query, ranking)` — run.py:184-192 — becomes
+ * submit(query i+1); wait(query i).) */
+int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
+                           int yes_id, int no_id, uint64_t* ticket);
+int b200rank_wait_yes_no(b200rank_engine* e, uint64_t ticket, float* logits2, float* scores);
+
 /* Measurement plumbing: CUDA events on the engine's own stream (torch.cuda.Event cannot see it). */
 int b200rank_event_record(b200rank_engine* e, int which /* 0 = start, 1 = stop */);
 int b200rank_event_elapsed_ms(b200rank_engine* e, float* ms); /* synchronises on the stop event */

@@ -86,6 +86,8 @@ def load_library() -> C.CDLL:
         "b200rank_run_yes_no_staged": [vp, C.c_int, C.c_int],
         "b200rank_fetch_yes_no": [vp, f32p, f32p],
         "b200rank_sync": [vp],
+        "b200rank_submit_yes_no": [vp, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)],
+        "b200rank_wait_yes_no": [vp, C.c_uint64, f32p, f32p],
         "b200rank_event_record": [vp, C.c_int],
         "b200rank_event_elapsed_ms": [vp, f32p],
         "b200rank_launch_count": [vp, C.POINTER(C.c_uint64)],
@@ -111,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "b200rank_version", "b200rank_last_error", "b200rank_create", "b200rank_destroy", "b200rank_load_tensor",
     "b200rank_missing_tensors", "b200rank_weights_blob", "b200rank_mark_weights_loaded", "b200rank_score_yes_no",
     "b200rank_score_qlm", "b200rank_logits_at", "b200rank_greedy", "b200rank_stage", "b200rank_run_yes_no_staged",
-    "b200rank_fetch_yes_no", "b200rank_sync", "b200rank_event_record", "b200rank_event_elapsed_ms",
+    "b200rank_fetch_yes_no", "b200rank_sync", "b200rank_submit_yes_no", "b200rank_wait_yes_no", "b200rank_event_record", "b200rank_event_elapsed_ms",
     "b200rank_launch_count", "b200rank_flush_l2", "b200rank_profile", "b200rank_profile_report", "b200rank_device_info", "b200rank_test_gemm",
     "b200rank_test_enc_attention", "b200rank_rel_bucket",
 ]
@@ -261,6 +263,27 @@ class Engine:
         logits2 = np.empty((n, 2), np.float32)
         scores = np.empty((n,), np.float32)
         _check(self.lib.b200rank_fetch_yes_no(self._h, _p(logits2, C.c_float), _p(scores, C.c_float)))
+        return logits2, scores
+
+    def submit_yes_no(self, ids, lengths, yes_id: int, no_id: int) -> Tuple[int, int]:
+        """Asynchronous scoring (at most two batches in flight). Returns (ticket, n_docs) for wait_yes_no."""
+        ids, lengths = self._ids_lengths(ids, lengths)
+        t = C.c_uint64()
+        _check(self.lib.b200rank_submit_yes_no(self._h, _p(ids, C.c_int32), _p(lengths, C.c_int32), ids.shape[0], ids.shape[1],
+                                               yes_id, no_id, C.byref(t)))
+        return int(t.value), ids.shape[0]
+
+    def submit_yes_no_staged(self, yes_id: int, no_id: int) -> Tuple[int, int]:
+        """Asynchronous scoring of the batch `stage()` left in device memory (no host->device copy)."""
+        t = C.c_uint64()
+        _check(self.lib.b200rank_submit_yes_no(self._h, None, None, 0, 0, yes_id, no_id, C.byref(t)))
+        return int(t.value), self._staged_n
+
+    def wait_yes_no(self, ticket: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:
+        t, n = ticket
+        logits2 = np.empty((n, 2), np.float32)
+        scores = np.empty((n,), np.float32)
+        _check(self.lib.b200rank_wait_yes_no(self._h, t, _p(logits2, C.c_float), _p(scores, C.c_float)))
         return logits2, scores
 
     def sync(self) -> None:

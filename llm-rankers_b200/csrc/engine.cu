@@ -243,6 +243,20 @@ struct b200rank_engine {
     uint8_t* l2_scratch = nullptr; size_t l2_scratch_bytes = 0;
     size_t workspace_bytes = 0;
 
+    // two-deep pipeline (b200rank_submit_yes_no / _wait_yes_no): encoder passes run on `stream`, decoder passes on `stream_dec`;
+    // the only tensors handed from one to the other are the encoder output and cu_seqlens, so those are double-buffered.
+    cudaStream_t stream_main = nullptr, stream_dec = nullptr;
+    bf16* enc_out[2] = {nullptr, nullptr};       // [cap_tokens, d] final-normed encoder output per slot
+    int* d_cu_slot[2] = {nullptr, nullptr};
+    bf16* enc_out_cur = nullptr;                  // what run_encoder writes / run_decoder reads
+    int* d_cu_cur = nullptr;
+    int* h_ids_slot[2] = {nullptr, nullptr}; int* h_cu_slot[2] = {nullptr, nullptr}; float* h_out_slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev_enc[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    struct Slot { int docs = 0, tokens = 0, maxlen = 0; bool busy = false; uint64_t ticket = 0; } slot[2];
+    uint64_t next_ticket = 1;
+    int gemm_sm_cap = 0;                          // > 0: persistent GEMMs use at most this many SMs (the rest serve the other stream)
+    int pipe_reserve_sms = 8;
+
     // pinned host staging
     int* h_ids = nullptr; int* h_cu = nullptr; float* h_out = nullptr; int* h_int = nullptr;
     int* h_small = nullptr; size_t h_small_cap = 0, h_small_off = 0;  // pinned bump buffer for small async uploads
@@ -341,7 +355,8 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
     GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch};
-    RET_IF(launch_gemm_tc(e->stream, e->num_sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
+    const int sms = (e->gemm_sm_cap > 0 && bn == 256 && M > 1024) ? std::min(e->gemm_sm_cap, e->num_sms) : e->num_sms;
+    RET_IF(launch_gemm_tc(e->stream, sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
 }
 
@@ -391,7 +406,7 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
-                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->d_ids, e->d_cu, e->d_dec_ids, e->d_cols, e->d_labels,
+                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
                      e->d_int_out, e->d_finished, e->l2_scratch};
     for (void* p : frees)
         if (p) cudaFree(p);
@@ -400,6 +415,16 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_int) cudaFreeHost(e->h_int);
     if (e->h_small) cudaFreeHost(e->h_small);
+    for (int b = 0; b < 2; ++b) {
+        if (e->enc_out[b]) cudaFree(e->enc_out[b]);
+        if (e->d_cu_slot[b]) cudaFree(e->d_cu_slot[b]);
+        if (e->h_ids_slot[b]) cudaFreeHost(e->h_ids_slot[b]);
+        if (e->h_cu_slot[b]) cudaFreeHost(e->h_cu_slot[b]);
+        if (e->h_out_slot[b]) cudaFreeHost(e->h_out_slot[b]);
+        if (e->ev_enc[b]) cudaEventDestroy(e->ev_enc[b]);
+        if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
+    }
+    if (e->stream_dec) cudaStreamDestroy(e->stream_dec);
     for (int i = 0; i < 2; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
@@ -417,6 +442,13 @@ static int create_impl(b200rank_engine* e) {
                          prop.minor);
     e->num_sms = prop.multiProcessorCount;
     CU_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->stream_main = e->stream;
+    CU_OK(cudaStreamCreateWithFlags(&e->stream_dec, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CU_OK(cudaEventCreateWithFlags(&e->ev_enc[b], cudaEventDisableTiming));
+        CU_OK(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+    }
+    if (getenv("B200RANK_PIPE_RESERVE_SMS")) e->pipe_reserve_sms = atoi(getenv("B200RANK_PIPE_RESERVE_SMS"));
     CU_OK(cudaEventCreate(&e->ev[0]));
     CU_OK(cudaEventCreate(&e->ev[1]));
     e->debug_simt = getenv("B200RANK_DEBUG_SIMT_GEMM") && atoi(getenv("B200RANK_DEBUG_SIMT_GEMM")) != 0;
@@ -494,7 +526,17 @@ static int create_impl(b200rank_engine* e) {
     RET_IF(dev_alloc(e, &e->logits, (size_t)e->cap_logit_rows * V));
     RET_IF(dev_alloc(e, &e->qp, (size_t)align_up(e->cap_docs, 128) * e->H * d)); RET_IF(dev_alloc(e, &e->ctxb, (size_t)align_up(e->cap_docs, 128) * e->H * d));
     RET_IF(dev_alloc(e, &e->small_out, R * 32)); RET_IF(dev_alloc(e, &e->small_out2, (size_t)e->cap_docs * 32));
-    RET_IF(dev_alloc(e, &e->d_ids, Tk)); RET_IF(dev_alloc(e, &e->d_cu, (size_t)e->cap_docs + 1));
+    RET_IF(dev_alloc(e, &e->d_ids, Tk));
+    for (int b = 0; b < 2; ++b) {
+        RET_IF(dev_alloc(e, &e->enc_out[b], Tk * d));
+        RET_IF(dev_alloc(e, &e->d_cu_slot[b], (size_t)e->cap_docs + 1));
+        CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ids_slot[b]), Tk * sizeof(int), cudaHostAllocDefault));
+        CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_cu_slot[b]), ((size_t)e->cap_docs + 1) * sizeof(int), cudaHostAllocDefault));
+        CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_out_slot[b]), (size_t)e->cap_docs * 4 * sizeof(float), cudaHostAllocDefault));
+    }
+    e->enc_out_cur = e->enc_out[0];
+    e->d_cu = e->d_cu_slot[0];
+    e->d_cu_cur = e->d_cu;
     RET_IF(dev_alloc(e, &e->d_dec_ids, R)); RET_IF(dev_alloc(e, &e->d_cols, 64)); RET_IF(dev_alloc(e, &e->d_labels, R));
     RET_IF(dev_alloc(e, &e->d_int_out, (size_t)e->cap_docs * 16)); RET_IF(dev_alloc(e, &e->d_finished, (size_t)e->cap_docs));
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ids), Tk * sizeof(int), cudaHostAllocDefault));
@@ -849,15 +891,16 @@ static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
         const LayerW& w = e->enc[l];
         // h = norm1(x) was produced by the previous layer's last GEMM (or the line above for layer 0)
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
-        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0));
+        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu_cur, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0));
         RET_IF(gemm_resid_then_norm(e, e->ao, I, Tk, w.wo, I, d, n, I, e->x, w.ln2, e->h));
         RET_IF(gemm(e, e->h, d, Tk, w.wi, d, 2 * F, n, 2 * F, d, EPI_GATED_BF16, e->g, F));
-        const float* next_ln = (l + 1 < e->Le) ? e->enc[l + 1].ln1 : e->enc_final_ln;
-        RET_IF(gemm_resid_then_norm(e, e->g, F, Tk, w.wff, F, d, n, F, e->x, next_ln, e->h));
+        const bool last = (l + 1 == e->Le);  // the final layer norm lands in the slot buffer the decoder reads
+        RET_IF(gemm_resid_then_norm(e, e->g, F, Tk, w.wff, F, d, n, F, e->x, last ? e->enc_final_ln : e->enc[l + 1].ln1,
+                                    last ? e->enc_out_cur : e->h));
     }
     if (!need_ckv) return B200RANK_OK;  // re-associated T=1 decoder attends against the encoder output itself
     const int NC = e->Ld * 2 * I;
-    RET_IF(gemm(e, e->h, d, Tk, e->wckv, d, NC, n, NC, d, EPI_BF16, e->ckv, NC));
+    RET_IF(gemm(e, e->enc_out_cur, d, Tk, e->wckv, d, NC, n, NC, d, EPI_BF16, e->ckv, NC));
     return B200RANK_OK;
 }
 
@@ -907,7 +950,7 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             RET_IF(gemm(e, e->qd, I, cap, w.wkT, 64, HD, R, HD, 64, EPI_BF16, e->qp, HD, 0, nullptr, nullptr, /*n_per_batch=*/d, /*a_cols=*/I));
             const int s_pad = (max_len + 15) & ~15;
             prof_begin(e, "cross_ctx_t1");
-            launch_k(cross_ctx_t1_kernel, dim3(nd), dim3(kCtxThreads), cross_ctx_smem_bytes(s_pad), e->stream, e->qp, e->h, e->d_cu + doc0, e->ctxb, e->H, d, s_pad);
+            launch_k(cross_ctx_t1_kernel, dim3(nd), dim3(kCtxThreads), cross_ctx_smem_bytes(s_pad), e->stream, e->qp, e->enc_out_cur, e->d_cu_cur + doc0, e->ctxb, e->H, d, s_pad);
             RET_IF(post_launch(e, "cross_ctx_t1"));
             const bf16* wv_l = e->wckv + ((size_t)l * 2 * I + I) * d;
             RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, nullptr, nullptr, /*n_per_batch=*/64, /*a_cols=*/HD));
@@ -920,13 +963,13 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
         prof_begin(e, "cross_attention");
         if (T == 1 && e->H % 4 == 0 && max_len <= 256)
-            cross_attention_t1_kernel<8><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+            cross_attention_t1_kernel<8><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         else if (T == 1 && e->H % 4 == 0 && max_len <= 2048)
-            cross_attention_t1_kernel<64><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+            cross_attention_t1_kernel<64><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         else if (T <= 4)
-            cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+            cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         else
-            cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu + doc0, e->aod, I);
+            cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         RET_IF(post_launch(e, "cross_attention"));
         RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
         RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
@@ -946,7 +989,13 @@ static int check_ready(b200rank_engine* e) {
     if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
     if (!e->weights_ready) return set_error(B200RANK_ERR_STATE, "weights are not fully loaded (%d tensors missing)", b200rank_missing_tensors(e, nullptr, 0));
     CU_OK(cudaSetDevice(e->device));
+    if (e->slot[0].busy || e->slot[1].busy)
+        return set_error(B200RANK_ERR_STATE, "pipelined batches are in flight: call b200rank_wait_yes_no() for every ticket before using the synchronous API");
     e->h_small_off = 0;
+    e->stream = e->stream_main;
+    e->enc_out_cur = e->enc_out[0];
+    e->d_cu_cur = e->d_cu_slot[0];
+    e->gemm_sm_cap = 0;
     return B200RANK_OK;
 }
 
@@ -1062,6 +1111,118 @@ extern "C" int b200rank_sync(b200rank_engine* e) {
     if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
     CU_OK(cudaSetDevice(e->device));
     CU_OK(cudaStreamSynchronize(e->stream));
+    return B200RANK_OK;
+}
+
+
+// ------------------------------------------------------------------ two-deep pipeline (submit / wait)
+// submit: pack + H2D + encoder pass on the main stream, then the decoder pass + D2H on the decoder stream; returns without
+// synchronising. While the latency-bound decoder chain of batch i (a few hundred small dependent kernels on a handful of SMs)
+// runs, the main stream already executes the encoder GEMMs of batch i+1 on the remaining SMs (persistent GEMM grids are capped
+// at num_sms - pipe_reserve_sms while a pipeline is active).
+static int check_ready_async(b200rank_engine* e) {
+    if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
+    if (!e->weights_ready) return set_error(B200RANK_ERR_STATE, "weights are not fully loaded");
+    CU_OK(cudaSetDevice(e->device));
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
+                                      int yes_id, int no_id, uint64_t* ticket) {
+    RET_IF(check_ready_async(e));
+    if (!ticket) return set_error(B200RANK_ERR_ARG, "bad arguments");
+    if (yes_id < 0 || yes_id >= e->V || no_id < 0 || no_id >= e->V) return set_error(B200RANK_ERR_ARG, "yes/no ids out of vocabulary");
+    const int b = static_cast<int>(e->next_ticket & 1);
+    if (e->slot[b].busy) return set_error(B200RANK_ERR_STATE, "two batches are already in flight: wait for ticket %llu first", (unsigned long long)e->slot[b].ticket);
+    const bool resident = (ids == nullptr);  // ids == NULL: score the batch b200rank_stage() left in device memory (no H2D)
+    int tok = 0, maxlen = 0;
+    if (resident) {
+        if (e->staged_docs <= 0) return set_error(B200RANK_ERR_STATE, "nothing staged (b200rank_stage) for a resident submit");
+        n_docs = e->staged_docs; tok = e->staged_tokens; maxlen = e->staged_maxlen;
+    } else {
+        if (!lengths || n_docs <= 0 || stride <= 0) return set_error(B200RANK_ERR_ARG, "bad arguments");
+        // the batch must fit one device pass and take the T = 1 fast path (no stacked cross-K|V buffer is double-buffered)
+        if (n_docs > e->cap_docs) return set_error(B200RANK_ERR_CAPACITY, "%d documents exceed max_docs %d", n_docs, e->cap_docs);
+        for (int i = 0; i < n_docs; ++i) {
+            const int len = lengths[i];
+            if (len <= 0 || len > stride) return set_error(B200RANK_ERR_ARG, "lengths[%d]=%d out of range (stride %d)", i, len, stride);
+            tok += len; maxlen = std::max(maxlen, len);
+        }
+        if (tok > e->cap_tokens) return set_error(B200RANK_ERR_CAPACITY, "%d tokens exceed max_tokens %d", tok, e->cap_tokens);
+    }
+    if (maxlen > 240 || e->debug_simt) return set_error(B200RANK_ERR_ARG, "pipelined submit supports documents of at most 240 tokens");
+
+    e->stream = e->stream_main;
+    CU_OK(cudaStreamWaitEvent(e->stream_main, e->ev_done[b], 0));  // the decoder that last read this slot has finished
+    if (resident) {
+        if (b != 0) CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], e->d_cu_slot[0], (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyDeviceToDevice, e->stream_main));
+    } else {
+        // host packing into this slot's pinned staging (its previous H2D finished before the slot was waited on)
+        int* hid = e->h_ids_slot[b]; int* hcu = e->h_cu_slot[b];
+        hcu[0] = 0; tok = 0;
+        for (int i = 0; i < n_docs; ++i) {
+            memcpy(hid + tok, ids + (size_t)i * stride, (size_t)lengths[i] * sizeof(int));
+            tok += lengths[i];
+            hcu[i + 1] = tok;
+        }
+        CU_OK(cudaMemcpyAsync(e->d_ids, hid, (size_t)tok * sizeof(int), cudaMemcpyHostToDevice, e->stream_main));
+        CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], hcu, (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream_main));
+        e->staged_docs = n_docs; e->staged_tokens = tok; e->staged_maxlen = maxlen;
+    }
+    e->slot[b].docs = n_docs; e->slot[b].tokens = tok; e->slot[b].maxlen = maxlen;
+    e->enc_out_cur = e->enc_out[b];
+    e->d_cu_cur = e->d_cu_slot[b];
+    e->gemm_sm_cap = std::max(2, (e->num_sms - std::max(0, e->pipe_reserve_sms)) & ~1);
+    int rc = run_encoder(e, /*need_ckv=*/false);
+    e->gemm_sm_cap = 0;
+    if (rc == B200RANK_OK) { cudaError_t er = cudaEventRecord(e->ev_enc[b], e->stream_main); if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "event record: %s", cudaGetErrorString(er)); }
+
+    // ---- decoder + head + D2H on the decoder stream
+    if (rc == B200RANK_OK) {
+        e->stream = e->stream_dec;
+        cudaStreamWaitEvent(e->stream_dec, e->ev_enc[b], 0);
+        e->h_small_off = (size_t)b * (e->h_small_cap / 2);  // per-slot half of the pinned bump buffer
+        std::vector<int> dec(n_docs, e->cfg.pad_id);
+        rc = upload_ints(e, e->d_dec_ids, dec);
+        if (rc == B200RANK_OK) rc = upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id});
+        if (rc == B200RANK_OK) rc = run_decoder(e, 0, n_docs, 1);
+        if (rc == B200RANK_OK) {
+            prof_begin(e, "lm_head_cols");
+            launch_k(lm_head_cols_kernel, dim3(n_docs), dim3(64), 0, e->stream, e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
+            rc = post_launch(e, "lm_head_cols");
+        }
+        if (rc == B200RANK_OK) {
+            prof_begin(e, "yes_no_score");
+            launch_k(yes_no_score_kernel, dim3((n_docs + 127) / 128), dim3(128), 0, e->stream, e->small_out, e->small_out2, n_docs);
+            rc = post_launch(e, "yes_no_score");
+        }
+        if (rc == B200RANK_OK) {
+            float* ho = e->h_out_slot[b];
+            cudaMemcpyAsync(ho, e->small_out, (size_t)n_docs * 2 * sizeof(float), cudaMemcpyDeviceToHost, e->stream_dec);
+            cudaMemcpyAsync(ho + 2 * (size_t)n_docs, e->small_out2, (size_t)n_docs * sizeof(float), cudaMemcpyDeviceToHost, e->stream_dec);
+            cudaError_t er = cudaEventRecord(e->ev_done[b], e->stream_dec);
+            if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "event record: %s", cudaGetErrorString(er));
+        }
+    }
+    e->stream = e->stream_main;
+    e->enc_out_cur = e->enc_out[0];
+    e->d_cu_cur = e->d_cu_slot[0];
+    if (rc != B200RANK_OK) return rc;
+    e->slot[b].busy = true;
+    e->slot[b].ticket = e->next_ticket;
+    *ticket = e->next_ticket++;
+    return B200RANK_OK;
+}
+
+extern "C" int b200rank_wait_yes_no(b200rank_engine* e, uint64_t ticket, float* logits2, float* scores) {
+    RET_IF(check_ready_async(e));
+    const int b = static_cast<int>(ticket & 1);
+    if (!e->slot[b].busy || e->slot[b].ticket != ticket) return set_error(B200RANK_ERR_STATE, "ticket %llu is not in flight", (unsigned long long)ticket);
+    CU_OK(cudaEventSynchronize(e->ev_done[b]));
+    const int nd = e->slot[b].docs;
+    if (logits2) memcpy(logits2, e->h_out_slot[b], (size_t)nd * 2 * sizeof(float));
+    if (scores) memcpy(scores, e->h_out_slot[b] + 2 * (size_t)nd, (size_t)nd * sizeof(float));
+    e->slot[b].busy = false;
     return B200RANK_OK;
 }
 
@@ -1220,7 +1381,10 @@ extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int
 extern "C" int b200rank_event_record(b200rank_engine* e, int which) {
     if (!e || which < 0 || which > 1) return set_error(B200RANK_ERR_ARG, "bad arguments");
     CU_OK(cudaSetDevice(e->device));
-    CU_OK(cudaEventRecord(e->ev[which], e->stream));
+    if (which == 1) {  // "stop" = after everything enqueued so far, including decoder passes of pipelined batches
+        for (int b = 0; b < 2; ++b) CU_OK(cudaStreamWaitEvent(e->stream_main, e->ev_done[b], 0));
+    }
+    CU_OK(cudaEventRecord(e->ev[which], e->stream_main));
     return B200RANK_OK;
 }
 extern "C" int b200rank_event_elapsed_ms(b200rank_engine* e, float* ms) {

@@ -372,6 +372,34 @@ def test_large_yes_no_properties_and_oracle_sample():
     assert np.abs(sc[pick] - ref_sc).max() < 0.03
 
 
+def test_pipelined_submit_wait_matches_synchronous_call():
+    """Two batches in flight (encoder of batch i+1 on the main stream while the decoder of batch i runs on the second stream,
+    GEMM grids capped to leave SMs free) must reproduce the synchronous call bit for bit, for host and for resident inputs."""
+    from b200rank.synthetic import NO_ID, YES_ID, synthetic_prompt_ids
+    e, cfg, w = large_engine()
+    batches = [synthetic_prompt_ids(n, 32, 128, seed=100 + i, ragged=(i % 2 == 1)) for i, n in enumerate((100, 37, 64, 100, 5))]
+    want = [e.score_yes_no(ids, lens, YES_ID, NO_ID)[0] for ids, lens in batches]
+    got, prev = [], None
+    for ids, lens in batches:
+        t = e.submit_yes_no(ids, lens, YES_ID, NO_ID)
+        if prev is not None:
+            got.append(e.wait_yes_no(prev)[0])
+        prev = t
+    got.append(e.wait_yes_no(prev)[0])
+    for g, wnt in zip(got, want):
+        assert np.array_equal(g, wnt)
+    ids, lens = batches[0]
+    e.stage(ids, lens)
+    t1 = e.submit_yes_no_staged(YES_ID, NO_ID)
+    t2 = e.submit_yes_no_staged(YES_ID, NO_ID)
+    import b200rank as br
+    with pytest.raises(br.B200RankError):
+        e.submit_yes_no_staged(YES_ID, NO_ID)      # a third batch needs a wait first
+    with pytest.raises(br.B200RankError):
+        e.score_yes_no(ids, lens, YES_ID, NO_ID)   # synchronous API refuses while batches are in flight
+    assert np.array_equal(e.wait_yes_no(t1)[0], want[0]) and np.array_equal(e.wait_yes_no(t2)[0], want[0])
+
+
 def test_large_ragged_matches_oracle_sample():
     from b200rank.synthetic import NO_ID, YES_ID, synthetic_prompt_ids
     from oracle.t5_oracle import T5Oracle
