@@ -100,6 +100,14 @@ class T5Backend:
         ids, lengths = self.pad_rows(rows, self.pad_id)
         return self.engine.score_yes_no(ids, lengths, yes_id, no_id)
 
+    def submit_yes_no(self, rows, yes_id: int, no_id: int):
+        """Asynchronous score_yes_no (two batches in flight, see b200rank_submit_yes_no); returns a ticket for wait_yes_no."""
+        ids, lengths = self.pad_rows(rows, self.pad_id)
+        return self.engine.submit_yes_no(ids, lengths, yes_id, no_id)
+
+    def wait_yes_no(self, ticket):
+        return self.engine.wait_yes_no(ticket)
+
     def score_qlm(self, rows, labels: Sequence[int]) -> np.ndarray:
         ids, lengths = self.pad_rows(rows, self.pad_id)
         return self.engine.score_qlm(ids, lengths, labels)

@@ -62,6 +62,40 @@ class PointwiseLlmRanker(LlmRanker):
         # any other method: like the reference, nothing is scored and the input order is sorted by its existing scores
         return sorted(ranking, key=lambda x: x.score, reverse=True)
 
+    def rerank_many(self, requests):
+        """Extension (not in the reference): rerank an iterable of (query, ranking) pairs with two queries in flight on the GPU
+        — query i+1 is tokenised, copied and its encoder pass started while query i's decoder pass finishes. Yields the same
+        list `rerank(query, ranking)` would return for each pair, in order; counters hold the totals of the last query.
+        Only the yes_no method is pipelined (the headline path); other methods fall back to rerank()."""
+        if self.method != "yes_no":
+            for query, ranking in requests:
+                yield self.rerank(query, ranking)
+            return
+        yes_id = self.tokenizer.encode("Yes", add_special_tokens=False)[0]
+        no_id = self.tokenizer.encode("No", add_special_tokens=False)[0]
+        pending = None  # (ticket, ranking, rows)
+
+        def finish(item):
+            ticket, ranking, rows = item
+            self.total_compare = 0
+            self.total_completion_tokens = 0
+            self.total_prompt_tokens = 0
+            self._count_batches(rows, 1)
+            if ticket is not None:
+                _, scores = self.backend.wait_yes_no(ticket)
+                for doc, s in zip(ranking, scores):
+                    doc.score = float(s)
+            return sorted(ranking, key=lambda x: x.score, reverse=True)
+
+        for query, ranking in requests:
+            rows = self.backend.tokenize_prompts([YES_NO_PROMPT.format(text=doc.text, query=query) for doc in ranking])
+            ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
+            if pending is not None:
+                yield finish(pending)
+            pending = (ticket, ranking, rows)
+        if pending is not None:
+            yield finish(pending)
+
     def truncate(self, text, length):
         return self.tokenizer.convert_tokens_to_string(self.tokenizer.tokenize(text)[:length])
 

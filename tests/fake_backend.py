@@ -20,6 +20,12 @@ class OracleBackend(T5Backend):
         ids, mask = self._padded(rows)
         return self.oracle.score_yes_no(ids, mask, yes_id, no_id)
 
+    def submit_yes_no(self, rows, yes_id, no_id):
+        return ("ticket", self.score_yes_no(rows, yes_id, no_id))
+
+    def wait_yes_no(self, ticket):
+        return ticket[1]
+
     def score_qlm(self, rows, labels):
         ids, mask = self._padded(rows)
         return self.oracle.score_qlm(ids, mask, labels)

@@ -97,6 +97,17 @@ def test_pointwise_sort_is_stable_and_empty_ok():
     assert r.total_compare == 2
 
 
+def test_rerank_many_equals_rerank():
+    from llmrankers.pointwise import PointwiseLlmRanker
+    m = golden_meta()["tiny"]
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=backend())
+    reqs = [(m["query"], docs_from(m["docs"])), ("w3 w4", docs_from(m["docs"][:3])), ("w9", []), (m["query"], docs_from(m["docs"][::-1]))]
+    want = [[(d.docid, d.score) for d in r.rerank(q, copy.deepcopy(rk))] for q, rk in reqs]
+    got = [[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs])]
+    assert got == want
+    assert r.total_compare == 3  # counters describe the last query (10 docs, batch_size 4)
+
+
 def test_unsupported_variants_fail_loudly():
     from llmrankers.listwise import ListwiseLlmRanker
     from llmrankers.pairwise import DuoT5LlmRanker
