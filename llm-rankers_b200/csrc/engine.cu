@@ -255,7 +255,7 @@ struct b200rank_engine {
     struct Slot { int docs = 0, tokens = 0, maxlen = 0; bool busy = false; uint64_t ticket = 0; } slot[2];
     uint64_t next_ticket = 1;
     int gemm_sm_cap = 0;                          // > 0: persistent GEMMs use at most this many SMs (the rest serve the other stream)
-    int pipe_reserve_sms = 8;
+    int pipe_reserve_sms = 0;  // measured on B200 (profiles/r01_bench_n1_v10_*): capping the encoder GEMM grids does not pay off
 
     // pinned host staging
     int* h_ids = nullptr; int* h_cu = nullptr; float* h_out = nullptr; int* h_int = nullptr;
@@ -443,7 +443,14 @@ static int create_impl(b200rank_engine* e) {
     e->num_sms = prop.multiProcessorCount;
     CU_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->stream_main = e->stream;
-    CU_OK(cudaStreamCreateWithFlags(&e->stream_dec, cudaStreamNonBlocking));
+    {
+        // the decoder stream carries short latency-bound kernels: give it the highest priority so that its CTAs are dispatched
+        // first whenever an SM frees up next to the long-running encoder kernels of the other stream
+        int prio_lo = 0, prio_hi = 0;
+        CU_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const bool hi = !(getenv("B200RANK_PIPE_PRIORITY") && atoi(getenv("B200RANK_PIPE_PRIORITY")) == 0);
+        CU_OK(cudaStreamCreateWithPriority(&e->stream_dec, cudaStreamNonBlocking, hi ? prio_hi : prio_lo));
+    }
     for (int b = 0; b < 2; ++b) {
         CU_OK(cudaEventCreateWithFlags(&e->ev_enc[b], cudaEventDisableTiming));
         CU_OK(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
