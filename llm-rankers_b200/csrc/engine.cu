@@ -444,11 +444,11 @@ static int create_impl(b200rank_engine* e) {
     CU_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->stream_main = e->stream;
     {
-        // the decoder stream carries short latency-bound kernels: give it the highest priority so that its CTAs are dispatched
-        // first whenever an SM frees up next to the long-running encoder kernels of the other stream
+        // Decoder stream priority: equal to the main stream by default. Measured on B200 (profiles/r01_bench_n1_v11_*): giving the
+        // short decoder kernels the HIGHEST priority costs ~4 % (they cut into the encoder GEMM waves); B200RANK_PIPE_PRIORITY=1 selects it.
         int prio_lo = 0, prio_hi = 0;
         CU_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        const bool hi = !(getenv("B200RANK_PIPE_PRIORITY") && atoi(getenv("B200RANK_PIPE_PRIORITY")) == 0);
+        const bool hi = getenv("B200RANK_PIPE_PRIORITY") && atoi(getenv("B200RANK_PIPE_PRIORITY")) != 0;
         CU_OK(cudaStreamCreateWithPriority(&e->stream_dec, cudaStreamNonBlocking, hi ? prio_hi : prio_lo));
     }
     for (int b = 0; b < 2; ++b) {
