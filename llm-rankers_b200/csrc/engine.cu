@@ -818,15 +818,15 @@ static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int 
 }
 
 // Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length),
-// 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256), 4 = mma.sync scores-in-registers (len <= 256).
-// B200RANK_ATTN=tiled|resident|tc|regs overrides mode 0.
+// 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256), 4 = mma.sync scores-in-registers (len <= 256),
+// 5 = persistent tcgen05 (len <= 192). B200RANK_ATTN=tiled|resident|tc|regs|tc2 overrides mode 0.
 static int attn_default_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* s = getenv("B200RANK_ATTN");
         // default: mma.sync tiles. The round-1 tcgen05 kernel is correct but 1.7x slower at S=184 (one 168 KB CTA per SM, phases not
         // pipelined across work items: profiles/r01_bench_n1_v5*.json); it is opt-in until it is made persistent.
-        mode = !s ? 1 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : 1)));
+        mode = !s ? 1 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : 1))));
     }
     return mode;
 }
@@ -842,11 +842,32 @@ static int launch_attn_tc(const bf16* qkv, int ld, uint64_t qkv_rows, int inner,
     launch_k(kern, dim3(dim3(H, nd)), dim3(kAttnTcThreads), AttnTcCfg<NKB>::kSmemBytes, st, *tm, inner, d_cu, bias, out, ldo);
     return B200RANK_OK;
 }
+static int device_sm_count() {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    return sms;
+}
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
                                 int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode) {
     static bool attr_set = false;
     if (mode == 0) mode = attn_default_mode();
     if (maxlen > 256) mode = 1;
+    if (mode == 5 && maxlen > 192) mode = 1;
+    if (mode == 5) {
+        // persistent tcgen05 kernel: one CTA per SM walks the (document, head) items
+        CUtensorMap local;
+        const CUtensorMap* tm = &local;
+        if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
+        else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
+        static bool attr5 = false;
+        auto kern = enc_attention_tc2_kernel<3>;
+        if (!attr5) { CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr5 = true; }
+        const int n_items = nd * H;
+        if (e) prof_begin(e, "enc_attention_tc2");
+        CU_OK(launch_k(kern, dim3(std::min(n_items, device_sm_count())), dim3(kAttnTcThreads), AttnTc2Cfg<3>::smem_bytes(H), st, *tm, inner, d_cu, bias,
+                       out, ldo, H, n_items));
+        return e ? post_launch(e, "enc_attention_tc2") : B200RANK_OK;
+    }
     if (mode == 3) {
         CUtensorMap local;
         const CUtensorMap* tm = &local;

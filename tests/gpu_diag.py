@@ -106,7 +106,7 @@ def run_attn_case(lens, H, mode=0):
     ref = attention_reference(qkv, cu, H, bias)
     err = np.abs(out - ref)
     tol = 0.03 * np.abs(ref).max()
-    res = dict(kind="attn", lens=list(map(int, lens)), H=H, mode=mode, finite=bool(np.isfinite(out).all()), max_err=float(err.max()), mean_err=float(err.mean()), tol=float(tol),
+    res = dict(kind="attn", lens=list(map(int, lens))[:16], n_docs=len(lens), H=H, mode=mode, finite=bool(np.isfinite(out).all()), max_err=float(err.max()), mean_err=float(err.mean()), tol=float(tol),
                ok=bool(err.max() <= tol))
     if not res["ok"]:
         bad = np.argwhere(err > tol)
@@ -148,6 +148,9 @@ def all_cases():
     # scores-in-registers mma.sync attention (mode 4)
     cases += ["attn:64:1:4", "attn:128:1:4", "attn:184:2:4", "attn:7,64,65,128,129,184,192:3:4", "attn:250,256,130,193:2:4",
               "attn:184,184,184,184:16:4", "attn:1,2,3,8,9,15,16,17:2:4"]
+    # persistent tcgen05 attention (mode 5): single item, two tiles, ragged, more items than SMs (the pipelined phases)
+    cases += ["attn:64:1:5", "attn:128:1:5", "attn:184:2:5", "attn:7,64,65,128,129,184,192:3:5", "attn:1,2,3,8,9,15,16,17,33,100,150:2:5",
+              "attn:184,184,184,184:16:5", "attn:rand300:16:5", "attn:rand37:5:5", "attn:rand20:32:5", "attn:rand40:12:5"]
     return cases
 
 
@@ -157,7 +160,11 @@ def run_one(spec):
         M, N, K, epi, bn, simt = map(int, parts[1:7])
         return run_gemm_case(M, N, K, epi, bn, simt, parts[7] if len(parts) > 7 else "rand")
     if parts[0] == "attn":
-        return run_attn_case([int(x) for x in parts[1].split(",")], int(parts[2]), int(parts[3]) if len(parts) > 3 else 0)
+        if parts[1].startswith("rand"):  # randN: N ragged documents of 1..192 tokens
+            lens = np.random.default_rng(int(parts[1][4:])).integers(1, 193, size=int(parts[1][4:])).tolist()
+        else:
+            lens = [int(x) for x in parts[1].split(",")]
+        return run_attn_case(lens, int(parts[2]), int(parts[3]) if len(parts) > 3 else 0)
     raise ValueError(spec)
 
 
