@@ -175,6 +175,36 @@ def workload_config(world, sample_docs=None):
     }
 
 
+def text_api_docs_per_s(eng, cfg, n_queries):
+    """docs/s through `PointwiseLlmRanker.rerank_many` on TEXT: every query brings 100 documents the tokenizer has never seen
+    (128 words each, query 32 words => 185 tokens per prompt with the synthetic vocabulary), so the per-document token cache only
+    helps with the query and the template; tokenisation runs on worker threads ahead of the GPU."""
+    from b200rank.synthetic import synthetic_tokenizer
+    from llmrankers._backend import T5Backend
+    from llmrankers.pointwise import PointwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    rng = np.random.default_rng(SEED + 7)
+    ranker = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=32, backend=T5Backend(eng, synthetic_tokenizer(), cfg))
+
+    def requests(n):
+        for _ in range(n):
+            words = rng.integers(0, 2000, size=(HITS + 1, P_LEN))
+            query = " ".join(f"w{int(x)}" for x in words[HITS, :Q_LEN])
+            yield query, [SearchResult(docid=str(i), score=0.0, text=" ".join(f"w{int(x)}" for x in words[i])) for i in range(HITS)]
+
+    warm = list(requests(4))
+    timed = list(requests(n_queries))     # text generation is not the system under test: build the requests first
+    for _ in ranker.rerank_many(iter(warm)):
+        pass
+    t0 = time.perf_counter()
+    n_docs = 0
+    for out in ranker.rerank_many(iter(timed)):
+        n_docs += len(out)
+    dt = time.perf_counter() - t0
+    return {"value": n_docs / dt, "unit": "docs/s", "queries": n_queries, "ms_per_query": dt / n_queries * 1e3,
+            "tokenizer_threads": 4, "what": "strings -> prompt assembly + tokenisation (host threads) -> submit/wait pipeline -> sorted SearchResults"}
+
+
 def run_engine(args):
     rank, world, local = dist_env()
     import b200rank as br
@@ -282,6 +312,12 @@ def run_engine(args):
     h2d = n_tok * 4 + (HITS + 1) * 4 + HITS * 4 + 2 * 4  # packed ids + cu_seqlens + decoder ids + (yes,no) ids
     d2h = HITS * 3 * 4                                   # (yes, no) logits + P(yes) per document
 
+    # ---- informational: the same workload through the drop-in Python API with TEXT (llmrankers PointwiseLlmRanker.rerank_many):
+    # prompt assembly + tokenisation of 100 never-seen documents per query on the host, then the same submit/wait pipeline.
+    api_text = None
+    if rank == 0 and world == 1 and not args.no_text_api:
+        api_text = text_api_docs_per_s(eng, cfg, n_queries=min(args.steps, 30))
+
     # ---- roofline for the dominant kernel: per-launch CUDA events in a separate profiled pass
     roofline = None
     cpu_baseline = None
@@ -348,7 +384,7 @@ def run_engine(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "api_text": api_text,
             "weights_load_s": round(t_load, 2), "sample_scores": [float(x) for x in scores_dev[:4]],
         }
         print(json.dumps(line))
@@ -367,6 +403,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -50,7 +50,7 @@ typedef struct b200rank_config {
     int32_t rel_buckets;           /* relative_attention_num_buckets (32) */
     int32_t rel_max_distance;      /* relative_attention_max_distance (128) */
     float layer_norm_eps;          /* 1e-6 */
-    int32_t gated_gelu;            /* 1: feed_forward_proj == "gated-gelu" (all Flan-T5); 0 unsupported */
+    int32_t gated_gelu;            /* 1: feed_forward_proj "gated-gelu" (Flan-T5, T5 v1.1: wi_0, wi_1); 0: "relu" (T5 v1.0, monoT5/duoT5: wi) */
     int32_t scale_decoder_outputs; /* 1 iff tie_word_embeddings: hidden *= d_model^-0.5 before lm_head ($TF:1105-1108) */
     int32_t pad_id;                /* 0 */
     int32_t eos_id;                /* 1 */

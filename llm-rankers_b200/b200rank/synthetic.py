@@ -15,6 +15,7 @@ import numpy as np
 PROMPT_WORDS = ["Passage", "Query", "Does", "the", "passage", "answer", "query", "Answer", "Yes", "No", "or", "Please",
                 "write", "a", "question", "based", "on", "this", "Given", "which", "of", "following", "passages", "is",
                 "most", "relevant", "one", "to", "Output", "only", "label", "two", "more", "Relevant", "Document"]
+# NB: "Relevant:", "Document:", "Document0:", "Document1:" of the monoT5 / duoT5 prompts tokenise into these pieces + characters
 LABELS = [chr(ord("A") + i) for i in range(23)]  # setwise.py:22-23 CHARACTERS
 N_FILLER_WORDS = 2000
 
@@ -52,8 +53,10 @@ def synthetic_weights(cfg: Dict, seed: int, lm_head_std: float = 0.05) -> Dict[s
         return (rng.standard_normal(shape, dtype=np.float32) * np.float32(std)).astype(np.float32)
 
     w: Dict[str, np.ndarray] = {}
+    gated = cfg.get("feed_forward_proj", "gated-gelu") == "gated-gelu"
     w["shared.weight"] = n((V, d), 1.0)
-    w["lm_head.weight"] = n((V, d), lm_head_std)
+    if not cfg.get("tie_word_embeddings", False):   # tied (T5 v1.0): lm_head IS shared, logits scaled by d_model^-0.5
+        w["lm_head.weight"] = n((V, d), lm_head_std)
     for stack, L in (("encoder", cfg["num_layers"]), ("decoder", cfg["num_decoder_layers"])):
         w[f"{stack}.final_layer_norm.weight"] = 1.0 + n((d,), 0.1)
         w[f"{stack}.block.0.layer.0.SelfAttention.relative_attention_bias.weight"] = n((nb, H), 0.5)
@@ -66,8 +69,11 @@ def synthetic_weights(cfg: Dict, seed: int, lm_head_std: float = 0.05) -> Dict[s
                 w[f"{p}.{att}.v.weight"] = n((I, d), d ** -0.5)
                 w[f"{p}.{att}.o.weight"] = n((d, I), I ** -0.5)
             ff = "layer.2" if stack == "decoder" else "layer.1"
-            w[f"{p}.{ff}.DenseReluDense.wi_0.weight"] = n((F, d), d ** -0.5)
-            w[f"{p}.{ff}.DenseReluDense.wi_1.weight"] = n((F, d), d ** -0.5)
+            if gated:
+                w[f"{p}.{ff}.DenseReluDense.wi_0.weight"] = n((F, d), d ** -0.5)
+                w[f"{p}.{ff}.DenseReluDense.wi_1.weight"] = n((F, d), d ** -0.5)
+            else:
+                w[f"{p}.{ff}.DenseReluDense.wi.weight"] = n((F, d), (d / 2) ** -0.5)  # relu halves the variance
             w[f"{p}.{ff}.DenseReluDense.wo.weight"] = n((d, F), F ** -0.5)
             for j in range(3 if stack == "decoder" else 2):
                 w[f"{p}.layer.{j}.layer_norm.weight"] = 1.0 + n((d,), 0.1)
@@ -79,11 +85,14 @@ def model_cfg(name: str, vocab_size: int = 32128) -> Dict:
     from . import MODEL_SHAPES
     shapes = dict(MODEL_SHAPES)
     shapes["t5-tiny"] = dict(d_model=128, num_heads=2, d_ff=256, num_layers=2, num_decoder_layers=2)
+    shapes["t5v10-tiny"] = dict(d_model=128, num_heads=2, d_ff=256, num_layers=2, num_decoder_layers=2, v10=True)
     if name not in shapes:
         raise KeyError(f"unknown synthetic model {name}; known: {sorted(shapes)}")
     cfg = dict(shapes[name])
+    v10 = cfg.pop("v10", False)   # T5 v1.0 (monoT5 / duoT5 checkpoints): relu feed-forward, tied embeddings => scaled logits
     cfg.update(vocab_size=vocab_size, d_kv=64, rel_buckets=32, rel_max_distance=128, layer_norm_eps=1e-6,
-               scale_decoder_outputs=False, pad_id=0, eos_id=1)
+               scale_decoder_outputs=bool(v10), pad_id=0, eos_id=1)
+    cfg.update(feed_forward_proj="relu" if v10 else "gated-gelu", gated_gelu=not v10, tie_word_embeddings=bool(v10))
     return cfg
 
 

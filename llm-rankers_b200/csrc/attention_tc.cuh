@@ -257,7 +257,7 @@ struct AttnTc2Cfg {
 template <int NKB>
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
-                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items) {
+                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items, int spin) {
     using Cfg = AttnTc2Cfg<NKB>;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -309,6 +309,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     const int stride = gridDim.x;
+    auto wait = [&](uint64_t* bar, uint32_t parity) { if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); };
 
     if (warp_idx == 0) {
         if (lane == 0) {
@@ -320,13 +321,13 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 const int nitem = item + stride, ndoc = nitem < n_items ? nitem / H : 0;
                 const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];        // next item's extent: in flight during this one
                 const int nkb_used = (tok1 - tok0 + 63) >> 6;
-                if (k > 0) mbar_wait(qk_free, (k - 1) & 1);
+                if (k > 0) wait(qk_free, (k - 1) & 1);
                 mbar_arrive_expect_tx(bar_qk, 2 * nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b) {
                     tma_load_2d(sQ + b * 8192, &tmap_qkv, bar_qk, h * 64, tok0 + b * 64, kEvictFirst);
                     tma_load_2d(sK + b * 8192, &tmap_qkv, bar_qk, inner + h * 64, tok0 + b * 64, kEvictFirst);
                 }
-                if (k > 0) mbar_wait(v_free, (k - 1) & 1);
+                if (k > 0) wait(v_free, (k - 1) & 1);
                 mbar_arrive_expect_tx(bar_v, nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b)
                     tma_load_2d(sV + b * 8192, &tmap_qkv, bar_v, 2 * inner + h * 64, tok0 + b * 64, kEvictFirst);
@@ -349,14 +350,14 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 int nlen = 0;
                 if (have && nitem < n_items) { const int ndoc = nitem / H; nlen = cu[ndoc + 1] - cu[ndoc]; }
                 const int nt_cur = have ? (len + 127) >> 7 : 0, nkb_cur = (len + 63) >> 6;
-                if (have) { mbar_wait(bar_qk, k & 1); tc_fence_after(); }
+                if (have) { wait(bar_qk, k & 1); tc_fence_after(); }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     uint32_t& use = t == 0 ? use0 : use1;
                     if (t < nt_prev) {
-                        if (t == 0) mbar_wait(bar_v, (k - 1) & 1);
-                        mbar_wait(&bar_p[t], use & 1);
-                        if (use > 0) mbar_wait(&o_free[t], (use - 1) & 1);
+                        if (t == 0) wait(bar_v, (k - 1) & 1);
+                        wait(&bar_p[t], use & 1);
+                        if (use > 0) wait(&o_free[t], (use - 1) & 1);
                         tc_fence_after();
                         for (int kb = 0; kb < nkb_prev; ++kb) {
                             const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP + t * Cfg::kPBytes + kb * 16384));
@@ -401,6 +402,47 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
         int item = blockIdx.x;
         int doc = item < n_items ? item / H : 0;
         int tok0 = cu[doc], tok1 = cu[doc + 1];
+        // ---- deferred epilogue of the previous item on this tile slot: O_t / l -> bf16 -> global
+        bool pend = false, p_active = false;
+        float p_l = 0.f;
+        int p_tok0 = 0, p_len = 0, p_h = 0;
+        uint32_t p_par = 0;
+        auto epilogue = [&]() {
+            wait(&bar_o[t], p_par);
+            tc_fence_after();
+            if (p_active) {
+                uint32_t o0[32], o1[32];
+                tmem_ld32(taddr_o, o0);
+                tmem_ld32(taddr_o + 32, o1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_free[t]);
+                if (qi < p_len) {
+                    const float inv = 1.f / p_l;
+                    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p_tok0 + qi) * ldo + p_h * 64);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+                        v.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+                        v.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+                        v.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+                        dst[i] = v;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+                        v.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+                        v.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+                        v.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+                        dst[4 + i] = v;
+                    }
+                }
+            } else {
+                mbar_arrive(&o_free[t]);
+            }
+        };
         while (item < n_items) {
             const int h = item - doc * H;
             const int len = tok1 - tok0, my_tok0 = tok0;
@@ -421,7 +463,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 h_loaded = h;
             }
             const uint32_t sBrow = smem_u32(sB) + (255 - qi) * 4;   // [sBrow + 4 j] = log2(e) * bias(j - qi)
-            mbar_wait(&bar_s[t], use & 1);
+            wait(&bar_s[t], use & 1);
             tc_fence_after();
             float m = -INFINITY, l = 0.f;
             if (active) {
@@ -463,6 +505,11 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                     }
                 }
                 m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            }
+            // The previous item's epilogue runs HERE, between the passes: by now its MMA-2 has long retired (no wait on the
+            // tensor core), and passing bar_o also licenses pass 2 to overwrite the P_t tile that MMA-2 was reading.
+            if (pend) { epilogue(); pend = false; }
+            if (active) {
                 tmem_st_wait();
                 // ---- pass 2: p = 2^(v - m), row sum, bf16 P into the swizzled A-operand tile (zeros past the document)
                 float l4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -507,43 +554,10 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
             tc_fence_before();      // TMEM reads/writes of S_t are complete before MMA-1 of the next use overwrites it
             fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&bar_p[t]);
-            // ---- epilogue: O_t / l -> bf16 -> global
-            mbar_wait(&bar_o[t], use & 1);
-            tc_fence_after();
-            if (active) {
-                uint32_t o0[32], o1[32];
-                tmem_ld32(taddr_o, o0);
-                tmem_ld32(taddr_o + 32, o1);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&o_free[t]);
-                if (qi < len) {
-                    const float inv = 1.f / l;
-                    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(my_tok0 + qi) * ldo + h * 64);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
-                        v.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
-                        v.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
-                        v.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
-                        dst[i] = v;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
-                        v.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
-                        v.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
-                        v.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
-                        dst[4 + i] = v;
-                    }
-                }
-            } else {
-                mbar_arrive(&o_free[t]);
-            }
+            pend = true; p_active = active; p_l = l; p_tok0 = my_tok0; p_len = len; p_h = h; p_par = use & 1;
             ++use;
         }
+        if (pend) epilogue();
     }
     tc_fence_before();
     __syncthreads();

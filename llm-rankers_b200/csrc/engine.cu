@@ -207,6 +207,7 @@ struct b200rank_engine {
     b200rank_config cfg;
     int device = 0, num_sms = 0;
     int d = 0, inner = 0, H = 0, F = 0, V = 0, Le = 0, Ld = 0;
+    bool gated = true;  // feed_forward_proj: gated-gelu (wi_0, wi_1) vs relu (wi)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool debug_simt = false, debug_sync = false, direct_epi = false;
@@ -333,7 +334,8 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     if (M <= 0) return B200RANK_OK;
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
-    int bn = force_bn ? force_bn : pick_block_n(M, N, epi, e->num_sms);
+    const int relu = (epi == EPI_RELU_BF16);
+    int bn = force_bn ? force_bn : pick_block_n(M, N, relu ? EPI_BF16 : epi, e->num_sms);
     if (epi == EPI_RESID_NORM) bn = 256;
     char label[96];
     if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);  // cta group: pick_cta_group
@@ -346,6 +348,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
         gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi == EPI_RESID_NORM ? EPI_RESID_F32 : epi, 256, out, ldo);
         return post_launch(e, "gemm_simt_debug");
     }
+    if (relu) epi = EPI_BF16;
     const int cg = e->direct_epi ? 1 : pick_cta_group(M, N, bn, e->num_sms);
     const CUtensorMap *ta, *tb, *tout;
     RET_IF(engine_tmap(e, A, a_rows, a_cols > 0 ? a_cols : K, lda, kGemmBlockM, 0, &ta));
@@ -354,7 +357,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
-    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch};
+    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch, relu};
     const int sms = (e->gemm_sm_cap > 0 && bn == 256 && M > 1024) ? std::min(e->gemm_sm_cap, e->num_sms) : e->num_sms;
     RET_IF(launch_gemm_tc(e->stream, sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
@@ -481,14 +484,14 @@ static int create_impl(b200rank_engine* e) {
         LayerW& w = e->enc[l];
         reserve((void**)&w.ln1, d * 4); reserve((void**)&w.ln2, d * 4);
         reserve((void**)&w.wqkv, 3 * I * d * 2); reserve((void**)&w.wo, d * I * 2);
-        reserve((void**)&w.wi, 2 * F * d * 2); reserve((void**)&w.wff, d * F * 2);
+        reserve((void**)&w.wi, (e->gated ? 2 : 1) * F * d * 2); reserve((void**)&w.wff, d * F * 2);
     }
     for (int l = 0; l < e->Ld; ++l) {
         LayerW& w = e->dec[l];
         reserve((void**)&w.ln1, d * 4); reserve((void**)&w.ln_c, d * 4); reserve((void**)&w.ln2, d * 4);
         reserve((void**)&w.wqkv, 3 * I * d * 2); reserve((void**)&w.wo, d * I * 2);
         reserve((void**)&w.wq_c, I * d * 2); reserve((void**)&w.wo_c, d * I * 2); reserve((void**)&w.wov, d * d * 2); reserve((void**)&w.wkT, (size_t)e->H * d * 64 * 2);
-        reserve((void**)&w.wi, 2 * F * d * 2); reserve((void**)&w.wff, d * F * 2);
+        reserve((void**)&w.wi, (e->gated ? 2 : 1) * F * d * 2); reserve((void**)&w.wff, d * F * 2);
     }
     e->arena_bytes = off;
     CU_OK(cudaMalloc(reinterpret_cast<void**>(&e->arena), e->arena_bytes));
@@ -504,7 +507,10 @@ static int create_impl(b200rank_engine* e) {
     for (int l = 0; l < e->Le; ++l) {
         for (const char* m : {"q", "k", "v", "o"}) { snprintf(nm, sizeof nm, "encoder.block.%d.layer.0.SelfAttention.%s.weight", l, m); expect(e, nm); }
         snprintf(nm, sizeof nm, "encoder.block.%d.layer.0.layer_norm.weight", l); expect(e, nm);
-        for (const char* m : {"wi_0", "wi_1", "wo"}) { snprintf(nm, sizeof nm, "encoder.block.%d.layer.1.DenseReluDense.%s.weight", l, m); expect(e, nm); }
+        for (const char* m : {"wi_0", "wi_1", "wi", "wo"}) {
+            if ((m[2] == '_') != e->gated && m[1] == 'i') continue;  // gated: wi_0 + wi_1, T5 v1.0: wi
+            snprintf(nm, sizeof nm, "encoder.block.%d.layer.1.DenseReluDense.%s.weight", l, m); expect(e, nm);
+        }
         snprintf(nm, sizeof nm, "encoder.block.%d.layer.1.layer_norm.weight", l); expect(e, nm);
     }
     for (int l = 0; l < e->Ld; ++l) {
@@ -513,7 +519,10 @@ static int create_impl(b200rank_engine* e) {
             snprintf(nm, sizeof nm, "decoder.block.%d.layer.1.EncDecAttention.%s.weight", l, m); expect(e, nm);
         }
         for (int j = 0; j < 3; ++j) { snprintf(nm, sizeof nm, "decoder.block.%d.layer.%d.layer_norm.weight", l, j); expect(e, nm); }
-        for (const char* m : {"wi_0", "wi_1", "wo"}) { snprintf(nm, sizeof nm, "decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, m); expect(e, nm); }
+        for (const char* m : {"wi_0", "wi_1", "wi", "wo"}) {
+            if ((m[2] == '_') != e->gated && m[1] == 'i') continue;
+            snprintf(nm, sizeof nm, "decoder.block.%d.layer.2.DenseReluDense.%s.weight", l, m); expect(e, nm);
+        }
     }
 
     // ---- workspaces (row capacities rounded to the 128-row GEMM tile)
@@ -560,7 +569,6 @@ extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_
     if (!cfg || !out) return set_error(B200RANK_ERR_ARG, "null argument");
     *out = nullptr;
     if (cfg->d_kv != 64) return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (kernels are specialised for 64)", cfg->d_kv);
-    if (!cfg->gated_gelu) return set_error(B200RANK_ERR_ARG, "only gated-gelu feed-forward (Flan-T5) is supported");
     if (cfg->d_model % 64 || cfg->d_ff % 128 || cfg->d_model > 4096 || cfg->vocab_size % 8)
         return set_error(B200RANK_ERR_ARG, "unsupported dims d_model=%d d_ff=%d vocab=%d", cfg->d_model, cfg->d_ff, cfg->vocab_size);
     if (cfg->num_heads <= 0 || cfg->num_layers <= 0 || cfg->num_decoder_layers <= 0)
@@ -576,6 +584,7 @@ extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_
     e->device = device;
     e->d = cfg->d_model; e->H = cfg->num_heads; e->inner = cfg->num_heads * cfg->d_kv; e->F = cfg->d_ff; e->V = cfg->vocab_size;
     e->Le = cfg->num_layers; e->Ld = cfg->num_decoder_layers;
+    e->gated = cfg->gated_gelu != 0;
     int r = create_impl(e);
     if (r != B200RANK_OK) { std::string keep = g_last_error; b200rank_destroy(e); g_last_error = keep; return r; }
     *out = e;
@@ -740,12 +749,15 @@ extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, con
         } else if (rs.rfind("DenseReluDense.", 0) == 0 && sub == ff_sub) {
             std::string m = rs.substr(15);
             if (m == "wo.weight") { RET_IF(shape_check(hf_name, rows, cols, d, F)); r = put_bf16_rows(e, w.wff, F, data, dtype, rows, cols, ident); }
-            else if (m == "wi_0.weight" || m == "wi_1.weight") {
+            else if ((m == "wi_0.weight" || m == "wi_1.weight") && e->gated) {
                 RET_IF(shape_check(hf_name, rows, cols, F, d));
                 // tile interleave for the gated epilogue: N-tile nb of 256 accumulator columns =
                 // [wi_0 rows nb*128 .. +128 | wi_1 rows nb*128 .. +128]
                 const int64_t add = (m == "wi_1.weight") ? 128 : 0;
                 r = put_bf16_rows(e, w.wi, d, data, dtype, rows, cols, [add](int64_t f) { return (f / 128) * 256 + add + (f % 128); });
+            } else if (m == "wi.weight" && !e->gated) {
+                RET_IF(shape_check(hf_name, rows, cols, F, d));
+                r = put_bf16_rows(e, w.wi, d, data, dtype, rows, cols, ident);
             } else return set_error(B200RANK_ERR_ARG, "unknown feed-forward tensor %s", hf_name);
         } else {
             return set_error(B200RANK_ERR_ARG, "unknown tensor %s", hf_name);
@@ -824,9 +836,10 @@ static int attn_default_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* s = getenv("B200RANK_ATTN");
-        // default: mma.sync tiles. The round-1 tcgen05 kernel is correct but 1.7x slower at S=184 (one 168 KB CTA per SM, phases not
-        // pipelined across work items: profiles/r01_bench_n1_v5*.json); it is opt-in until it is made persistent.
-        mode = !s ? 1 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : 1))));
+        // default: the persistent tcgen05 kernel for documents of <= 192 tokens (launch_enc_attention falls back to the mma.sync tiles
+        // above that): 1.93 vs 2.32 ms per 100 documents at S=184, +3.7 % docs/s with two queries in flight
+        // (profiles/r01_bench_attn_ab.txt). The first, unpipelined tcgen05 kernel ("tc") was 1.7x slower than the tiles.
+        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : 1))));
     }
     return mode;
 }
@@ -863,9 +876,11 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         auto kern = enc_attention_tc2_kernel<3>;
         if (!attr5) { CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr5 = true; }
         const int n_items = nd * H;
+        static int spin = -1;
+        if (spin < 0) spin = getenv("B200RANK_ATTN_SPIN") ? atoi(getenv("B200RANK_ATTN_SPIN")) : 0;
         if (e) prof_begin(e, "enc_attention_tc2");
         CU_OK(launch_k(kern, dim3(std::min(n_items, device_sm_count())), dim3(kAttnTcThreads), AttnTc2Cfg<3>::smem_bytes(H), st, *tm, inner, d_cu, bias,
-                       out, ldo, H, n_items));
+                       out, ldo, H, n_items, spin));
         return e ? post_launch(e, "enc_attention_tc2") : B200RANK_OK;
     }
     if (mode == 3) {
@@ -909,6 +924,14 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
     return e ? post_launch(e, "enc_attention") : B200RANK_OK;
 }
 
+// First feed-forward GEMM: gated-gelu (T5 v1.1 / Flan-T5, modeling_t5.py:115-132: gelu_new(wi_0 h) * wi_1 h, tile-interleaved
+// weights, product in the epilogue) or plain relu (T5 v1.0 / monoT5, modeling_t5.py:88-103: relu(wi h)).
+static int ffn_in(b200rank_engine* e, const bf16* h, int h_rows, const bf16* wi, int M, bf16* g) {
+    const int d = e->d, F = e->F;
+    if (e->gated) return gemm(e, h, d, h_rows, wi, d, 2 * F, M, 2 * F, d, EPI_GATED_BF16, g, F);
+    return gemm(e, h, d, h_rows, wi, d, F, M, F, d, EPI_RELU_BF16, g, F);
+}
+
 // Encoder over the staged batch + stacked cross-attention K|V projection of its output.
 static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
     const int n = e->staged_tokens, nd = e->staged_docs;
@@ -921,7 +944,7 @@ static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
         RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu_cur, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0));
         RET_IF(gemm_resid_then_norm(e, e->ao, I, Tk, w.wo, I, d, n, I, e->x, w.ln2, e->h));
-        RET_IF(gemm(e, e->h, d, Tk, w.wi, d, 2 * F, n, 2 * F, d, EPI_GATED_BF16, e->g, F));
+        RET_IF(ffn_in(e, e->h, Tk, w.wi, n, e->g));
         const bool last = (l + 1 == e->Le);  // the final layer norm lands in the slot buffer the decoder reads
         RET_IF(gemm_resid_then_norm(e, e->g, F, Tk, w.wff, F, d, n, F, e->x, last ? e->enc_final_ln : e->enc[l + 1].ln1,
                                     last ? e->enc_out_cur : e->h));
@@ -984,7 +1007,7 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, nullptr, nullptr, /*n_per_batch=*/64, /*a_cols=*/HD));
             RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
             RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
-            RET_IF(gemm(e, e->hd, d, cap, w.wi, d, 2 * F, R, 2 * F, d, EPI_GATED_BF16, e->gd, F));
+            RET_IF(ffn_in(e, e->hd, cap, w.wi, R, e->gd));
             RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
             continue;
         }
@@ -1001,7 +1024,7 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         RET_IF(post_launch(e, "cross_attention"));
         RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
         RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
-        RET_IF(gemm(e, e->hd, d, cap, w.wi, d, 2 * F, R, 2 * F, d, EPI_GATED_BF16, e->gd, F));
+        RET_IF(ffn_in(e, e->hd, cap, w.wi, R, e->gd));
         RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
     }
     RET_IF(k_rmsnorm(e, e->xd, e->dec_final_ln, e->hd, R));
@@ -1510,7 +1533,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
         if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn / cg);
         if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
-        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f, 0};
+        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f, 0, 0};
         if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct, cg);
     }
     if (rc == B200RANK_OK) {

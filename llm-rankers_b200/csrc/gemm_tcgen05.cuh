@@ -24,6 +24,7 @@ enum EpiMode : int {
     EPI_F32 = 3,        // out_f32[m, n]             = acc
     EPI_RESID_NORM = 4, // EPI_RESID_F32 with N == row width, plus: every unit owns whole 128-row blocks (all N-tiles), and once a
                         // block's adds have landed it re-reads those rows from L2 and writes norm_out = bf16(T5LayerNorm(out))
+    EPI_RELU_BF16 = 5,  // host-side alias: launched as EPI_BF16 with GemmArgs::relu = 1 (out_bf16 = max(acc, 0))
 };
 
 struct GemmArgs {
@@ -37,6 +38,7 @@ struct GemmArgs {
     // Block-diagonal GEMM (n_per_batch > 0): column block b = n / n_per_batch of the output contracts A[:, b*K : (b+1)*K]
     // with W rows of that block, i.e. out[:, b-th block] = A_b . W_b^T for per-head weight slices (decoder T=1 fast path).
     int n_per_batch;
+    int relu;      // EPI_BF16 only: out = max(acc, 0) (T5 v1.0 DenseReluDense, modeling_t5.py:88-103)
 };
 
 constexpr int kGemmBlockM = 128;
@@ -258,6 +260,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tmem_ld32(taddr + c + 32, r1);
                         tmem_ld_wait();
                         if (c + 64 == BLOCK_N) { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
+                        if (args.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                r0[j] = __float_as_uint(fmaxf(__uint_as_float(r0[j]), 0.f));
+                                r1[j] = __float_as_uint(fmaxf(__uint_as_float(r1[j]), 0.f));
+                            }
+                        }
                         stage_open();
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -358,6 +367,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (row_ok) {
                         if constexpr (EPI == EPI_BF16) {
                             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<size_t>(row) * args.ldo;
+                            if (args.relu) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+                            }
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
                                 if (col0 + j < args.N) {

@@ -512,6 +512,7 @@ __global__ void gemm_simt_debug_kernel(const __nv_bfloat16* __restrict__ a, int 
     } else {
         const float acc = dot(c);
         if (epi == 0) reinterpret_cast<__nv_bfloat16*>(out)[static_cast<size_t>(m) * ldo + c] = __float2bfloat16(acc);
+        else if (epi == 5) reinterpret_cast<__nv_bfloat16*>(out)[static_cast<size_t>(m) * ldo + c] = __float2bfloat16(fmaxf(acc, 0.f));
         else if (epi == 1) reinterpret_cast<float*>(out)[static_cast<size_t>(m) * ldo + c] += acc;
         else reinterpret_cast<float*>(out)[static_cast<size_t>(m) * ldo + c] = acc;
     }

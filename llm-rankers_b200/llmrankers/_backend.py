@@ -168,11 +168,13 @@ def _cfg_from_hf(hf: Dict) -> Dict:
     if hf.get("model_type", "t5") != "t5":
         raise NotImplementedError(f"Model type {hf.get('model_type')} is not supported by the B200 engine (Flan-T5 only)")
     proj = hf.get("feed_forward_proj", "relu")
-    if proj != "gated-gelu":
-        raise NotImplementedError(f"feed_forward_proj={proj!r}: only gated-gelu (Flan-T5 / T5 v1.1) is implemented")
+    if proj not in ("gated-gelu", "relu"):
+        raise NotImplementedError(f"feed_forward_proj={proj!r}: gated-gelu (Flan-T5 / T5 v1.1) and relu (T5 v1.0: monoT5, duoT5) are implemented")
+    if hf["d_kv"] != 64:
+        raise NotImplementedError(f"d_kv={hf['d_kv']}: the attention kernels are specialised for 64 (the 3B T5 v1.0 checkpoints use 128)")
     return dict(vocab_size=hf["vocab_size"], d_model=hf["d_model"], d_kv=hf["d_kv"], num_heads=hf["num_heads"], d_ff=hf["d_ff"],
                 num_layers=hf["num_layers"], num_decoder_layers=hf.get("num_decoder_layers") or hf["num_layers"],
                 rel_buckets=hf.get("relative_attention_num_buckets", 32), rel_max_distance=hf.get("relative_attention_max_distance", 128),
-                layer_norm_eps=hf.get("layer_norm_epsilon", 1e-6), gated_gelu=True,
+                layer_norm_eps=hf.get("layer_norm_epsilon", 1e-6), gated_gelu=proj == "gated-gelu",
                 scale_decoder_outputs=bool(hf.get("tie_word_embeddings", True)), pad_id=hf.get("pad_token_id", 0),
                 eos_id=hf.get("eos_token_id", 1))

@@ -117,9 +117,31 @@ class PairwiseLlmRanker(LlmRanker):
         return self.tokenizer.convert_tokens_to_string(self.tokenizer.tokenize(text)[:length])
 
 
+DUOT5_PROMPT = 'Query: {query} Document0: {doc1} Document1: {doc2} Relevant:'
+
+
 class DuoT5LlmRanker(PairwiseLlmRanker):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("duoT5 (T5 v1.0 relu feed-forward) is not implemented by the B200 engine yet (SURVEY.md §8f)")
+    """pairwise.py:296-352 — duoT5 (T5 v1.0: relu feed-forward, tied embeddings). compare() scores both presentation orders
+    in one batch of two, P(true) = softmax(logits[:, 0, [6136, 1176]])[:, 1], and returns P(order 1) > P(order 2);
+    rerank() supports heapsort only, like the reference."""
+
+    def compare(self, query: str, docs: List[str]) -> bool:
+        self.total_compare += 1
+        self.prompt = DUOT5_PROMPT
+        inputs = [self.prompt.format(query=query, doc1=docs[0], doc2=docs[1]),
+                  self.prompt.format(query=query, doc1=docs[1], doc2=docs[0])]
+        rows = self.tokenizer(inputs, truncation=True)["input_ids"]   # padding=True happens in pad_rows
+        self.total_prompt_tokens += 2 * max(len(r) for r in rows)
+        _, probs = self.backend.score_yes_no(rows, 1176, 6136)
+        return bool(probs[0] > probs[1])
+
+    def _first_wins(self, query: str, a, b) -> bool:
+        return self.compare(query, [a.text, b.text])
+
+    def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
+        if self.method != "heapsort":
+            raise NotImplementedError(f'Method {self.method} is not implemented.')
+        return super().rerank(query, ranking)
 
 
 class OpenAiPairwiseLlmRanker(PairwiseLlmRanker):

@@ -8,7 +8,11 @@ device passes itself; per-document results do not depend on batch composition) a
 """
 from typing import List, Optional
 
+import os
+from collections import deque
+
 from ._backend import T5Backend
+from ._prompts import PromptAssembler
 from .rankers import LlmRanker, SearchResult
 
 YES_NO_PROMPT = "Passage: {text}\nQuery: {query}\nDoes the passage answer the query? Answer 'Yes' or 'No'"
@@ -29,6 +33,17 @@ class PointwiseLlmRanker(LlmRanker):
         self.total_compare = 0
         self.total_completion_tokens = 0
         self.total_prompt_tokens = 0
+        self._assemblers = {}
+
+    def _rows(self, template: str, fields: List[dict]) -> List[List[int]]:
+        """Token-id rows of `template.format(**f)` for every f — what `Text2TextGenerationDataset` (pairwise.py:17-26) produces,
+        through token-level assembly + a per-document token cache (_prompts.py; B200RANK_PROMPT_ASSEMBLY=0 tokenises whole strings)."""
+        if os.environ.get("B200RANK_PROMPT_ASSEMBLY", "1") == "0":
+            return self.backend.tokenize_prompts([template.format(**f) for f in fields])
+        a = self._assemblers.get(template)
+        if a is None:
+            a = self._assemblers[template] = PromptAssembler(self.tokenizer, template)
+        return a.rows(fields)
 
     def _count_batches(self, rows: List[List[int]], dec_len: int) -> None:
         """Counters exactly as the reference accumulates them per DataLoader batch (pointwise.py:64-70, 106-115):
@@ -44,7 +59,7 @@ class PointwiseLlmRanker(LlmRanker):
         self.total_completion_tokens = 0
         self.total_prompt_tokens = 0
         if self.method == "qlm":
-            rows = self.backend.tokenize_prompts([QLM_PROMPT.format(text=doc.text) for doc in ranking])
+            rows = self._rows(QLM_PROMPT, [dict(text=doc.text) for doc in ranking])
             labels = self.tokenizer.encode(f"<pad> {query}", add_special_tokens=False)  # pointwise.py:58-60
             self._count_batches(rows, len(labels))
             scores = self.backend.score_qlm(rows, labels) if rows else []
@@ -53,7 +68,7 @@ class PointwiseLlmRanker(LlmRanker):
         elif self.method == "yes_no":
             yes_id = self.tokenizer.encode("Yes", add_special_tokens=False)[0]
             no_id = self.tokenizer.encode("No", add_special_tokens=False)[0]
-            rows = self.backend.tokenize_prompts([YES_NO_PROMPT.format(text=doc.text, query=query) for doc in ranking])
+            rows = self._rows(YES_NO_PROMPT, [dict(text=doc.text, query=query) for doc in ranking])
             self._count_batches(rows, 1)
             if rows:
                 _, scores = self.backend.score_yes_no(rows, yes_id, no_id)
@@ -62,18 +77,19 @@ class PointwiseLlmRanker(LlmRanker):
         # any other method: like the reference, nothing is scored and the input order is sorted by its existing scores
         return sorted(ranking, key=lambda x: x.score, reverse=True)
 
-    def rerank_many(self, requests):
-        """Extension (not in the reference): rerank an iterable of (query, ranking) pairs with two queries in flight on the GPU
-        — query i+1 is tokenised, copied and its encoder pass started while query i's decoder pass finishes. Yields the same
-        list `rerank(query, ranking)` would return for each pair, in order; counters hold the totals of the last query.
+    def rerank_many(self, requests, tokenizer_threads: int = 4, lookahead: int = 8):
+        """Extension (not in the reference): rerank an iterable of (query, ranking) pairs as a pipeline. Upcoming queries are
+        tokenised on `tokenizer_threads` worker threads (the Rust tokenizer releases the GIL), up to `lookahead` queries ahead, and
+        two queries are in flight on the GPU — query i+1's encoder pass runs while query i's decoder pass finishes. Yields the
+        same list `rerank(query, ranking)` would return for each pair, in order; counters hold the totals of the last query.
         Only the yes_no method is pipelined (the headline path); other methods fall back to rerank()."""
         if self.method != "yes_no":
             for query, ranking in requests:
                 yield self.rerank(query, ranking)
             return
+        from concurrent.futures import ThreadPoolExecutor
         yes_id = self.tokenizer.encode("Yes", add_special_tokens=False)[0]
         no_id = self.tokenizer.encode("No", add_special_tokens=False)[0]
-        pending = None  # (ticket, ranking, rows)
 
         def finish(item):
             ticket, ranking, rows = item
@@ -87,22 +103,53 @@ class PointwiseLlmRanker(LlmRanker):
                     doc.score = float(s)
             return sorted(ranking, key=lambda x: x.score, reverse=True)
 
-        for query, ranking in requests:
-            rows = self.backend.tokenize_prompts([YES_NO_PROMPT.format(text=doc.text, query=query) for doc in ranking])
-            ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
+        def tokenise(query, ranking):
+            return self._rows(YES_NO_PROMPT, [dict(text=doc.text, query=query) for doc in ranking])
+
+        it = iter(requests)
+        window = deque()   # (ranking, future of rows), in request order
+        pending = None     # (ticket, ranking, rows) of the query whose decoder pass is still running
+        with ThreadPoolExecutor(max(1, tokenizer_threads)) as pool:
+            def refill():
+                while len(window) < max(1, lookahead):
+                    try:
+                        query, ranking = next(it)
+                    except StopIteration:
+                        return
+                    window.append((ranking, pool.submit(tokenise, query, ranking)))
+            refill()
+            while window:
+                ranking, fut = window.popleft()
+                rows = fut.result()
+                refill()
+                ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
+                if pending is not None:
+                    yield finish(pending)
+                pending = (ticket, ranking, rows)
             if pending is not None:
                 yield finish(pending)
-            pending = (ticket, ranking, rows)
-        if pending is not None:
-            yield finish(pending)
 
     def truncate(self, text, length):
         return self.tokenizer.convert_tokens_to_string(self.tokenizer.tokenize(text)[:length])
 
 
+MONOT5_PROMPT = "Query: {query} Document: {document} Relevant:"
+MONOT5_FALSE_ID, MONOT5_TRUE_ID = 6136, 1176  # "the indexes of the tokens false and true in T5" (pointwise.py:176)
+
+
 class MonoT5LlmRanker(PointwiseLlmRanker):
-    """pointwise.py:136-186 — monoT5 checkpoints are T5 v1.0 (ungated ReLU feed-forward, tied embeddings); the engine
-    implements the gated-GELU Flan-T5 family only, so construction fails loudly at weight load."""
+    """pointwise.py:136-186 — monoT5 checkpoints are T5 v1.0 (relu feed-forward, tied embeddings => logits scaled by
+    d_model^-0.5); the score is softmax(logits[:, 0, [false, true]])[:, 1], i.e. the yes_no entry point of the engine with
+    (yes, no) = (true, false). Counters as the reference: one compare per batch, B x longest row + B decoder tokens."""
 
     def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
-        raise NotImplementedError("MonoT5 (T5 v1.0 relu feed-forward) is not implemented by the B200 engine yet")
+        self.total_compare = 0
+        self.total_completion_tokens = 0
+        self.total_prompt_tokens = 0
+        rows = self._rows(MONOT5_PROMPT, [dict(query=query, document=doc.text) for doc in ranking])
+        self._count_batches(rows, 1)
+        if rows:
+            _, scores = self.backend.score_yes_no(rows, MONOT5_TRUE_ID, MONOT5_FALSE_ID)
+            for doc, s in zip(ranking, scores):
+                doc.score = float(s)
+        return sorted(ranking, key=lambda x: x.score, reverse=True)

@@ -113,7 +113,7 @@ class T5Oracle:
         self.w = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
         if self.bf16:
             for k in list(self.w):
-                if k.endswith((".q.weight", ".k.weight", ".v.weight", ".o.weight", ".wi_0.weight", ".wi_1.weight", ".wo.weight")) or k == "lm_head.weight":
+                if k.endswith((".q.weight", ".k.weight", ".v.weight", ".o.weight", ".wi_0.weight", ".wi_1.weight", ".wi.weight", ".wo.weight")) or k == "lm_head.weight":
                     self.w[k] = round_bf16(self.w[k])
         if "lm_head.weight" not in self.w:
             self.w["lm_head.weight"] = round_bf16(self.w["shared.weight"]) if self.bf16 else self.w["shared.weight"]
@@ -144,8 +144,11 @@ class T5Oracle:
         o = self._r((p @ v).transpose(0, 2, 1, 3).reshape(B, Tq, H * dk))
         return o @ self.w[prefix + ".o.weight"].T
 
-    # $TF:115-132 T5DenseGatedActDense
+    # $TF:115-132 T5DenseGatedActDense (T5 v1.1 / Flan-T5: feed_forward_proj "gated-gelu");
+    # $TF:88-103 T5DenseActDense (T5 v1.0 / monoT5 / duoT5: feed_forward_proj "relu": wo(relu(wi x)))
     def _ff(self, prefix: str, x: np.ndarray) -> np.ndarray:
+        if prefix + ".wi.weight" in self.w:
+            return self._r(np.maximum(x @ self.w[prefix + ".wi.weight"].T, 0.0)) @ self.w[prefix + ".wo.weight"].T
         g = gelu_new(x @ self.w[prefix + ".wi_0.weight"].T)
         l = x @ self.w[prefix + ".wi_1.weight"].T
         return self._r(g * l) @ self.w[prefix + ".wo.weight"].T

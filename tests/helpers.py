@@ -23,6 +23,33 @@ def golden_npz(name):
     return _cache[name]
 
 
+def golden_v10_meta():
+    """Fixtures of tests/golden/make_golden_v10.py: the reference's MonoT5LlmRanker / DuoT5LlmRanker on T5 v1.0 models."""
+    if "meta_v10" not in _cache:
+        with open(os.path.join(GOLDEN, "golden_v10_meta.json")) as f:
+            _cache["meta_v10"] = json.load(f)
+    return _cache["meta_v10"]
+
+
+def v10_model_and_weights(which):
+    """which in {'tiny', 'small'}: (cfg, weights) of the T5 v1.0 (relu, tied embeddings) golden models."""
+    from b200rank.synthetic import model_cfg, synthetic_weights
+    key = ("v10", which)
+    if key not in _cache:
+        m = golden_v10_meta()[which]
+        cfg = model_cfg(m["model"], m["vocab_size"])
+        _cache[key] = (cfg, synthetic_weights(cfg, m["seed"]))
+    return _cache[key]
+
+
+def v10_oracle_for(which):
+    from oracle.t5_oracle import T5Oracle
+    key = ("v10_oracle", which)
+    if key not in _cache:
+        _cache[key] = T5Oracle(*v10_model_and_weights(which))
+    return _cache[key]
+
+
 def model_and_weights(which, label_favouring=False):
     """Rebuild the (cfg, weights) a golden case was generated with: which in {'tiny', 'small'}."""
     from b200rank.synthetic import model_cfg, synthetic_weights

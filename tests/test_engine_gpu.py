@@ -103,6 +103,25 @@ def test_enc_attention_vs_numpy():
     assert np.abs(out - ref).max() <= 0.03 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("mode,H,n_docs", [(5, 16, 300), (5, 32, 20), (5, 3, 7), (1, 3, 7), (4, 3, 7), (3, 3, 7)])
+def test_enc_attention_kernels_vs_numpy(mode, H, n_docs):
+    """Every encoder-attention kernel against numpy on ragged documents of <= 192 tokens; mode 5 (persistent tcgen05, the default)
+    with more (document, head) items than SMs, and with more heads than bias windows fit in shared memory (H = 32)."""
+    import b200rank as br
+    from gpu_diag import attention_reference
+    rng = np.random.default_rng(100 * mode + H)
+    lens = rng.integers(1, 193, size=n_docs).tolist()
+    lens[:4] = [192, 1, 128, 129][: min(4, n_docs)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    qkv = rng.standard_normal((int(cu[-1]), 3 * H * 64)).astype(np.float32)
+    qkv[:, : H * 64] *= 0.35
+    bias = rng.standard_normal((H, br.ATTN_BIAS_LEN)).astype(np.float32)
+    out = br.test_enc_attention(qkv, cu, H, bias, mode=mode)
+    ref = attention_reference(qkv, cu, H, bias)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() <= 0.03 * np.abs(ref).max()
+
+
 def test_rel_bucket_matches_hf():
     import b200rank as br
     g = golden_npz("buckets.npz")
@@ -231,6 +250,83 @@ def test_pairwise_ranker_on_gpu(case):
            (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
 
 
+# ---------------------------------------------------------------------------------------- T5 v1.0: monoT5 / duoT5
+def v10_engine(which):
+    import b200rank as br
+    from helpers import v10_model_and_weights
+    key = ("v10", which)
+    if key not in _engines:
+        cfg, w = v10_model_and_weights(which)
+        c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                           vocab_size=cfg["vocab_size"], gated_gelu=False, scale_decoder_outputs=True, max_tokens=8192, max_docs=256)
+        e = br.Engine(c, 0)
+        e.load_state_dict(w.items())   # no lm_head.weight in a tied checkpoint: falls back to shared.weight
+        _engines[key] = e
+    return _engines[key]
+
+
+def v10_backend(which):
+    from b200rank.synthetic import synthetic_tokenizer
+    from helpers import v10_model_and_weights
+    from llmrankers._backend import T5Backend
+    key = ("v10_backend", which)
+    if key not in _engines:
+        _engines[key] = T5Backend(v10_engine(which), synthetic_tokenizer(), v10_model_and_weights(which)[0])
+    return _engines[key]
+
+
+@pytest.mark.parametrize("which,case", [("tiny", "mono"), ("small", "small_mono")])
+def test_monot5_vs_golden(which, case):
+    """relu feed-forward + tied, d_model^-0.5-scaled lm_head through the C-ABI against the reference's MonoT5LlmRanker run."""
+    from helpers import golden_v10_meta
+    from llmrankers.pointwise import MonoT5LlmRanker
+    meta = golden_v10_meta()
+    m, c = meta[which], meta["cases"][case]
+    e = v10_engine(which)
+    got, gold = [], []
+    for call in calls(golden_npz("golden_v10.npz"), case):
+        ids, lengths = rows_from_padded(call["input_ids"], call["attention_mask"])
+        lg, _ = e.score_yes_no(ids, lengths, meta["true_id"], meta["false_id"])
+        g = call["logits"][:, 0, :]
+        gold.append(g[:, [meta["true_id"], meta["false_id"]]] if g.shape[-1] > 2 else g[:, [1, 0]])
+        got.append(lg)
+    assert_close_logits(f"v10/{case}", np.concatenate(got), np.concatenate(gold))
+    r = MonoT5LlmRanker(None, None, "cuda", batch_size=4, backend=v10_backend(which))
+    out = r.rerank(m["query"], _docs(m["docs"]))
+    ids = [d["docid"] for d in m["docs"]]
+    sc = {d.docid: d.score for d in out}
+    assert np.abs(np.asarray([sc[i] for i in ids]) - np.asarray([c["scores"][i] for i in ids])).max() < 0.02
+    assert_same_order_within_tol(f"v10/{case}", ids, [sc[i] for i in ids], [c["scores"][i] for i in ids], tol=0.02)
+    assert (r.total_compare, r.total_prompt_tokens, r.total_completion_tokens) == \
+           (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+def test_duot5_vs_golden():
+    from helpers import golden_v10_meta
+    from llmrankers.pairwise import DuoT5LlmRanker
+    meta = golden_v10_meta()
+    m, c = meta["tiny"], meta["cases"]["duo_heap"]
+    e = v10_engine("tiny")
+    worst_gap = 1.0
+    for call, v in zip(calls(golden_npz("golden_v10.npz"), "duo_heap"), c["verdicts"]):
+        ids, lengths = rows_from_padded(call["input_ids"], call["attention_mask"])
+        _, p = e.score_yes_no(ids, lengths, meta["true_id"], meta["false_id"])
+        assert np.abs(p - np.asarray(v["p"])).max() < 0.01
+        gap = abs(v["p"][0] - v["p"][1])
+        worst_gap = min(worst_gap, gap)
+        if gap > 0.02:   # the verdict is well defined at the engine's tolerance
+            assert bool(p[0] > p[1]) == v["first_wins"]
+    r = DuoT5LlmRanker(None, None, "cuda", method="heapsort", k=c["k"], backend=v10_backend("tiny"))
+    out = r.rerank(m["query"], _docs(m["docs"][:7]))
+    record("v10/duo_heap", same_order=[d.docid for d in out] == c["order"], compares=r.total_compare, ref_compares=c["total_compare"],
+           smallest_reference_gap=worst_gap)
+    assert sorted(d.docid for d in out) == sorted(c["order"]) and [d.score for d in out] == c["scores"]
+    if [d.docid for d in out] != c["order"]:   # a near-tie compare (gap below bf16 tolerance) flipped: the path may legitimately differ
+        assert worst_gap <= 0.02
+    else:
+        assert (r.total_compare, r.total_prompt_tokens) == (c["total_compare"], c["total_prompt_tokens"])
+
+
 def test_synthetic_model_loads_through_the_public_constructor():
     from llmrankers.pointwise import PointwiseLlmRanker
     from llmrankers.rankers import SearchResult
@@ -300,7 +396,8 @@ def test_greedy_vs_golden(case):
 def test_kernel_variants_agree(tmp_path):
     """The optional kernel variants are re-schedulings of the same arithmetic: CTA-pair (cta_group::2) vs single-CTA GEMM
     tiles, fused residual+RMSNorm epilogue vs separate kernel, TMA-store vs direct-store epilogue must agree BIT-EXACTLY;
-    tcgen05 vs mma.sync attention (different softmax blocking) must agree to bf16 noise."""
+    the attention kernels (persistent tcgen05 = default, mma.sync tiles, mma.sync registers, first tcgen05 version: different
+    softmax blocking) must agree to bf16 noise."""
     import subprocess
     import sys
     runner = os.path.join(ROOT, "tests", "gpu_variant_runner.py")
@@ -322,7 +419,7 @@ def test_kernel_variants_agree(tmp_path):
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
     # different arithmetic (re-blocked softmax / re-associated products): agreement to bf16 noise
-    for name, env in [("attn_tc", {"B200RANK_ATTN": "tc"}), ("attn_regs", {"B200RANK_ATTN": "regs"}),
+    for name, env in [("attn_tiled", {"B200RANK_ATTN": "tiled"}), ("attn_tc", {"B200RANK_ATTN": "tc"}), ("attn_regs", {"B200RANK_ATTN": "regs"}),
                       ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))

@@ -53,6 +53,41 @@ def test_pointwise_matches_reference(which, method, case):
     check_counters(r, c)
 
 
+def v10_backend(which="tiny"):
+    from helpers import v10_model_and_weights, v10_oracle_for
+    return OracleBackend(v10_oracle_for(which), tokenizer(), v10_model_and_weights(which)[0])
+
+
+@pytest.mark.parametrize("which,case", [("tiny", "mono"), ("small", "small_mono")])
+def test_monot5_matches_reference(which, case):
+    """MonoT5LlmRanker.rerank (pointwise.py:136-186) on a T5 v1.0 model: order, scores, counters."""
+    from helpers import golden_v10_meta
+    from llmrankers.pointwise import MonoT5LlmRanker
+    meta = golden_v10_meta()
+    m, c = meta[which], meta["cases"][case]
+    r = MonoT5LlmRanker(None, None, "cuda", batch_size=4, backend=v10_backend(which))
+    out = r.rerank(m["query"], docs_from(m["docs"]))
+    assert [d.docid for d in out] == c["order"]
+    for d in out:
+        assert d.score == pytest.approx(c["scores"][d.docid], abs=1e-5) and d.text is not None
+    check_counters(r, c)
+
+
+def test_duot5_matches_reference():
+    """DuoT5LlmRanker.rerank heapsort (pairwise.py:296-352): compare sequence, order, scores, counters."""
+    from helpers import golden_v10_meta
+    from llmrankers.pairwise import DuoT5LlmRanker
+    meta = golden_v10_meta()
+    m, c = meta["tiny"], meta["cases"]["duo_heap"]
+    r = DuoT5LlmRanker(None, None, "cuda", method="heapsort", k=c["k"], backend=v10_backend("tiny"))
+    out = r.rerank(m["query"], docs_from(m["docs"][:7]))
+    assert [d.docid for d in out] == c["order"] and [d.score for d in out] == c["scores"]
+    assert all(d.text is None for d in out)
+    check_counters(r, c)
+    with pytest.raises(NotImplementedError):
+        DuoT5LlmRanker(None, None, "cuda", method="allpair", backend=v10_backend("tiny")).rerank(m["query"], docs_from(m["docs"][:3]))
+
+
 @pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik", "setwise_bubble_lik", "setwise_bubble_gen"])
 def test_setwise_matches_reference(case, capsys):
     from llmrankers.setwise import SetwiseLlmRanker
@@ -108,11 +143,78 @@ def test_rerank_many_equals_rerank():
     assert r.total_compare == 3  # counters describe the last query (10 docs, batch_size 4)
 
 
+# ------------------------------------------------------------------------------------------- token-level prompt assembly (§8f-1)
+def test_prompt_assembler_equals_whole_string_tokenisation():
+    from llmrankers._prompts import PromptAssembler
+    from llmrankers.pairwise import PAIRWISE_PROMPT
+    from llmrankers.pointwise import MONOT5_PROMPT, QLM_PROMPT, YES_NO_PROMPT
+    tok = tokenizer()
+    rng = np.random.default_rng(3)
+    texts = [" ".join(f"w{int(x)}" for x in rng.integers(0, 2000, int(rng.integers(1, 40)))) for _ in range(30)]
+    texts += ["", " ", "  leading and trailing  ", "new\nline\tand tab", "Punct, here! (yes?) 'q' \"dq\"", "w1  w2   w3", "unknown-\u00e9\u4e2d words"]
+    query = "w5  w6 Query: Passage"
+    for template, fields in ((YES_NO_PROMPT, [dict(text=t, query=query) for t in texts]), (QLM_PROMPT, [dict(text=t) for t in texts]),
+                             (MONOT5_PROMPT, [dict(query=query, document=t) for t in texts])):
+        a = PromptAssembler(tok, template, verify=0)   # verify=0: no safety net, the assembly itself must be right
+        assert a.eligible
+        want = tok([template.format(**f) for f in fields])["input_ids"]
+        assert a.rows(fields) == want
+        assert a.rows(fields) == want and a.hits > 0          # second time from the cache
+    # fields glued to punctuation (quoted passages of the pairwise / setwise prompts) are not eligible: whole-string path
+    a = PromptAssembler(tok, PAIRWISE_PROMPT)
+    assert not a.eligible
+    f = [dict(query=query, doc1=texts[0], doc2=texts[1])]
+    assert a.rows(f) == tok([PAIRWISE_PROMPT.format(**f[0])])["input_ids"]
+    assert PromptAssembler(tok, YES_NO_PROMPT).rows([]) == []
+
+
+def test_prompt_assembler_falls_back_when_the_tokenizer_is_not_word_local():
+    """A tokenizer whose segmentation depends on the neighbouring word breaks the assembly argument: the built-in check must
+    notice on the first prompts and switch to whole-string tokenisation for good."""
+    from llmrankers._prompts import PromptAssembler
+
+    class Contextual:
+        eos_token_id = 1
+        is_fast = False
+
+        def _ids(self, text, specials):
+            words = text.split()
+            ids = [10 + (len(w) + (len(words[i - 1]) if i else 0)) % 50 for i, w in enumerate(words)]   # depends on the previous word
+            return ids + ([1] if specials else [])
+
+        def encode(self, text, add_special_tokens=True):
+            return self._ids(text, add_special_tokens)
+
+        def __call__(self, texts, add_special_tokens=True):
+            return {"input_ids": [self._ids(t, add_special_tokens) for t in texts]}
+
+    tok = Contextual()
+    a = PromptAssembler(tok, "Passage: {text}\nQuery: {query}", verify=4)
+    fields = [dict(text=f"abc de{'f' * i}", query="gh ijk") for i in range(6)]
+    want = tok(["Passage: {text}\nQuery: {query}".format(**f) for f in fields])["input_ids"]
+    assert a.rows(fields) == want and not a.eligible
+    assert a.rows(fields) == want
+
+
+def test_prompt_assembler_is_thread_safe():
+    from concurrent.futures import ThreadPoolExecutor
+    from llmrankers._prompts import PromptAssembler
+    from llmrankers.pointwise import YES_NO_PROMPT
+    tok = tokenizer()
+    a = PromptAssembler(tok, YES_NO_PROMPT, cache_size=64)   # small cache: evictions race with lookups
+    rng = np.random.default_rng(4)
+    texts = [" ".join(f"w{int(x)}" for x in rng.integers(0, 2000, 20)) for _ in range(200)]
+    jobs = [[dict(text=texts[int(i)], query=f"w{q}") for i in rng.integers(0, 200, 40)] for q in range(16)]
+    want = [tok([YES_NO_PROMPT.format(**f) for f in job])["input_ids"] for job in jobs]
+    with ThreadPoolExecutor(8) as pool:
+        got = list(pool.map(a.rows, jobs))
+    assert got == want
+
+
 def test_unsupported_variants_fail_loudly():
     from llmrankers.listwise import ListwiseLlmRanker
-    from llmrankers.pairwise import DuoT5LlmRanker
     from llmrankers.setwise import OpenAiSetwiseLlmRanker, SetwiseLlmRanker
-    for cls in (ListwiseLlmRanker, DuoT5LlmRanker, OpenAiSetwiseLlmRanker):
+    for cls in (ListwiseLlmRanker, OpenAiSetwiseLlmRanker):
         with pytest.raises(NotImplementedError):
             cls("x", "y")
     r = SetwiseLlmRanker(None, None, "cuda", method="quicksort", backend=backend())

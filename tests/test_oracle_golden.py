@@ -100,3 +100,46 @@ def test_generation_ids(case, lab):
             assert np.all((new[:, :steps] == 1).any(axis=1))  # all rows hit eos, so HF stopped
         n += 1
     assert n == golden_meta()["cases"][case]["n_calls"]
+
+
+# ---------------------------------------------------------------- T5 v1.0 (monoT5 / duoT5): relu feed-forward, tied + scaled lm_head
+def test_v10_synthetic_model_is_relu_and_tied():
+    from helpers import v10_model_and_weights
+    cfg, w = v10_model_and_weights("tiny")
+    assert cfg["scale_decoder_outputs"] and not cfg["gated_gelu"] and "lm_head.weight" not in w
+    assert "encoder.block.0.layer.1.DenseReluDense.wi.weight" in w and "encoder.block.0.layer.1.DenseReluDense.wi_0.weight" not in w
+
+
+@pytest.mark.parametrize("which,case", [("tiny", "mono"), ("small", "small_mono")])
+def test_monot5_logits_scores_order(which, case):
+    from helpers import golden_v10_meta, v10_oracle_for
+    meta = golden_v10_meta()
+    m, c = meta[which], meta["cases"][case]
+    f_id, t_id = meta["false_id"], meta["true_id"]
+    orc = v10_oracle_for(which)
+    docs = [d["docid"] for d in m["docs"]]
+    scores = []
+    for call in calls(golden_npz("golden_v10.npz"), case):
+        lg, sc = orc.score_yes_no(call["input_ids"], call["attention_mask"], t_id, f_id)   # (yes, no) = (true, false)
+        gold = call["logits"][:, 0, :]
+        gold2 = gold[:, [t_id, f_id]] if gold.shape[-1] > 2 else gold[:, [1, 0]]            # stored columns are [false, true]
+        np.testing.assert_allclose(lg, gold2, atol=ATOL, rtol=1e-4)
+        if gold.shape[-1] > 2:   # tiny: the whole scaled-tied-lm_head logits row
+            full = orc.logits(call["input_ids"], call["attention_mask"], call["decoder_input_ids"])
+            np.testing.assert_allclose(full, call["logits"], atol=ATOL, rtol=1e-4)
+        scores.extend(sc.tolist())
+    np.testing.assert_allclose(scores, [c["scores"][d] for d in docs], atol=1e-5)
+    assert [d for d, _ in sorted(zip(docs, scores), key=lambda t: t[1], reverse=True)] == c["order"]
+
+
+def test_duot5_compare_probabilities():
+    from helpers import golden_v10_meta, v10_oracle_for
+    meta = golden_v10_meta()
+    c = meta["cases"]["duo_heap"]
+    orc = v10_oracle_for("tiny")
+    got = []
+    for call, v in zip(calls(golden_npz("golden_v10.npz"), "duo_heap"), c["verdicts"]):
+        _, p = orc.score_yes_no(call["input_ids"], call["attention_mask"], meta["true_id"], meta["false_id"])
+        np.testing.assert_allclose(p, v["p"], atol=1e-5)
+        got.append(bool(p[0] > p[1]))
+    assert got == [v["first_wins"] for v in c["verdicts"]]
