@@ -110,6 +110,16 @@ def load_peaks():
     return FALLBACK_PEAK_TFLOPS, "fallback (B200_PROFILING.md sustained figure; MEASURED_PEAKS.json absent)"
 
 
+def load_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if d.get("hbm_gbs"):
+            return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (device copy, read+write bytes)"
+    return 6500.0, "fallback (B200_PROFILING.md copy bandwidth; MEASURED_PEAKS.json absent)"
+
+
 def cpu_oracle_docs_per_s(n_docs, repeats=1):
     """Times the CPU oracle (numpy fp32 port of the transformers path the reference runs) on n_docs of the workload."""
     from b200rank.synthetic import NO_ID, YES_ID, model_cfg, synthetic_prompt_ids, synthetic_weights
@@ -371,6 +381,16 @@ def run_engine(args):
             "step_frac": (value / world) * GF_PER_DOC * 1e9 / (peak * 1e12),
             "by_kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:14]},
         }
+        # the HBM-bound kernel with the largest share: T5LayerNorm over the fp32 residual stream (read 4 B + write 2 B per element).
+        # Launch times come from event pairs around each launch and include the inter-kernel gap, so this is a lower bound.
+        if "rmsnorm" in rep:
+            rows_per_step = (2 * cfg["num_layers"] + 1) * n_tok + (3 * cfg["num_decoder_layers"] + 1) * HITS
+            nbytes = rows_per_step * cfg["d_model"] * 6.0
+            hbm_peak, hbm_src = load_hbm_peak()
+            gbs = nbytes / (rep["rmsnorm"]["ms"] / prof_steps * 1e-3) / 1e9
+            roofline["hbm_kernels"] = [{"kernel": "rmsnorm_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": gbs / hbm_peak, "bytes_per_step": nbytes, "launches_per_step": rep["rmsnorm"]["n"] / prof_steps,
+                                        "peak_source": hbm_src}]
         if world == 1 and not args.no_cpu_baseline:
             n_sample = 8
             cb, secs = cpu_oracle_docs_per_s(n_sample, repeats=2)

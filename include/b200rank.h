@@ -149,7 +149,7 @@ int b200rank_device_info(b200rank_engine* e, int* sm_count, size_t* weight_bytes
 int b200rank_test_gemm(int device, const void* a_bf16, const void* w_bf16, int M, int N, int K, int epi, int block_n,
                        int use_simt, void* out, float* elapsed_ms);
 /* encoder attention on packed qkv [tokens][3*inner] bf16; bias [H][257] fp32; out [tokens][inner] bf16.
- * mode: 0 = engine default, 1 = mma.sync 64-query tiles, 2 = mma.sync resident-KV, 3 = tcgen05, 5 = persistent tcgen05 (len <= 192),
+ * mode: 0 = engine default, 1 = mma.sync 64-query tiles, 2 = mma.sync resident-KV, 3 = tcgen05, 5 = persistent tcgen05 (len <= 192), 6 = same with the row-split softmax,
  * 4 = mma.sync scores-in-registers (2, 3, 4: len <= 256) */
 int b200rank_test_enc_attention(int device, const void* qkv_bf16, const int32_t* cu_seqlens, int n_docs, int num_heads,
                                 const float* bias, void* out_bf16, int mode);

@@ -245,7 +245,7 @@ struct AttnTc2Cfg {
     static constexpr int kQKVBytes = kRows * 128;
     static constexpr int kPBytes = NKB * 128 * 128;
     static constexpr int kWideBias = 512;                 // 511 used: index (j - i) + 255
-    static constexpr int kFixedBytes = 3 * kQKVBytes + 2 * kPBytes + 16 * 8 + 16 + 1024;
+    static constexpr int kFixedBytes = 3 * kQKVBytes + 2 * kPBytes + 16 * 8 + 16 + 2048 + 1024;
     static constexpr int kMaxResidentHeads = (227 * 1024 - kFixedBytes) / (kWideBias * 4);
     // bias windows: one per head when they all fit next to the tiles (resident for the whole kernel), else one per warpgroup
     static constexpr int smem_bytes(int H) { return kFixedBytes + (H <= kMaxResidentHeads ? (H < 2 ? 2 : H) : 2) * kWideBias * 4; }
@@ -254,7 +254,7 @@ struct AttnTc2Cfg {
     static_assert(kOCol0 + 128 <= 512, "S and O tiles must fit the 512 TMEM columns side by side");
 };
 
-template <int NKB>
+template <int NKB, bool SPLIT>
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items, int spin) {
@@ -276,7 +276,8 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
     uint64_t* bar_o = bars + 8;    // [2] O_t ready in TMEM
     uint64_t* o_free = bars + 10;  // [2] O_t drained by the epilogue (128 arrivals)
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
-    float* sBiasW = reinterpret_cast<float*>(tmem_base_smem + 4);   // [H or 2][kWideBias]
+    float* sRed = reinterpret_cast<float*>(tmem_base_smem + 4);     // [4][128] row max / row sum exchange of the SPLIT softmax
+    float* sBiasW = sRed + 512;                                     // [H or 2][kWideBias]
     const bool bias_resident = H <= Cfg::kMaxResidentHeads;
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,9 +290,9 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
         mbar_init(v_free, 1);
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bar_s[t], 1);
-            mbar_init(&bar_p[t], 128);
+            mbar_init(&bar_p[t], SPLIT ? 256 : 128);
             mbar_init(&bar_o[t], 1);
-            mbar_init(&o_free[t], 128);
+            mbar_init(&o_free[t], SPLIT ? 256 : 128);
         }
         fence_barrier_init();
     }
@@ -387,7 +388,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 item = nitem; len = nlen;
             }
         }
-    } else {
+    } else if constexpr (!SPLIT) {
         const int t = (warp_idx - 2) >> 2;            // query tile slot of this warpgroup
         const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
         const int wg_tid = threadIdx.x - 64 - t * 128;
@@ -558,6 +559,152 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
             ++use;
         }
         if (pend) epilogue();
+    } else {
+        // ---- SPLIT: every query row is shared by TWO threads (one per warpgroup, 32*NKB columns each). The scores of a row
+        // are read from TMEM ONCE and stay in registers (96 fp32 at NKB = 3) between the max and the exp phase; row max and row
+        // sum are exchanged through shared memory (two 256-thread named barriers per tile). Both warpgroups work on tile slot 0,
+        // then on slot 1. Half the TMEM traffic and half the serial chain of the one-thread-per-row version.
+        constexpr int HC = 32 * NKB;                  // columns per thread
+        const int g = (warp_idx - 2) >> 2;            // column half of this warpgroup
+        const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
+        const int wg_tid = threadIdx.x - 64 - g * 128;
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        float* sRedM = sRed;                          // [2][128] partial row maxima
+        float* sRedL = sRed + 256;                    // [2][128] partial row sums
+        uint32_t use0 = 0, use1 = 0;
+        int h_loaded = -1;
+        // deferred epilogues, one per tile slot
+        bool pend[2] = {false, false}, p_active[2] = {false, false};
+        float p_l[2] = {0.f, 0.f};
+        int p_tok0[2] = {0, 0}, p_len[2] = {0, 0}, p_h[2] = {0, 0};
+        uint32_t p_par[2] = {0, 0};
+        auto epilogue = [&](int t) {
+            wait(&bar_o[t], p_par[t]);
+            tc_fence_after();
+            if (p_active[t]) {
+                uint32_t o[32];
+                tmem_ld32(tmem_base + lane_off + Cfg::kOCol0 + t * 64 + g * 32, o);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_free[t]);
+                const int qi = t * 128 + row_in_tile;
+                if (qi < p_len[t]) {
+                    const float inv = 1.f / p_l[t];
+                    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p_tok0[t] + qi) * ldo + p_h[t] * 64 + g * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                        v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                        v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                        v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                        dst[i] = v;
+                    }
+                }
+            } else {
+                mbar_arrive(&o_free[t]);
+            }
+            pend[t] = false;
+        };
+        int item = blockIdx.x;
+        int doc = item < n_items ? item / H : 0;
+        int tok0 = cu[doc], tok1 = cu[doc + 1];
+        while (item < n_items) {
+            const int h = item - doc * H;
+            const int len = tok1 - tok0, my_tok0 = tok0;
+            const int nitem = item + stride, ndoc = nitem < n_items ? nitem / H : 0;
+            const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
+            item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
+            const int ntiles = (len + 127) >> 7;
+            float* sB = sBiasW + (bias_resident ? h : g) * Cfg::kWideBias;
+            if (!bias_resident && h != h_loaded) {
+                named_bar_sync(1 + g, 128);
+                for (int i = wg_tid; i < 511; i += 128) {
+                    const int rel = max(-kAttnRelClamp, min(kAttnRelClamp, i - 255));
+                    sB[i] = bias[h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
+                }
+                named_bar_sync(1 + g, 128);
+                h_loaded = h;
+            }
+#pragma unroll 1
+            for (int t = 0; t < ntiles; ++t) {
+                uint32_t& use = t == 0 ? use0 : use1;
+                const int qi = t * 128 + row_in_tile;
+                const bool active = (t * 128 + quarter * 32) < len;   // warp-uniform, and the same in both warpgroups
+                const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol + g * HC;
+                const uint32_t sBrow = smem_u32(sB) + (255 - qi + g * HC) * 4;   // [sBrow + 4 c] = log2(e) * bias(g*HC + c - qi)
+                wait(&bar_s[t], use & 1);
+                tc_fence_after();
+                uint32_t v[NKB][32];
+                float m = -INFINITY, l = 0.f;
+                if (active) {
+#pragma unroll
+                    for (int cc = 0; cc < NKB; ++cc) tmem_ld32(taddr_s + 32 * cc, v[cc]);
+                    tmem_ld_wait();
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                    for (int cc = 0; cc < NKB; ++cc) {
+                        const int c0 = g * HC + 32 * cc;       // first key of this chunk
+                        if (c0 + 32 <= len) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) {
+                                const float x = fmaf(__uint_as_float(v[cc][e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (32 * cc + e)));
+                                m4[e & 3] = fmaxf(m4[e & 3], x);
+                                v[cc][e] = __float_as_uint(x);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) {
+                                float x = fmaf(__uint_as_float(v[cc][e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (32 * cc + e)));
+                                x = (c0 + e < len) ? x : -INFINITY;
+                                m4[e & 3] = fmaxf(m4[e & 3], x);
+                                v[cc][e] = __float_as_uint(x);
+                            }
+                        }
+                    }
+                    m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    sRedM[g * 128 + row_in_tile] = m;
+                }
+                tc_fence_before();                // S_t is in registers: its TMEM columns are free once every thread got here
+                named_bar_sync(3, 256);
+                if (active) m = fmaxf(m, sRedM[(1 - g) * 128 + row_in_tile]);   // finite: key 0 of every row lies in half 0
+                // the previous use of this tile slot: its MMA-2 retired long ago; passing bar_o also frees P_t for the writes below
+                if (pend[t]) epilogue(t);
+                if (active) {
+                    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+                    uint8_t* prow = sP + t * Cfg::kPBytes + row_in_tile * 128;
+#pragma unroll
+                    for (int cc = 0; cc < NKB; ++cc) {
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            const float p0 = ex2_approx(__uint_as_float(v[cc][e]) - m);
+                            const float p1 = ex2_approx(__uint_as_float(v[cc][e + 1]) - m);
+                            l4[(e >> 1) & 3] += p0 + p1;
+                            packed[e >> 1] = pack_bf16(p0, p1);
+                        }
+                        const int c = g * HC + 32 * cc;
+                        uint8_t* kblk = prow + (c >> 6) * 16384;
+                        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), packed[4 * i], packed[4 * i + 1],
+                                         packed[4 * i + 2], packed[4 * i + 3]);
+                    }
+                    l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+                    sRedL[g * 128 + row_in_tile] = l;
+                }
+                fence_proxy_async();    // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
+                named_bar_sync(3, 256);
+                if (active) l += sRedL[(1 - g) * 128 + row_in_tile];
+                mbar_arrive(&bar_p[t]);
+                pend[t] = true; p_active[t] = active; p_l[t] = l; p_tok0[t] = my_tok0; p_len[t] = len; p_h[t] = h; p_par[t] = use & 1;
+                ++use;
+            }
+        }
+        if (pend[0]) epilogue(0);
+        if (pend[1]) epilogue(1);
     }
     tc_fence_before();
     __syncthreads();

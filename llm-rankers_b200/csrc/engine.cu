@@ -839,7 +839,7 @@ static int attn_default_mode() {
         // default: the persistent tcgen05 kernel for documents of <= 192 tokens (launch_enc_attention falls back to the mma.sync tiles
         // above that): 1.93 vs 2.32 ms per 100 documents at S=184, +3.7 % docs/s with two queries in flight
         // (profiles/r01_bench_attn_ab.txt). The first, unpipelined tcgen05 kernel ("tc") was 1.7x slower than the tiles.
-        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : 1))));
+        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc3") ? 6 : 1)))));
     }
     return mode;
 }
@@ -865,16 +865,22 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
     static bool attr_set = false;
     if (mode == 0) mode = attn_default_mode();
     if (maxlen > 256) mode = 1;
-    if (mode == 5 && maxlen > 192) mode = 1;
-    if (mode == 5) {
+    if ((mode == 5 || mode == 6) && maxlen > 192) mode = 1;
+    if (mode == 5 || mode == 6) {
         // persistent tcgen05 kernel: one CTA per SM walks the (document, head) items
         CUtensorMap local;
         const CUtensorMap* tm = &local;
         if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
         else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
         static bool attr5 = false;
-        auto kern = enc_attention_tc2_kernel<3>;
-        if (!attr5) { CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr5 = true; }
+        static int split = -1;
+        if (split < 0) split = getenv("B200RANK_ATTN_SPLIT") ? atoi(getenv("B200RANK_ATTN_SPLIT")) : 0;
+        auto kern = (split || mode == 6) ? enc_attention_tc2_kernel<3, true> : enc_attention_tc2_kernel<3, false>;
+        if (!attr5) {
+            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr5 = true;
+        }
         const int n_items = nd * H;
         static int spin = -1;
         if (spin < 0) spin = getenv("B200RANK_ATTN_SPIN") ? atoi(getenv("B200RANK_ATTN_SPIN")) : 0;

@@ -151,6 +151,9 @@ def all_cases():
     # persistent tcgen05 attention (mode 5): single item, two tiles, ragged, more items than SMs (the pipelined phases)
     cases += ["attn:64:1:5", "attn:128:1:5", "attn:184:2:5", "attn:7,64,65,128,129,184,192:3:5", "attn:1,2,3,8,9,15,16,17,33,100,150:2:5",
               "attn:184,184,184,184:16:5", "attn:rand300:16:5", "attn:rand37:5:5", "attn:rand20:32:5", "attn:rand40:12:5"]
+    # column-split softmax variant of the persistent kernel (mode 6)
+    cases += ["attn:64:1:6", "attn:128:1:6", "attn:184:2:6", "attn:7,64,65,128,129,184,192:3:6", "attn:1,2,3,8,9,15,16,17,33,95,96,97,100,150:2:6",
+              "attn:184,184,184,184:16:6", "attn:rand300:16:6", "attn:rand37:5:6", "attn:rand20:32:6"]
     return cases
 
 
