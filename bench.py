@@ -215,6 +215,121 @@ def text_api_docs_per_s(eng, cfg, n_queries):
             "tokenizer_threads": 4, "what": "strings -> prompt assembly + tokenisation (host threads) -> submit/wait pipeline -> sorted SearchResults"}
 
 
+def run_setwise(args):
+    """Secondary workload (BASELINE configs[2]): SetwiseLlmRanker heapsort, flan-t5-large, num_child 10, k 10,
+    100 hits/query, generation scoring — through the drop-in Python API on TEXT. A compare prompt holds 11 passages x 128 words + the
+    query (S ~ 1.5 k tokens); the sort is a chain of dependent compares, so the unit is the query latency. Reports the level-parallel
+    heap build (default) against the reference's one-compare-at-a-time order (B200RANK_BATCHED_SORT=0); results are identical."""
+    import contextlib
+    import io
+    import b200rank as br
+    from b200rank.synthetic import LABELS, model_cfg, synthetic_tokenizer, synthetic_weights
+    from llmrankers._backend import T5Backend
+    from llmrankers.rankers import SearchResult
+    from llmrankers.setwise import SetwiseLlmRanker
+    cfg = model_cfg(MODEL)
+    tok = synthetic_tokenizer()
+    w = synthetic_weights(cfg, SEED)
+    label_ids = [tok.convert_tokens_to_ids("\u2581" + c) for c in LABELS[:11]]
+    w["lm_head.weight"][label_ids] *= 30.0   # label-favouring lm_head (SURVEY.md §7): generation emits passage labels, the heap really sifts
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                       max_tokens=20480, max_docs=64, max_dec_len=8, max_logit_rows=256)
+    eng = br.Engine(c, 0)
+    eng.load_state_dict(w.items())
+    be = T5Backend(eng, tok, cfg)
+    rng = np.random.default_rng(SEED)
+    n_q = max(2, min(args.steps, 8))
+
+    def query_set():
+        words = rng.integers(0, 2000, size=(HITS + 1, P_LEN))
+        return (" ".join(f"w{int(x)}" for x in words[HITS, :Q_LEN]),
+                [SearchResult(docid=str(i), score=0.0, text=" ".join(f"w{int(x)}" for x in words[i])) for i in range(HITS)])
+    sets = [query_set() for _ in range(n_q + 1)]
+    res = {}
+    for mode, flag in (("batched", "1"), ("sequential", "0")):
+        os.environ["B200RANK_BATCHED_SORT"] = flag
+        r = SetwiseLlmRanker(None, None, "cuda", num_child=10, k=10, scoring="generation", method="heapsort", backend=be)
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink):
+            r.rerank(sets[0][0], list(sets[0][1]))   # warm-up
+            eng.sync()
+            t0 = time.perf_counter()
+            compares, orders, tokens = 0, [], 0
+            for q, docs in sets[1:]:
+                out = r.rerank(q, list(docs))
+                compares += r.total_compare
+                tokens += r.total_prompt_tokens
+                orders.append([d.docid for d in out])
+            eng.sync()
+            dt = time.perf_counter() - t0
+        res[mode] = dict(s_per_query=dt / n_q, compares_per_query=compares / n_q, prompt_tokens_per_query=tokens / n_q, orders=orders)
+    assert res["batched"]["orders"] == res["sequential"]["orders"], "batched and sequential heapsort disagree"
+    b, q = res["batched"], res["sequential"]
+    line = {"metric": "docs reranked/sec, setwise heapsort (flan-t5-large, num_child 10, k 10, 100 hits, generation)", "value": HITS / b["s_per_query"],
+            "unit": "docs/s", "n_gpus": 1, "steps": n_q, "warmup": 1, "ms_per_step": b["s_per_query"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "flan-t5-large setwise heapsort c=10 k=10 generation, 100 hits/query, text API (BASELINE configs[2])",
+                       "compares_per_query": b["compares_per_query"], "prompt_tokens_per_query": b["prompt_tokens_per_query"]},
+            "sequential_order": {"value": HITS / q["s_per_query"], "ms_per_step": q["s_per_query"] * 1e3,
+                                 "what": "B200RANK_BATCHED_SORT=0: the reference's one-compare-per-call heapify order (same results)"},
+            "speedup_from_level_parallel_heap_build": q["s_per_query"] / b["s_per_query"]}
+    print(json.dumps(line))
+    eng.close()
+    return 0
+
+
+def run_pairwise(args):
+    """Secondary workload (BASELINE configs[3]): PairwiseLlmRanker allpair, flan-t5-xl, batch_size 2 (the
+    reference default), through the drop-in Python API on TEXT; 24 hits/query (552 prompts of S ~ 320) instead of 100 (9900 prompts)
+    to keep the run short. Reports prompts/s with the reference's DataLoader batches merged into large engine calls (default)
+    against one engine call per reference batch (B200RANK_BATCHED_SORT=0); outputs are identical."""
+    import b200rank as br
+    from b200rank.synthetic import model_cfg, synthetic_tokenizer, synthetic_weights
+    from llmrankers._backend import T5Backend
+    from llmrankers.pairwise import PairwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    model, hits = "flan-t5-xl", 24
+    cfg = model_cfg(model)
+    tok = synthetic_tokenizer()
+    w = synthetic_weights(cfg, SEED)
+    lab = [tok.convert_tokens_to_ids("\u2581" + c) for c in "AB"]
+    w["lm_head.weight"][lab] *= 30.0   # label-favouring lm_head: generation emits "Passage A/B"
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                       max_tokens=32768, max_docs=256, max_dec_len=8, max_logit_rows=256)
+    eng = br.Engine(c, 0)
+    eng.load_state_dict(w.items())
+    del w
+    be = T5Backend(eng, tok, cfg)
+    rng = np.random.default_rng(SEED)
+    words = rng.integers(0, 2000, size=(hits + 1, P_LEN))
+    query = " ".join(f"w{int(x)}" for x in words[hits, :Q_LEN])
+    docs = [SearchResult(docid=str(i), score=0.0, text=" ".join(f"w{int(x)}" for x in words[i])) for i in range(hits)]
+    res = {}
+    for mode, flag in (("merged", "1"), ("per_batch", "0")):
+        os.environ["B200RANK_BATCHED_SORT"] = flag
+        r = PairwiseLlmRanker(None, None, "cuda", method="allpair", batch_size=2, k=10, backend=be)
+        r.rerank(query, list(docs[:6]))   # warm-up
+        eng.sync()
+        t0 = time.perf_counter()
+        out = r.rerank(query, list(docs))
+        eng.sync()
+        dt = time.perf_counter() - t0
+        res[mode] = dict(s=dt, prompts=hits * (hits - 1), order=[d.docid for d in out], tokens=r.total_prompt_tokens, compares=r.total_compare)
+    assert res["merged"]["order"] == res["per_batch"]["order"] and res["merged"]["tokens"] == res["per_batch"]["tokens"]
+    m, b = res["merged"], res["per_batch"]
+    line = {"metric": "prompts/sec, pairwise allpair (flan-t5-xl, batch_size 2, generation)", "value": m["prompts"] / m["s"], "unit": "prompts/s",
+            "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": m["s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"flan-t5-xl pairwise allpair, {hits} hits/query -> {m['prompts']} prompts, batch_size 2, text API (BASELINE configs[3] at reduced hits)",
+                       "padded_prompt_tokens": m["tokens"], "reference_batches": m["compares"]},
+            "per_reference_batch": {"value": b["prompts"] / b["s"], "ms_per_step": b["s"] * 1e3,
+                                    "what": "B200RANK_BATCHED_SORT=0: one engine call per DataLoader batch of 2, as the reference loops (same outputs)"},
+            "speedup_from_merged_batches": b["s"] / m["s"]}
+    print(json.dumps(line))
+    eng.close()
+    return 0
+
+
 def run_engine(args):
     rank, world, local = dist_env()
     import b200rank as br
@@ -422,12 +537,18 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise"],
+                    help="pointwise = the headline (BASELINE configs[1], default); setwise / pairwise = configs[2] / configs[3] through the text API, 1 GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "setwise":
+        return run_setwise(args)
+    if args.workload == "pairwise":
+        return run_pairwise(args)
     rank, world, _ = dist_env()
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when asked for N > 1 directly

@@ -137,6 +137,62 @@ class T5Backend:
         return np.concatenate([prefix, new[:, :steps].astype(np.int64)], axis=1)
 
 
+    def generate_batches(self, batches: Sequence[np.ndarray], dec_prefix: Sequence[int], max_new: int) -> List[np.ndarray]:
+        """`[self.generate(b, dec_prefix, max_new) for b in batches]` as ONE engine call. Each element is one padded batch of the
+        reference's DataLoader (pairwise.py:175-200); what a row sees of its padding is decided per reference batch exactly as in
+        generate() (B200RANK_GENERATE_MASK: 'ones' = the batch's pads are attended like tokens, 'infer' = they are masked), so every
+        row's tokens — and every batch's early-stopping length — equal those of the one-batch-at-a-time loop; only the engine's
+        device passes get larger (a reference batch of 2 x 320 tokens fills 4 % of a B200)."""
+        if not batches:
+            return []
+        infer = generate_mask_mode() == "infer"
+        width = max(int(b.shape[1]) for b in batches)
+        total = sum(int(b.shape[0]) for b in batches)
+        ids = np.full((total, width), self.pad_id, np.int32)
+        lengths = np.empty((total,), np.int32)
+        r = 0
+        for b in batches:
+            b = np.asarray(b, np.int32)
+            n, s = b.shape
+            ids[r:r + n, :s] = b
+            lengths[r:r + n] = (b != self.pad_id).sum(axis=1) if infer and (b == self.pad_id).any() else s
+            r += n
+        new = self.engine.greedy(ids, lengths, dec_prefix, max_new)
+        prefix = np.asarray(dec_prefix, np.int64)[None]
+        outs, r = [], 0
+        for b in batches:
+            n = int(b.shape[0])
+            blk = new[r:r + n]
+            finished = np.zeros(n, bool)
+            steps = max_new
+            for st in range(max_new):
+                finished |= blk[:, st] == self.eos_id
+                if finished.all():
+                    steps = st + 1
+                    break
+            outs.append(np.concatenate([np.tile(prefix, (n, 1)), blk[:, :steps].astype(np.int64)], axis=1))
+            r += n
+        return outs
+
+    def generate_rows(self, rows: Sequence[Sequence[int]], dec_prefix: Sequence[int], max_new: int) -> List[np.ndarray]:
+        """B independent `generate(input_ids=[row], ...)` calls (batch of 1 each: no padding, so no mask question) as ONE engine
+        call: the engine packs the real tokens of every row, and a row's result does not depend on what else is in the batch.
+        Returns one HF-shaped 1-D output per row: prefix + new tokens up to and including eos (or max_new)."""
+        if not rows:
+            return []
+        ids, lengths = self.pad_rows(rows, self.pad_id)
+        new = self.engine.greedy(ids, lengths, dec_prefix, max_new)
+        return self._trim_rows(new, dec_prefix, max_new)
+
+    def _trim_rows(self, new: np.ndarray, dec_prefix: Sequence[int], max_new: int) -> List[np.ndarray]:
+        prefix = np.asarray(dec_prefix, np.int64)
+        outs = []
+        for r in range(new.shape[0]):
+            hit = np.nonzero(new[r, :max_new] == self.eos_id)[0]
+            steps = int(hit[0]) + 1 if hit.size else max_new
+            outs.append(np.concatenate([prefix, new[r, :steps].astype(np.int64)]))
+        return outs
+
 def _load_checkpoint(path: str, cache_dir=None):
     """(cfg dict, iterable of (name, fp32 ndarray)) from a local HF checkpoint dir, else via transformers on the CPU."""
     if os.path.isdir(path) and os.path.exists(os.path.join(path, "config.json")):

@@ -34,6 +34,63 @@ def heap_top_k(arr: List, num_child: int, k: int, pick_best: Callable[[List, Lis
         sift(i, 0)
 
 
+def _lockstep(gens, answer_many: Callable[[List], List]) -> None:
+    """Drive generators that yield compare requests and receive answers: every round gathers the pending request of each live
+    generator and resolves them with ONE call. With a single generator this is the sequential algorithm."""
+    pending = []
+    for g in gens:
+        try:
+            pending.append((g, next(g)))
+        except StopIteration:
+            pass
+    while pending:
+        answers = answer_many([req for _, req in pending])
+        nxt = []
+        for (g, _), a in zip(pending, answers):
+            try:
+                nxt.append((g, g.send(a)))
+            except StopIteration:
+                pass
+        pending = nxt
+
+
+def heap_top_k_batched(arr: List, num_child: int, k: int, pick_best_many: Callable[[List], List[int]]) -> None:
+    """heap_top_k with level-parallel heap construction. The reference builds the heap with
+    `for i in range(n // c, -1, -1): heapify(arr, n, i)` (setwise.py:219-223); heapify(i) only ever touches the subtree of i, and
+    nodes of one tree level have disjoint subtrees, so the sift-downs of a level can advance in lockstep: round r issues the
+    r-th compare of every still-moving sift of that level as ONE batch. The array after each level — hence the final order —
+    and the multiset of compares (total_compare, prompt / completion token counters) are identical to the sequential build;
+    only the interleaving of compares across independent subtrees changes. The k extractions are inherently sequential.
+    pick_best_many([(docs, inds), ...]) -> [arr-index of the preferred element among inds, ...]."""
+    n = len(arr)
+
+    def sift(limit: int, i: int):
+        while num_child * i + 1 < limit:
+            lo, hi = num_child * i + 1, min(num_child * (i + 1) + 1, limit)
+            inds = [i] + list(range(lo, hi))
+            largest = yield ([arr[j] for j in inds], inds)
+            if largest == i:
+                return
+            arr[i], arr[largest] = arr[largest], arr[i]
+            i = largest
+
+    # tree levels: level L holds indices [first(L), first(L+1)), first(L+1) = first(L) * c + 1
+    levels, first = [], 0
+    while first <= n // num_child:
+        nxt = first * num_child + 1
+        levels.append(range(first, min(nxt, n // num_child + 1)))
+        first = nxt
+    for level in reversed(levels):
+        _lockstep([sift(n, i) for i in reversed(level)], pick_best_many)
+    ranked = 0
+    for i in range(n - 1, 0, -1):
+        arr[i], arr[0] = arr[0], arr[i]
+        ranked += 1
+        if ranked == k:
+            break
+        _lockstep([sift(i, 0)], pick_best_many)
+
+
 def binary_heap_top_k(arr: List, k: int, greater: Callable[[object, object], bool]) -> None:
     """pairwise.py:133-162: binary max-heap where `greater(a, b)` costs one LLM compare; left child is tested first and
     the right child is compared against the current largest."""
@@ -60,6 +117,40 @@ def binary_heap_top_k(arr: List, k: int, greater: Callable[[object, object], boo
         if ranked == k:
             break
         sift(i, 0)
+
+
+def binary_heap_top_k_batched(arr: List, k: int, greater_many: Callable[[List], List[bool]]) -> None:
+    """binary_heap_top_k with level-parallel heap construction (see heap_top_k_batched): the sift-downs of one tree level touch
+    disjoint subtrees, so their compares are gathered into one `greater_many([(a, b), ...]) -> [bool, ...]` call per round.
+    Same final array and the same multiset of compares as pairwise.py:133-162; the k extractions stay sequential."""
+    n = len(arr)
+
+    def sift(limit: int, i: int):
+        while True:
+            largest, l, r = i, 2 * i + 1, 2 * i + 2
+            if l < limit and (yield (arr[l], arr[i])):
+                largest = l
+            if r < limit and (yield (arr[r], arr[largest])):
+                largest = r
+            if largest == i:
+                return
+            arr[i], arr[largest] = arr[largest], arr[i]
+            i = largest
+
+    levels, first = [], 0
+    while first <= n // 2:
+        nxt = 2 * first + 1
+        levels.append(range(first, min(nxt, n // 2 + 1)))
+        first = nxt
+    for level in reversed(levels):
+        _lockstep([sift(n, i) for i in reversed(level)], greater_many)
+    ranked = 0
+    for i in range(n - 1, 0, -1):
+        arr[i], arr[0] = arr[0], arr[i]
+        ranked += 1
+        if ranked == k:
+            break
+        _lockstep([sift(i, 0)], greater_many)
 
 
 def setwise_bubble_top_k(ranking: List, num_child: int, k: int, best_index: Callable[[Sequence], int]) -> None:

@@ -6,12 +6,13 @@ engine in the reference's batch order (batch composition matters here: generate(
 mask, so how pads are treated follows B200RANK_GENERATE_MASK, see _backend.generate_mask_mode).
 """
 import copy
+import os
 from collections import defaultdict
 from itertools import combinations
 from typing import List, Optional
 
 from ._backend import T5Backend
-from ._sorting import binary_heap_top_k, pairwise_bubble_top_k
+from ._sorting import binary_heap_top_k, binary_heap_top_k_batched, pairwise_bubble_top_k
 from .rankers import LlmRanker, SearchResult
 from .setwise import _assemble
 
@@ -70,6 +71,24 @@ class PairwiseLlmRanker(LlmRanker):
         out = self.compare(query, [a.text, b.text])
         return out[0] == "Passage A" and out[1] == "Passage B"
 
+    def _first_wins_many(self, query: str, pairs: List) -> List[bool]:
+        """`_first_wins` for several independent pairs in one engine call: every pair stays its own padded batch of two
+        (T5Backend.generate_batches), so strings and counters equal those of len(pairs) compare() calls."""
+        prompts = []
+        for a, b in pairs:
+            prompts.append(self.prompt.format(query=query, doc1=a.text, doc2=b.text))
+            prompts.append(self.prompt.format(query=query, doc1=b.text, doc2=a.text))
+        rows = self.backend.tokenize_prompts(prompts)
+        batches = [self.backend.pad_rows(rows[i:i + 2], self.backend.pad_id)[0] for i in range(0, len(rows), 2)]
+        wins = []
+        for ids, out in zip(batches, self.backend.generate_batches(batches, self.decoder_input_ids, 2)):
+            self.total_compare += 1
+            self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
+            self.total_completion_tokens += out.shape[0] * out.shape[1]
+            txt = self.tokenizer.batch_decode(out.tolist(), skip_special_tokens=True)
+            wins.append(txt[0] == "Passage A" and txt[1] == "Passage B")
+        return wins
+
     def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
         original_ranking = copy.deepcopy(ranking)
         self.total_compare = 0
@@ -83,13 +102,16 @@ class PairwiseLlmRanker(LlmRanker):
                 prompts.append(self.prompt.format(query=query, doc1=d2.text, doc2=d1.text))
             rows = self.backend.tokenize_prompts(prompts) if prompts else []
             outputs = []
-            for i in range(0, len(rows), self.batch_size):
-                ids, _ = self.backend.pad_rows(rows[i:i + self.batch_size], self.backend.pad_id)
-                self.total_compare += 1
-                self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
-                out = self.backend.generate(ids, self.decoder_input_ids, 2)
-                self.total_completion_tokens += out.shape[0] * out.shape[1]
-                outputs.extend(out.tolist())
+            # the reference's DataLoader batches (batch_size rows, padded to the batch's longest), many of them per engine call
+            batches = [self.backend.pad_rows(rows[i:i + self.batch_size], self.backend.pad_id)[0] for i in range(0, len(rows), self.batch_size)]
+            per_call = max(1, 4096 // max(1, self.batch_size)) if os.environ.get("B200RANK_BATCHED_SORT", "1") != "0" else 1
+            for c0 in range(0, len(batches), per_call):
+                chunk = batches[c0:c0 + per_call]
+                for ids, out in zip(chunk, self.backend.generate_batches(chunk, self.decoder_input_ids, 2)):
+                    self.total_compare += 1
+                    self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
+                    self.total_completion_tokens += out.shape[0] * out.shape[1]
+                    outputs.extend(out.tolist())
             outputs = self.tokenizer.batch_decode(outputs, skip_special_tokens=True)
             scores = defaultdict(float)
             for i in range(0, len(outputs), 2):
@@ -105,7 +127,10 @@ class PairwiseLlmRanker(LlmRanker):
                              key=lambda x: x.score, reverse=True)
         elif self.method == "heapsort":
             arr = list(ranking)
-            binary_heap_top_k(arr, self.k, lambda a, b: self._first_wins(query, a, b))
+            if type(self)._first_wins is PairwiseLlmRanker._first_wins and os.environ.get("B200RANK_BATCHED_SORT", "1") != "0":
+                binary_heap_top_k_batched(arr, self.k, lambda pairs: self._first_wins_many(query, pairs))   # level-parallel build
+            else:
+                binary_heap_top_k(arr, self.k, lambda a, b: self._first_wins(query, a, b))
             ranking = [SearchResult(docid=doc.docid, score=-i, text=None) for i, doc in enumerate(reversed(arr))]
         elif self.method == "bubblesort":
             pairwise_bubble_top_k(ranking, self.k, lambda a, b: self._first_wins(query, a, b))

@@ -6,6 +6,7 @@ sort drivers reproduce the reference's compare sequence (setwise.py:200-313) via
 The llama / OpenAI / Rank-R1(vLLM) variants of the reference are different model families and out of scope.
 """
 import copy
+import os
 import random
 from collections import Counter
 from typing import List, Optional
@@ -13,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 from ._backend import T5Backend
-from ._sorting import heap_top_k, setwise_bubble_top_k
+from ._sorting import heap_top_k, heap_top_k_batched, setwise_bubble_top_k
 from .rankers import LlmRanker, SearchResult
 
 random.seed(929)  # setwise.py:18
@@ -102,6 +103,31 @@ class SetwiseLlmRanker(LlmRanker):
         best = [c for c, n in counts.items() if n == top]
         return self.CHARACTERS[best[0] if len(best) == 1 else random.choice(best)]
 
+    def _compare_many(self, query: str, doc_sets: List[List]) -> List[str]:
+        """`compare()` for several independent document sets in ONE engine call (num_permutation == 1). Every prompt is a batch of
+        one in the reference (no padding, setwise.py:90), the engine packs real tokens only and a row's result does not depend on
+        its neighbours, so labels and counters equal those of len(doc_sets) sequential compare() calls."""
+        self.total_compare += len(doc_sets)
+        rows = self.backend.tokenize_prompts([self._prompt(query, [d.text for d in docs], self.CHARACTERS) for docs in doc_sets])
+        self.total_prompt_tokens += sum(len(r) for r in rows)
+        outputs = []
+        if self.scoring == 'generation':
+            for out in self.backend.generate_rows(rows, self.decoder_input_ids, 2):
+                self.total_completion_tokens += int(out.shape[0])
+                outputs.append(self.tokenizer.decode(out.tolist(), skip_special_tokens=True).strip()[-1])
+        elif self.scoring == 'likelihood':
+            width = max(len(docs) for docs in doc_sets)
+            probs = self.backend.label_probs(rows, self.decoder_input_ids, self.target_token_ids[:width])
+            for docs, p in zip(doc_sets, probs):
+                ranked = sorted(zip(self.CHARACTERS[:len(docs)], p[:len(docs)]), key=lambda x: x[1], reverse=True)
+                outputs.append(ranked[0][0])
+        else:
+            raise NotImplementedError
+        for output in outputs:
+            if not (len(output) == 1 and output in self.CHARACTERS):
+                print(f"Unexpected output: {output}")
+        return outputs
+
     def _best_index(self, query: str, docs: List) -> int:
         """Label -> position in the compared set; an unknown label keeps the head (setwise.py:206-209, 252-255)."""
         try:
@@ -118,7 +144,18 @@ class SetwiseLlmRanker(LlmRanker):
             def pick(docs, inds):
                 b = self._best_index(query, docs)
                 return inds[b] if b < len(inds) else inds[0]  # a label beyond the set keeps the parent (setwise.py:210-213)
-            heap_top_k(ranking, self.num_child, self.k, pick)
+            if self.num_permutation == 1 and os.environ.get("B200RANK_BATCHED_SORT", "1") != "0":
+                # level-parallel heap construction: the compares of independent subtrees go to the GPU as one batch (_sorting.py)
+                def pick_many(requests):
+                    labels = self._compare_many(query, [docs for docs, _ in requests])
+                    picks = []
+                    for (docs, inds), lab in zip(requests, labels):
+                        b = self.CHARACTERS.index(lab) if lab in self.CHARACTERS else 0
+                        picks.append(inds[b] if b < len(inds) else inds[0])
+                    return picks
+                heap_top_k_batched(ranking, self.num_child, self.k, pick_many)
+            else:
+                heap_top_k(ranking, self.num_child, self.k, pick)
             ranking = list(reversed(ranking))
         elif self.method == "bubblesort":
             setwise_bubble_top_k(ranking, self.num_child, self.k, lambda window: self._best_index(query, window))

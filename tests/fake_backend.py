@@ -47,3 +47,13 @@ class OracleBackend(T5Backend):
                 break
         prefix = np.tile(np.asarray(dec_prefix, np.int64)[None], (ids.shape[0], 1))
         return np.concatenate([prefix, new[:, :steps]], axis=1)
+
+    def generate_rows(self, rows, dec_prefix, max_new):
+        if not rows:
+            return []
+        ids, mask = self._padded(rows)
+        new = self.oracle.greedy(ids, mask, dec_prefix, max_new, self.eos_id, self.pad_id)
+        return self._trim_rows(new, dec_prefix, max_new)
+
+    def generate_batches(self, batches, dec_prefix, max_new):
+        return [self.generate(b, dec_prefix, max_new) for b in batches]   # the definition the product's merged call must reproduce

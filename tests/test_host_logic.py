@@ -143,6 +143,114 @@ def test_rerank_many_equals_rerank():
     assert r.total_compare == 3  # counters describe the last query (10 docs, batch_size 4)
 
 
+# ------------------------------------------------------------------------------------------- level-parallel heap build (§8f-2)
+@pytest.mark.parametrize("n,c,k", [(100, 10, 10), (100, 3, 10), (37, 2, 5), (12, 3, 3), (5, 10, 3), (1, 3, 1), (64, 4, 64)])
+def test_batched_heap_equals_sequential_heap(n, c, k):
+    """Same final array, same multiset of compares as the reference's sequential heapify order, for a NON-transitive, noisy
+    comparison (the sort must not rely on the comparator being an order) — and far fewer sequential rounds."""
+    from llmrankers._sorting import heap_top_k, heap_top_k_batched
+    rng = np.random.default_rng(n * 100 + c)
+    noise = rng.standard_normal((n, n))
+    vals = rng.permutation(n)
+
+    def best(docs):   # deliberately context dependent: the winner depends on who else is in the set
+        return int(np.argmax([vals[d] + noise[d, docs[0]] for d in docs]))
+
+    seq_calls, bat_calls, rounds = [], [], []
+    a = list(range(n))
+    heap_top_k(a, c, k, lambda docs, inds: (seq_calls.append(tuple(docs)), inds[best(docs)])[1])
+    b = list(range(n))
+
+    def many(reqs):
+        rounds.append(len(reqs))
+        bat_calls.extend(tuple(docs) for docs, _ in reqs)
+        return [inds[best(docs)] for docs, inds in reqs]
+    heap_top_k_batched(b, c, k, many)
+    assert a == b
+    assert sorted(seq_calls) == sorted(bat_calls)
+    assert len(rounds) <= len(seq_calls) and (n < 20 or len(rounds) < len(seq_calls))
+
+
+@pytest.mark.parametrize("n,k", [(100, 10), (37, 5), (6, 3), (2, 1), (1, 1), (33, 33)])
+def test_batched_binary_heap_equals_sequential(n, k):
+    from llmrankers._sorting import binary_heap_top_k, binary_heap_top_k_batched
+    rng = np.random.default_rng(n)
+    noise = rng.standard_normal((n, n))
+    vals = rng.permutation(n).astype(float)
+    greater = lambda a, b: bool(vals[a] + noise[a, b] > vals[b])   # noisy, non-transitive
+    seq, bat, rounds = [], [], []
+    a = list(range(n))
+    binary_heap_top_k(a, k, lambda x, y: (seq.append((x, y)), greater(x, y))[1])
+    b = list(range(n))
+
+    def many(pairs):
+        rounds.append(len(pairs))
+        bat.extend(pairs)
+        return [greater(x, y) for x, y in pairs]
+    binary_heap_top_k_batched(b, k, many)
+    assert a == b and sorted(seq) == sorted(bat) and len(rounds) <= len(seq)
+
+
+def test_pairwise_batched_and_sequential_heapsort_agree(monkeypatch):
+    from llmrankers.pairwise import PairwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"]["pairwise_heap"]
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200RANK_BATCHED_SORT", flag)
+        r = PairwiseLlmRanker(None, None, "cuda", method="heapsort", batch_size=c["batch_size"], k=c["k"], backend=backend("tiny", True))
+        out = r.rerank(m["query"], docs_from(m["docs12"][:6]))
+        outs.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+    assert outs[0] == outs[1]
+    assert outs[0][0] == c["order"] and outs[0][2:] == (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+@pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik"])
+def test_setwise_batched_and_sequential_heapsort_agree(case, monkeypatch, capsys):
+    from llmrankers.setwise import SetwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"][case]
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200RANK_BATCHED_SORT", flag)
+        r = SetwiseLlmRanker(None, None, "cuda", num_child=c["num_child"], k=c["k"], scoring=c["scoring"], method="heapsort",
+                             backend=backend("tiny", c["label_favouring"]))
+        out = r.rerank(m["query"], docs_from(m["docs12"]))
+        outs.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+    assert outs[0] == outs[1]
+    assert outs[0][0] == c["order"] and outs[0][2:] == (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+@pytest.mark.parametrize("mode", ["ones", "infer"])
+def test_merged_generate_batches_equals_batch_by_batch(mode, monkeypatch):
+    """T5Backend.generate_batches (many reference batches in one engine call, per-row lengths carrying each batch's own padding
+    semantics) against T5Backend.generate called batch by batch — on an engine stand-in that runs the oracle row by row."""
+    from llmrankers._backend import T5Backend
+    monkeypatch.setenv("B200RANK_GENERATE_MASK", mode)
+    orc = oracle_for("tiny", True)
+    cfg, _ = model_and_weights("tiny", True)
+
+    class RowWiseEngine:   # same contract as b200rank.Engine.greedy: right-padded ids + true lengths, rows independent
+        def greedy(self, ids, lengths, dec_prefix, max_new):
+            out = np.zeros((ids.shape[0], max_new), np.int32)
+            for r in range(ids.shape[0]):
+                row = np.asarray(ids[r:r + 1, : int(lengths[r])], np.int64)
+                out[r] = orc.greedy(row, np.ones_like(row), dec_prefix, max_new, 1, 0)[0]
+            return out
+
+    be = T5Backend(RowWiseEngine(), tokenizer(), cfg)
+    rng = np.random.default_rng(11)
+    prefix = tokenizer().encode("<pad> Passage", add_special_tokens=False)
+    batches = []
+    for n, lo, hi in ((2, 5, 9), (2, 12, 12), (1, 7, 7), (3, 4, 15)):
+        rows = [rng.integers(3, 2000, int(rng.integers(lo, hi + 1))).tolist() + [1] for _ in range(n)]
+        batches.append(be.pad_rows(rows, 0)[0])
+    want = [be.generate(b, prefix, 2) for b in batches]
+    got = be.generate_batches(batches, prefix, 2)
+    assert len(got) == len(want) and all(np.array_equal(g, w) for g, w in zip(got, want))
+    assert be.generate_batches([], prefix, 2) == []
+
+
 # ------------------------------------------------------------------------------------------- token-level prompt assembly (§8f-1)
 def test_prompt_assembler_equals_whole_string_tokenisation():
     from llmrankers._prompts import PromptAssembler
