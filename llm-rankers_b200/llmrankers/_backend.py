@@ -81,6 +81,26 @@ class T5Backend:
         return be
 
     # ---------------------------------------------------------------- host-side token plumbing
+    def assembler(self, template: str):
+        """PromptAssembler for `template` sharing this backend's token cache (_prompts.py): a passage tokenised for one prompt is
+        reused by every other prompt / ranker on this tokenizer. B200RANK_PROMPT_ASSEMBLY=0 -> None (callers tokenise whole strings)."""
+        if os.environ.get("B200RANK_PROMPT_ASSEMBLY", "1") == "0":
+            return None
+        from ._prompts import PromptAssembler, TokenCache
+        if not hasattr(self, "_token_cache"):
+            self._token_cache, self._assemblers = TokenCache(), {}
+        a = self._assemblers.get(template)
+        if a is None:
+            a = self._assemblers[template] = PromptAssembler(self.tokenizer, template, cache=self._token_cache)
+        return a
+
+    def prompt_rows(self, template: str, fields: Sequence[Dict[str, str]]) -> List[List[int]]:
+        """Token-id rows of `template.format(**f)` for every f: what `tokenizer(prompts)` returns for the rendered strings."""
+        a = self.assembler(template)
+        if a is None:
+            return self.tokenize_prompts([template.format(**f) for f in fields])
+        return a.rows(fields)
+
     def tokenize_prompts(self, prompts: Sequence[str]) -> List[List[int]]:
         """`tokenizer(data)` of Text2TextGenerationDataset (pairwise.py:17-26): appends </s>, no padding, no truncation."""
         prompts = list(prompts)

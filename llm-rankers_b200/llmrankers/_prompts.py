@@ -9,9 +9,10 @@ T5's tokenizer (SentencePiece Unigram, `split_by_whitespace`; the `tokenizers` p
 segments every whitespace-delimited word independently, so a prompt whose `{fields}` are bounded by whitespace tokenises to
 the concatenation of the tokenisations of its pieces: literal | field | literal | ... | </s>. `PromptAssembler` splits a
 template once, tokenises the literals once, caches field values (LRU by string) and concatenates ids. It does NOT trust that
-argument blindly: the first `verify` prompts of every assembler (and every prompt whose field is not whitespace-bounded) are
-checked against the tokenizer on the whole string, and on any mismatch the assembler permanently falls back to whole-string
-tokenisation. Templates whose fields touch punctuation (the quoted passages of the setwise / pairwise prompts) are not eligible.
+argument blindly: the first `verify` prompts of every assembler are checked against the tokenizer on the whole string, and on
+any mismatch the assembler permanently falls back to whole-string tokenisation. Punctuation glued to a field (the quotes of the
+setwise / pairwise prompts, `Passage A: "{text}"`) becomes part of the cached unit, so those prompts assemble too — a passage that
+appears in 198 pair prompts of an allpair rerank is tokenised once.
 """
 import threading
 from collections import OrderedDict
@@ -19,33 +20,52 @@ from string import Formatter
 from typing import Dict, List, Sequence
 
 
+class TokenCache:
+    """LRU text -> token ids, shareable between assemblers (one per tokenizer), safe to use from several threads."""
+
+    def __init__(self, size: int = 200_000):
+        self.data: "OrderedDict[str, List[int]]" = OrderedDict()
+        self.size = size
+        self.lock = threading.Lock()
+        self.hits = self.misses = 0
+
+
 class PromptAssembler:
-    def __init__(self, tokenizer, template: str, cache_size: int = 200_000, verify: int = 16):
+    def __init__(self, tokenizer, template: str, cache_size: int = 200_000, verify: int = 16, cache: TokenCache = None):
         self.tokenizer = tokenizer
         self.template = template
-        self.cache: "OrderedDict[str, List[int]]" = OrderedDict()
-        self.cache_size = cache_size
+        self.tc = cache if cache is not None else TokenCache(cache_size)
         self.verify_left = verify
-        self.hits = self.misses = 0
         self.eos = tokenizer.eos_token_id
-        self.lock = threading.Lock()   # rerank_many tokenises upcoming queries on worker threads
         # the Rust tokenizer behind a fast tokenizer: encode_batch releases the GIL and does not touch the truncation / padding
         # state that transformers' __call__ mutates (which is what makes concurrent __call__s raise "Already borrowed")
         self.raw = getattr(tokenizer, "backend_tokenizer", None) if getattr(tokenizer, "is_fast", False) else None
-        self.parts = []      # [(literal ids, field name | None)]
         self.eligible = True
-        pieces = list(Formatter().parse(template))
-        for i, (lit, field, spec, conv) in enumerate(pieces):
-            if spec or conv:
-                self.eligible = False
-            if field is not None:
-                before_ok = (lit == "" and i == 0) or (lit != "" and lit[-1].isspace())
-                nxt = pieces[i + 1][0] if i + 1 < len(pieces) else ""
-                after_ok = (i + 1 == len(pieces)) or (nxt != "" and nxt[0].isspace())
-                if not (before_ok and after_ok):
-                    self.eligible = False   # a field glued to punctuation changes the segmentation of its first / last word
-            self.parts.append((self._encode(lit) if lit else [], field))
+        # Split the template into literals and fields. Punctuation glued to a field (the quotes of `Passage A: "{text}"`) moves
+        # out of the literals into the field's unit: the cached string is glue + value + glue, which IS bounded by whitespace.
+        pieces = [(lit, field) for lit, field, spec, conv in Formatter().parse(template)]
+        if any(spec or conv for _, _, spec, conv in Formatter().parse(template)):
+            self.eligible = False
+        lits = [lit for lit, _ in pieces] + [""]            # literal before every field, plus the tail after the last one
+        fields = [f for _, f in pieces]
+        if fields and fields[-1] is None:                   # trailing literal came as (lit, None)
+            lits[-1] = lits[-2]
+            lits.pop(-2)
+            fields.pop()
+        self.units = []                                     # [(glue_before, field, glue_after)]
+        for i, f in enumerate(fields):
+            before, after = lits[i], lits[i + 1]
+            nb = _trailing_nonspace(before)
+            na = _leading_nonspace(after)
+            if i + 1 < len(fields) and na == len(after) and after != "":
+                self.eligible = False                       # two fields joined by punctuation only: not separable
+            gb, ga = before[len(before) - nb:], after[:na]
+            lits[i], lits[i + 1] = before[:len(before) - nb], after[na:]
+            self.units.append((gb, f, ga))
+        self.lit_ids = [self._encode(l) if l.strip() else [] for l in lits]
+        self.hits = self.misses = 0
 
+    # ------------------------------------------------------------------ tokenizer access
     def _encode(self, text: str) -> List[int]:
         return self.tokenizer.encode(text, add_special_tokens=False)
 
@@ -54,32 +74,45 @@ class PromptAssembler:
             return [e.ids for e in self.raw.encode_batch(texts, add_special_tokens=specials)]
         return self.tokenizer(texts, add_special_tokens=specials)["input_ids"]
 
-    def _field_ids(self, values: Sequence[str]) -> List[List[int]]:
-        """Token ids of every value, through the LRU cache; misses are tokenised in ONE batched tokenizer call."""
-        out: List = [None] * len(values)
+    def _unit_ids(self, texts: Sequence[str]) -> List[List[int]]:
+        """Token ids of every unit string, through the shared LRU cache; misses are tokenised in ONE batched tokenizer call."""
+        tc = self.tc
+        out: List = [None] * len(texts)
         todo: Dict[str, List[int]] = {}
-        with self.lock:
-            for i, v in enumerate(values):
-                ids = self.cache.get(v)
+        with tc.lock:
+            for i, v in enumerate(texts):
+                ids = tc.data.get(v)
                 if ids is None:
                     todo.setdefault(v, []).append(i)
                 else:
-                    self.cache.move_to_end(v)
+                    tc.data.move_to_end(v)
                     out[i] = ids
+                    tc.hits += 1
                     self.hits += 1
         if todo:
-            texts = list(todo)
-            enc = self._encode_batch(texts, False)
-            with self.lock:
-                for t, ids in zip(texts, enc):
+            keys = list(todo)
+            enc = self._encode_batch(keys, False)
+            with tc.lock:
+                for t, ids in zip(keys, enc):
+                    tc.misses += len(todo[t])
                     self.misses += len(todo[t])
-                    self.cache[t] = ids
+                    tc.data[t] = ids
                     for i in todo[t]:
                         out[i] = ids
-                while len(self.cache) > self.cache_size:
-                    self.cache.popitem(last=False)
+                while len(tc.data) > tc.size:
+                    tc.data.popitem(last=False)
         return out
 
+    def warm(self, field: str, values: Sequence[str]) -> None:
+        """Tokenise the units of `field` for all `values` in one batched call (e.g. every candidate passage at the start of a
+        sort-based rerank, whose compares then only concatenate cached ids)."""
+        if not self.eligible:
+            return
+        for gb, f, ga in self.units:
+            if f == field:
+                self._unit_ids([gb + v + ga for v in values])
+
+    # ------------------------------------------------------------------ rows
     def whole_string(self, rows_fields: Sequence[Dict[str, str]]) -> List[List[int]]:
         prompts = [self.template.format(**f) for f in rows_fields]
         return self._encode_batch(prompts, True) if prompts else []
@@ -91,15 +124,15 @@ class PromptAssembler:
             return []
         if not self.eligible:
             return self.whole_string(rows_fields)
-        names = [f for _, f in self.parts if f is not None]
-        per_field = {n: self._field_ids([rf[n] for rf in rows_fields]) for n in set(names)}
+        n_u = len(self.units)
+        flat = self._unit_ids([gb + rf[f] + ga for rf in rows_fields for gb, f, ga in self.units])
         rows = []
         for r in range(len(rows_fields)):
             ids: List[int] = []
-            for lit, field in self.parts:
-                ids += lit
-                if field is not None:
-                    ids += per_field[field][r]
+            for u in range(n_u):
+                ids += self.lit_ids[u]
+                ids += flat[r * n_u + u]
+            ids += self.lit_ids[n_u]
             ids.append(self.eos)
             rows.append(ids)
         if self.verify_left > 0:
@@ -110,3 +143,17 @@ class PromptAssembler:
                 self.eligible = False     # this vocabulary / normaliser does not segment per word: never assemble again
                 return self.whole_string(rows_fields)
         return rows
+
+
+def _trailing_nonspace(s: str) -> int:
+    n = 0
+    while n < len(s) and not s[len(s) - 1 - n].isspace():
+        n += 1
+    return n
+
+
+def _leading_nonspace(s: str) -> int:
+    n = 0
+    while n < len(s) and not s[n].isspace():
+        n += 1
+    return n

@@ -59,8 +59,7 @@ class PairwiseLlmRanker(LlmRanker):
         """Both presentation orders of (doc1, doc2) in one padded batch of 2 -> two decoded strings (pairwise.py:84-103)."""
         self.total_compare += 1
         doc1, doc2 = docs[0], docs[1]
-        rows = self.backend.tokenize_prompts([self.prompt.format(query=query, doc1=doc1, doc2=doc2),
-                                              self.prompt.format(query=query, doc1=doc2, doc2=doc1)])
+        rows = self.backend.prompt_rows(self.prompt, [dict(query=query, doc1=doc1, doc2=doc2), dict(query=query, doc1=doc2, doc2=doc1)])
         ids, _ = self.backend.pad_rows(rows, self.backend.pad_id)
         self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
         out = self.backend.generate(ids, self.decoder_input_ids, 2)
@@ -74,11 +73,11 @@ class PairwiseLlmRanker(LlmRanker):
     def _first_wins_many(self, query: str, pairs: List) -> List[bool]:
         """`_first_wins` for several independent pairs in one engine call: every pair stays its own padded batch of two
         (T5Backend.generate_batches), so strings and counters equal those of len(pairs) compare() calls."""
-        prompts = []
+        fields = []
         for a, b in pairs:
-            prompts.append(self.prompt.format(query=query, doc1=a.text, doc2=b.text))
-            prompts.append(self.prompt.format(query=query, doc1=b.text, doc2=a.text))
-        rows = self.backend.tokenize_prompts(prompts)
+            fields.append(dict(query=query, doc1=a.text, doc2=b.text))
+            fields.append(dict(query=query, doc1=b.text, doc2=a.text))
+        rows = self.backend.prompt_rows(self.prompt, fields)
         batches = [self.backend.pad_rows(rows[i:i + 2], self.backend.pad_id)[0] for i in range(0, len(rows), 2)]
         wins = []
         for ids, out in zip(batches, self.backend.generate_batches(batches, self.decoder_input_ids, 2)):
@@ -96,11 +95,11 @@ class PairwiseLlmRanker(LlmRanker):
         self.total_prompt_tokens = 0
         if self.method == "allpair":
             doc_pairs = list(combinations(ranking, 2))
-            prompts = []
+            fields = []
             for d1, d2 in doc_pairs:
-                prompts.append(self.prompt.format(query=query, doc1=d1.text, doc2=d2.text))
-                prompts.append(self.prompt.format(query=query, doc1=d2.text, doc2=d1.text))
-            rows = self.backend.tokenize_prompts(prompts) if prompts else []
+                fields.append(dict(query=query, doc1=d1.text, doc2=d2.text))
+                fields.append(dict(query=query, doc1=d2.text, doc2=d1.text))
+            rows = self.backend.prompt_rows(self.prompt, fields) if fields else []
             outputs = []
             # the reference's DataLoader batches (batch_size rows, padded to the batch's longest), many of them per engine call
             batches = [self.backend.pad_rows(rows[i:i + self.batch_size], self.backend.pad_id)[0] for i in range(0, len(rows), self.batch_size)]

@@ -8,11 +8,9 @@ device passes itself; per-document results do not depend on batch composition) a
 """
 from typing import List, Optional
 
-import os
 from collections import deque
 
 from ._backend import T5Backend
-from ._prompts import PromptAssembler
 from .rankers import LlmRanker, SearchResult
 
 YES_NO_PROMPT = "Passage: {text}\nQuery: {query}\nDoes the passage answer the query? Answer 'Yes' or 'No'"
@@ -33,17 +31,11 @@ class PointwiseLlmRanker(LlmRanker):
         self.total_compare = 0
         self.total_completion_tokens = 0
         self.total_prompt_tokens = 0
-        self._assemblers = {}
 
     def _rows(self, template: str, fields: List[dict]) -> List[List[int]]:
         """Token-id rows of `template.format(**f)` for every f — what `Text2TextGenerationDataset` (pairwise.py:17-26) produces,
         through token-level assembly + a per-document token cache (_prompts.py; B200RANK_PROMPT_ASSEMBLY=0 tokenises whole strings)."""
-        if os.environ.get("B200RANK_PROMPT_ASSEMBLY", "1") == "0":
-            return self.backend.tokenize_prompts([template.format(**f) for f in fields])
-        a = self._assemblers.get(template)
-        if a is None:
-            a = self._assemblers[template] = PromptAssembler(self.tokenizer, template)
-        return a.rows(fields)
+        return self.backend.prompt_rows(template, fields)
 
     def _count_batches(self, rows: List[List[int]], dec_len: int) -> None:
         """Counters exactly as the reference accumulates them per DataLoader batch (pointwise.py:64-70, 106-115):

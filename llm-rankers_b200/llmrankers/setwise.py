@@ -49,11 +49,30 @@ class SetwiseLlmRanker(LlmRanker):
         return (f'Given a query "{query}", which of the following passages is the most relevant one to the query?\n\n'
                 + passages + '\n\nOutput only the passage label of the most relevant passage:')
 
+    @staticmethod
+    def _template(n_docs: int, labels: List[str]) -> str:
+        """_prompt as a format template with fields {query}, {d0} .. {d<n-1>} for the token-level assembler (braces in the text
+        itself never pass through str.format this way)."""
+        passages = "\n\n".join('Passage %s: "{d%d}"' % (labels[i], i) for i in range(n_docs))
+        return ('Given a query "{query}", which of the following passages is the most relevant one to the query?\n\n'
+                + passages + '\n\nOutput only the passage label of the most relevant passage:')
+
+    def _rows(self, query: str, doc_sets: List[List], label_sets: Optional[List[List[str]]] = None) -> List[List[int]]:
+        """Token rows of `_prompt(query, texts, labels)` for every document set: quoted passages and the quoted query are cached
+        units, so a passage is tokenised once per rerank however many compares it takes part in."""
+        rows = []
+        for i, docs in enumerate(doc_sets):
+            labels = label_sets[i] if label_sets is not None else self.CHARACTERS
+            fields = {"query": query}
+            fields.update({f"d{j}": d.text for j, d in enumerate(docs)})
+            rows.extend(self.backend.prompt_rows(self._template(len(docs), list(labels[:len(docs)])), [fields]))
+        return rows
+
     def compare(self, query: str, docs: List):
         self.total_compare += 1 if self.num_permutation == 1 else self.num_permutation
         if self.scoring == 'generation':
             if self.num_permutation == 1:
-                row = self.backend.tokenize_prompts([self._prompt(query, [d.text for d in docs], self.CHARACTERS)])[0]
+                row = self._rows(query, [docs])[0]
                 self.total_prompt_tokens += len(row)
                 out = self.backend.generate(np.asarray([row], np.int32), self.decoder_input_ids, 2)[0]
                 self.total_completion_tokens += int(out.shape[0])
@@ -62,7 +81,7 @@ class SetwiseLlmRanker(LlmRanker):
             else:
                 output = self._compare_permutations(query, docs)
         elif self.scoring == 'likelihood':
-            row = self.backend.tokenize_prompts([self._prompt(query, [d.text for d in docs], self.CHARACTERS)])[0]
+            row = self._rows(query, [docs])[0]
             self.total_prompt_tokens += len(row)
             probs = self.backend.label_probs([row], self.decoder_input_ids, self.target_token_ids[:len(docs)])[0]
             ranked = sorted(zip(self.CHARACTERS[:len(docs)], probs), key=lambda x: x[1], reverse=True)
@@ -82,8 +101,8 @@ class SetwiseLlmRanker(LlmRanker):
             perm = random.sample(id_passage, len(id_passage))
             chars = random.sample(labels, len(labels))
             refs.append(([p[0] for p in perm], chars))
-            prompts.append(self._prompt(query, [p[1].text for p in perm], chars))
-        rows = self.backend.tokenize_prompts(prompts)
+            prompts.append(([p[1] for p in perm], chars))
+        rows = self._rows(query, [p[0] for p in prompts], [p[1] for p in prompts])
         ids, _ = self.backend.pad_rows(rows, self.backend.pad_id)
         self.total_prompt_tokens += ids.shape[1] * ids.shape[0]
         out = self.backend.generate(ids, self.decoder_input_ids, 2)
@@ -108,7 +127,7 @@ class SetwiseLlmRanker(LlmRanker):
         one in the reference (no padding, setwise.py:90), the engine packs real tokens only and a row's result does not depend on
         its neighbours, so labels and counters equal those of len(doc_sets) sequential compare() calls."""
         self.total_compare += len(doc_sets)
-        rows = self.backend.tokenize_prompts([self._prompt(query, [d.text for d in docs], self.CHARACTERS) for docs in doc_sets])
+        rows = self._rows(query, doc_sets)
         self.total_prompt_tokens += sum(len(r) for r in rows)
         outputs = []
         if self.scoring == 'generation':
@@ -140,6 +159,9 @@ class SetwiseLlmRanker(LlmRanker):
         self.total_compare = 0
         self.total_completion_tokens = 0
         self.total_prompt_tokens = 0
+        a = self.backend.assembler(self._template(1, self.CHARACTERS))
+        if a is not None:
+            a.warm("d0", [d.text for d in ranking])   # every candidate passage tokenised once, in one batched call
         if self.method == "heapsort":
             def pick(docs, inds):
                 b = self._best_index(query, docs)

@@ -268,12 +268,29 @@ def test_prompt_assembler_equals_whole_string_tokenisation():
         want = tok([template.format(**f) for f in fields])["input_ids"]
         assert a.rows(fields) == want
         assert a.rows(fields) == want and a.hits > 0          # second time from the cache
-    # fields glued to punctuation (quoted passages of the pairwise / setwise prompts) are not eligible: whole-string path
-    a = PromptAssembler(tok, PAIRWISE_PROMPT)
-    assert not a.eligible
-    f = [dict(query=query, doc1=texts[0], doc2=texts[1])]
-    assert a.rows(f) == tok([PAIRWISE_PROMPT.format(**f[0])])["input_ids"]
+    # punctuation glued to a field (the quoted passages of the pairwise / setwise prompts) joins the cached unit
+    a = PromptAssembler(tok, PAIRWISE_PROMPT, verify=0)
+    assert a.eligible
+    f = [dict(query=query, doc1=texts[i], doc2=texts[j]) for i in range(len(texts)) for j in (0, len(texts) - 1, len(texts) - 3, 31, 32)]
+    assert a.rows(f) == tok([PAIRWISE_PROMPT.format(**x) for x in f])["input_ids"]
+    assert len(a.tc.data) <= len(set(texts)) + 1              # one cached unit per distinct quoted passage + the quoted query
+    assert a.rows(f[:10]) == tok([PAIRWISE_PROMPT.format(**x) for x in f[:10]])["input_ids"] and a.hits >= 30
+    setwise_like = 'Given a query "{query}", which?\n\nPassage A: "{d0}"\n\nPassage B: "{d1}"\n\nOutput only the passage label:'
+    shared = PromptAssembler(tok, setwise_like, verify=0, cache=a.tc)    # shares the pairwise assembler's token cache
+    f = [dict(query=query, d0=texts[i], d1=texts[-1 - i]) for i in range(len(texts))]
+    assert shared.rows(f) == tok([setwise_like.format(**x) for x in f])["input_ids"]
+    # not separable: two fields joined by punctuation only, or a format spec -> whole-string path (still correct)
+    for template in ("Pair: {a}-{b} end", "Value: {a:>8} end"):
+        bad = PromptAssembler(tok, template)
+        assert not bad.eligible
+        ff = [dict(a="w1 w2", b="w3")] if "{b}" in template else [dict(a="w1")]
+        assert bad.rows(ff) == tok([template.format(**ff[0])])["input_ids"]
     assert PromptAssembler(tok, YES_NO_PROMPT).rows([]) == []
+    warm = PromptAssembler(tok, PAIRWISE_PROMPT, verify=0)
+    warm.warm("doc1", texts)
+    n0 = len(warm.tc.data)
+    warm.rows([dict(query=query, doc1=t, doc2=texts[0]) for t in texts[1:5]])
+    assert len(warm.tc.data) == n0 + 1     # only the quoted query was new: doc1 / doc2 units are the same strings
 
 
 def test_prompt_assembler_falls_back_when_the_tokenizer_is_not_word_local():
