@@ -278,6 +278,56 @@ def run_setwise(args):
     return 0
 
 
+def run_qlm(args):
+    """Secondary workload (BASELINE configs[4] shape on one GPU, SURVEY.md §8d cfg5 at flan-t5-large): pointwise qlm — S = 144
+    (p128 + 16 template ids), labels T = 33 (`<pad>` + 32 query ids), 100 hits per step, through b200rank_score_qlm with HOST
+    buffers (pack + H2D + encoder + 33-position decoder + full-vocab log-softmax + D2H inside the timed region)."""
+    import b200rank as br
+    from b200rank.synthetic import model_cfg, synthetic_weights
+    cfg = model_cfg(MODEL)
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                       max_tokens=HITS * 160, max_docs=128, max_dec_len=40, max_logit_rows=HITS * 40)
+    eng = br.Engine(c, 0)
+    eng.load_state_dict(synthetic_weights(cfg, SEED).items())
+    rng = np.random.default_rng(SEED)
+    S, T = P_LEN + 16, Q_LEN + 1
+    ids = rng.integers(3, 32000, size=(HITS, S)).astype(np.int32)
+    ids[:, -1] = 1
+    lengths = np.full((HITS,), S, np.int32)
+    labels = [0] + rng.integers(3, 32000, size=Q_LEN).tolist()
+    for _ in range(max(args.warmup, 3)):
+        sc = eng.score_qlm(ids, lengths, labels)
+    eng.sync()
+    steps = max(5, min(args.steps, 30))
+    eng.profile(True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sc = eng.score_qlm(ids, lengths, labels)
+    eng.sync()
+    dt = time.perf_counter() - t0
+    rep = eng.profile_report()
+    eng.profile(False)
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        sc = eng.score_qlm(ids, lengths, labels)
+    eng.sync()
+    dt = time.perf_counter() - t1          # timed without the per-launch profiling events
+    gf = (cfg["num_layers"] * (8 * 1024 * 1024 * S + 6 * 1024 * 2816 * S + 4 * S * S * 1024) + cfg["num_decoder_layers"] * 4 * 1024 * 1024 * S
+          + cfg["num_decoder_layers"] * (8 * 1024 * 1024 * T + 4 * T * T * 1024 + 4 * 1024 * 1024 * T + 4 * T * S * 1024 + 6 * 1024 * 2816 * T)
+          + 2 * 1024 * 32128 * T) / 1e9
+    peak, _ = load_peaks()
+    line = {"metric": "docs scored/sec, pointwise qlm (flan-t5-large, S 144, T 33)", "value": HITS * steps / dt, "unit": "docs/s", "n_gpus": 1,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "flan-t5-large pointwise qlm, 100 hits/step, S 144, labels T 33 (BASELINE configs[4] shape, 1 GPU)",
+                       "algorithmic_gflop_per_doc": gf},
+            "step_frac": HITS * steps / dt * gf * 1e9 / (peak * 1e12), "finite_scores": bool(np.isfinite(sc).all()),
+            "by_kernel_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:14]}}
+    print(json.dumps(line))
+    eng.close()
+    return 0
+
+
 def run_pairwise(args):
     """Secondary workload (BASELINE configs[3]): PairwiseLlmRanker allpair, flan-t5-xl, batch_size 2 (the
     reference default), through the drop-in Python API on TEXT; 24 hits/query (552 prompts of S ~ 320) instead of 100 (9900 prompts)
@@ -537,7 +587,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise"],
+    ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise", "qlm"],
                     help="pointwise = the headline (BASELINE configs[1], default); setwise / pairwise = configs[2] / configs[3] through the text API, 1 GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
@@ -549,6 +599,8 @@ def main():
         return run_setwise(args)
     if args.workload == "pairwise":
         return run_pairwise(args)
+    if args.workload == "qlm":
+        return run_qlm(args)
     rank, world, _ = dist_env()
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when asked for N > 1 directly

@@ -19,6 +19,7 @@
 #include "../../include/b200rank.h"
 #include "attention_enc.cuh"
 #include "attention_tc.cuh"
+#include "attention_dec.cuh"
 #include "cross_ctx_t1.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels_misc.cuh"
@@ -969,6 +970,14 @@ static bool use_reassoc_t1(const b200rank_engine* e, int T) {
     return pref && T == 1 && e->staged_maxlen <= 240 && !e->debug_simt && e->d % kCtxKC == 0;  // 240: 3-stage ring fits 227 KB
 }
 
+// Many decoder positions (qlm labels, long prefixes): tensor-core attention kernels (attention_dec.cuh); the CUDA-core kernels
+// remain for the 1-4 position prefixes of yes_no / generation. B200RANK_DEC_ATTN=simt forces the CUDA-core kernels everywhere.
+static bool dec_attn_mma(int T) {
+    static int pref = -1;
+    if (pref < 0) pref = (getenv("B200RANK_DEC_ATTN") && !strcmp(getenv("B200RANK_DEC_ATTN"), "simt")) ? 0 : 1;
+    return pref && T > 4;
+}
+
 // Decoder over documents [doc0, doc0+nd) with T positions each; dec ids in d_dec_ids[nd*T].
 // Leaves the final-normed hidden states in hd[nd*T, d].
 static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
@@ -995,8 +1004,15 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             RET_IF(gemm(e, e->hd, d, cap, w.wov, d, d, R, d, d, EPI_RESID_F32, e->xd, d));
         } else {
             RET_IF(gemm(e, e->hd, d, cap, w.wqkv, d, 3 * I, R, 3 * I, d, EPI_BF16, e->qkvd, 3 * I));
-            prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
-            RET_IF(post_launch(e, "dec_self_attention"));
+            if (dec_attn_mma(T)) {
+                prof_begin(e, "dec_self_attention_mma");
+                launch_k(dec_attention_mma_kernel<true>, dim3((T + 63) / 64, e->H, nd), dim3(128), 0, e->stream, e->qkvd, 3 * I, T, e->qkvd, (size_t)3 * I, I, 2 * I,
+                         (const int*)nullptr, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+                RET_IF(post_launch(e, "dec_self_attention_mma"));
+            } else {
+                prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+                RET_IF(post_launch(e, "dec_self_attention"));
+            }
             RET_IF(gemm(e, e->aod, I, cap, w.wo, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
         }
         RET_IF(k_rmsnorm(e, e->xd, w.ln_c, e->hd, R));
@@ -1018,6 +1034,17 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             continue;
         }
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
+        if (dec_attn_mma(T)) {
+            prof_begin(e, "cross_attention_mma");
+            launch_k(dec_attention_mma_kernel<false>, dim3((T + 63) / 64, e->H, nd), dim3(128), 0, e->stream, e->qd, I, T, e->ckv, ldkv, k_off, v_off,
+                     (const int*)(e->d_cu_cur + doc0), (const float*)nullptr, 0, e->aod, I);
+            RET_IF(post_launch(e, "cross_attention_mma"));
+            RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+            RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
+            RET_IF(ffn_in(e, e->hd, cap, w.wi, R, e->gd));
+            RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
+            continue;
+        }
         prof_begin(e, "cross_attention");
         if (T == 1 && e->H % 4 == 0 && max_len <= 256)
             cross_attention_t1_kernel<8><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
