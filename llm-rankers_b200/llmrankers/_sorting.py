@@ -34,9 +34,9 @@ def heap_top_k(arr: List, num_child: int, k: int, pick_best: Callable[[List, Lis
         sift(i, 0)
 
 
-def _lockstep(gens, answer_many: Callable[[List], List]) -> None:
-    """Drive generators that yield compare requests and receive answers: every round gathers the pending request of each live
-    generator and resolves them with ONE call. With a single generator this is the sequential algorithm."""
+def _rounds(gens):
+    """Sub-generator: advance request-yielding generators in lockstep. Yields one ROUND (the list of the pending request of every
+    live generator) at a time and is sent the list of answers; with a single generator this is the sequential algorithm."""
     pending = []
     for g in gens:
         try:
@@ -44,7 +44,7 @@ def _lockstep(gens, answer_many: Callable[[List], List]) -> None:
         except StopIteration:
             pass
     while pending:
-        answers = answer_many([req for _, req in pending])
+        answers = yield [req for _, req in pending]
         nxt = []
         for (g, _), a in zip(pending, answers):
             try:
@@ -54,14 +54,25 @@ def _lockstep(gens, answer_many: Callable[[List], List]) -> None:
         pending = nxt
 
 
-def heap_top_k_batched(arr: List, num_child: int, k: int, pick_best_many: Callable[[List], List[int]]) -> None:
-    """heap_top_k with level-parallel heap construction. The reference builds the heap with
-    `for i in range(n // c, -1, -1): heapify(arr, n, i)` (setwise.py:219-223); heapify(i) only ever touches the subtree of i, and
-    nodes of one tree level have disjoint subtrees, so the sift-downs of a level can advance in lockstep: round r issues the
-    r-th compare of every still-moving sift of that level as ONE batch. The array after each level — hence the final order —
-    and the multiset of compares (total_compare, prompt / completion token counters) are identical to the sequential build;
-    only the interleaving of compares across independent subtrees changes. The k extractions are inherently sequential.
-    pick_best_many([(docs, inds), ...]) -> [arr-index of the preferred element among inds, ...]."""
+def drive_rounds(gen, answer_many: Callable[[List], List]) -> None:
+    """Run a round generator to completion against a batch oracle."""
+    try:
+        reqs = next(gen)
+        while True:
+            reqs = gen.send(answer_many(reqs))
+    except StopIteration:
+        pass
+
+
+def heap_top_k_rounds(arr: List, num_child: int, k: int):
+    """heap_top_k as a generator of compare ROUNDS with level-parallel heap construction. The reference builds
+    the heap with `for i in range(n // c, -1, -1): heapify(arr, n, i)` (setwise.py:219-223); heapify(i) only ever touches the
+    subtree of i, and nodes of one tree level have disjoint subtrees, so the sift-downs of a level can advance in lockstep: round r
+    holds the r-th compare of every still-moving sift of that level. The array after each level — hence the final order — and the
+    multiset of compares (total_compare, prompt / completion token counters) are identical to the sequential build; only the
+    interleaving of compares across independent subtrees changes. The k extractions are inherently sequential (rounds of one).
+    Yields [(docs, inds), ...]; expects [arr-index of the preferred element among inds, ...]. Being a generator, several
+    queries' sorts can be advanced together (SetwiseLlmRanker.rerank_many)."""
     n = len(arr)
 
     def sift(limit: int, i: int):
@@ -81,14 +92,19 @@ def heap_top_k_batched(arr: List, num_child: int, k: int, pick_best_many: Callab
         levels.append(range(first, min(nxt, n // num_child + 1)))
         first = nxt
     for level in reversed(levels):
-        _lockstep([sift(n, i) for i in reversed(level)], pick_best_many)
+        yield from _rounds([sift(n, i) for i in reversed(level)])
     ranked = 0
     for i in range(n - 1, 0, -1):
         arr[i], arr[0] = arr[0], arr[i]
         ranked += 1
         if ranked == k:
             break
-        _lockstep([sift(i, 0)], pick_best_many)
+        yield from _rounds([sift(i, 0)])
+
+
+def heap_top_k_batched(arr: List, num_child: int, k: int, pick_best_many: Callable[[List], List[int]]) -> None:
+    """In place, like heap_top_k, with the compares of every round resolved by ONE pick_best_many call."""
+    drive_rounds(heap_top_k_rounds(arr, num_child, k), pick_best_many)
 
 
 def binary_heap_top_k(arr: List, k: int, greater: Callable[[object, object], bool]) -> None:
@@ -142,15 +158,17 @@ def binary_heap_top_k_batched(arr: List, k: int, greater_many: Callable[[List], 
         nxt = 2 * first + 1
         levels.append(range(first, min(nxt, n // 2 + 1)))
         first = nxt
-    for level in reversed(levels):
-        _lockstep([sift(n, i) for i in reversed(level)], greater_many)
-    ranked = 0
-    for i in range(n - 1, 0, -1):
-        arr[i], arr[0] = arr[0], arr[i]
-        ranked += 1
-        if ranked == k:
-            break
-        _lockstep([sift(i, 0)], greater_many)
+    def rounds():
+        for level in reversed(levels):
+            yield from _rounds([sift(n, i) for i in reversed(level)])
+        ranked = 0
+        for i in range(n - 1, 0, -1):
+            arr[i], arr[0] = arr[0], arr[i]
+            ranked += 1
+            if ranked == k:
+                break
+            yield from _rounds([sift(i, 0)])
+    drive_rounds(rounds(), greater_many)
 
 
 def setwise_bubble_top_k(ranking: List, num_child: int, k: int, best_index: Callable[[Sequence], int]) -> None:

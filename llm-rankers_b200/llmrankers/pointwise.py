@@ -69,19 +69,27 @@ class PointwiseLlmRanker(LlmRanker):
         # any other method: like the reference, nothing is scored and the input order is sorted by its existing scores
         return sorted(ranking, key=lambda x: x.score, reverse=True)
 
+    def _pipeline_spec(self):
+        """(prompt template, field builder, yes id, no id) of the single-decoder-position scoring this ranker does, or None if
+        rerank_many has to fall back to rerank() (qlm: 33 decoder positions, not pipelined)."""
+        if self.method != "yes_no":
+            return None
+        return (YES_NO_PROMPT, lambda query, doc: dict(text=doc.text, query=query),
+                self.tokenizer.encode("Yes", add_special_tokens=False)[0], self.tokenizer.encode("No", add_special_tokens=False)[0])
+
     def rerank_many(self, requests, tokenizer_threads: int = 4, lookahead: int = 8):
         """Extension (not in the reference): rerank an iterable of (query, ranking) pairs as a pipeline. Upcoming queries are
         tokenised on `tokenizer_threads` worker threads (the Rust tokenizer releases the GIL), up to `lookahead` queries ahead, and
         two queries are in flight on the GPU — query i+1's encoder pass runs while query i's decoder pass finishes. Yields the
         same list `rerank(query, ranking)` would return for each pair, in order; counters hold the totals of the last query.
         Only the yes_no method is pipelined (the headline path); other methods fall back to rerank()."""
-        if self.method != "yes_no":
+        spec = self._pipeline_spec()
+        if spec is None:
             for query, ranking in requests:
                 yield self.rerank(query, ranking)
             return
         from concurrent.futures import ThreadPoolExecutor
-        yes_id = self.tokenizer.encode("Yes", add_special_tokens=False)[0]
-        no_id = self.tokenizer.encode("No", add_special_tokens=False)[0]
+        template, fields_of, yes_id, no_id = spec
 
         def finish(item):
             ticket, ranking, rows = item
@@ -96,7 +104,7 @@ class PointwiseLlmRanker(LlmRanker):
             return sorted(ranking, key=lambda x: x.score, reverse=True)
 
         def tokenise(query, ranking):
-            return self._rows(YES_NO_PROMPT, [dict(text=doc.text, query=query) for doc in ranking])
+            return self._rows(template, [fields_of(query, doc) for doc in ranking])
 
         it = iter(requests)
         window = deque()   # (ranking, future of rows), in request order
@@ -133,6 +141,9 @@ class MonoT5LlmRanker(PointwiseLlmRanker):
     """pointwise.py:136-186 — monoT5 checkpoints are T5 v1.0 (relu feed-forward, tied embeddings => logits scaled by
     d_model^-0.5); the score is softmax(logits[:, 0, [false, true]])[:, 1], i.e. the yes_no entry point of the engine with
     (yes, no) = (true, false). Counters as the reference: one compare per batch, B x longest row + B decoder tokens."""
+
+    def _pipeline_spec(self):
+        return (MONOT5_PROMPT, lambda query, doc: dict(query=query, document=doc.text), MONOT5_TRUE_ID, MONOT5_FALSE_ID)
 
     def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
         self.total_compare = 0

@@ -14,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 from ._backend import T5Backend
-from ._sorting import heap_top_k, heap_top_k_batched, setwise_bubble_top_k
+from ._sorting import heap_top_k, heap_top_k_batched, heap_top_k_rounds, setwise_bubble_top_k
 from .rankers import LlmRanker, SearchResult
 
 random.seed(929)  # setwise.py:18
@@ -122,30 +122,110 @@ class SetwiseLlmRanker(LlmRanker):
         best = [c for c, n in counts.items() if n == top]
         return self.CHARACTERS[best[0] if len(best) == 1 else random.choice(best)]
 
-    def _compare_many(self, query: str, doc_sets: List[List]) -> List[str]:
-        """`compare()` for several independent document sets in ONE engine call (num_permutation == 1). Every prompt is a batch of
-        one in the reference (no padding, setwise.py:90), the engine packs real tokens only and a row's result does not depend on
-        its neighbours, so labels and counters equal those of len(doc_sets) sequential compare() calls."""
-        self.total_compare += len(doc_sets)
-        rows = self._rows(query, doc_sets)
-        self.total_prompt_tokens += sum(len(r) for r in rows)
-        outputs = []
+    def _compare_items(self, items: List) -> List:
+        """Labels for several independent (query, docs) compare sets in ONE engine call (num_permutation == 1). Every prompt is a
+        batch of one in the reference (no padding, setwise.py:90), the engine packs real tokens only and a row's result does not
+        depend on its neighbours, so each label equals that of a sequential compare(). Returns [(label, prompt_tokens,
+        completion_tokens)] and leaves the counters to the caller (the sets may belong to different queries)."""
+        rows = []
+        for query, docs in items:
+            rows.extend(self._rows(query, [docs]))
+        out = []
         if self.scoring == 'generation':
-            for out in self.backend.generate_rows(rows, self.decoder_input_ids, 2):
-                self.total_completion_tokens += int(out.shape[0])
-                outputs.append(self.tokenizer.decode(out.tolist(), skip_special_tokens=True).strip()[-1])
+            for row, gen in zip(rows, self.backend.generate_rows(rows, self.decoder_input_ids, 2)):
+                out.append((self.tokenizer.decode(gen.tolist(), skip_special_tokens=True).strip()[-1], len(row), int(gen.shape[0])))
         elif self.scoring == 'likelihood':
-            width = max(len(docs) for docs in doc_sets)
+            width = max(len(docs) for _, docs in items)
             probs = self.backend.label_probs(rows, self.decoder_input_ids, self.target_token_ids[:width])
-            for docs, p in zip(doc_sets, probs):
+            for row, (_, docs), p in zip(rows, items, probs):
                 ranked = sorted(zip(self.CHARACTERS[:len(docs)], p[:len(docs)]), key=lambda x: x[1], reverse=True)
-                outputs.append(ranked[0][0])
+                out.append((ranked[0][0], len(row), 0))
         else:
             raise NotImplementedError
-        for output in outputs:
-            if not (len(output) == 1 and output in self.CHARACTERS):
-                print(f"Unexpected output: {output}")
-        return outputs
+        for label, _, _ in out:
+            if not (len(label) == 1 and label in self.CHARACTERS):
+                print(f"Unexpected output: {label}")
+        return out
+
+    def _compare_many(self, query: str, doc_sets: List[List]) -> List[str]:
+        """`compare()` for several independent document sets of one query; counters as len(doc_sets) sequential compare() calls."""
+        res = self._compare_items([(query, docs) for docs in doc_sets])
+        self.total_compare += len(res)
+        self.total_prompt_tokens += sum(r[1] for r in res)
+        self.total_completion_tokens += sum(r[2] for r in res)
+        return [r[0] for r in res]
+
+    def _pick(self, label: str, inds: List[int]) -> int:
+        """Label -> arr index: an unknown label keeps the parent, and so does a label beyond the compared set (setwise.py:206-213)."""
+        b = self.CHARACTERS.index(label) if label in self.CHARACTERS else 0
+        return inds[b] if b < len(inds) else inds[0]
+
+    def rerank_many(self, requests, window: int = 8):
+        """Extension (not in the reference): heapsort-rerank an iterable of (query, ranking) pairs with up to `window` queries
+        advancing in lockstep — every round sends the pending compares of all active queries (several per query while a heap level
+        is being built) to the GPU as one batch. A compare is latency-bound by its two ~250-kernel decoder passes, so batching
+        across queries multiplies throughput; each query's compares, order, scores and counters are exactly those of rerank().
+        Yields rerank()'s result for each pair in request order; after each yield the three counters hold that query's totals.
+        Other methods / num_permutation > 1 fall back to rerank()."""
+        if self.method != "heapsort" or self.num_permutation != 1:
+            for query, ranking in requests:
+                yield self.rerank(query, ranking)
+            return
+        it = iter(requests)
+        active, done, next_out, seq = [], {}, 0, 0
+        template1 = self._template(1, self.CHARACTERS)
+
+        def admit():
+            nonlocal seq
+            while len(active) < max(1, window):
+                try:
+                    query, ranking = next(it)
+                except StopIteration:
+                    return
+                ranking = list(ranking)
+                a = self.backend.assembler(template1)
+                if a is not None:
+                    a.warm("d0", [d.text for d in ranking])
+                st = dict(seq=seq, query=query, original=copy.deepcopy(ranking), arr=ranking, counters=[0, 0, 0])
+                st["gen"] = heap_top_k_rounds(st["arr"], self.num_child, self.k)
+                try:
+                    st["round"] = next(st["gen"])
+                    active.append(st)
+                except StopIteration:       # nothing to compare (fewer than two documents)
+                    st["round"] = None
+                    finish(st)
+                seq += 1
+
+        def finish(st):
+            done[st["seq"]] = (_assemble(list(reversed(st["arr"])), st["original"], self.k), st["counters"])
+
+        admit()
+        while active or next_out in done:
+            while next_out in done:
+                result, c = done.pop(next_out)
+                self.total_compare, self.total_prompt_tokens, self.total_completion_tokens = c
+                next_out += 1
+                yield result
+            if not active:
+                break
+            items = [(st["query"], docs) for st in active for docs, _ in st["round"]]
+            res = self._compare_items(items)
+            pos, still = 0, []
+            for st in active:
+                n = len(st["round"])
+                mine = res[pos:pos + n]
+                pos += n
+                st["counters"][0] += n
+                st["counters"][1] += sum(r[1] for r in mine)
+                st["counters"][2] += sum(r[2] for r in mine)
+                picks = [self._pick(r[0], inds) for r, (_, inds) in zip(mine, st["round"])]
+                try:
+                    st["round"] = st["gen"].send(picks)
+                    still.append(st)
+                except StopIteration:
+                    finish(st)
+            active[:] = still
+            admit()
 
     def _best_index(self, query: str, docs: List) -> int:
         """Label -> position in the compared set; an unknown label keeps the head (setwise.py:206-209, 252-255)."""
@@ -170,11 +250,7 @@ class SetwiseLlmRanker(LlmRanker):
                 # level-parallel heap construction: the compares of independent subtrees go to the GPU as one batch (_sorting.py)
                 def pick_many(requests):
                     labels = self._compare_many(query, [docs for docs, _ in requests])
-                    picks = []
-                    for (docs, inds), lab in zip(requests, labels):
-                        b = self.CHARACTERS.index(lab) if lab in self.CHARACTERS else 0
-                        picks.append(inds[b] if b < len(inds) else inds[0])
-                    return picks
+                    return [self._pick(lab, inds) for (_, inds), lab in zip(requests, labels)]
                 heap_top_k_batched(ranking, self.num_child, self.k, pick_many)
             else:
                 heap_top_k(ranking, self.num_child, self.k, pick)

@@ -8,6 +8,7 @@ Differences, all additive: ir_datasets / pyserini are imported lazily (absent on
 """
 import argparse
 import json
+import os
 import logging
 import random
 import sys
@@ -144,15 +145,29 @@ def main(args):
 
     reranked, n_cmp, n_prompt, n_completion = [], 0, 0, 0
     tic = time.time()
-    for qid, query, ranking in first_stage:
-        if args.run.shuffle_ranking is not None:
-            if args.run.shuffle_ranking == 'random':
-                random.shuffle(ranking)
-            elif args.run.shuffle_ranking == 'inverse':
-                ranking = ranking[::-1]
-            else:
-                raise ValueError(f'Invalid shuffle ranking method: {args.run.shuffle_ranking}.')
-        reranked.append((qid, query, ranker.rerank(query, ranking)))
+
+    def prepared():
+        """(qid, query, ranking) in file order with --shuffle_ranking applied (run.py:181-189)."""
+        for qid, query, ranking in first_stage:
+            if args.run.shuffle_ranking is not None:
+                if args.run.shuffle_ranking == 'random':
+                    random.shuffle(ranking)
+                elif args.run.shuffle_ranking == 'inverse':
+                    ranking = ranking[::-1]
+                else:
+                    raise ValueError(f'Invalid shuffle ranking method: {args.run.shuffle_ranking}.')
+            yield qid, query, ranking
+
+    # The reference calls ranker.rerank() once per query (run.py:190). Rankers of this package that offer rerank_many (pointwise:
+    # two queries in flight + tokenisation look-ahead; setwise heapsort: several queries' sorts in lockstep) yield exactly
+    # rerank()'s result and counters per query, in order — B200RANK_RERANK_MANY=0 restores the one-call-per-query loop.
+    items = list(prepared())
+    if hasattr(ranker, 'rerank_many') and os.environ.get('B200RANK_RERANK_MANY', '1') != '0':
+        results = ranker.rerank_many((query, ranking) for _, query, ranking in items)
+    else:
+        results = (ranker.rerank(query, ranking) for _, query, ranking in items)
+    for (qid, query, _), result in zip(items, results):
+        reranked.append((qid, query, result))
         n_cmp += ranker.total_compare
         n_prompt += ranker.total_prompt_tokens
         n_completion += ranker.total_completion_tokens

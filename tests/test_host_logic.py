@@ -73,6 +73,19 @@ def test_monot5_matches_reference(which, case):
     check_counters(r, c)
 
 
+def test_monot5_rerank_many_equals_rerank():
+    from helpers import golden_v10_meta
+    from llmrankers.pointwise import MonoT5LlmRanker
+    meta = golden_v10_meta()
+    m, c = meta["tiny"], meta["cases"]["mono"]
+    r = MonoT5LlmRanker(None, None, "cuda", batch_size=4, backend=v10_backend("tiny"))
+    reqs = [(m["query"], docs_from(m["docs"])), ("w1 w2", docs_from(m["docs"][:3])), (m["query"], [])]
+    outs = list(r.rerank_many(iter(reqs)))
+    assert [d.docid for d in outs[0]] == c["order"] and len(outs[1]) == 3 and outs[2] == []
+    for d in outs[0]:
+        assert d.score == pytest.approx(c["scores"][d.docid], abs=1e-5)
+
+
 def test_duot5_matches_reference():
     """DuoT5LlmRanker.rerank heapsort (pairwise.py:296-352): compare sequence, order, scores, counters."""
     from helpers import golden_v10_meta
@@ -203,6 +216,31 @@ def test_pairwise_batched_and_sequential_heapsort_agree(monkeypatch):
         outs.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
     assert outs[0] == outs[1]
     assert outs[0][0] == c["order"] and outs[0][2:] == (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+@pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik"])
+def test_setwise_rerank_many_equals_rerank(case, capsys):
+    """Cross-query lockstep (rerank_many) must reproduce rerank() per query: order, scores, counters — including queries of
+    different sizes entering and leaving the window at different times."""
+    from llmrankers.setwise import SetwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"][case]
+    mk = lambda: SetwiseLlmRanker(None, None, "cuda", num_child=c["num_child"], k=c["k"], scoring=c["scoring"], method="heapsort",
+                                  backend=backend("tiny", c["label_favouring"]))
+    docs12 = m["docs12"]
+    requests = [(m["query"], docs12), ("w7 w8", docs12[:5]), ("w1 w2 w3", docs12[3:]), (m["query"], docs12[:1]), ("w9", docs12[::-1]), ("w4", [])]
+    want = []
+    for q, dd in requests:
+        r = mk()
+        out = r.rerank(q, docs_from(dd))
+        want.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+    assert want[0][0] == c["order"] and want[0][2] == c["total_compare"]
+    for window in (1, 3, 8):
+        r = mk()
+        got = []
+        for out in r.rerank_many([(q, docs_from(dd)) for q, dd in requests], window=window):
+            got.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+        assert got == want, window
 
 
 @pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik"])
