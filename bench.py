@@ -307,11 +307,14 @@ def run_qlm(args):
     buffers (pack + H2D + encoder + 33-position decoder + full-vocab log-softmax + D2H inside the timed region)."""
     import b200rank as br
     from b200rank.synthetic import model_cfg, synthetic_weights
-    cfg = model_cfg(MODEL)
+    model = args.model or MODEL
+    cfg = model_cfg(model)
     c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
                        max_tokens=HITS * 160, max_docs=128, max_dec_len=40, max_logit_rows=HITS * 40)
     eng = br.Engine(c, 0)
+    t_w = time.time()
     eng.load_state_dict(synthetic_weights(cfg, SEED).items())
+    t_w = time.time() - t_w
     rng = np.random.default_rng(SEED)
     S, T = P_LEN + 16, Q_LEN + 1
     ids = rng.integers(3, 32000, size=(HITS, S)).astype(np.int32)
@@ -335,15 +338,16 @@ def run_qlm(args):
         sc = eng.score_qlm(ids, lengths, labels)
     eng.sync()
     dt = time.perf_counter() - t1          # timed without the per-launch profiling events
-    gf = (cfg["num_layers"] * (8 * 1024 * 1024 * S + 6 * 1024 * 2816 * S + 4 * S * S * 1024) + cfg["num_decoder_layers"] * 4 * 1024 * 1024 * S
-          + cfg["num_decoder_layers"] * (8 * 1024 * 1024 * T + 4 * T * T * 1024 + 4 * 1024 * 1024 * T + 4 * T * S * 1024 + 6 * 1024 * 2816 * T)
-          + 2 * 1024 * 32128 * T) / 1e9
+    dm, I, F, V = cfg["d_model"], cfg["num_heads"] * 64, cfg["d_ff"], cfg["vocab_size"]     # SURVEY.md §8d formula
+    gf = (cfg["num_layers"] * (8 * dm * I * S + 6 * dm * F * S + 4 * S * S * I) + cfg["num_decoder_layers"] * 4 * dm * I * S
+          + cfg["num_decoder_layers"] * (8 * dm * I * T + 4 * T * T * I + 4 * dm * I * T + 4 * T * S * I + 6 * dm * F * T)
+          + 2 * dm * V * T) / 1e9
     peak, _ = load_peaks()
-    line = {"metric": "docs scored/sec, pointwise qlm (flan-t5-large, S 144, T 33)", "value": HITS * steps / dt, "unit": "docs/s", "n_gpus": 1,
+    line = {"metric": f"docs scored/sec, pointwise qlm ({model}, S 144, T 33)", "value": HITS * steps / dt, "unit": "docs/s", "n_gpus": 1,
             "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "flan-t5-large pointwise qlm, 100 hits/step, S 144, labels T 33 (BASELINE configs[4] shape, 1 GPU)",
-                       "algorithmic_gflop_per_doc": gf},
+            "config": {"workload": f"{model} pointwise qlm, 100 hits/step, S 144, labels T 33 (BASELINE configs[4] shape, 1 GPU)",
+                       "algorithmic_gflop_per_doc": gf, "weights_load_s": round(t_w, 1)},
             "step_frac": HITS * steps / dt * gf * 1e9 / (peak * 1e12), "finite_scores": bool(np.isfinite(sc).all()),
             "by_kernel_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:14]}}
     print(json.dumps(line))
@@ -615,6 +619,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise", "qlm"],
                     help="pointwise = the headline (BASELINE configs[1], default); setwise / pairwise = configs[2] / configs[3] through the text API, 1 GPU")
+    ap.add_argument("--model", default=None, help="qlm workload only: synthetic model shape (default flan-t5-large; BASELINE configs[4] is flan-t5-xxl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")

@@ -135,10 +135,10 @@ def binary_heap_top_k(arr: List, k: int, greater: Callable[[object, object], boo
         sift(i, 0)
 
 
-def binary_heap_top_k_batched(arr: List, k: int, greater_many: Callable[[List], List[bool]]) -> None:
-    """binary_heap_top_k with level-parallel heap construction (see heap_top_k_batched): the sift-downs of one tree level touch
-    disjoint subtrees, so their compares are gathered into one `greater_many([(a, b), ...]) -> [bool, ...]` call per round.
-    Same final array and the same multiset of compares as pairwise.py:133-162; the k extractions stay sequential."""
+def binary_heap_top_k_rounds(arr: List, k: int):
+    """binary_heap_top_k as a generator of compare rounds with level-parallel heap construction (see heap_top_k_rounds): yields
+    [(a, b), ...] and expects [greater(a, b), ...]. Same final array and the same multiset of compares as pairwise.py:133-162;
+    the k extractions stay sequential (rounds of one)."""
     n = len(arr)
 
     def sift(limit: int, i: int):
@@ -158,17 +158,20 @@ def binary_heap_top_k_batched(arr: List, k: int, greater_many: Callable[[List], 
         nxt = 2 * first + 1
         levels.append(range(first, min(nxt, n // 2 + 1)))
         first = nxt
-    def rounds():
-        for level in reversed(levels):
-            yield from _rounds([sift(n, i) for i in reversed(level)])
-        ranked = 0
-        for i in range(n - 1, 0, -1):
-            arr[i], arr[0] = arr[0], arr[i]
-            ranked += 1
-            if ranked == k:
-                break
-            yield from _rounds([sift(i, 0)])
-    drive_rounds(rounds(), greater_many)
+    for level in reversed(levels):
+        yield from _rounds([sift(n, i) for i in reversed(level)])
+    ranked = 0
+    for i in range(n - 1, 0, -1):
+        arr[i], arr[0] = arr[0], arr[i]
+        ranked += 1
+        if ranked == k:
+            break
+        yield from _rounds([sift(i, 0)])
+
+
+def binary_heap_top_k_batched(arr: List, k: int, greater_many: Callable[[List], List[bool]]) -> None:
+    """In place, like binary_heap_top_k, with the compares of every round resolved by ONE greater_many call."""
+    drive_rounds(binary_heap_top_k_rounds(arr, k), greater_many)
 
 
 def setwise_bubble_top_k(ranking: List, num_child: int, k: int, best_index: Callable[[Sequence], int]) -> None:

@@ -12,7 +12,7 @@ from itertools import combinations
 from typing import List, Optional
 
 from ._backend import T5Backend
-from ._sorting import binary_heap_top_k, binary_heap_top_k_batched, pairwise_bubble_top_k
+from ._sorting import binary_heap_top_k, binary_heap_top_k_batched, binary_heap_top_k_rounds, pairwise_bubble_top_k
 from .rankers import LlmRanker, SearchResult
 from .setwise import _assemble
 
@@ -70,23 +70,87 @@ class PairwiseLlmRanker(LlmRanker):
         out = self.compare(query, [a.text, b.text])
         return out[0] == "Passage A" and out[1] == "Passage B"
 
-    def _first_wins_many(self, query: str, pairs: List) -> List[bool]:
-        """`_first_wins` for several independent pairs in one engine call: every pair stays its own padded batch of two
-        (T5Backend.generate_batches), so strings and counters equal those of len(pairs) compare() calls."""
+    def _compare_items(self, items: List) -> List:
+        """Verdicts for several independent (query, a, b) compares in one engine call: every pair stays its own padded batch of
+        two (T5Backend.generate_batches), so each verdict equals compare()'s. Returns [(first_wins, prompt_tokens,
+        completion_tokens)]; counters are left to the caller (the pairs may belong to different queries)."""
         fields = []
-        for a, b in pairs:
+        for query, a, b in items:
             fields.append(dict(query=query, doc1=a.text, doc2=b.text))
             fields.append(dict(query=query, doc1=b.text, doc2=a.text))
         rows = self.backend.prompt_rows(self.prompt, fields)
         batches = [self.backend.pad_rows(rows[i:i + 2], self.backend.pad_id)[0] for i in range(0, len(rows), 2)]
-        wins = []
+        res = []
         for ids, out in zip(batches, self.backend.generate_batches(batches, self.decoder_input_ids, 2)):
-            self.total_compare += 1
-            self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
-            self.total_completion_tokens += out.shape[0] * out.shape[1]
             txt = self.tokenizer.batch_decode(out.tolist(), skip_special_tokens=True)
-            wins.append(txt[0] == "Passage A" and txt[1] == "Passage B")
-        return wins
+            res.append((txt[0] == "Passage A" and txt[1] == "Passage B", ids.shape[0] * ids.shape[1], out.shape[0] * out.shape[1]))
+        return res
+
+    def _first_wins_many(self, query: str, pairs: List) -> List[bool]:
+        """`_first_wins` for several independent pairs of one query; counters as len(pairs) compare() calls."""
+        res = self._compare_items([(query, a, b) for a, b in pairs])
+        self.total_compare += len(res)
+        self.total_prompt_tokens += sum(r[1] for r in res)
+        self.total_completion_tokens += sum(r[2] for r in res)
+        return [r[0] for r in res]
+
+    def rerank_many(self, requests, window: int = 8):
+        """Extension (not in the reference): heapsort-rerank an iterable of (query, ranking) pairs with up to `window` queries'
+        sorts advancing in lockstep, every round one engine batch of all their pending pair compares (see
+        SetwiseLlmRanker.rerank_many). Per-query compares, order, scores and counters are exactly rerank()'s. Other methods
+        (allpair is already one large batch per query; bubblesort) and subclasses with their own compare fall back to rerank()."""
+        if self.method != "heapsort" or type(self)._first_wins is not PairwiseLlmRanker._first_wins:
+            for query, ranking in requests:
+                yield self.rerank(query, ranking)
+            return
+        it = iter(requests)
+        active, done, next_out, seq = [], {}, 0, 0
+
+        def finish(st):
+            ranking = [SearchResult(docid=doc.docid, score=-i, text=None) for i, doc in enumerate(reversed(st["arr"]))]
+            done[st["seq"]] = (_assemble(ranking, st["original"], self.k), st["counters"])
+
+        def admit():
+            nonlocal seq
+            while len(active) < max(1, window):
+                try:
+                    query, ranking = next(it)
+                except StopIteration:
+                    return
+                st = dict(seq=seq, query=query, original=copy.deepcopy(ranking), arr=list(ranking), counters=[0, 0, 0])
+                st["gen"] = binary_heap_top_k_rounds(st["arr"], self.k)
+                seq += 1
+                try:
+                    st["round"] = next(st["gen"])
+                    active.append(st)
+                except StopIteration:
+                    finish(st)
+
+        admit()
+        while active or next_out in done:
+            while next_out in done:
+                result, c = done.pop(next_out)
+                self.total_compare, self.total_prompt_tokens, self.total_completion_tokens = c
+                next_out += 1
+                yield result
+            if not active:
+                break
+            res = self._compare_items([(st["query"], a, b) for st in active for a, b in st["round"]])
+            pos, still = 0, []
+            for st in active:
+                n = len(st["round"])
+                mine = res[pos:pos + n]
+                pos += n
+                st["counters"][0] += n
+                st["counters"][1] += sum(r[1] for r in mine)
+                st["counters"][2] += sum(r[2] for r in mine)
+                try:
+                    st["round"] = st["gen"].send([r[0] for r in mine])
+                    still.append(st)
+                except StopIteration:
+                    finish(st)
+            active[:] = still
+            admit()
 
     def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
         original_ranking = copy.deepcopy(ranking)

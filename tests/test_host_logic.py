@@ -218,6 +218,30 @@ def test_pairwise_batched_and_sequential_heapsort_agree(monkeypatch):
     assert outs[0][0] == c["order"] and outs[0][2:] == (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
 
 
+def test_pairwise_rerank_many_equals_rerank():
+    from llmrankers.pairwise import PairwiseLlmRanker
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"]["pairwise_heap"]
+    mk = lambda method="heapsort": PairwiseLlmRanker(None, None, "cuda", method=method, batch_size=c["batch_size"], k=c["k"], backend=backend("tiny", True))
+    d12 = m["docs12"]
+    requests = [(m["query"], d12[:6]), ("w7 w8", d12[4:9]), ("w1", d12[:1]), (m["query"], d12[::-1][:7]), ("w4", [])]
+    want = []
+    for q, dd in requests:
+        r = mk()
+        out = r.rerank(q, docs_from(dd))
+        want.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+    assert want[0][0] == c["order"] and want[0][2] == c["total_compare"]
+    for window in (1, 2, 8):
+        r = mk()
+        got = []
+        for out in r.rerank_many([(q, docs_from(dd)) for q, dd in requests], window=window):
+            got.append(([d.docid for d in out], [d.score for d in out], r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+        assert got == want, window
+    r = mk("allpair")   # falls back to rerank()
+    outs = list(r.rerank_many([(m["query"], docs_from(d12[:4]))]))
+    assert [d.docid for d in outs[0]] == [d.docid for d in mk("allpair").rerank(m["query"], docs_from(d12[:4]))]
+
+
 @pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik"])
 def test_setwise_rerank_many_equals_rerank(case, capsys):
     """Cross-query lockstep (rerank_many) must reproduce rerank() per query: order, scores, counters — including queries of
