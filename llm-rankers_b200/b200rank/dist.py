@@ -67,3 +67,11 @@ def score_sharded(score_fn, rows: Sequence, group=None) -> np.ndarray:
     lo, hi = shard_bounds(len(rows), rank, world)
     local = np.asarray(score_fn(list(rows[lo:hi])), dtype=np.float32) if hi > lo else np.zeros((0,), np.float32)
     return all_gather_variable(local, group)
+
+
+def gather_lists(local: List, group=None) -> List:
+    """Concatenate per-rank Python lists in rank order on every rank (picklable items; gloo or nccl)."""
+    import torch.distributed as dist
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, list(local), group=group)
+    return [x for part in parts for x in part]

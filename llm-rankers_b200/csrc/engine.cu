@@ -151,10 +151,27 @@ static int gemm_cta_group_pref() {
     return pref;
 }
 
-static int pick_block_n(int M, int N, int epi, int num_sms) {
+static int pick_block_n(int M, int N, int K, int epi, int num_sms) {
     if (epi == EPI_GATED_BF16) return 256;  // weight packing fixes the tile (HALF = 128)
     const int tiles_m = (M + kGemmBlockM - 1) / kGemmBlockM;
     const int cands[4] = {256, 128, 64, 32};
+    if (M > 2 * kGemmBlockM) {
+        // Several row tiles (encoder passes of any size, qlm decoder rows): minimise waves x time per tile. A tile costs its MMA
+        // columns plus a fixed part (pipeline fill + epilogue drain ~ 2 us ~ 120 columns at K = 1024, relatively more for short K).
+        // The largest-tile-that-fills-the-SMs rule below picked 256 for 156 tiles on 148 SMs (a second wave 5 % full) and 128 for
+        // M 3300 x N 1024 (two waves where one wave of 256-wide tiles is 30 % cheaper: qlm decoder GEMMs ran at 375 TFLOP/s).
+        const double fixed = 120.0 * 1024.0 / std::max(K, 64);
+        int best = 256;
+        double best_cost = 1e30;
+        for (int i = 0; i < 4; ++i) {
+            const int bn = cands[i];
+            const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
+            const double cost = (double)((tiles + num_sms - 1) / num_sms) * (bn + fixed);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }   // ties keep the larger tile
+        }
+        return best;
+    }
+    // one or two row tiles (the 100-row T = 1 decoder chain, generation prefixes): spread over the SMs
     for (int i = 0; i < 4; ++i) {
         const int bn = cands[i];
         if (tiles_m * ((N + bn - 1) / bn) >= num_sms) return bn;
@@ -336,7 +353,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     const int relu = (epi == EPI_RELU_BF16);
-    int bn = force_bn ? force_bn : pick_block_n(M, N, relu ? EPI_BF16 : epi, e->num_sms);
+    int bn = force_bn ? force_bn : pick_block_n(M, N, K, relu ? EPI_BF16 : epi, e->num_sms);
     if (epi == EPI_RESID_NORM) bn = 256;
     char label[96];
     if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);  // cta group: pick_cta_group
@@ -1559,7 +1576,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
         gemm_simt_debug_kernel<<<grd, blk>>>(dA, K, dW, K, M, N, K, epi, 256, dO, n_out);
     } else {
-        const int bn = block_n ? block_n : pick_block_n(M, N, epi, prop.multiProcessorCount);
+        const int bn = block_n ? block_n : pick_block_n(M, N, K, epi, prop.multiProcessorCount);
         CUtensorMap ta, tb, tout;
         const bool direct = getenv("B200RANK_GEMM_DIRECT_EPI") && atoi(getenv("B200RANK_GEMM_DIRECT_EPI")) != 0;
         const int cg = direct ? 1 : pick_cta_group(M, N, bn, prop.multiProcessorCount);

@@ -137,7 +137,27 @@ def read_first_stage(run, ranker, query_map, get_text):
     return rankings
 
 
+def _dist_setup(args):
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU, queries sharded contiguously over the ranks (every
+    query's rerank is independent; sort-based methods shard by query). Returns (rank, world); rank 0 gathers and writes the run."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if str(args.run.device).startswith('cuda'):
+        args.run.device = f'cuda:{local}'
+    if not dist.is_initialized():
+        use_nccl = torch.cuda.is_available() and str(args.run.device).startswith('cuda')
+        if use_nccl:
+            torch.cuda.set_device(local)
+        dist.init_process_group('nccl' if use_nccl else 'gloo')
+    return dist.get_rank(), world
+
+
 def main(args):
+    rank, world = _dist_setup(args)
     ranker = build_ranker(args)
     query_map, get_text = load_sources(args.run, ranker)
     logger.info(f'Loading first stage run from {args.run.run_path}.')
@@ -162,6 +182,11 @@ def main(args):
     # two queries in flight + tokenisation look-ahead; setwise heapsort: several queries' sorts in lockstep) yield exactly
     # rerank()'s result and counters per query, in order — B200RANK_RERANK_MANY=0 restores the one-call-per-query loop.
     items = list(prepared())
+    n_queries = len(items)
+    if world > 1:
+        from b200rank.dist import shard_bounds
+        lo, hi = shard_bounds(n_queries, rank, world)
+        items = items[lo:hi]
     if hasattr(ranker, 'rerank_many') and os.environ.get('B200RANK_RERANK_MANY', '1') != '0':
         results = ranker.rerank_many((query, ranking) for _, query, ranking in items)
     else:
@@ -172,6 +197,14 @@ def main(args):
         n_prompt += ranker.total_prompt_tokens
         n_completion += ranker.total_completion_tokens
     toc = time.time()
+    if world > 1:
+        import torch.distributed as dist
+        from b200rank.dist import gather_lists
+        reranked = gather_lists(reranked)                       # rank order == file order (contiguous shards)
+        n_cmp, n_prompt, n_completion = (sum(x) for x in zip(*gather_lists([(n_cmp, n_prompt, n_completion)])))
+        dist.barrier()
+        if rank != 0:
+            return
     print(f'Avg comparisons: {n_cmp / len(reranked)}')
     print(f'Avg prompt tokens: {n_prompt / len(reranked)}')
     print(f'Avg completion tokens: {n_completion / len(reranked)}')

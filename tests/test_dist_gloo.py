@@ -57,3 +57,53 @@ def test_two_rank_sharded_scoring_matches_single_rank(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o[-2000:]
+
+
+CLI_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, os.path.join(r"{root}", "llm-rankers_b200")); sys.path.insert(0, r"{root}"); sys.path.insert(0, os.path.join(r"{root}", "tests"))
+    os.environ.update(RANK=sys.argv[1], LOCAL_RANK=sys.argv[1], WORLD_SIZE=sys.argv[2], MASTER_ADDR="127.0.0.1", MASTER_PORT="{port}")
+    import torch
+    torch.cuda.is_available = lambda: False            # CPU box / CPU test: rendezvous on gloo
+    import run as cli_mod
+    from llmrankers import _backend
+    from fake_backend import OracleBackend
+    from helpers import model_and_weights, oracle_for
+    from b200rank.synthetic import synthetic_tokenizer
+    cfg, _ = model_and_weights("tiny")
+    be = OracleBackend(oracle_for("tiny"), synthetic_tokenizer(), cfg)
+    _backend.T5Backend.load = classmethod(lambda cls, *a, **k: be)    # the oracle stands in for the GPU engine (host logic under test)
+    d = r"{tmp}"
+    cli_mod.cli(["run", "--model_name_or_path", "synthetic:t5-tiny", "--run_path", d + "/run.txt", "--save_path", d + "/out_w" + sys.argv[2] + ".txt",
+                 "--queries_tsv", d + "/queries.tsv", "--collection_tsv", d + "/docs.tsv", "--query_length", "32", "--passage_length", "128",
+                 "pointwise", "--method", "yes_no", "--batch_size", "4"])
+    print("RANK_OK", sys.argv[1])
+""")
+
+
+def test_cli_shards_queries_over_ranks(tmp_path):
+    """run.py under a 2-rank rendezvous: queries are split contiguously, rank 0 gathers and writes — the run file and the summary
+    counters equal the single-process run."""
+    from helpers import golden_meta
+    m = golden_meta()["tiny"]
+    queries = [("q1", m["query"]), ("q2", "w3 w4 w5"), ("q3", "w100 w7"), ("q4", "w9"), ("q5", "w1 w2 w3 w4")]
+    (tmp_path / "queries.tsv").write_text("".join(f"{q}\t{t}\n" for q, t in queries))
+    (tmp_path / "docs.tsv").write_text("".join(f"{d['docid']}\t{d['text']}\n" for d in m["docs"]))
+    lines = []
+    for qi, (q, _) in enumerate(queries):
+        docs = m["docs"][qi:] + m["docs"][:qi]
+        lines += [f"{q} Q0 {d['docid']} {i + 1} {10 - i} bm25\n" for i, d in enumerate(docs[: 10 - qi])]
+    (tmp_path / "run.txt").write_text("".join(lines))
+    script = tmp_path / "cli_worker.py"
+    script.write_text(CLI_WORKER.format(root=ROOT, port=29541, tmp=str(tmp_path)))
+    outs = {}
+    for world in (1, 2):
+        procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for r in range(world)]
+        logs = [p.communicate(timeout=900)[0] for p in procs]
+        for r, (p, o) in enumerate(zip(procs, logs)):
+            assert p.returncode == 0 and f"RANK_OK {r}" in o, o[-3000:]
+        outs[world] = ((tmp_path / f"out_w{world}.txt").read_text(), [l for l in logs[0].splitlines() if l.startswith("Avg ") and "time" not in l])
+        assert not any(l.startswith("Avg ") for o in logs[1:] for l in o.splitlines())   # only rank 0 reports
+    assert outs[1][0] == outs[2][0] and len(outs[1][0].splitlines()) == sum(10 - i for i in range(5))
+    assert outs[1][1] == outs[2][1] and len(outs[1][1]) == 3
