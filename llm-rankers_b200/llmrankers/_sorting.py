@@ -174,6 +174,33 @@ def binary_heap_top_k_batched(arr: List, k: int, greater_many: Callable[[List], 
     drive_rounds(binary_heap_top_k_rounds(arr, k), greater_many)
 
 
+def setwise_bubble_rounds(ranking: List, num_child: int, k: int):
+    """setwise_bubble_top_k as a generator of compare rounds (always one request: the passes are a dependent chain), so that the
+    bubble sorts of several queries can advance together. Yields [window]; expects [index of the preferred doc in the window]."""
+    width = num_child + 1
+    last_start = len(ranking) - width
+    for i in range(k):
+        start, end = last_start, last_start + width
+        changed = False
+        while True:
+            if start < i:
+                start = i
+            window = ranking[start:end]
+            b = (yield [window])[0]
+            if b != 0:
+                ranking[start], ranking[start + b] = ranking[start + b], ranking[start]
+                if not changed:
+                    changed = True
+                    if last_start != len(ranking) - width and b == len(window) - 1:
+                        last_start += len(window) - 1
+            if start == i:
+                break
+            if not changed:
+                last_start -= num_child
+            start -= num_child
+            end -= num_child
+
+
 def setwise_bubble_top_k(ranking: List, num_child: int, k: int, best_index: Callable[[Sequence], int]) -> None:
     """setwise.py:243-273: k passes of a (num_child+1)-wide window sliding from the tail to position i, with the
     'skip the unchanged tail' bookkeeping (last_start). best_index(window) -> index of the preferred doc in the window

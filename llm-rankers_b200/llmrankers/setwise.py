@@ -14,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 from ._backend import T5Backend
-from ._sorting import heap_top_k, heap_top_k_batched, heap_top_k_rounds, setwise_bubble_top_k
+from ._sorting import heap_top_k, heap_top_k_batched, heap_top_k_rounds, setwise_bubble_rounds, setwise_bubble_top_k
 from .rankers import LlmRanker, SearchResult
 
 random.seed(929)  # setwise.py:18
@@ -161,16 +161,17 @@ class SetwiseLlmRanker(LlmRanker):
         return inds[b] if b < len(inds) else inds[0]
 
     def rerank_many(self, requests, window: int = 8):
-        """Extension (not in the reference): heapsort-rerank an iterable of (query, ranking) pairs with up to `window` queries
-        advancing in lockstep — every round sends the pending compares of all active queries (several per query while a heap level
+        """Extension (not in the reference): rerank an iterable of (query, ranking) pairs (heapsort or bubblesort) with up to `window`
+        queries advancing in lockstep — every round sends the pending compares of all active queries (several per query while a heap level
         is being built) to the GPU as one batch. A compare is latency-bound by its two ~250-kernel decoder passes, so batching
         across queries multiplies throughput; each query's compares, order, scores and counters are exactly those of rerank().
         Yields rerank()'s result for each pair in request order; after each yield the three counters hold that query's totals.
         Other methods / num_permutation > 1 fall back to rerank()."""
-        if self.method != "heapsort" or self.num_permutation != 1:
+        if self.method not in ("heapsort", "bubblesort") or self.num_permutation != 1:
             for query, ranking in requests:
                 yield self.rerank(query, ranking)
             return
+        heap = self.method == "heapsort"
         it = iter(requests)
         active, done, next_out, seq = [], {}, 0, 0
         template1 = self._template(1, self.CHARACTERS)
@@ -187,7 +188,8 @@ class SetwiseLlmRanker(LlmRanker):
                 if a is not None:
                     a.warm("d0", [d.text for d in ranking])
                 st = dict(seq=seq, query=query, original=copy.deepcopy(ranking), arr=ranking, counters=[0, 0, 0])
-                st["gen"] = heap_top_k_rounds(st["arr"], self.num_child, self.k)
+                st["gen"] = (heap_top_k_rounds(st["arr"], self.num_child, self.k) if heap
+                             else setwise_bubble_rounds(st["arr"], self.num_child, self.k))
                 try:
                     st["round"] = next(st["gen"])
                     active.append(st)
@@ -197,7 +199,7 @@ class SetwiseLlmRanker(LlmRanker):
                 seq += 1
 
         def finish(st):
-            done[st["seq"]] = (_assemble(list(reversed(st["arr"])), st["original"], self.k), st["counters"])
+            done[st["seq"]] = (_assemble(list(reversed(st["arr"])) if heap else st["arr"], st["original"], self.k), st["counters"])
 
         admit()
         while active or next_out in done:
@@ -208,7 +210,8 @@ class SetwiseLlmRanker(LlmRanker):
                 yield result
             if not active:
                 break
-            items = [(st["query"], docs) for st in active for docs, _ in st["round"]]
+            # a heap round holds (docs, arr indices) requests, a bubble round one bare window
+            items = [(st["query"], req[0] if heap else req) for st in active for req in st["round"]]
             res = self._compare_items(items)
             pos, still = 0, []
             for st in active:
@@ -218,7 +221,13 @@ class SetwiseLlmRanker(LlmRanker):
                 st["counters"][0] += n
                 st["counters"][1] += sum(r[1] for r in mine)
                 st["counters"][2] += sum(r[2] for r in mine)
-                picks = [self._pick(r[0], inds) for r, (_, inds) in zip(mine, st["round"])]
+                if heap:
+                    picks = [self._pick(r[0], inds) for r, (_, inds) in zip(mine, st["round"])]
+                else:   # bubblesort: label -> index in the window (unknown label keeps the head; beyond the window raises, :259)
+                    picks = [self.CHARACTERS.index(r[0]) if r[0] in self.CHARACTERS else 0 for r in mine]
+                    for b, win in zip(picks, st["round"]):
+                        if b >= len(win):
+                            raise IndexError("list index out of range")
                 try:
                     st["round"] = st["gen"].send(picks)
                     still.append(st)

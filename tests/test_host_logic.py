@@ -242,17 +242,19 @@ def test_pairwise_rerank_many_equals_rerank():
     assert [d.docid for d in outs[0]] == [d.docid for d in mk("allpair").rerank(m["query"], docs_from(d12[:4]))]
 
 
-@pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik"])
+@pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik", "setwise_bubble_lik", "setwise_bubble_gen"])
 def test_setwise_rerank_many_equals_rerank(case, capsys):
     """Cross-query lockstep (rerank_many) must reproduce rerank() per query: order, scores, counters — including queries of
     different sizes entering and leaving the window at different times."""
     from llmrankers.setwise import SetwiseLlmRanker
     meta = golden_meta()
     m, c = meta["tiny"], meta["cases"][case]
-    mk = lambda: SetwiseLlmRanker(None, None, "cuda", num_child=c["num_child"], k=c["k"], scoring=c["scoring"], method="heapsort",
+    mk = lambda: SetwiseLlmRanker(None, None, "cuda", num_child=c["num_child"], k=c["k"], scoring=c["scoring"], method=c["method"],
                                   backend=backend("tiny", c["label_favouring"]))
     docs12 = m["docs12"]
-    requests = [(m["query"], docs12), ("w7 w8", docs12[:5]), ("w1 w2 w3", docs12[3:]), (m["query"], docs12[:1]), ("w9", docs12[::-1]), ("w4", [])]
+    requests = [(m["query"], docs12), ("w7 w8", docs12[:5]), ("w1 w2 w3", docs12[3:]), (m["query"], docs12[:4]), ("w9", docs12[::-1])]
+    if c["method"] == "heapsort":
+        requests += [(m["query"], docs12[:1]), ("w4", [])]
     want = []
     for q, dd in requests:
         r = mk()
