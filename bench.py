@@ -414,6 +414,9 @@ def run_engine(args):
 
     use_dist = world > 1
     if use_dist:
+        # stdout carries exactly ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION is in the environment
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)

@@ -903,7 +903,10 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         static int spin = -1;
         if (spin < 0) spin = getenv("B200RANK_ATTN_SPIN") ? atoi(getenv("B200RANK_ATTN_SPIN")) : 0;
         if (e) prof_begin(e, "enc_attention_tc2");
-        CU_OK(launch_k(kern, dim3(std::min(n_items, device_sm_count())), dim3(kAttnTcThreads), AttnTc2Cfg<3>::smem_bytes(H), st, *tm, inner, d_cu, bias,
+        static int attn_sms = -1;   // B200RANK_ATTN_SMS=n: cap the persistent grid (leaves SMs to the decoder stream of the other query in flight)
+        if (attn_sms < 0) attn_sms = getenv("B200RANK_ATTN_SMS") ? std::max(1, atoi(getenv("B200RANK_ATTN_SMS"))) : 0;
+        const int grid_cap = attn_sms > 0 ? std::min(attn_sms, device_sm_count()) : device_sm_count();
+        CU_OK(launch_k(kern, dim3(std::min(n_items, grid_cap)), dim3(kAttnTcThreads), AttnTc2Cfg<3>::smem_bytes(H), st, *tm, inner, d_cu, bias,
                        out, ldo, H, n_items, spin));
         return e ? post_launch(e, "enc_attention_tc2") : B200RANK_OK;
     }
