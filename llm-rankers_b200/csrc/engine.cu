@@ -252,6 +252,8 @@ struct b200rank_engine {
     float* logits = nullptr;       // [cap_logit_rows, V]
     float* small_out = nullptr;    // [cap_rows * 32] generic fp32 results
     float* small_out2 = nullptr;   // [cap_docs * 32]
+    float* xattn_partial = nullptr;  // key-split cross-attention partials: [docs][H][nsplit][T][66] fp32 (few documents, long prompts)
+    size_t xattn_partial_bytes = 0;
     int* d_ids = nullptr;          // [cap_tokens]
     int* d_cu = nullptr;           // [cap_docs + 1]
     int* d_dec_ids = nullptr;      // [cap_rows]
@@ -427,7 +429,7 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
-                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
+                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->xattn_partial, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
                      e->d_int_out, e->d_finished, e->l2_scratch};
     for (void* p : frees)
         if (p) cudaFree(p);
@@ -560,6 +562,8 @@ static int create_impl(b200rank_engine* e) {
     RET_IF(dev_alloc(e, &e->logits, (size_t)e->cap_logit_rows * V));
     RET_IF(dev_alloc(e, &e->qp, (size_t)align_up(e->cap_docs, 128) * e->H * d)); RET_IF(dev_alloc(e, &e->ctxb, (size_t)align_up(e->cap_docs, 128) * e->H * d));
     RET_IF(dev_alloc(e, &e->small_out, R * 32)); RET_IF(dev_alloc(e, &e->small_out2, (size_t)e->cap_docs * 32));
+    e->xattn_partial_bytes = (size_t)2 * e->num_sms * 16 * 4 * 66 * sizeof(float);   // H*nd < SMs, nsplit <= 16, T <= 4
+    RET_IF(dev_alloc(e, &e->xattn_partial, e->xattn_partial_bytes / sizeof(float)));
     RET_IF(dev_alloc(e, &e->d_ids, Tk));
     for (int b = 0; b < 2; ++b) {
         RET_IF(dev_alloc(e, &e->enc_out[b], Tk * d));
@@ -990,6 +994,11 @@ static bool use_reassoc_t1(const b200rank_engine* e, int T) {
     return pref && T == 1 && e->staged_maxlen <= 240 && !e->debug_simt && e->d % kCtxKC == 0;  // 240: 3-stage ring fits 227 KB
 }
 
+static bool cross_split_off() {   // read per call (not cached): tests flip B200RANK_CROSS_SPLIT in-process for the A/B
+    const char* v = getenv("B200RANK_CROSS_SPLIT");
+    return v && atoi(v) == 0;
+}
+
 // Many decoder positions (qlm labels, long prefixes): tensor-core attention kernels (attention_dec.cuh); the CUDA-core kernels
 // remain for the 1-4 position prefixes of yes_no / generation. B200RANK_DEC_ATTN=simt forces the CUDA-core kernels everywhere.
 static bool dec_attn_mma(int T) {
@@ -1070,8 +1079,21 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             cross_attention_t1_kernel<8><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         else if (T == 1 && e->H % 4 == 0 && max_len <= 2048)
             cross_attention_t1_kernel<64><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
-        else if (T <= 4)
-            cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
+        else if (T <= 4) {
+            // long prompts, few documents (setwise / pairwise compares): split the keys over CTAs so that more than H x nd SMs work
+            const int chunks = (max_len + 127) / 128;
+            int nsplit = 1;
+            if (e->H * nd < e->num_sms && chunks > 1 && !cross_split_off())
+                nsplit = std::min(std::min(chunks, 16), std::max(1, 2 * e->num_sms / (e->H * nd)));
+            if (nsplit > 1 && (size_t)nd * e->H * nsplit * T * 66 * sizeof(float) <= e->xattn_partial_bytes) {
+                cross_attention_kernel<4, 128><<<dim3(e->H, nd, nsplit), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I, e->xattn_partial);
+                RET_IF(post_launch(e, "cross_attention"));
+                prof_begin(e, "cross_attention_combine");
+                cross_attention_combine_kernel<<<dim3(e->H, nd), 64, 0, e->stream>>>(e->xattn_partial, nsplit, T, e->aod, I);
+            } else {
+                cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
+            }
+        }
         else
             cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         RET_IF(post_launch(e, "cross_attention"));

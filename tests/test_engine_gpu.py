@@ -571,6 +571,31 @@ def test_xxl_width_qlm():
     e.close()
 
 
+def test_key_split_cross_attention_matches_single_cta():
+    """Long prompts, few documents (setwise / pairwise compares): the key-split cross-attention (flash-decoding partials + exact
+    log-sum-exp merge) against the one-CTA-per-head kernel at decoder prefixes of 2 and 3 tokens — same label logits to bf16
+    rounding noise; ragged lengths so that some splits are empty for the shorter prompts."""
+    e, cfg, w = large_engine()
+    rng = np.random.default_rng(16)
+    lens = [1536, 700, 129]
+    ids = np.zeros((3, 1536), np.int32)
+    for i, n in enumerate(lens):
+        ids[i, :n] = rng.integers(3, 32000, size=n)
+        ids[i, n - 1] = 1
+    lengths = np.asarray(lens, np.int32)
+    cols = [71, 272, 205, 309, 262, 377, 350, 454, 27, 446, 480]
+    res = {}
+    for flag in ("1", "0"):
+        os.environ["B200RANK_CROSS_SPLIT"] = flag
+        res[flag] = (e.logits_at(ids, lengths, [0, 5], cols, normalize=False), e.logits_at(ids, lengths, [0, 5, 71], cols, normalize=False))
+    os.environ.pop("B200RANK_CROSS_SPLIT")
+    diff = max(float(np.abs(res["1"][i] - res["0"][i]).max()) for i in range(2))
+    record("variant/cross_attention_key_split", max_abs_diff=diff)
+    # not bit-exact: the splits merge in a different order and the bf16 attention output may round differently; generated tokens are
+    # not compared because a random-init lm_head leaves near-ties among 32 k tokens (the oracle test below gates on the top-2 gap)
+    assert diff < 3e-2
+
+
 def test_large_setwise_prompt_length():
     """BASELINE config 3 shape: one setwise compare prompt of 11 passages (S = 1536) on the full flan-t5-large: label
     probabilities (likelihood scoring) and the first generated token against the fp32 oracle; exercises the long-sequence
