@@ -20,6 +20,7 @@
 #include "attention_enc.cuh"
 #include "attention_tc.cuh"
 #include "attention_dec.cuh"
+#include "skinny_gemv.cuh"
 #include "cross_ctx_t1.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels_misc.cuh"
@@ -1007,6 +1008,59 @@ static bool dec_attn_mma(int T) {
     return pref && T > 4;
 }
 
+// ---- decoder projections: tcgen05 GEMM (+ separate T5LayerNorm launch) or, for a handful of rows, skinny_gemv.cuh
+// OFF by default (B200RANK_SKINNY=1 enables it): measured on a setwise compare (tests/gpu_prof_setwise.py) the fused kernels only
+// save the T5LayerNorm launches (9.4 vs 10.5 ms of profiled GPU time per compare; a skinny launch costs as much as a 2-row tcgen05
+// GEMM launch, both are latency-bound), while they give up a property the batched sort drivers rely on: with the GEMM path a row's
+// result is bit-identical whatever else is in the batch, so rerank_many / level-parallel heaps reproduce rerank() exactly.
+static bool use_skinny(const b200rank_engine* e, int R) {
+    static int pref = -1;
+    if (pref < 0) pref = (getenv("B200RANK_SKINNY") && atoi(getenv("B200RANK_SKINNY")) == 1) ? 1 : 0;
+    return pref && R <= kSkinnyMaxRows && !e->debug_simt && e->d % 8 == 0 && e->F % 8 == 0 && e->inner % 8 == 0;
+}
+
+template <int EPI>
+static int launch_skinny(b200rank_engine* e, const char* label, const float* x, const bf16* a, int lda, const float* ln_w, const bf16* W,
+                         int ldw, int R, int n_out, int K, void* out, int ldo) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_OK(cudaFuncSetAttribute(skinny_gemv_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnyMaxRows * 10240 * 2));
+        attr_set = true;
+    }
+    if ((size_t)R * K * 2 > (size_t)kSkinnyMaxRows * 10240 * 2) return set_error(B200RANK_ERR_CAPACITY, "skinny GEMV: K=%d too long", K);
+    prof_begin(e, label);
+    const int grid = std::min((n_out + 7) / 8, 8 * e->num_sms);
+    CU_OK(launch_k(skinny_gemv_kernel<EPI>, dim3(grid), dim3(kSkinnyThreads), (size_t)R * K * 2, e->stream, x, a, lda, ln_w, e->cfg.layer_norm_eps, W, ldw,
+                   R, n_out, K, out, ldo));
+    return post_launch(e, label);
+}
+
+// out_bf16[R, N] = T5LayerNorm(xd; ln_w) . W^T   (W: [N, d])
+static int dec_norm_proj(b200rank_engine* e, const float* ln_w, const bf16* W, int N, int R, bf16* out, int ldo) {
+    const int d = e->d;
+    if (use_skinny(e, R)) return launch_skinny<SK_BF16>(e, "skinny_norm_proj", e->xd, nullptr, 0, ln_w, W, d, R, N, d, out, ldo);
+    RET_IF(k_rmsnorm(e, e->xd, ln_w, e->hd, R));
+    return gemm(e, e->hd, d, e->cap_rows, W, d, N, R, N, d, EPI_BF16, out, ldo);
+}
+
+// xd[R, d] += A[R, K] . W^T   (W: [d, K])
+static int dec_resid_proj(b200rank_engine* e, const bf16* A, int lda, const bf16* W, int K, int R) {
+    const int d = e->d;
+    if (use_skinny(e, R)) return launch_skinny<SK_RESID_F32>(e, "skinny_resid_proj", nullptr, A, lda, nullptr, W, K, R, d, K, e->xd, d);
+    return gemm(e, A, lda, e->cap_rows, W, K, d, R, d, K, EPI_RESID_F32, e->xd, d);
+}
+
+// gd[R, F] = act(T5LayerNorm(xd; ln2) . wi^T)  (gated-gelu over the tile-interleaved wi_0 | wi_1 packing, or relu)
+static int dec_norm_ffn_in(b200rank_engine* e, const float* ln_w, const bf16* wi, int R) {
+    const int d = e->d, F = e->F;
+    if (use_skinny(e, R)) {
+        if (e->gated) return launch_skinny<SK_GATED_BF16>(e, "skinny_norm_ffn_in", e->xd, nullptr, 0, ln_w, wi, d, R, F, d, e->gd, F);
+        return launch_skinny<SK_RELU_BF16>(e, "skinny_norm_ffn_in", e->xd, nullptr, 0, ln_w, wi, d, R, F, d, e->gd, F);
+    }
+    RET_IF(k_rmsnorm(e, e->xd, ln_w, e->hd, R));
+    return ffn_in(e, e->hd, e->cap_rows, wi, R, e->gd);
+}
+
 // Decoder over documents [doc0, doc0+nd) with T positions each; dec ids in d_dec_ids[nd*T].
 // Leaves the final-normed hidden states in hd[nd*T, d].
 static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
@@ -1027,12 +1081,13 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
     }
     for (int l = 0; l < e->Ld; ++l) {
         const LayerW& w = e->dec[l];
-        RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
         if (T == 1) {
-            // one decoder position: softmax over a single key is 1, so the block is x += W_o W_v norm(x) (derive_weights)
-            RET_IF(gemm(e, e->hd, d, cap, w.wov, d, d, R, d, d, EPI_RESID_F32, e->xd, d));
+            // one decoder position: softmax over a single key is 1, so the block is x += W_o W_v norm(x) (derive_weights).
+            // Input and output are both xd, so the norm stays a kernel of its own (a fused norm would race with the adds).
+            RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
+            RET_IF(dec_resid_proj(e, e->hd, d, w.wov, d, R));
         } else {
-            RET_IF(gemm(e, e->hd, d, cap, w.wqkv, d, 3 * I, R, 3 * I, d, EPI_BF16, e->qkvd, 3 * I));
+            RET_IF(dec_norm_proj(e, w.ln1, w.wqkv, 3 * I, R, e->qkvd, 3 * I));
             if (dec_attn_mma(T)) {
                 prof_begin(e, "dec_self_attention_mma");
                 launch_k(dec_attention_mma_kernel<true>, dim3((T + 63) / 64, e->H, nd), dim3(128), 0, e->stream, e->qkvd, 3 * I, T, e->qkvd, (size_t)3 * I, I, 2 * I,
@@ -1042,10 +1097,9 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
                 prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
                 RET_IF(post_launch(e, "dec_self_attention"));
             }
-            RET_IF(gemm(e, e->aod, I, cap, w.wo, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
+            RET_IF(dec_resid_proj(e, e->aod, I, w.wo, I, R));
         }
-        RET_IF(k_rmsnorm(e, e->xd, w.ln_c, e->hd, R));
-        RET_IF(gemm(e, e->hd, d, cap, w.wq_c, d, I, R, I, d, EPI_BF16, e->qd, I));
+        RET_IF(dec_norm_proj(e, w.ln_c, w.wq_c, I, R, e->qd, I));
         if (reassoc) {
             // cross_ctx_t1.cuh: scores = (W_k,h^T q_h) . e_j and out_h = W_v,h (sum_j p_j e_j): no K/V projection of the encoder
             const int HD = e->H * d, dcap = (int)align_up(e->cap_docs, 128);
@@ -1056,10 +1110,9 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             RET_IF(post_launch(e, "cross_ctx_t1"));
             const bf16* wv_l = e->wckv + ((size_t)l * 2 * I + I) * d;
             RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, nullptr, nullptr, /*n_per_batch=*/64, /*a_cols=*/HD));
-            RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
-            RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
-            RET_IF(ffn_in(e, e->hd, cap, w.wi, R, e->gd));
-            RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
+            RET_IF(dec_resid_proj(e, e->aod, I, w.wo_c, I, R));
+            RET_IF(dec_norm_ffn_in(e, w.ln2, w.wi, R));
+            RET_IF(dec_resid_proj(e, e->gd, F, w.wff, F, R));
             continue;
         }
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
@@ -1068,10 +1121,9 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             launch_k(dec_attention_mma_kernel<false>, dim3((T + 63) / 64, e->H, nd), dim3(128), 0, e->stream, e->qd, I, T, e->ckv, ldkv, k_off, v_off,
                      (const int*)(e->d_cu_cur + doc0), (const float*)nullptr, 0, e->aod, I);
             RET_IF(post_launch(e, "cross_attention_mma"));
-            RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
-            RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
-            RET_IF(ffn_in(e, e->hd, cap, w.wi, R, e->gd));
-            RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
+            RET_IF(dec_resid_proj(e, e->aod, I, w.wo_c, I, R));
+            RET_IF(dec_norm_ffn_in(e, w.ln2, w.wi, R));
+            RET_IF(dec_resid_proj(e, e->gd, F, w.wff, F, R));
             continue;
         }
         prof_begin(e, "cross_attention");
@@ -1097,10 +1149,9 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         else
             cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         RET_IF(post_launch(e, "cross_attention"));
-        RET_IF(gemm(e, e->aod, I, cap, w.wo_c, I, d, R, d, I, EPI_RESID_F32, e->xd, d));
-        RET_IF(k_rmsnorm(e, e->xd, w.ln2, e->hd, R));
-        RET_IF(ffn_in(e, e->hd, cap, w.wi, R, e->gd));
-        RET_IF(gemm(e, e->gd, F, cap, w.wff, F, d, R, d, F, EPI_RESID_F32, e->xd, d));
+        RET_IF(dec_resid_proj(e, e->aod, I, w.wo_c, I, R));
+        RET_IF(dec_norm_ffn_in(e, w.ln2, w.wi, R));
+        RET_IF(dec_resid_proj(e, e->gd, F, w.wff, F, R));
     }
     RET_IF(k_rmsnorm(e, e->xd, e->dec_final_ln, e->hd, R));
     return B200RANK_OK;
