@@ -222,6 +222,8 @@ struct LayerW {
     bf16* wkT = nullptr;  // decoder only, derived at load: per-head transposed cross W_k, [H*d, 64] (q'_h = W_k,h^T q_h)
 };
 
+constexpr int kXAttnSplit = 8;   // key splits of the 2-4-position cross-attention (fixed: see run_decoder)
+
 struct b200rank_engine {
     b200rank_config cfg;
     int device = 0, num_sms = 0;
@@ -563,7 +565,7 @@ static int create_impl(b200rank_engine* e) {
     RET_IF(dev_alloc(e, &e->logits, (size_t)e->cap_logit_rows * V));
     RET_IF(dev_alloc(e, &e->qp, (size_t)align_up(e->cap_docs, 128) * e->H * d)); RET_IF(dev_alloc(e, &e->ctxb, (size_t)align_up(e->cap_docs, 128) * e->H * d));
     RET_IF(dev_alloc(e, &e->small_out, R * 32)); RET_IF(dev_alloc(e, &e->small_out2, (size_t)e->cap_docs * 32));
-    e->xattn_partial_bytes = (size_t)2 * e->num_sms * 16 * 4 * 66 * sizeof(float);   // H*nd < SMs, nsplit <= 16, T <= 4
+    e->xattn_partial_bytes = (size_t)std::min(e->cap_docs, 256) * e->H * kXAttnSplit * 4 * 66 * sizeof(float);   // groups of <= 256 documents, T <= 4
     RET_IF(dev_alloc(e, &e->xattn_partial, e->xattn_partial_bytes / sizeof(float)));
     RET_IF(dev_alloc(e, &e->d_ids, Tk));
     for (int b = 0; b < 2; ++b) {
@@ -1132,16 +1134,23 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         else if (T == 1 && e->H % 4 == 0 && max_len <= 2048)
             cross_attention_t1_kernel<64><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         else if (T <= 4) {
-            // long prompts, few documents (setwise / pairwise compares): split the keys over CTAs so that more than H x nd SMs work
-            const int chunks = (max_len + 127) / 128;
-            int nsplit = 1;
-            if (e->H * nd < e->num_sms && chunks > 1 && !cross_split_off())
-                nsplit = std::min(std::min(chunks, 16), std::max(1, 2 * e->num_sms / (e->H * nd)));
-            if (nsplit > 1 && (size_t)nd * e->H * nsplit * T * 66 * sizeof(float) <= e->xattn_partial_bytes) {
-                cross_attention_kernel<4, 128><<<dim3(e->H, nd, nsplit), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I, e->xattn_partial);
-                RET_IF(post_launch(e, "cross_attention"));
-                prof_begin(e, "cross_attention_combine");
-                cross_attention_combine_kernel<<<dim3(e->H, nd), 64, 0, e->stream>>>(e->xattn_partial, nsplit, T, e->aod, I);
+            // Generation / likelihood prefixes (2-4 decoder positions). The keys of every (document, head) are ALWAYS split 8 ways
+            // (CTA z takes the 128-key chunks z, z+8, ...; flash-decoding partials + exact log-sum-exp merge): a setwise compare
+            // (1 document, 1.5 k keys) otherwise runs on 16 CTAs of a 148-SM GPU, 100 us per layer. The split is a function of the
+            // document alone — not of how many documents share the pass — so a row's result stays bit-identical across batch
+            // compositions (what lets rerank_many / the level-parallel heaps reproduce rerank() exactly).
+            if (!cross_split_off()) {
+                const int group = (int)(e->xattn_partial_bytes / ((size_t)e->H * kXAttnSplit * T * 66 * sizeof(float)));
+                for (int g0 = 0; g0 < nd; g0 += group) {
+                    const int gn = std::min(group, nd - g0);
+                    if (g0) prof_begin(e, "cross_attention");
+                    cross_attention_kernel<4, 128><<<dim3(e->H, gn, kXAttnSplit), 128, 0, e->stream>>>(e->qd + (size_t)g0 * T * I, I, T, e->ckv, ldkv, k_off, v_off,
+                                                                                                        e->d_cu_cur + doc0 + g0, e->aod + (size_t)g0 * T * I, I, e->xattn_partial);
+                    RET_IF(post_launch(e, "cross_attention"));
+                    prof_begin(e, "cross_attention_combine");
+                    cross_attention_combine_kernel<<<dim3(e->H, gn), 64, 0, e->stream>>>(e->xattn_partial, kXAttnSplit, T, e->aod + (size_t)g0 * T * I, I);
+                    if (g0 + gn < nd) RET_IF(post_launch(e, "cross_attention_combine"));
+                }
             } else {
                 cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
             }
