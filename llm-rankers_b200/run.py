@@ -212,46 +212,34 @@ def main(args):
     write_run_file(args.run.save_path, reranked, 'LLMRankers')
 
 
+# The reference's CLI grammar (run.py:206-258) as data: sub-command -> [(flag, type, default, choices, help)]. Flags, defaults and
+# choices are the interface contract; --queries_tsv / --collection_tsv are this package's offline sources.
+CLI_GRAMMAR = {
+    'run': [('run_path', str, None, None, 'first-stage run file (TREC format) to rerank'),
+            ('save_path', str, None, None, 'where to write the reranked run file (TREC format)'),
+            ('model_name_or_path', str, None, None, 'checkpoint directory / hub id, or synthetic:<shape>'),
+            ('tokenizer_name_or_path', str, None, None, None), ('ir_dataset_name', str, None, None, None),
+            ('pyserini_index', str, None, None, None), ('hits', int, 100, None, None), ('query_length', int, 128, None, None),
+            ('passage_length', int, 128, None, None), ('device', str, 'cuda', None, None), ('cache_dir', str, None, None, None),
+            ('openai_key', str, None, None, None), ('scoring', str, 'generation', ['generation', 'likelihood'], None),
+            ('shuffle_ranking', str, None, ['inverse', 'random'], None),
+            ('queries_tsv', str, None, None, '(extension) qid<TAB>text'), ('collection_tsv', str, None, None, '(extension) docid<TAB>text')],
+    'pointwise': [('method', str, 'yes_no', ['qlm', 'yes_no'], None), ('batch_size', int, 2, None, None)],
+    'pairwise': [('method', str, 'allpair', ['allpair', 'heapsort', 'bubblesort'], None), ('batch_size', int, 2, None, None),
+                 ('k', int, 10, None, None)],
+    'setwise': [('num_child', int, 3, None, None), ('method', str, 'heapsort', ['heapsort', 'bubblesort'], None), ('k', int, 10, None, None),
+                ('num_permutation', int, 1, None, None)],
+    'listwise': [('window_size', int, 3, None, None), ('step_size', int, 1, None, None), ('num_repeat', int, 1, None, None)],
+}
+
+
 def make_parser():
     parser = argparse.ArgumentParser()
     commands = parser.add_subparsers(title='sub-commands')
-    run = commands.add_parser('run')
-    run.add_argument('--run_path', type=str, help='Path to the first stage run file (TREC format) to rerank.')
-    run.add_argument('--save_path', type=str, help='Path to save the reranked run file (TREC format).')
-    run.add_argument('--model_name_or_path', type=str, help='Checkpoint directory / hub id, or synthetic:<flan-t5-size>')
-    run.add_argument('--tokenizer_name_or_path', type=str, default=None)
-    run.add_argument('--ir_dataset_name', type=str, default=None)
-    run.add_argument('--pyserini_index', type=str, default=None)
-    run.add_argument('--hits', type=int, default=100)
-    run.add_argument('--query_length', type=int, default=128)
-    run.add_argument('--passage_length', type=int, default=128)
-    run.add_argument('--device', type=str, default='cuda')
-    run.add_argument('--cache_dir', type=str, default=None)
-    run.add_argument('--openai_key', type=str, default=None)
-    run.add_argument('--scoring', type=str, default='generation', choices=['generation', 'likelihood'])
-    run.add_argument('--shuffle_ranking', type=str, default=None, choices=['inverse', 'random'])
-    run.add_argument('--queries_tsv', type=str, default=None, help='(extension) qid<TAB>text')
-    run.add_argument('--collection_tsv', type=str, default=None, help='(extension) docid<TAB>text')
-
-    pointwise = commands.add_parser('pointwise')
-    pointwise.add_argument('--method', type=str, default='yes_no', choices=['qlm', 'yes_no'])
-    pointwise.add_argument('--batch_size', type=int, default=2)
-
-    pairwise = commands.add_parser('pairwise')
-    pairwise.add_argument('--method', type=str, default='allpair', choices=['allpair', 'heapsort', 'bubblesort'])
-    pairwise.add_argument('--batch_size', type=int, default=2)
-    pairwise.add_argument('--k', type=int, default=10)
-
-    setwise = commands.add_parser('setwise')
-    setwise.add_argument('--num_child', type=int, default=3)
-    setwise.add_argument('--method', type=str, default='heapsort', choices=['heapsort', 'bubblesort'])
-    setwise.add_argument('--k', type=int, default=10)
-    setwise.add_argument('--num_permutation', type=int, default=1)
-
-    listwise = commands.add_parser('listwise')
-    listwise.add_argument('--window_size', type=int, default=3)
-    listwise.add_argument('--step_size', type=int, default=1)
-    listwise.add_argument('--num_repeat', type=int, default=1)
+    for name, flags in CLI_GRAMMAR.items():
+        sub = commands.add_parser(name)
+        for flag, typ, default, choices, text in flags:
+            sub.add_argument('--' + flag, type=typ, default=default, choices=choices, help=text)
     return parser, commands
 
 

@@ -438,6 +438,35 @@ def test_cli_pointwise_end_to_end(tmp_path, monkeypatch, capsys):
     assert f"Avg comparisons: {float(c['total_compare'])}" in printed and "Avg time per query:" in printed
 
 
+@pytest.mark.parametrize("sub,case,extra", [("setwise", "setwise_heap_lik", ["--num_child", "3", "--method", "heapsort", "--k", "3"]),
+                                            ("setwise", "setwise_bubble_lik", ["--num_child", "3", "--method", "bubblesort", "--k", "3"]),
+                                            ("pairwise", "pairwise_heap", ["--method", "heapsort", "--batch_size", "2", "--k", "3"]),
+                                            ("pairwise", "pairwise_allpair", ["--method", "allpair", "--batch_size", "4", "--k", "3"])])
+def test_cli_sort_rankers_end_to_end(sub, case, extra, tmp_path, monkeypatch, capsys):
+    """run.py with the setwise / pairwise sub-commands (rerank_many drives the loop): run file and summary counters against the
+    reference's own rerank() outputs for the same candidates."""
+    import run as cli_mod
+    from llmrankers import _backend
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"][case]
+    lab = c.get("label_favouring", sub == "pairwise")
+    monkeypatch.setattr(_backend.T5Backend, "load", classmethod(lambda cls, *a, **k: backend("tiny", lab)))
+    docs = m["docs12"] if sub == "setwise" else m["docs12"][:6]
+    (tmp_path / "queries.tsv").write_text(f"q1\t{m['query']}\n")
+    (tmp_path / "docs.tsv").write_text("".join(f"{d['docid']}\t{d['text']}\n" for d in docs))
+    (tmp_path / "run.txt").write_text("".join(f"q1 Q0 {d['docid']} {i + 1} {d['score']} bm25\n" for i, d in enumerate(docs)))
+    out = tmp_path / "out.txt"
+    scoring = ["--scoring", c["scoring"]] if sub == "setwise" else []
+    cli_mod.cli(["run", "--model_name_or_path", "synthetic:t5-tiny", "--run_path", str(tmp_path / "run.txt"), "--save_path", str(out),
+                 "--queries_tsv", str(tmp_path / "queries.tsv"), "--collection_tsv", str(tmp_path / "docs.tsv"),
+                 "--query_length", "32", "--passage_length", "128"] + scoring + [sub] + extra)
+    assert [l.split("\t")[2] for l in out.read_text().splitlines()] == c["order"]
+    printed = capsys.readouterr().out
+    assert f"Avg comparisons: {float(c['total_compare'])}" in printed
+    assert f"Avg prompt tokens: {float(c['total_prompt_tokens'])}" in printed
+    assert f"Avg completion tokens: {float(c['total_completion_tokens'])}" in printed
+
+
 def test_cli_grammar_errors():
     import run as cli_mod
     with pytest.raises(ValueError):
