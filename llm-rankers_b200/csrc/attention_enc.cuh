@@ -63,7 +63,7 @@ __device__ __forceinline__ void load_tile_64x64(__nv_bfloat16* smem_tile, const 
 // bias: [H][kAttnBiasLen] fp32, index clamp(j - i, -128, 128) + 128  (bidirectional buckets).
 __global__ void __launch_bounds__(128, 4)
 enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, const int* __restrict__ cu,
-                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo) {
+                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int skip_upto) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64];
@@ -75,7 +75,7 @@ enc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, c
     const int tok0 = cu[doc];
     const int len = cu[doc + 1] - tok0;
     const int q0 = qt * 64;
-    if (q0 >= len) return;
+    if (q0 >= len || len <= skip_upto) return;   // skip_upto > 0: the short documents of a mixed batch go to the tcgen05 kernel
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
 

@@ -257,7 +257,8 @@ struct AttnTc2Cfg {
 template <int NKB, bool SPLIT>
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
-                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items, int spin) {
+                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items, int spin,
+                         int len_limit) {
     using Cfg = AttnTc2Cfg<NKB>;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -310,16 +311,27 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     const int stride = gridDim.x;
+    // Documents longer than len_limit (= 64 * NKB) belong to the mma.sync tile kernel launched next to this one: every role walks
+    // only the qualifying items, so the barrier bookkeeping never sees the others. Which kernel a document gets is thereby a
+    // property of the document, not of the batch it happens to be scored in (bit-identical results across batch compositions).
+    auto qualify = [&](int it) {
+        while (it < n_items) {
+            const int dd = it / H;
+            if (cu[dd + 1] - cu[dd] <= len_limit) break;
+            it += stride;
+        }
+        return it;
+    };
     auto wait = [&](uint64_t* bar, uint32_t parity) { if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); };
 
     if (warp_idx == 0) {
         if (lane == 0) {
-            int item = blockIdx.x;
+            int item = qualify(blockIdx.x);
             int doc = item < n_items ? item / H : 0;
             int tok0 = cu[doc], tok1 = cu[doc + 1];
             for (int k = 0; item < n_items; ++k) {
                 const int h = item - doc * H;
-                const int nitem = item + stride, ndoc = nitem < n_items ? nitem / H : 0;
+                const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
                 const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];        // next item's extent: in flight during this one
                 const int nkb_used = (tok1 - tok0 + 63) >> 6;
                 if (k > 0) wait(qk_free, (k - 1) & 1);
@@ -341,13 +353,13 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
             constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
             uint32_t use0 = 0, use1 = 0;     // completed uses of tile slots 0 / 1
             int nt_prev = 0, nkb_prev = 0;
-            int item = blockIdx.x;
+            int item = qualify(blockIdx.x);
             int len = 0;
             if (item < n_items) { const int doc = item / H; len = cu[doc + 1] - cu[doc]; }
             // iteration k issues, per tile slot, MMA-2 of item k-1 and then MMA-1 of item k; one extra iteration drains the last item
             for (int k = 0; item < n_items || nt_prev > 0; ++k) {
                 const bool have = item < n_items;
-                const int nitem = item + stride;
+                const int nitem = qualify(item + stride);
                 int nlen = 0;
                 if (have && nitem < n_items) { const int ndoc = nitem / H; nlen = cu[ndoc + 1] - cu[ndoc]; }
                 const int nt_cur = have ? (len + 127) >> 7 : 0, nkb_cur = (len + 63) >> 6;
@@ -400,7 +412,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
         uint8_t* prow = sP + t * Cfg::kPBytes + row_in_tile * 128;
         uint32_t use = 0;
         int h_loaded = -1;
-        int item = blockIdx.x;
+        int item = qualify(blockIdx.x);
         int doc = item < n_items ? item / H : 0;
         int tok0 = cu[doc], tok1 = cu[doc + 1];
         // ---- deferred epilogue of the previous item on this tile slot: O_t / l -> bf16 -> global
@@ -447,7 +459,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
         while (item < n_items) {
             const int h = item - doc * H;
             const int len = tok1 - tok0, my_tok0 = tok0;
-            const int nitem = item + stride, ndoc = nitem < n_items ? nitem / H : 0;
+            const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
             const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
             item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
             if (t >= ((len + 127) >> 7)) continue;
@@ -607,13 +619,13 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
             }
             pend[t] = false;
         };
-        int item = blockIdx.x;
+        int item = qualify(blockIdx.x);
         int doc = item < n_items ? item / H : 0;
         int tok0 = cu[doc], tok1 = cu[doc + 1];
         while (item < n_items) {
             const int h = item - doc * H;
             const int len = tok1 - tok0, my_tok0 = tok0;
-            const int nitem = item + stride, ndoc = nitem < n_items ? nitem / H : 0;
+            const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
             const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
             item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
             const int ntiles = (len + 127) >> 7;

@@ -1,6 +1,7 @@
 // Host side of libb200rank.so: weight arena + layout conversion, workspaces, the Flan-T5
 // encoder/decoder pass as a sequence of sm_100a kernel launches on one stream, and the C-ABI
 // declared in include/b200rank.h. No torch, no cuBLAS, no CPU fallback.
+#include <climits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -285,6 +286,7 @@ struct b200rank_engine {
     int* h_ids = nullptr; int* h_cu = nullptr; float* h_out = nullptr; int* h_int = nullptr;
     int* h_small = nullptr; size_t h_small_cap = 0, h_small_off = 0;  // pinned bump buffer for small async uploads
     int staged_docs = 0, staged_tokens = 0, staged_maxlen = 0;
+    int staged_minlen = 0;   // shortest document of the staged pass (0 = not tracked on this path)
 
     std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, int>, CUtensorMap> tmaps;
 
@@ -886,11 +888,15 @@ static int device_sm_count() {
     return sms;
 }
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
-                                int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode) {
+                                int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0) {
     static bool attr_set = false;
     if (mode == 0) mode = attn_default_mode();
-    if (maxlen > 256) mode = 1;
-    if ((mode == 5 || mode == 6) && maxlen > 192) mode = 1;
+    if (maxlen > 256 && mode != 5 && mode != 6) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
+    // Mixed batch under the default mode: documents of <= 192 tokens still get the tcgen05 kernel (it walks only those), the longer
+    // ones the mma.sync tiles (which skip the short ones) — the kernel is chosen per document, so a document's result does not
+    // depend on what it is batched with.
+    const bool mixed = (mode == 5 || mode == 6) && maxlen > 192;
+    if ((mode == 5 || mode == 6) && minlen > 192) mode = 1;   // known: no document qualifies for the tcgen05 kernel
     if (mode == 5 || mode == 6) {
         // persistent tcgen05 kernel: one CTA per SM walks the (document, head) items
         CUtensorMap local;
@@ -914,8 +920,12 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         if (attn_sms < 0) attn_sms = getenv("B200RANK_ATTN_SMS") ? std::max(1, atoi(getenv("B200RANK_ATTN_SMS"))) : 0;
         const int grid_cap = attn_sms > 0 ? std::min(attn_sms, device_sm_count()) : device_sm_count();
         CU_OK(launch_k(kern, dim3(std::min(n_items, grid_cap)), dim3(kAttnTcThreads), AttnTc2Cfg<3>::smem_bytes(H), st, *tm, inner, d_cu, bias,
-                       out, ldo, H, n_items, spin));
-        return e ? post_launch(e, "enc_attention_tc2") : B200RANK_OK;
+                       out, ldo, H, n_items, spin, 192));
+        if (e) RET_IF(post_launch(e, "enc_attention_tc2"));
+        if (!mixed) return B200RANK_OK;
+        if (e) prof_begin(e, "enc_attention");
+        launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo, 192);
+        return e ? post_launch(e, "enc_attention") : B200RANK_OK;
     }
     if (mode == 3) {
         CUtensorMap local;
@@ -954,7 +964,7 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         return e ? post_launch(e, "enc_attention_resident") : B200RANK_OK;
     }
     if (e) prof_begin(e, "enc_attention");
-    launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo);
+    launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo, 0);
     return e ? post_launch(e, "enc_attention") : B200RANK_OK;
 }
 
@@ -976,7 +986,7 @@ static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
         const LayerW& w = e->enc[l];
         // h = norm1(x) was produced by the previous layer's last GEMM (or the line above for layer 0)
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
-        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu_cur, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0));
+        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu_cur, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0, e->staged_minlen));
         RET_IF(gemm_resid_then_norm(e, e->ao, I, Tk, w.wo, I, d, n, I, e->x, w.ln2, e->h));
         RET_IF(ffn_in(e, e->h, Tk, w.wi, n, e->g));
         const bool last = (l + 1 == e->Le);  // the final layer norm lands in the slot buffer the decoder reads
@@ -1187,16 +1197,17 @@ static int check_ready(b200rank_engine* e) {
 
 // Pack documents [d0, d1) into the pinned staging buffers and copy to the device (async on the stream).
 static int stage_range(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int stride, int d0, int d1) {
-    int tok = 0, maxlen = 0;
+    int tok = 0, maxlen = 0, minlen = INT_MAX;
     e->h_cu[0] = 0;
     for (int i = d0; i < d1; ++i) {
         const int len = lengths[i];
         memcpy(e->h_ids + tok, ids + (size_t)i * stride, (size_t)len * sizeof(int));
         tok += len;
         maxlen = std::max(maxlen, len);
+        minlen = std::min(minlen, len);
         e->h_cu[i - d0 + 1] = tok;
     }
-    e->staged_docs = d1 - d0; e->staged_tokens = tok; e->staged_maxlen = maxlen;
+    e->staged_docs = d1 - d0; e->staged_tokens = tok; e->staged_maxlen = maxlen; e->staged_minlen = d1 > d0 ? minlen : 0;
     CU_OK(cudaMemcpyAsync(e->d_ids, e->h_ids, (size_t)tok * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CU_OK(cudaMemcpyAsync(e->d_cu, e->h_cu, (size_t)(d1 - d0 + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     return B200RANK_OK;
@@ -1355,6 +1366,7 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
         CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], hcu, (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream_main));
         e->staged_docs = n_docs; e->staged_tokens = tok; e->staged_maxlen = maxlen;
     }
+    e->staged_minlen = 0;   // not tracked here: a mixed batch (192 < maxlen <= 240) launches both attention kernels
     e->slot[b].docs = n_docs; e->slot[b].tokens = tok; e->slot[b].maxlen = maxlen;
     e->enc_out_cur = e->enc_out[b];
     e->d_cu_cur = e->d_cu_slot[b];

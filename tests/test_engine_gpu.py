@@ -596,6 +596,31 @@ def test_key_split_cross_attention_matches_single_cta():
     assert diff < 3e-2
 
 
+def test_generation_prefix_results_do_not_depend_on_batch_composition():
+    """What lets rerank_many / the level-parallel heaps reproduce rerank() exactly: the label logits (decoder prefixes of 2 and 3
+    tokens) and the greedy tokens of a prompt are BIT-identical whether it is scored alone, with other prompts, or in another
+    order — the GEMMs are row-independent, attention is per document, and the cross-attention key split is a function of the
+    document alone."""
+    e, cfg, w = large_engine()
+    rng = np.random.default_rng(26)
+    lens = [1536, 700, 129, 40, 1000]
+    ids = np.zeros((len(lens), 1536), np.int32)
+    for i, n in enumerate(lens):
+        ids[i, :n] = rng.integers(3, 32000, size=n)
+        ids[i, n - 1] = 1
+    lengths = np.asarray(lens, np.int32)
+    cols = [71, 272, 205, 309, 262, 377, 350, 454, 27, 446, 480]
+    together2 = e.logits_at(ids, lengths, [0, 5], cols, normalize=False)
+    together3 = e.logits_at(ids, lengths, [0, 5, 71], cols, normalize=True)
+    tokens = e.greedy(ids, lengths, [0, 5], 2)
+    for i in range(len(lens)):
+        assert np.array_equal(e.logits_at(ids[i:i + 1], lengths[i:i + 1], [0, 5], cols, normalize=False)[0], together2[i]), i
+        assert np.array_equal(e.greedy(ids[i:i + 1], lengths[i:i + 1], [0, 5], 2)[0], tokens[i]), i
+    perm = [3, 0, 4, 2, 1]
+    assert np.array_equal(e.logits_at(ids[perm], lengths[perm], [0, 5, 71], cols, normalize=True), together3[perm])
+    assert np.array_equal(e.greedy(ids[perm][:3], lengths[perm][:3], [0, 5], 2), tokens[perm][:3])
+
+
 def test_large_setwise_prompt_length():
     """BASELINE config 3 shape: one setwise compare prompt of 11 passages (S = 1536) on the full flan-t5-large: label
     probabilities (likelihood scoring) and the first generated token against the fp32 oracle; exercises the long-sequence
