@@ -8,7 +8,7 @@ reproducible across machines (numpy PCG64, not the torch RNG). `synthetic_tokeni
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List
 
 import numpy as np
 

@@ -1,11 +1,9 @@
 """world_size-2 gloo tests of the N>1 host logic (sharding + gather); the NCCL weight broadcast itself needs GPUs and is
 exercised by bench.py --gpus N on the box."""
-import os
 import subprocess
 import sys
 import textwrap
 
-import numpy as np
 
 from helpers import ROOT
 
