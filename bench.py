@@ -148,33 +148,105 @@ def cpu_oracle_docs_per_s(n_docs, repeats=1):
     return n_docs / best, best
 
 
+def cpu_reference_setup(weights=None):
+    """The reference's own CPU path (oracle/hf_cpu.py: transformers T5ForConditionalGeneration, fp32, torch on all host threads,
+    called like llmrankers/pointwise.py:117-124) over the bench workload. Returns (model, ids, mask) or raises."""
+    from b200rank.synthetic import model_cfg, synthetic_prompt_ids, synthetic_weights
+    from oracle import hf_cpu
+    cfg = model_cfg(MODEL)
+    model = hf_cpu.build_model(cfg, weights if weights is not None else synthetic_weights(cfg, SEED))
+    ids, lengths = synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED)
+    mask = (np.arange(ids.shape[1])[None] < lengths[:, None]).astype(np.int64)
+    return model, ids.astype(np.int64), mask
+
+
+def cpu_reference_baseline(weights, eng_logits, eng_scores, n_sample=32, budget_s=25.0):
+    """cpu_baseline for the engine arm: one reference batch (batch_size 32) of the headline query on the host cores, plus the
+    full-size parity of the engine's answers for those documents against it (logits, P(yes), order)."""
+    import torch
+    from b200rank.synthetic import NO_ID, YES_ID
+    from oracle import hf_cpu
+    model, ids, mask = cpu_reference_setup(weights)
+    t0 = time.perf_counter()
+    hf_cpu.score_yes_no(model, ids[:2], mask[:2], YES_ID, NO_ID, 32)          # warm-up (thread pool, oneDNN primitives)
+    per_doc = (time.perf_counter() - t0) / 2
+    n_sample = int(max(2, min(n_sample, budget_s / max(per_doc, 1e-3) / 2)))   # two timed repeats inside the budget
+    v, secs, ref_logits = hf_cpu.timed_docs_per_s(model, ids[:n_sample], mask[:n_sample], YES_ID, NO_ID, 32, repeats=2)
+    ref_scores = np.exp(ref_logits[:, 0]) / np.exp(ref_logits).sum(1)
+    dl = np.abs(eng_logits[:n_sample] - ref_logits)
+    tol = 0.06 + 0.03 * np.abs(ref_logits)                                     # DESIGN.md §2: bf16 engine vs fp32 reference
+    order_ref = np.argsort(-ref_scores, kind="stable")
+    order_eng = np.argsort(-eng_scores[:n_sample], kind="stable")
+    baseline = {"value": v, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{n_sample} of the {HITS} documents of one query (one reference batch, S={Q_LEN + P_LEN + 24}), best of 2, {secs:.1f} s; "
+                          f"transformers {__import__('transformers').__version__} T5ForConditionalGeneration fp32 on torch CPU ({torch.get_num_threads()} threads of "
+                          f"{os.cpu_count()} logical cores) called as llmrankers/pointwise.py:117-124 does (the reference has no native code to compile into oracle/_ref)"}
+    parity = {"against": "the cpu_baseline run (fp32 transformers on the same token ids, same weights), full-size model", "docs": n_sample,
+              "max_abs_logit_diff": float(dl.max()), "within_logit_tolerance": bool((dl <= tol).all()), "tolerance": "0.06 + 0.03*|ref|",
+              "max_abs_score_diff": float(np.abs(eng_scores[:n_sample] - ref_scores).max()),
+              "order_identical": bool(np.array_equal(order_ref, order_eng)),
+              "top10_identical": bool(np.array_equal(order_ref[:10], order_eng[:10]))}
+    # pairs the two orders disagree on, and how far apart the reference's own (yes - no) margins of those pairs are at most:
+    # an order difference is a parity failure only if that gap exceeds what the stated logit tolerance allows
+    m_ref = ref_logits[:, 0] - ref_logits[:, 1]
+    m_eng = eng_logits[:n_sample, 0] - eng_logits[:n_sample, 1]
+    i, j = np.triu_indices(n_sample, 1)
+    disc = np.sign(m_ref[i] - m_ref[j]) * np.sign(m_eng[i] - m_eng[j]) < 0
+    parity["discordant_pairs"] = int(disc.sum())
+    parity["max_ref_margin_gap_of_discordant_pairs"] = float(np.abs(m_ref[i] - m_ref[j])[disc].max()) if disc.any() else 0.0
+    return baseline, parity
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores, same metric/config; every step is a
+    bounded sample of the query (rows of one reference batch) sized so that warmup + steps finish within ~3 minutes."""
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    cores = os.cpu_count()
-    sample = 8
-    from b200rank.synthetic import NO_ID, YES_ID, model_cfg, synthetic_prompt_ids, synthetic_weights
-    from oracle.t5_oracle import T5Oracle
-    cfg = model_cfg(MODEL)
-    orc = T5Oracle(cfg, synthetic_weights(cfg, SEED))
-    ids, _ = synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED)
-    ids = ids[:sample].astype(np.int64)
-    mask = np.ones_like(ids)
+    from b200rank.synthetic import NO_ID, YES_ID
+    budget_s = 150.0
+    kind = "reference"
+    try:
+        import torch
+        from oracle import hf_cpu
+        model, ids, mask = cpu_reference_setup()
+        step_fn = lambda n: hf_cpu.score_yes_no(model, ids[:n], mask[:n], YES_ID, NO_ID, 32)  # noqa: E731
+        cores = torch.get_num_threads()
+        how = (f"transformers {__import__('transformers').__version__} T5ForConditionalGeneration fp32 on torch CPU ({cores} threads) "
+               f"called as llmrankers/pointwise.py:117-124 does")
+    except Exception as exc:  # noqa: BLE001 - transformers/torch CPU path unusable: time the numpy port instead, and say so
+        from b200rank.synthetic import model_cfg, synthetic_prompt_ids, synthetic_weights
+        from oracle.t5_oracle import T5Oracle
+        kind = "port"
+        cfg = model_cfg(MODEL)
+        orc = T5Oracle(cfg, synthetic_weights(cfg, SEED))
+        ids, _ = synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED)
+        ids = ids.astype(np.int64)
+        mask = np.ones_like(ids)
+        step_fn = lambda n: orc.score_yes_no(ids[:n], mask[:n], YES_ID, NO_ID)  # noqa: E731
+        cores = os.cpu_count()
+        how = f"numpy fp32 oracle port on all host threads (transformers CPU path unavailable: {type(exc).__name__}: {exc})"
+    # calibrate on two documents (also the first warm-up), then size the per-step sample for the time budget
+    t0 = time.perf_counter()
+    step_fn(2)
+    per_doc = (time.perf_counter() - t0) / 2
+    n_steps_total = max(1, args.steps + args.warmup)
+    sample = int(max(1, min(32, budget_s / n_steps_total / max(per_doc, 1e-4))))
     for _ in range(args.warmup):
-        orc.score_yes_no(ids, mask, YES_ID, NO_ID)
+        step_fn(sample)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.score_yes_no(ids, mask, YES_ID, NO_ID)
+        step_fn(sample)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    desc = f"{sample} of the {HITS} documents of one query per step (S={Q_LEN + P_LEN + 24}, fp32, numpy/OpenBLAS on all host threads)"
+    desc = f"{sample} of the {HITS} documents of one query per step (S={Q_LEN + P_LEN + 24}); {how}"
     line = {
         "impl": "reference", "metric": "docs scored/sec (flan-t5-large q32/p128, pointwise yes_no)", "value": value, "unit": "docs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, sample_docs=sample),
-        "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": dict(workload_config(1, sample_docs=sample), parallelism="host threads of one process (rank 0 only)", pipeline="none: one batch at a time",
+                       weights=f"seeded random init (numpy PCG64 seed {SEED}), fp32 on the host", l2="n/a (CPU)"),
+        "cpu_baseline": {"value": value, "unit": "docs/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -526,8 +598,10 @@ def run_engine(args):
     # ---- roofline for the dominant kernel: per-launch CUDA events in a separate profiled pass
     roofline = None
     cpu_baseline = None
+    parity = None
     if rank == 0:
         prof_steps = min(args.steps, 10)
+        eng.stage(ids, lengths)  # the text-API measurement above staged its own documents: profile the headline input again
         eng.profile(True)
         for _ in range(prof_steps):
             eng.run_yes_no_staged(YES_ID, NO_ID)
@@ -590,10 +664,14 @@ def run_engine(args):
                                         "frac": gbs / hbm_peak, "bytes_per_step": nbytes, "launches_per_step": rep["rmsnorm"]["n"] / prof_steps,
                                         "peak_source": hbm_src}]
         if world == 1 and not args.no_cpu_baseline:
-            n_sample = 8
-            cb, secs = cpu_oracle_docs_per_s(n_sample, repeats=2)
-            cpu_baseline = {"value": cb, "unit": "docs/s", "cores": os.cpu_count(), "kind": "port",
-                            "sample": f"{n_sample} of the {HITS} documents of one query (S={Q_LEN + P_LEN + 24}), best of 2, {secs:.1f} s, numpy fp32 oracle on all host threads"}
+            try:   # the reference's own CPU path (transformers fp32 on the host cores) + full-size parity of the engine against it
+                cpu_baseline, parity = cpu_reference_baseline(synthetic_weights(cfg, SEED), np.asarray(logits_dev), np.asarray(scores_dev))
+            except Exception as exc:  # noqa: BLE001 - never lose the bench line to the baseline leg: fall back to the numpy port
+                n_sample = 4
+                cb, secs = cpu_oracle_docs_per_s(n_sample, repeats=1)
+                cpu_baseline = {"value": cb, "unit": "docs/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{n_sample} of the {HITS} documents of one query (S={Q_LEN + P_LEN + 24}), {secs:.1f} s, numpy fp32 oracle on all host "
+                                          f"threads (transformers CPU leg failed: {type(exc).__name__}: {exc})"}
 
     if rank == 0:
         line = {
@@ -602,7 +680,7 @@ def run_engine(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "api_text": api_text,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "api_text": api_text,
             "weights_load_s": round(t_load, 2), "sample_scores": [float(x) for x in scores_dev[:4]],
         }
         print(json.dumps(line))

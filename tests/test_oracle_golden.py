@@ -143,3 +143,33 @@ def test_duot5_compare_probabilities():
         np.testing.assert_allclose(p, v["p"], atol=1e-5)
         got.append(bool(p[0] > p[1]))
     assert got == [v["first_wins"] for v in c["verdicts"]]
+
+
+@pytest.mark.parametrize("which", ["tiny", "small"])
+def test_hf_cpu_baseline_leg_reproduces_reference_fixtures(which):
+    """oracle/hf_cpu.py (bench.py's cpu_baseline / --impl reference leg: transformers fp32 on torch CPU, called like
+    pointwise.py:117-124) rebuilt from (model, seed) gives the logits and scores the reference's own rerank() recorded."""
+    from helpers import model_and_weights
+    from oracle import hf_cpu
+    meta = golden_meta()
+    m = meta[which]
+    c = meta["cases"]["yes_no" if which == "tiny" else "small_yes_no"]
+    cfg, w = model_and_weights(which)
+    model = hf_cpu.build_model(cfg, w, threads=2)
+    docs = [d["docid"] for d in m["docs"]]
+    scores = []
+    for call in calls(golden_npz(f"golden_{which}.npz"), "yes_no"):
+        lg, sc = hf_cpu.score_yes_no(model, call["input_ids"], call["attention_mask"], m["yes_id"], m["no_id"], batch_size=64)
+        gold = call["logits"][:, 0, :]
+        gold2 = gold[:, [m["yes_id"], m["no_id"]]] if gold.shape[-1] > 2 else gold
+        np.testing.assert_allclose(lg, gold2, atol=ATOL, rtol=1e-4)
+        scores.extend(sc.tolist())
+    np.testing.assert_allclose(scores, [c["scores"][d] for d in docs], atol=1e-5)
+    # and the numpy oracle agrees with it on a fresh ragged batch (what bench.py's `parity` object relies on)
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(9, 41, size=5)
+    mask = (np.arange(40)[None] < lengths[:, None]).astype(np.int64)
+    ids = rng.integers(3, cfg["vocab_size"] - 128, size=(5, 40)) * mask
+    a, _ = hf_cpu.score_yes_no(model, ids, mask, m["yes_id"], m["no_id"], batch_size=2)
+    b, _ = oracle_for(which).score_yes_no(ids.astype(np.int64), mask, m["yes_id"], m["no_id"])
+    np.testing.assert_allclose(a, b, atol=ATOL, rtol=1e-4)
