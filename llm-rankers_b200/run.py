@@ -72,8 +72,12 @@ def build_ranker(args):
         cls = DuoT5LlmRanker if 'duot5' in run.model_name_or_path else PairwiseLlmRanker
         return cls(method=args.pairwise.method, batch_size=args.pairwise.batch_size, k=args.pairwise.k, **common)
     if args.listwise:
-        cls = OpenAiListwiseLlmRanker if run.openai_key else ListwiseLlmRanker
-        return cls(model_name_or_path=run.model_name_or_path)
+        if run.openai_key:
+            return OpenAiListwiseLlmRanker(model_name_or_path=run.model_name_or_path, api_key=run.openai_key,
+                                           window_size=args.listwise.window_size, step_size=args.listwise.step_size,
+                                           num_repeat=args.listwise.num_repeat)
+        return ListwiseLlmRanker(window_size=args.listwise.window_size, step_size=args.listwise.step_size, scoring=run.scoring,
+                                 num_repeat=args.listwise.num_repeat, **common)
     raise ValueError('Must specify either --pointwise, --setwise, --pairwise or --listwise.')
 
 

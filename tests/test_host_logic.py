@@ -401,9 +401,9 @@ def test_prompt_assembler_is_thread_safe():
 
 
 def test_unsupported_variants_fail_loudly():
-    from llmrankers.listwise import ListwiseLlmRanker
+    from llmrankers.listwise import OpenAiListwiseLlmRanker
     from llmrankers.setwise import OpenAiSetwiseLlmRanker, SetwiseLlmRanker
-    for cls in (ListwiseLlmRanker, OpenAiSetwiseLlmRanker):
+    for cls in (OpenAiListwiseLlmRanker, OpenAiSetwiseLlmRanker):
         with pytest.raises(NotImplementedError):
             cls("x", "y")
     r = SetwiseLlmRanker(None, None, "cuda", method="quicksort", backend=backend())
