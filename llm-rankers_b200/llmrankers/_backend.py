@@ -213,24 +213,49 @@ class T5Backend:
             outs.append(np.concatenate([prefix, new[r, :steps].astype(np.int64)]))
         return outs
 
+def _checkpoint_files(path: str) -> List[str]:
+    """Weight files of a local HF checkpoint directory, in load order: a single `model.safetensors` / `pytorch_model.bin`, or the shards
+    an index json lists (`model.safetensors.index.json` / `pytorch_model.bin.index.json` — how the hub stores flan-t5-xl / -xxl).
+    safetensors is preferred when both formats are present, like `from_pretrained`."""
+    for single, index in (("model.safetensors", "model.safetensors.index.json"), ("pytorch_model.bin", "pytorch_model.bin.index.json")):
+        if os.path.exists(os.path.join(path, single)):
+            return [os.path.join(path, single)]
+        if os.path.exists(os.path.join(path, index)):
+            with open(os.path.join(path, index)) as f:
+                shards = sorted(set(json.load(f)["weight_map"].values()))
+            missing = [sh for sh in shards if not os.path.exists(os.path.join(path, sh))]
+            if missing:
+                raise FileNotFoundError(f"{path}: {index} lists shards that are not there: {missing}")
+            return [os.path.join(path, sh) for sh in shards]
+    return []
+
+
+def _iter_checkpoint_tensors(files: Sequence[str]):
+    """(name, fp32 ndarray) for every tensor of every file, one tensor in host memory at a time. Tensors are read through torch so
+    that bf16 / fp16 checkpoints load too (numpy has no bfloat16); the engine converts to its own storage types on upload."""
+    import torch
+    for fn in files:
+        if fn.endswith(".safetensors"):
+            from safetensors import safe_open
+            with safe_open(fn, framework="pt", device="cpu") as f:
+                for name in f.keys():
+                    yield name, f.get_tensor(name).to(torch.float32).numpy()
+        else:
+            sd = torch.load(fn, map_location="cpu", weights_only=True)
+            for name in list(sd.keys()):
+                yield name, sd.pop(name).to(torch.float32).numpy()
+
+
 def _load_checkpoint(path: str, cache_dir=None):
     """(cfg dict, iterable of (name, fp32 ndarray)) from a local HF checkpoint dir, else via transformers on the CPU."""
     if os.path.isdir(path) and os.path.exists(os.path.join(path, "config.json")):
         with open(os.path.join(path, "config.json")) as f:
             hf = json.load(f)
         cfg = _cfg_from_hf(hf)
-        st = os.path.join(path, "model.safetensors")
-        if os.path.exists(st):
-            from safetensors import safe_open
-
-            def gen():
-                with safe_open(st, framework="np") as f:
-                    for name in f.keys():
-                        yield name, np.asarray(f.get_tensor(name), dtype=np.float32)
-            return cfg, gen()
-        import torch
-        sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
-        return cfg, ((k, v.float().numpy()) for k, v in sd.items())
+        files = _checkpoint_files(path)
+        if not files:
+            raise FileNotFoundError(f"{path}: no model.safetensors / pytorch_model.bin (single file or sharded with an index json)")
+        return cfg, _iter_checkpoint_tensors(files)
     from transformers import AutoConfig, T5ForConditionalGeneration
     hf_cfg = AutoConfig.from_pretrained(path, cache_dir=cache_dir)
     if hf_cfg.model_type != "t5":
