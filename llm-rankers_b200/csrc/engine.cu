@@ -831,11 +831,13 @@ static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h
     const int grid = (n + 7) / 8;
     static int rev = -1;
     if (rev < 0) rev = (getenv("B200RANK_RMSNORM_REV") && atoi(getenv("B200RANK_RMSNORM_REV")) == 0) ? 0 : 1;
-    prof_begin(e, "rmsnorm");
+    // profile label: the encoder-sized launches (HBM-bound) apart from the 100-row decoder launches (launch-latency-bound)
+    const char* label = n >= 4096 ? "rmsnorm" : "rmsnorm_small";
+    prof_begin(e, label);
     if (e->d <= 1024) launch_k(rmsnorm_kernel<8>, dim3(grid), dim3(256), 0, e->stream, x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
     else if (e->d <= 2048) launch_k(rmsnorm_kernel<16>, dim3(grid), dim3(256), 0, e->stream, x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
     else launch_k(rmsnorm_kernel<32>, dim3(grid), dim3(256), 0, e->stream, x, w, h, n, e->d, e->cfg.layer_norm_eps, rev);
-    return post_launch(e, "rmsnorm");
+    return post_launch(e, label);
 }
 
 // x += A.W^T, then h = bf16(T5LayerNorm(x) * norm_w). Fused into one launch (EPI_RESID_NORM: row-block-owning units re-read
