@@ -95,3 +95,50 @@ def lengths_from_ids(ids, pad_id=0):
     """generate() without a mask: HF infers attention_mask = ids != pad (generation/utils.py:731-763)."""
     ids = np.asarray(ids)
     return (ids != pad_id).astype(np.int64)
+
+
+def c_example_model():
+    """The model and prompts examples/score_yes_no.c builds (same xorshift64* stream, same load order): (cfg, weights, ids, lengths)."""
+    from b200rank.synthetic import model_cfg
+    D, H, F, L, V, STRIDE = 128, 2, 256, 2, 2304, 24
+    M64 = (1 << 64) - 1
+    state = [0x9E3779B97F4A7C15]
+
+    def tensor(rows, cols, scale, offset):
+        n = rows * cols
+        raw = np.empty(n, np.float64)
+        s = state[0]
+        for i in range(n):
+            s ^= s >> 12
+            s ^= (s << 25) & M64
+            s ^= s >> 27
+            raw[i] = ((s * 0x2545F4914F6CDD1D) & M64) >> 40
+        state[0] = s
+        u = (raw / 16777216.0 * 2.0 - 1.0).astype(np.float32)
+        return (np.float32(offset) + u * np.float32(scale)).reshape(rows, cols) if rows > 1 else (np.float32(offset) + u * np.float32(scale))
+
+    w = {}
+    w["shared.weight"] = tensor(V, D, 1.0, 0.0)
+    w["lm_head.weight"] = tensor(V, D, 0.05, 0.0)
+    w["encoder.final_layer_norm.weight"] = tensor(1, D, 0.1, 1.0)
+    w["decoder.final_layer_norm.weight"] = tensor(1, D, 0.1, 1.0)
+    w["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"] = tensor(32, H, 0.5, 0.0)
+    w["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"] = tensor(32, H, 0.5, 0.0)
+    for l in range(L):
+        for m in "qkvo":
+            w[f"encoder.block.{l}.layer.0.SelfAttention.{m}.weight"] = tensor(D, D, 0.06, 0.0)
+            w[f"decoder.block.{l}.layer.0.SelfAttention.{m}.weight"] = tensor(D, D, 0.06, 0.0)
+            w[f"decoder.block.{l}.layer.1.EncDecAttention.{m}.weight"] = tensor(D, D, 0.06, 0.0)
+        for side, ffn in (("encoder", 1), ("decoder", 2)):
+            for k in range(ffn + 1):
+                w[f"{side}.block.{l}.layer.{k}.layer_norm.weight"] = tensor(1, D, 0.1, 1.0)
+            w[f"{side}.block.{l}.layer.{ffn}.DenseReluDense.wi_0.weight"] = tensor(F, D, 0.06, 0.0)
+            w[f"{side}.block.{l}.layer.{ffn}.DenseReluDense.wi_1.weight"] = tensor(F, D, 0.06, 0.0)
+            w[f"{side}.block.{l}.layer.{ffn}.DenseReluDense.wo.weight"] = tensor(D, F, 0.04, 0.0)
+    cfg = model_cfg("t5-tiny", V)
+    lengths = np.array([24, 9, 17], np.int32)
+    ids = np.zeros((3, STRIDE), np.int32)
+    for l in range(3):
+        for j in range(STRIDE):
+            ids[l, j] = 3 + (l * 131 + j * 17) % (V - 3) if j < lengths[l] - 1 else (1 if j == lengths[l] - 1 else 0)
+    return cfg, w, ids, lengths

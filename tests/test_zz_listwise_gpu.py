@@ -137,3 +137,13 @@ def test_listwise_generation_on_gpu(case):
     if near_ties == 0:
         assert [d.docid for d in out] == c["order"]
         assert (r.total_prompt_tokens, r.total_completion_tokens) == (c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+def test_c_example_on_gpu(tmp_path):
+    """examples/score_yes_no.c — a plain-C host of the ABI — built with gcc on the box, run on the B200, against the CPU oracle."""
+    import subprocess
+    from test_c_abi import build_example, check_against_oracle
+    exe = build_example(tmp_path)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, (p.stdout, p.stderr)
+    check_against_oracle(p.stdout)
