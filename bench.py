@@ -701,6 +701,23 @@ def run_engine(args):
                                 "sample": f"{n_sample} of the {HITS} documents of one query (S={Q_LEN + P_LEN + 24}), {secs:.1f} s, numpy fp32 oracle on all host "
                                           f"threads (transformers CPU leg failed: {type(exc).__name__}: {exc})"}
 
+    hf_cuda = None
+    if rank == 0 and world == 1 and args.hf_cuda:
+        try:
+            import torch
+            from oracle import hf_cpu
+            model, ids64, mask64 = cpu_reference_setup(synthetic_weights(cfg, SEED))
+            v, secs, hf_logits = hf_cpu.timed_docs_per_s_on_device(model, ids64, mask64, YES_ID, NO_ID, 32, f"cuda:{local}", "bfloat16")
+            hf_cuda = {"value": v, "unit": "docs/s", "ms_per_query": secs * 1e3, "dtype": "bf16", "batch_size": 32,
+                       "what": f"transformers {__import__('transformers').__version__} T5ForConditionalGeneration on this GPU via torch {torch.__version__} "
+                               "(cuBLAS GEMMs, eager attention), the reference's loop over 32/32/32/4 documents with ids resident on the device; wall clock, best of 3",
+                       "engine_speedup": value / v,
+                       "max_abs_logit_diff_vs_engine": float(np.abs(hf_logits - np.asarray(logits_dev)).max())}
+            del model
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 - informational leg
+            hf_cuda = {"unavailable": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         line = {
             "metric": "docs scored/sec (flan-t5-large q32/p128, pointwise yes_no)", "value": value, "unit": "docs/s",
@@ -708,7 +725,7 @@ def run_engine(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "api_text": api_text,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "api_text": api_text, "hf_cuda": hf_cuda,
             "weights_load_s": round(t_load, 2), "sample_scores": [float(x) for x in scores_dev[:4]],
         }
         print(json.dumps(line))
@@ -732,6 +749,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")
+    ap.add_argument("--hf-cuda", action="store_true",
+                    help="also time the reference's own GPU path (the transformers model in bf16 on this GPU through torch / cuBLAS, batch_size 32) "
+                         "after the engine has finished: an informational `hf_cuda` object, library kernels, never part of the product")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

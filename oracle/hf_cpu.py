@@ -83,3 +83,45 @@ def timed_docs_per_s(model, ids: np.ndarray, mask: np.ndarray, yes_id: int, no_i
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return ids.shape[0] / best, best, logits
+
+
+def timed_docs_per_s_on_device(model, ids: np.ndarray, mask: np.ndarray, yes_id: int, no_id: int, batch_size: int, device: str,
+                               dtype: str = "bfloat16", repeats: int = 3, warmup: int = 2):
+    """Optional second comparator: the SAME transformers model the reference would hold, moved to `device` in a reduced
+    precision and run by torch's stock kernels (cuBLAS GEMMs + eager attention on CUDA) — the reference's own GPU path
+    (pointwise.py:20-24 loads fp16 on 'cuda'; bf16 is used here because a random-init model overflows fp16 without the fp32 `wo`
+    carve-out that from_pretrained applies). Inputs are moved once; a pass = the reference's loop over batches of `batch_size` with one
+    device->host copy of the scores per batch (its per-document .item() calls would only be slower). Returns (docs/s, best seconds,
+    [n,2] logits as float32). Library code on the hot path — a baseline to beat, never part of the product."""
+    import torch
+
+    dt = getattr(torch, dtype)
+    m = model.to(device=device, dtype=dt)
+    ids_t = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).to(device)
+    mask_t = torch.from_numpy(np.ascontiguousarray(mask, dtype=np.int64)).to(device)
+    dec = torch.zeros((batch_size, 1), dtype=torch.long, device=device)
+    is_cuda = str(device).startswith("cuda")
+
+    def one_pass():
+        outs = []
+        with torch.no_grad():
+            for b0 in range(0, ids_t.shape[0], batch_size):
+                rows = slice(b0, min(b0 + batch_size, ids_t.shape[0]))
+                logits = m(input_ids=ids_t[rows], attention_mask=mask_t[rows], decoder_input_ids=dec[:rows.stop - rows.start]).logits
+                two = torch.cat((logits[:, :, yes_id], logits[:, :, no_id]), dim=1)
+                outs.append(two.float().cpu())          # the D2H copy of the batch's result (synchronises the batch)
+        return torch.cat(outs, 0).numpy()
+
+    for _ in range(warmup):
+        one_pass()
+    best, logits = None, None
+    for _ in range(max(1, repeats)):
+        if is_cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        logits = one_pass()
+        if is_cuda:
+            torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+        best = dtm if best is None else min(best, dtm)
+    return ids.shape[0] / best, best, logits

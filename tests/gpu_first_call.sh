@@ -21,7 +21,7 @@ for tool in memcheck racecheck; do
   echo "sanitizer $tool rc=$?" | tee -a $OUT/${TAG}_sanitizer_${tool}.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $OUT/${TAG}_sanitizer_${tool}.log | tail -2
 done
-timeout 900 python bench.py --steps 100 --warmup 5 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"
+timeout 900 python bench.py --steps 100 --warmup 5 --hf-cuda > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:
@@ -30,6 +30,7 @@ try:
     print("docs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "step_frac", round(r["step_frac"], 3), "dom", r["kernel"], round(r["frac"], 3),
           "traffic", r["traffic"], "clocks", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
     print("cpu_baseline", d["cpu_baseline"]["kind"], round(d["cpu_baseline"]["value"], 2), d["cpu_baseline"]["cores"], "parity", d.get("parity"))
+    print("hf_cuda", d.get("hf_cuda"))
 except Exception as e:
     print("bench line unreadable:", e)
 PY
