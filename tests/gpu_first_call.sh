@@ -8,6 +8,7 @@
 #   4. bench.py (headline, N=1)                  -> <tag>_bench_n1.json   (never under a profiler)
 #   5. reference arm                             -> <tag>_bench_reference.json
 #   6. ncu launch list of a 2-step bench run     -> <tag>_ncu_launches.csv (per-launch times are cold-cache: compare shares)
+#   7. experiments/epi_probe.cu                  -> <tag>_epi_probe.txt
 set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
@@ -37,4 +38,7 @@ PY
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+# 7. stand-alone design probes (experiments/README.md)
+nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
+  && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
 ls -la $OUT | tail -20
