@@ -25,6 +25,8 @@ enum EpiMode : int {
     EPI_RESID_NORM = 4, // EPI_RESID_F32 with N == row width, plus: every unit owns whole 128-row blocks (all N-tiles), and once a
                         // block's adds have landed it re-reads those rows from L2 and writes norm_out = bf16(T5LayerNorm(out))
     EPI_RELU_BF16 = 5,  // host-side alias: launched as EPI_BF16 with GemmArgs::relu = 1 (out_bf16 = max(acc, 0))
+    EPI_RESID_F32_PIPE = 6,  // EPI_RESID_F32 with the tcgen05.ld of chunk c+1 in flight while chunk c is staged (opt-in, B200RANK_EPI_PIPE=1:
+                             // experiments/epi_probe.cu shows the un-pipelined TMEM loads cost ~1.8 us of the ~6 us a 128 x 256 tile's epilogue takes)
 };
 
 struct GemmArgs {
@@ -106,7 +108,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (args.K + kGemmBlockK - 1) / kGemmBlockK;
     constexpr bool kRowOwner = (EPI == EPI_RESID_NORM);
-    constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_NORM);
+    constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_NORM || EPI == EPI_RESID_F32_PIPE);
     // it-th tile of this unit -> (m-block, n-block). Default: tiles round-robin over units, n fastest. Row-owner mode: a unit
     // takes whole m-blocks (all n-tiles back to back) so that it alone completes rows.
     auto get_tile = [&](int it, int& mb, int& nb) -> bool {
@@ -307,6 +309,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                         stage_close(nb * HALF + c);
+                    }
+                } else if constexpr (EPI == EPI_RESID_F32_PIPE) {
+                    // fp32 tiles of 32 columns, in-L2 add; two register buffers: the TMEM load of the next chunk flies during the
+                    // shared-memory staging (two named barriers + fence + bulk reduce issue) of the current one
+                    static_assert(BLOCK_N % 64 == 0, "pipelined fp32 epilogue walks pairs of 32-column chunks");
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr, ra);
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N; c += 64) {
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + c + 32, rb);
+                        stage_open();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) put16(j, ra[4 * j + 0], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
+                        stage_close(nb * BLOCK_N + c);
+                        tmem_ld_wait();
+                        if (c + 64 < BLOCK_N) tmem_ld32(taddr + c + 64, ra);
+                        else { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
+                        stage_open();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) put16(j, rb[4 * j + 0], rb[4 * j + 1], rb[4 * j + 2], rb[4 * j + 3]);
+                        stage_close(nb * BLOCK_N + c + 32);
                     }
                 } else {  // fp32 tiles of 32 columns: plain store (EPI_F32) or in-L2 add (EPI_RESID_F32)
 #pragma unroll 1

@@ -38,6 +38,18 @@ PY
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+# 6b. experimental kernel variants (compiled in round 1, not yet run): agreement test + A/B of the headline bench
+B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k variants_agree > $OUT/${TAG}_pytest_experimental.log 2>&1; echo "experimental variants rc=$?"
+tail -3 $OUT/${TAG}_pytest_experimental.log
+B200RANK_EPI_PIPE=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe.json 2> $OUT/${TAG}_bench_n1_epi_pipe.err; echo "bench epi_pipe rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_epi_pipe.json").read().strip().splitlines()[-1])
+    print("EPI_PIPE docs/s", round(d["value"]), {k: v for k, v in d["roofline"]["by_kernel_ms_per_step"].items() if "epi1" in k})
+except Exception as e:
+    print("epi_pipe bench line unreadable:", e)
+PY
 # 7. stand-alone design probes (experiments/README.md)
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
   && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt

@@ -418,6 +418,13 @@ def test_kernel_variants_agree(tmp_path):
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
+    # variants written after the round's GPU budget was spent: compiled, never run. B200RANK_TEST_EXPERIMENTAL=1 includes them
+    # (first thing to do with a fresh budget); until they have passed once they stay out of the default suite.
+    if os.environ.get("B200RANK_TEST_EXPERIMENTAL") == "1":
+        for name, env in [("epi_pipe", {"B200RANK_EPI_PIPE": "1"})]:
+            got = run(name, **env)
+            record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
+            assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
     # different arithmetic (re-blocked softmax / re-associated products): agreement to bf16 noise
     for name, env in [("attn_tiled", {"B200RANK_ATTN": "tiled"}), ("attn_tc", {"B200RANK_ATTN": "tc"}), ("attn_regs", {"B200RANK_ATTN": "regs"}),
                       ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
