@@ -290,6 +290,12 @@ struct b200rank_engine {
     cudaEvent_t ev_enc[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     struct Slot { int docs = 0, tokens = 0, maxlen = 0; bool busy = false; uint64_t ticket = 0; } slot[2];
     uint64_t next_ticket = 1;
+    // B200RANK_PIPE_DUAL=1 (experimental, off by default): the encoder passes of the two in-flight batches run on two streams with
+    // two sets of encoder workspaces, so that one batch's HBM/L2-bound kernels (T5LayerNorm, epilogue tails, attention tails) overlap
+    // the other batch's tensor-bound GEMMs instead of queueing behind them. Slot 0 = the ordinary set.
+    bool pipe_dual = false;
+    cudaStream_t stream_enc2 = nullptr;
+    struct EncWs { float* x = nullptr; bf16 *h = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr; int* d_ids = nullptr; } enc_ws[2];
     int gemm_sm_cap = 0;                          // > 0: persistent GEMMs use at most this many SMs (the rest serve the other stream)
     int pipe_reserve_sms = 0;  // measured on B200 (profiles/r01_bench_n1_v10_*): capping the encoder GEMM grids does not pay off
 
@@ -463,6 +469,12 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
         if (e->ev_enc[b]) cudaEventDestroy(e->ev_enc[b]);
         if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
     }
+    if (e->pipe_dual) {
+        void* dual[] = {e->enc_ws[1].x, e->enc_ws[1].h, e->enc_ws[1].qkv, e->enc_ws[1].ao, e->enc_ws[1].g, e->enc_ws[1].d_ids};
+        for (void* p : dual)
+            if (p) cudaFree(p);
+    }
+    if (e->stream_enc2) cudaStreamDestroy(e->stream_enc2);
     if (e->stream_dec) cudaStreamDestroy(e->stream_dec);
     for (int i = 0; i < 2; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -591,6 +603,15 @@ static int create_impl(b200rank_engine* e) {
     e->enc_out_cur = e->enc_out[0];
     e->d_cu = e->d_cu_slot[0];
     e->d_cu_cur = e->d_cu;
+    e->enc_ws[0].x = e->x; e->enc_ws[0].h = e->h; e->enc_ws[0].qkv = e->qkv; e->enc_ws[0].ao = e->ao; e->enc_ws[0].g = e->g;
+    e->enc_ws[0].d_ids = e->d_ids;
+    e->pipe_dual = getenv("B200RANK_PIPE_DUAL") && atoi(getenv("B200RANK_PIPE_DUAL")) != 0;
+    if (e->pipe_dual) {
+        auto& w = e->enc_ws[1];
+        RET_IF(dev_alloc(e, &w.x, Tk * d)); RET_IF(dev_alloc(e, &w.h, Tk * d)); RET_IF(dev_alloc(e, &w.qkv, Tk * 3 * I));
+        RET_IF(dev_alloc(e, &w.ao, Tk * I)); RET_IF(dev_alloc(e, &w.g, Tk * F)); RET_IF(dev_alloc(e, &w.d_ids, Tk));
+        CU_OK(cudaStreamCreateWithFlags(&e->stream_enc2, cudaStreamNonBlocking));
+    }
     RET_IF(dev_alloc(e, &e->d_dec_ids, R)); RET_IF(dev_alloc(e, &e->d_cols, 64)); RET_IF(dev_alloc(e, &e->d_labels, R));
     RET_IF(dev_alloc(e, &e->d_int_out, (size_t)e->cap_docs * 16)); RET_IF(dev_alloc(e, &e->d_finished, (size_t)e->cap_docs));
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ids), Tk * sizeof(int), cudaHostAllocDefault));
@@ -1362,10 +1383,20 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
     }
     if (maxlen > 240 || e->debug_simt) return set_error(B200RANK_ERR_ARG, "pipelined submit supports documents of at most 240 tokens");
 
-    e->stream = e->stream_main;
-    CU_OK(cudaStreamWaitEvent(e->stream_main, e->ev_done[b], 0));  // the decoder that last read this slot has finished
+    // the stream / encoder workspace set of this slot: the ordinary ones unless B200RANK_PIPE_DUAL runs slot 1 next to slot 0
+    const bool dual = e->pipe_dual && b == 1;
+    cudaStream_t s_enc = dual ? e->stream_enc2 : e->stream_main;
+    struct WsGuard {   // encoder members point at the slot's set while its pass is enqueued (kernel arguments are captured at launch)
+        b200rank_engine* e; bool on;
+        WsGuard(b200rank_engine* e_, bool on_) : e(e_), on(on_) { if (on) use(1); }
+        ~WsGuard() { if (on) use(0); }
+        void use(int k) { const auto& w = e->enc_ws[k]; e->x = w.x; e->h = w.h; e->qkv = w.qkv; e->ao = w.ao; e->g = w.g; e->d_ids = w.d_ids; }
+    } ws_guard(e, dual);
+    e->stream = s_enc;
+    CU_OK(cudaStreamWaitEvent(s_enc, e->ev_done[b], 0));  // the decoder that last read this slot has finished
     if (resident) {
-        if (b != 0) CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], e->d_cu_slot[0], (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyDeviceToDevice, e->stream_main));
+        if (b != 0) CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], e->d_cu_slot[0], (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s_enc));
+        if (dual) e->d_ids = e->enc_ws[0].d_ids;   // the staged ids are read-only and were uploaded synchronously: both slots read them in place
     } else {
         // host packing into this slot's pinned staging (its previous H2D finished before the slot was waited on)
         int* hid = e->h_ids_slot[b]; int* hcu = e->h_cu_slot[b];
@@ -1375,8 +1406,8 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
             tok += lengths[i];
             hcu[i + 1] = tok;
         }
-        CU_OK(cudaMemcpyAsync(e->d_ids, hid, (size_t)tok * sizeof(int), cudaMemcpyHostToDevice, e->stream_main));
-        CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], hcu, (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream_main));
+        CU_OK(cudaMemcpyAsync(e->d_ids, hid, (size_t)tok * sizeof(int), cudaMemcpyHostToDevice, s_enc));
+        CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], hcu, (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyHostToDevice, s_enc));
         e->staged_docs = n_docs; e->staged_tokens = tok; e->staged_maxlen = maxlen;
     }
     e->staged_minlen = 0;   // not tracked here: a mixed batch (192 < maxlen <= 240) launches both attention kernels
@@ -1386,7 +1417,7 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
     e->gemm_sm_cap = std::max(2, (e->num_sms - std::max(0, e->pipe_reserve_sms)) & ~1);
     int rc = run_encoder(e, /*need_ckv=*/false);
     e->gemm_sm_cap = 0;
-    if (rc == B200RANK_OK) { cudaError_t er = cudaEventRecord(e->ev_enc[b], e->stream_main); if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "event record: %s", cudaGetErrorString(er)); }
+    if (rc == B200RANK_OK) { cudaError_t er = cudaEventRecord(e->ev_enc[b], s_enc); if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "event record: %s", cudaGetErrorString(er)); }
 
     // ---- decoder + head + D2H on the decoder stream
     if (rc == B200RANK_OK) {

@@ -50,6 +50,18 @@ try:
 except Exception as e:
     print("epi_pipe bench line unreadable:", e)
 PY
+# 6c. two encoder streams (B200RANK_PIPE_DUAL=1, experimental): bit-identity of the pipelined path, then the A/B
+B200RANK_PIPE_DUAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "pipelined_submit or large_yes_no" > $OUT/${TAG}_pytest_pipe_dual.log 2>&1; echo "pipe_dual tests rc=$?"
+tail -3 $OUT/${TAG}_pytest_pipe_dual.log
+B200RANK_PIPE_DUAL=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_pipe_dual.json 2> $OUT/${TAG}_bench_n1_pipe_dual.err; echo "bench pipe_dual rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_pipe_dual.json").read().strip().splitlines()[-1])
+    print("PIPE_DUAL docs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "clocks", d["clocks"]["sm_mhz"])
+except Exception as e:
+    print("pipe_dual bench line unreadable:", e)
+PY
 # 7. stand-alone design probes (experiments/README.md)
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
   && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
