@@ -519,3 +519,39 @@ def test_rel_bucket_table_matches_hf_golden():
     g = golden_npz("buckets.npz")
     assert [br.rel_bucket(int(r), True) for r in g["rel"]] == g["bidirectional"].tolist()
     assert [br.rel_bucket(int(r), False) for r in g["rel"]] == g["unidirectional"].tolist()
+
+
+def test_prompt_assembler_with_a_trained_subword_vocabulary():
+    """§8f-1's open caveat, as far as it can be closed offline: a REAL sentencepiece unigram vocabulary (trained by
+    tests/golden/make_spm_vocab.py; subword pieces, punctuation, digits — the model family of Flan-T5's spiece.model) behind the same
+    transformers.T5Tokenizer class. Token-level assembly must equal whole-string tokenisation for every prompt template of the rankers
+    on natural prose, with verify=0 (no safety net), including text with quotes, brackets, unicode and odd whitespace."""
+    import json
+    from transformers import T5Tokenizer
+    from helpers import GOLDEN
+    from llmrankers._prompts import PromptAssembler
+    from llmrankers.pairwise import PAIRWISE_PROMPT
+    from llmrankers.pointwise import MONOT5_PROMPT, QLM_PROMPT, YES_NO_PROMPT
+    from llmrankers.setwise import SetwiseLlmRanker
+    with open(os.path.join(GOLDEN, "spm_unigram_vocab.json")) as f:
+        fx = json.load(f)
+    tok = T5Tokenizer(vocab=[(p, s) for p, s in fx["pieces"]])
+    assert (tok.pad_token_id, tok.eos_token_id, tok.unk_token_id) == (0, 1, 2)
+    texts = list(fx["sample_sentences"])
+    assert any(len(tok.tokenize(w)) > 1 for t in texts[:5] for w in t.split())        # the vocabulary really splits words
+    texts += ['He said: "quoted, (bracketed) text" -- and left.', "it's 3.14159, isn't it? 100% sure; e.g. x=1/2", "café naïve 中文 — dash",
+              "  leading, trailing   and   inner   runs  ", "tab\tand\nnewline\r\nmix", "", " ", "\"", "a\"b \"c\" d\"", "UPPER lower MiXeD snake_case camelCase"]
+    query = 'how to "sort" a list, in-place?'
+    cases = [(YES_NO_PROMPT, [dict(text=t, query=query) for t in texts]), (QLM_PROMPT, [dict(text=t) for t in texts]),
+             (MONOT5_PROMPT, [dict(query=query, document=t) for t in texts]),
+             (PAIRWISE_PROMPT, [dict(query=query, doc1=texts[i], doc2=texts[-1 - i]) for i in range(len(texts))]),
+             (SetwiseLlmRanker._template(3, ["A", "B", "C"]), [dict(query=query, d0=texts[i], d1=texts[(i + 7) % len(texts)], d2=texts[-1 - i])
+                                                               for i in range(len(texts))])]
+    for template, fields in cases:
+        a = PromptAssembler(tok, template, verify=0)
+        assert a.eligible, template
+        want = tok([template.format(**f) for f in fields])["input_ids"]
+        got = a.rows(fields)
+        bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+        assert not bad, (template[:30], fields[bad[0]])
+        assert a.rows(fields) == want     # from the cache
