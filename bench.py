@@ -217,6 +217,8 @@ def cpu_reference_baseline(weights, eng_logits, eng_scores, n_sample=32, budget_
     i, j = np.triu_indices(n_sample, 1)
     disc = np.sign(m_ref[i] - m_ref[j]) * np.sign(m_eng[i] - m_eng[j]) < 0
     parity["discordant_pairs"] = int(disc.sum())
+    parity["document_pairs"] = int(len(i))
+    parity["kendall_tau"] = float(1.0 - 2.0 * disc.sum() / max(1, len(i)))
     parity["max_ref_margin_gap_of_discordant_pairs"] = float(np.abs(m_ref[i] - m_ref[j])[disc].max()) if disc.any() else 0.0
     m_tol = tol.sum(1)   # a document's margin may move by the tolerance of both of its logits
     parity["order_identical_where_ref_gap_exceeds_tolerance"] = bool((np.abs(m_ref[i] - m_ref[j])[disc] <= (m_tol[i] + m_tol[j])[disc]).all())
