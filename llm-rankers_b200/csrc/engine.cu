@@ -194,6 +194,20 @@ static bool epi_pipe_pref() {
     return v != 0;
 }
 
+// B200RANK_EPI_HINT=last|first|normal (with B200RANK_EPI_PIPE=1): L2 policy of the residual reduce-add destination lines
+static unsigned long long epi_l2_hint() {
+    static int init = 0;
+    static unsigned long long v = 0;
+    if (!init) {
+        const char* s = getenv("B200RANK_EPI_HINT");
+        if (s && !strcmp(s, "last")) v = kEvictLast;
+        else if (s && !strcmp(s, "first")) v = kEvictFirst;
+        else if (s && !strcmp(s, "normal")) v = kEvictNormal;
+        init = 1;
+    }
+    return v;
+}
+
 static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                           const GemmArgs& a, int epi, int bn, bool tma_epi, int cg) {
     // the staged bf16 epilogue moves 64-column (128 B) tiles; a 32-column accumulator keeps the direct store path
@@ -399,7 +413,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
-    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch, relu};
+    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch, relu, epi_l2_hint()};
     const int sms = (e->gemm_sm_cap > 0 && bn == 256 && M > 1024) ? std::min(e->gemm_sm_cap, e->num_sms) : e->num_sms;
     RET_IF(launch_gemm_tc(e->stream, sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
@@ -1724,7 +1738,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
         if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn / cg);
         if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
-        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f, 0, 0};
+        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f, 0, 0, 0ull};
         if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct, cg);
     }
     if (rc == B200RANK_OK) {

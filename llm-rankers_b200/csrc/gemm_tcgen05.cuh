@@ -41,6 +41,7 @@ struct GemmArgs {
     // with W rows of that block, i.e. out[:, b-th block] = A_b . W_b^T for per-head weight slices (decoder T=1 fast path).
     int n_per_batch;
     int relu;      // EPI_BF16 only: out = max(acc, 0) (T5 v1.0 DenseReluDense, modeling_t5.py:88-103)
+    unsigned long long l2_hint;  // EPI_RESID_F32_PIPE only (experimental): L2 cache policy of the reduce-add destination, 0 = none
 };
 
 constexpr int kGemmBlockM = 128;
@@ -248,7 +249,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     named_bar_sync(1, 128);
                     if (issuer) {
                         const void* src = smem_stage + stage_sel * (kGemmBlockM * 128);
-                        if constexpr (kResid) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
+                        if constexpr (EPI == EPI_RESID_F32_PIPE) {
+                            if (args.l2_hint) tma_reduce_add_2d_hint(&tmap_out, src, out_col0, m0, args.l2_hint);
+                            else tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
+                        } else if constexpr (kResid) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
                         else tma_store_2d(&tmap_out, src, out_col0, m0);
                         tma_store_commit();
                     }

@@ -93,6 +93,14 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* 
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// same with an L2 cache policy for the destination lines (kEvictLast keeps the freshly reduced residual rows resident for the
+// T5LayerNorm pass that reads them next; experimental, used by EPI_RESID_F32_PIPE only)
+__device__ __forceinline__ void tma_reduce_add_2d_hint(const void* desc, const void* smem_src, int32_t c0, int32_t c1, uint64_t cache_hint) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(cache_hint)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

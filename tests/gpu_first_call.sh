@@ -50,6 +50,16 @@ try:
 except Exception as e:
     print("epi_pipe bench line unreadable:", e)
 PY
+B200RANK_EPI_PIPE=1 B200RANK_EPI_HINT=last timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe_evict_last.json 2> $OUT/${TAG}_bench_n1_epi_pipe_evict_last.err; echo "bench epi_pipe+evict_last rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_epi_pipe_evict_last.json").read().strip().splitlines()[-1])
+    k = d["roofline"]["by_kernel_ms_per_step"]
+    print("EPI_PIPE+EVICT_LAST docs/s", round(d["value"]), {x: v for x, v in k.items() if "epi1" in x or x == "rmsnorm"})
+except Exception as e:
+    print("epi_pipe+evict_last bench line unreadable:", e)
+PY
 # 6c. two encoder streams (B200RANK_PIPE_DUAL=1, experimental): bit-identity of the pipelined path, then the A/B
 B200RANK_PIPE_DUAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "pipelined_submit or large_yes_no" > $OUT/${TAG}_pytest_pipe_dual.log 2>&1; echo "pipe_dual tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_pipe_dual.log
