@@ -555,3 +555,62 @@ def test_prompt_assembler_with_a_trained_subword_vocabulary():
         bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
         assert not bad, (template[:30], fields[bad[0]])
         assert a.rows(fields) == want     # from the cache
+
+
+@pytest.mark.parametrize("source", ["ir_datasets", "pyserini"])
+def test_cli_reference_data_sources_with_stub_modules(source, tmp_path, monkeypatch, capsys):
+    """run.py keeps the reference's two data sources (run.py:135-149, 165-172) behind lazy imports; neither library exists offline,
+    so stand-ins with the same call surface are injected: queries from dataset.queries_iter() / get_topics(index + '-test'), document
+    text from docs_store().get(docid) (title prepended when the record has one) / LuceneSearcher.doc(docid).raw() JSON."""
+    import json
+    import sys
+    import types
+    import run as cli_mod
+    from llmrankers import _backend
+    meta = golden_meta()
+    m, c = meta["tiny"], meta["cases"]["yes_no"]
+    monkeypatch.setattr(_backend.T5Backend, "load", classmethod(lambda cls, *a, **k: backend("tiny")))
+    docs = {d["docid"]: d["text"] for d in m["docs"]}
+    # split every passage into a "title" (first word) and the rest: title + ' ' + text reproduces the fixture's passage
+    split = {k: v.split(" ", 1) for k, v in docs.items()}
+    if source == "ir_datasets":
+        class Doc:
+            def __init__(self, title, text):
+                self.title, self.text = title, text
+
+        class Store:
+            def get(self, docid):
+                return Doc(*split[docid])
+
+        class Dataset:
+            def queries_iter(self):
+                yield types.SimpleNamespace(query_id="q1", text=m["query"])
+
+            def docs_store(self):
+                return Store()
+        mod = types.ModuleType("ir_datasets")
+        mod.load = lambda name: Dataset()
+        monkeypatch.setitem(sys.modules, "ir_datasets", mod)
+        src_args = ["--ir_dataset_name", "stub/dataset"]
+    else:
+        class Searcher:
+            @classmethod
+            def from_prebuilt_index(cls, name):
+                assert name == "stub-index.flat"
+                return cls()
+
+            def doc(self, docid):
+                return types.SimpleNamespace(raw=lambda: json.dumps({"title": split[docid][0], "text": split[docid][1]}))
+        pkg, search = types.ModuleType("pyserini"), types.ModuleType("pyserini.search")
+        base, lucene = types.ModuleType("pyserini.search._base"), types.ModuleType("pyserini.search.lucene")
+        base.get_topics = lambda name: {"q1": {"title": m["query"]}} if name == "stub-index-test" else {}
+        lucene.LuceneSearcher = Searcher
+        for name, mod in (("pyserini", pkg), ("pyserini.search", search), ("pyserini.search._base", base), ("pyserini.search.lucene", lucene)):
+            monkeypatch.setitem(sys.modules, name, mod)
+        src_args = ["--pyserini_index", "stub-index"]
+    (tmp_path / "run.txt").write_text("".join(f"q1 Q0 {d['docid']} {i + 1} {d['score']} bm25\n" for i, d in enumerate(m["docs"])))
+    out = tmp_path / "out.txt"
+    cli_mod.cli(["run", "--model_name_or_path", "synthetic:t5-tiny", "--run_path", str(tmp_path / "run.txt"), "--save_path", str(out)] + src_args +
+                ["--query_length", "32", "--passage_length", "128", "pointwise", "--method", "yes_no", "--batch_size", "4"])
+    assert [l.split("\t")[2] for l in out.read_text().splitlines()] == c["order"]
+    assert f"Avg comparisons: {float(c['total_compare'])}" in capsys.readouterr().out
