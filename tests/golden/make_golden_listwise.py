@@ -84,11 +84,12 @@ def main():
     for resp, n, a, b in (("[2] > [1] > [3]", 6, 0, 3), ("[3] > [3] > [1]", 6, 2, 6), ("[9] > [2] > [0] > [1]", 5, 0, 4), ("no numbers here", 4, 0, 4),
                           ("2>1", 4, 1, 4), ("[4]>[3]>[2]>[1]", 4, 0, 4), ("12 1 2", 12, 0, 12), ("[1] > [2]", 3, 2, 10), ("", 3, 0, 3)):
         perm_cases.append((resp, n, a, b))
-    for _ in range(12):
-        n = int(rng.integers(2, 12)); a = int(rng.integers(0, n)); b = int(rng.integers(a + 1, n + 3))
+    for _ in range(200):
+        n = int(rng.integers(2, 24)); a = int(rng.integers(0, n)); b = int(rng.integers(a + 1, n + 3))
         w = min(b, n) - a
         nums = rng.integers(0, w + 3, size=int(rng.integers(0, w + 4)))
-        perm_cases.append((" > ".join(f"[{int(x)}]" for x in nums), n, a, b))
+        sep = [" > ", ">", ", ", " ", "] > [", " then "][int(rng.integers(0, 6))]
+        perm_cases.append((sep.join(f"[{int(x)}]" for x in nums) + ["", ".", " done 7", "\n"][int(rng.integers(0, 4))], n, a, b))
     meta["receive_permutation"] = []
     for resp, n, a, b in perm_cases:
         ranking = [SearchResult(docid=f"p{i}", score=0.0, text="") for i in range(n)]
