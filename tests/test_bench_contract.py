@@ -40,3 +40,114 @@ def test_engine_arm_fails_loudly_without_a_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-text-api"],
                        capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)   # no CPU fallback behind the bench either
+
+
+def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
+    """run_engine end to end on CPU: b200rank.Engine is replaced by a stand-in that answers with the transformers fp32 forward (+ noise of
+    bf16 size) and reports a canned per-kernel profile, so every leg that shapes the JSON line runs — value / e2e / launches / roofline
+    (dominant kernel, traffic lookup, HBM entry) / cpu_baseline / parity (incl. the bf16 yardstick and Kendall tau) / text API. This is a
+    test of bench.py's bookkeeping, not of performance: the numbers it prints here mean nothing."""
+    import json as _json
+    import time
+    import types
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    monkeypatch.setenv("B200RANK_BENCH_MODEL", "flan-t5-small")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    import importlib
+    import bench
+    bench = importlib.reload(bench)
+    import b200rank as br
+    from b200rank.synthetic import model_cfg
+    from oracle import hf_cpu
+
+    class StandIn:
+        def __init__(self, cfg, device):
+            self.model = None
+            self.staged = None
+            self.n_launch = 0
+            self.t = [0.0, 0.0]
+            self.prof = False
+            self.tick = 0
+            self.pending = {}
+            self.cache = {}
+
+        def load_state_dict(self, items):
+            self.model = hf_cpu.build_model(model_cfg(bench.MODEL), dict(items), threads=4)
+
+        def _score(self, ids, lengths, yes_id, no_id):
+            self.n_launch += 438
+            key = (np.asarray(ids).tobytes(), np.asarray(lengths).tobytes(), yes_id, no_id)
+            if key not in self.cache:       # the bench scores the same query over and over: one real forward is enough here
+                mask = (np.arange(ids.shape[1])[None] < np.asarray(lengths)[:, None]).astype(np.int64)
+                lg, _ = hf_cpu.score_yes_no(self.model, np.asarray(ids, np.int64) * mask, mask, yes_id, no_id, 32)
+                lg = (lg + np.random.default_rng(0).normal(0, 0.01, lg.shape)).astype(np.float32)
+                self.cache[key] = (lg, (np.exp(lg[:, 0]) / np.exp(lg).sum(1)).astype(np.float32))
+            return self.cache[key]
+
+        def stage(self, ids, lengths):
+            self.staged = (np.asarray(ids), np.asarray(lengths))
+
+        def submit_yes_no_staged(self, yes_id, no_id):
+            return self.submit_yes_no(self.staged[0], self.staged[1], yes_id, no_id)
+
+        def submit_yes_no(self, ids, lengths, yes_id, no_id):
+            self.tick += 1
+            self.pending[self.tick] = self._score(ids, lengths, yes_id, no_id)
+            return self.tick
+
+        def wait_yes_no(self, ticket):
+            return self.pending.pop(ticket)
+
+        def run_yes_no_staged(self, yes_id, no_id):
+            self.last = self._score(self.staged[0], self.staged[1], yes_id, no_id)
+
+        def fetch_yes_no(self):
+            return self.last
+
+        def event_record(self, which):
+            self.t[which] = time.perf_counter()
+
+        def event_elapsed_ms(self):
+            return (self.t[1] - self.t[0]) * 1e3
+
+        def launch_count(self):
+            return self.n_launch
+
+        def profile(self, on):
+            self.prof = on
+
+        def profile_report(self):
+            n_tok = int(self.staged[1].sum())
+            return {f"gemm_tcgen05<bn256,epi2> M{n_tok} N2048 K512": {"ms": 2.0, "n": 16}, f"gemm_tcgen05<bn256,epi0> M{n_tok} N1152 K512": {"ms": 1.0, "n": 16},
+                    "gemm_tcgen05<bn32,epi1> M100 N512 K384": {"ms": 0.2, "n": 16}, "rmsnorm": {"ms": 0.5, "n": 34}, "rmsnorm_small": {"ms": 0.1, "n": 50},
+                    "enc_attention_tc2": {"ms": 0.8, "n": 16}}
+
+        def sync(self):
+            pass
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(br, "Engine", StandIn)
+    monkeypatch.setattr(bench.ClockSampler, "run", lambda self: None)       # no nvidia-smi here
+    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=True, no_pipeline=False, hf_cuda=False)
+    assert bench.run_engine(args) == 0
+    line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(line) == 1
+    d = _json.loads(line[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["dtype"] == "bf16" and d["vs_baseline"] is None
+    assert d["gpu_launches"] == 3 * 438 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1200
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["kernel"].startswith("gemm_tcgen05<bn256,epi2> M18400") and r["unit"] == "TFLOP/s" and r["frac"] > 0
+    assert abs(r["flop_per_launch"] - 2.0 * 18400 * 2048 * 512) < 1 and r["launches_per_step"] == 16 / 3
+    assert r["hbm_kernels"][0]["kernel"] == "rmsnorm_kernel" and r["hbm_kernels"][0]["launches_per_step"] == 34 / 3
+    assert "rmsnorm_small" in r["by_kernel_ms_per_step"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    p = d["parity"]
+    assert p["docs"] >= 2 and p["within_logit_tolerance"] is True and p["max_abs_logit_diff"] < 0.06 and 0.9 < p["kendall_tau"] <= 1.0
+    assert p["order_identical_where_ref_gap_exceeds_tolerance"] is True and "max_abs_logit_diff" in p["reference_bf16_yardstick"]
