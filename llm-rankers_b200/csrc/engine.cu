@@ -406,16 +406,22 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     }
     if (relu) epi = EPI_BF16;
     const int cg = e->direct_epi ? 1 : pick_cta_group(M, N, bn, e->num_sms);
-    const CUtensorMap *ta, *tb, *tout;
-    RET_IF(engine_tmap(e, A, a_rows, a_cols > 0 ? a_cols : K, lda, kGemmBlockM, 0, &ta));
-    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn / cg, 0, &tb));
+    // The maps are COPIED out of the cache: a later lookup may clear it (it is bounded, and output maps are keyed by the live row
+    // count, so a long-running process does reach the bound), which would leave pointers into it dangling.
+    CUtensorMap ta, tb, tout;
+    const CUtensorMap* cached = nullptr;
+    RET_IF(engine_tmap(e, A, a_rows, a_cols > 0 ? a_cols : K, lda, kGemmBlockM, 0, &cached));
+    ta = *cached;
+    RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn / cg, 0, &cached));
+    tb = *cached;
     const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32 || epi == EPI_RESID_NORM);
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
-    RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &tout));
+    RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &cached));
+    tout = *cached;
     GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch, relu, epi_l2_hint()};
     const int sms = (e->gemm_sm_cap > 0 && bn == 256 && M > 1024) ? std::min(e->gemm_sm_cap, e->num_sms) : e->num_sms;
-    RET_IF(launch_gemm_tc(e->stream, sms, *ta, *tb, *tout, args, epi, bn, !e->direct_epi, cg));
+    RET_IF(launch_gemm_tc(e->stream, sms, ta, tb, tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
 }
 
