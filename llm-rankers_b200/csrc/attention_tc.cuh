@@ -254,12 +254,13 @@ struct AttnTc2Cfg {
     static_assert(kOCol0 + 128 <= 512, "S and O tiles must fit the 512 TMEM columns side by side");
 };
 
-template <int NKB, bool SPLIT>
+template <int NKB, int MODE>   // MODE 0: two TMEM passes (ships), 1: row split over two threads (tc3), 2: one pass with a provisional shift (tc4)
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items, int spin,
                          int len_limit) {
     using Cfg = AttnTc2Cfg<NKB>;
+    constexpr bool SPLIT = (MODE == 1);
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -400,7 +401,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 item = nitem; len = nlen;
             }
         }
-    } else if constexpr (!SPLIT) {
+    } else if constexpr (MODE == 0) {
         const int t = (warp_idx - 2) >> 2;            // query tile slot of this warpgroup
         const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
         const int wg_tid = threadIdx.x - 64 - t * 128;
@@ -565,6 +566,194 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
             }
             tc_fence_before();      // TMEM reads/writes of S_t are complete before MMA-1 of the next use overwrites it
+            fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&bar_p[t]);
+            pend = true; p_active = active; p_l = l; p_tok0 = my_tok0; p_len = len; p_h = h; p_par = use & 1;
+            ++use;
+        }
+        if (pend) epilogue();
+    } else if constexpr (MODE == 2) {
+        // ---- ONE PASS (tc4, experimental, B200RANK_ATTN=tc4): softmax is shift-invariant, and fp32 / bf16 share one exponent range, so
+        // the shift need not be the row maximum: any value within ~2^100 of it gives the same relative precision in p, in the row sum
+        // and in O = P V. The maximum of the row's FIRST 32-key chunk serves as the shift. Every chunk is then read from TMEM once and
+        // p = 2^(v - shift) goes straight into the P tile: no write-back of v (tcgen05.st), no second TMEM read, half the per-thread
+        // chain of the two-pass walk that bounds MODE 0 (profiles/r01_bench_attn_ab.txt). A row whose sum leaves [1/2, 2^100) — scores
+        // that climb by more than ~69 natural-log units after the first chunk, or non-finite scores — is redone with its exact maximum
+        // (S_t is still intact in TMEM); the decision is taken per warp because tcgen05.ld is warp-collective.
+        // The epilogue of the previous use of the tile slot runs BEFORE the wait on S_t: MMA-2(k-1, t) was issued ahead of MMA-1(k, t),
+        // so O_t is the older result; draining it overlaps MMA-1 and licenses the writes into P_t.
+        const int t = (warp_idx - 2) >> 2;            // query tile slot of this warpgroup
+        const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
+        const int wg_tid = threadIdx.x - 64 - t * 128;
+        const int row_in_tile = quarter * 32 + lane;
+        const int qi = t * 128 + row_in_tile;         // query index inside the document
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol;
+        const uint32_t taddr_o = tmem_base + lane_off + Cfg::kOCol0 + t * 64;
+        uint8_t* prow = sP + t * Cfg::kPBytes + row_in_tile * 128;
+        uint32_t use = 0;
+        int h_loaded = -1;
+        int item = qualify(blockIdx.x);
+        int doc = item < n_items ? item / H : 0;
+        int tok0 = cu[doc], tok1 = cu[doc + 1];
+        bool pend = false, p_active = false;
+        float p_l = 0.f;
+        int p_tok0 = 0, p_len = 0, p_h = 0;
+        uint32_t p_par = 0;
+        auto epilogue = [&]() {
+            wait(&bar_o[t], p_par);
+            tc_fence_after();
+            if (p_active) {
+                uint32_t o0[32], o1[32];
+                tmem_ld32(taddr_o, o0);
+                tmem_ld32(taddr_o + 32, o1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_free[t]);
+                if (qi < p_len) {
+                    const float inv = 1.f / p_l;
+                    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p_tok0 + qi) * ldo + p_h * 64);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+                        v.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+                        v.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+                        v.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+                        dst[i] = v;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v;
+                        v.x = pack_bf16(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+                        v.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+                        v.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+                        v.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+                        dst[4 + i] = v;
+                    }
+                }
+            } else {
+                mbar_arrive(&o_free[t]);
+            }
+        };
+        while (item < n_items) {
+            const int h = item - doc * H;
+            const int len = tok1 - tok0, my_tok0 = tok0;
+            const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
+            const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
+            item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
+            if (t >= ((len + 127) >> 7)) continue;
+            const int ncols = ((len + 63) >> 6) * 64;
+            const bool active = (t * 128 + quarter * 32) < len;   // warp-uniform: at least one real query row
+            float* sB = sBiasW + (bias_resident ? h : t) * Cfg::kWideBias;
+            if (!bias_resident && h != h_loaded) {
+                named_bar_sync(1 + t, 128);               // every warp of the group is past its reads of the old window
+                for (int i = wg_tid; i < 511; i += 128) {
+                    const int rel = max(-kAttnRelClamp, min(kAttnRelClamp, i - 255));
+                    sB[i] = bias[h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
+                }
+                named_bar_sync(1 + t, 128);
+                h_loaded = h;
+            }
+            const uint32_t sBrow = smem_u32(sB) + (255 - qi) * 4;   // [sBrow + 4 j] = log2(e) * bias(j - qi)
+            if (pend) { epilogue(); pend = false; }
+            wait(&bar_s[t], use & 1);
+            tc_fence_after();
+            float l = 0.f;
+            if (active) {
+                float shift = 0.f;
+                float l4[4];
+                // v_j = s_j * log2(e) + bias'(j - qi) of one 32-key chunk; keys past the document read as -inf (p = 0)
+                auto score = [&](uint32_t s_bits, int j) {
+                    return fmaf(__uint_as_float(s_bits), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * j));
+                };
+                auto chunk_max = [&](const uint32_t (&r)[32], int c, float (&m4)[4]) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        float v = score(r[e], c + e);
+                        if (c + 32 > len) v = (c + e < len) ? v : -INFINITY;
+                        m4[e & 3] = fmaxf(m4[e & 3], v);
+                    }
+                };
+                auto chunk_p = [&](const uint32_t (&r)[32], int c) {
+                    uint32_t packed[16];
+                    if (c + 32 <= len) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            const float p0 = ex2_approx(score(r[e], c + e) - shift);
+                            const float p1 = ex2_approx(score(r[e + 1], c + e + 1) - shift);
+                            l4[(e >> 1) & 3] += p0 + p1;
+                            packed[e >> 1] = pack_bf16(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float p0 = ex2_approx(score(r[e], c + e) - shift);
+                            float p1 = ex2_approx(score(r[e + 1], c + e + 1) - shift);
+                            p0 = (c + e < len) ? p0 : 0.f;
+                            p1 = (c + e + 1 < len) ? p1 : 0.f;
+                            l4[(e >> 1) & 3] += p0 + p1;
+                            packed[e >> 1] = pack_bf16(p0, p1);
+                        }
+                    }
+                    uint8_t* kblk = prow + (c >> 6) * 16384;
+                    const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), packed[4 * i], packed[4 * i + 1],
+                                     packed[4 * i + 2], packed[4 * i + 3]);
+                };
+                // one walk over the row's chunks, TMEM loads double-buffered in registers; FIRST: take the shift from chunk 0
+                auto walk_p = [&](bool first_chunk_shift) {
+                    l4[0] = l4[1] = l4[2] = l4[3] = 0.f;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr_s, ra);
+#pragma unroll 1
+                    for (int c = 0; c < len; c += 64) {
+                        tmem_ld_wait();
+                        if (c + 32 < len) tmem_ld32(taddr_s + c + 32, rb);
+                        if (first_chunk_shift && c == 0) {
+                            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                            chunk_max(ra, 0, m4);
+                            shift = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                        }
+                        chunk_p(ra, c);
+                        if (c + 32 < len) {
+                            tmem_ld_wait();
+                            if (c + 64 < len) tmem_ld32(taddr_s + c + 64, ra);
+                            chunk_p(rb, c + 32);
+                        }
+                    }
+                    return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+                };
+                l = walk_p(true);
+                const bool bad = !(l >= 0.5f && l < 1.2676506e30f);   // 2^100; also catches inf / NaN
+                if (__any_sync(0xffffffffu, bad)) {
+                    // rare: exact row maximum, then the same walk with it (every lane of the warp, each with its own maximum)
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    uint32_t ra[32];
+#pragma unroll 1
+                    for (int c = 0; c < len; c += 32) {
+                        tmem_ld32(taddr_s + c, ra);
+                        tmem_ld_wait();
+                        chunk_max(ra, c, m4);
+                    }
+                    shift = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    l = walk_p(false);
+                }
+                {
+                    const uint32_t zeros[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    for (int c = (len + 31) & ~31; c < ncols; c += 32) {
+                        uint8_t* kblk = prow + (c >> 6) * 16384;
+                        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), zeros[4 * i], zeros[4 * i + 1], zeros[4 * i + 2],
+                                         zeros[4 * i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();      // TMEM reads of S_t are complete before MMA-1 of the next use overwrites it
             fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&bar_p[t]);
             pend = true; p_active = active; p_l = l; p_tok0 = my_tok0; p_len = len; p_h = h; p_par = use & 1;

@@ -912,7 +912,8 @@ static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int 
 
 // Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length),
 // 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256), 4 = mma.sync scores-in-registers (len <= 256),
-// 5 = persistent tcgen05 (len <= 192). B200RANK_ATTN=tiled|resident|tc|regs|tc2 overrides mode 0.
+// 5 = persistent tcgen05 (len <= 192), 6 = its row-split variant (tc3), 7 = its one-pass variant (tc4, experimental).
+// B200RANK_ATTN=tiled|resident|tc|regs|tc2|tc3|tc4 overrides mode 0.
 static int attn_default_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -920,7 +921,7 @@ static int attn_default_mode() {
         // default: the persistent tcgen05 kernel for documents of <= 192 tokens (launch_enc_attention falls back to the mma.sync tiles
         // above that): 1.93 vs 2.32 ms per 100 documents at S=184, +3.7 % docs/s with two queries in flight
         // (profiles/r01_bench_attn_ab.txt). The first, unpipelined tcgen05 kernel ("tc") was 1.7x slower than the tiles.
-        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc3") ? 6 : 1)))));
+        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc3") ? 6 : (!strcmp(s, "tc4") ? 7 : 1))))));
     }
     return mode;
 }
@@ -945,13 +946,14 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
                                 int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0) {
     static bool attr_set = false;
     if (mode == 0) mode = attn_default_mode();
-    if (maxlen > 256 && mode != 5 && mode != 6) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
+    const bool persistent = (mode == 5 || mode == 6 || mode == 7);
+    if (maxlen > 256 && !persistent) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
     // Mixed batch under the default mode: documents of <= 192 tokens still get the tcgen05 kernel (it walks only those), the longer
     // ones the mma.sync tiles (which skip the short ones) — the kernel is chosen per document, so a document's result does not
     // depend on what it is batched with.
-    const bool mixed = (mode == 5 || mode == 6) && maxlen > 192;
-    if ((mode == 5 || mode == 6) && minlen > 192) mode = 1;   // known: no document qualifies for the tcgen05 kernel
-    if (mode == 5 || mode == 6) {
+    const bool mixed = persistent && maxlen > 192;
+    if (persistent && minlen > 192) mode = 1;   // known: no document qualifies for the tcgen05 kernel
+    if (mode == 5 || mode == 6 || mode == 7) {
         // persistent tcgen05 kernel: one CTA per SM walks the (document, head) items
         CUtensorMap local;
         const CUtensorMap* tm = &local;
@@ -960,10 +962,11 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         static bool attr5 = false;
         static int split = -1;
         if (split < 0) split = getenv("B200RANK_ATTN_SPLIT") ? atoi(getenv("B200RANK_ATTN_SPLIT")) : 0;
-        auto kern = (split || mode == 6) ? enc_attention_tc2_kernel<3, true> : enc_attention_tc2_kernel<3, false>;
+        auto kern = (split || mode == 6) ? enc_attention_tc2_kernel<3, 1> : (mode == 7 ? enc_attention_tc2_kernel<3, 2> : enc_attention_tc2_kernel<3, 0>);
         if (!attr5) {
-            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr5 = true;
         }
         const int n_items = nd * H;

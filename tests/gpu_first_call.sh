@@ -72,6 +72,19 @@ try:
 except Exception as e:
     print("pipe_dual bench line unreadable:", e)
 PY
+# 6d. one-pass softmax attention (B200RANK_ATTN=tc4, experimental): kernel against numpy incl. the exact-maximum redo, then the A/B
+B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "onepass" > $OUT/${TAG}_pytest_tc4.log 2>&1; echo "tc4 tests rc=$?"
+tail -3 $OUT/${TAG}_pytest_tc4.log
+B200RANK_ATTN=tc4 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_tc4.json 2> $OUT/${TAG}_bench_n1_tc4.err; echo "bench tc4 rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_tc4.json").read().strip().splitlines()[-1])
+    k = d["roofline"]["by_kernel_ms_per_step"]
+    print("ATTN=tc4 docs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), {x: v for x, v in k.items() if "attention" in x}, "clocks", d["clocks"]["sm_mhz"])
+except Exception as e:
+    print("tc4 bench line unreadable:", e)
+PY
 # 7. stand-alone design probes (experiments/README.md)
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
   && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt

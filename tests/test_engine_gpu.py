@@ -122,6 +122,31 @@ def test_enc_attention_kernels_vs_numpy(mode, H, n_docs):
     assert np.abs(out - ref).max() <= 0.03 * np.abs(ref).max()
 
 
+@pytest.mark.skipif(os.environ.get("B200RANK_TEST_EXPERIMENTAL") != "1",
+                    reason="tc4 (one-pass softmax) was written without GPU time: B200RANK_TEST_EXPERIMENTAL=1 runs it (tests/gpu_first_call.sh)")
+@pytest.mark.parametrize("H,n_docs,q_scale", [(16, 300, 0.35), (32, 20, 0.35), (3, 7, 0.35), (3, 40, 6.0), (2, 40, 40.0)])
+def test_enc_attention_onepass_vs_numpy(H, n_docs, q_scale):
+    """Mode 7 (B200RANK_ATTN=tc4): the persistent tcgen05 kernel with the provisional-shift one-pass softmax. q_scale 6 / 40 make the
+    scores span hundreds of log2 units, so rows overflow the provisional shift (maximum of the first 32 keys) and take the
+    exact-maximum redo; the result must still be the exact softmax."""
+    import b200rank as br
+    from gpu_diag import attention_reference
+    rng = np.random.default_rng(700 + H + n_docs)
+    lens = rng.integers(1, 193, size=n_docs).tolist()
+    lens[:6] = [192, 1, 128, 129, 31, 33][: min(6, n_docs)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    qkv = rng.standard_normal((int(cu[-1]), 3 * H * 64)).astype(np.float32)
+    qkv[:, : H * 64] *= q_scale
+    bias = rng.standard_normal((H, br.ATTN_BIAS_LEN)).astype(np.float32)
+    out = br.test_enc_attention(qkv, cu, H, bias, mode=7)
+    ref = attention_reference(qkv, cu, H, bias)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() <= 0.03 * np.abs(ref).max()
+    if q_scale == 0.35:   # same blocking, same bf16 P: the one-pass walk differs from the shipped two-pass kernel only by the shift
+        two_pass = br.test_enc_attention(qkv, cu, H, bias, mode=5)
+        assert np.abs(out - two_pass).max() <= 0.01 * np.abs(ref).max()
+
+
 def test_rel_bucket_matches_hf():
     import b200rank as br
     g = golden_npz("buckets.npz")
@@ -425,6 +450,9 @@ def test_kernel_variants_agree(tmp_path):
             got = run(name, **env)
             record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
             assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
+        got = run("attn_tc4", B200RANK_ATTN="tc4")
+        record("variant/attn_tc4", max_abs_diff=float(np.abs(got - base).max()))
+        assert np.abs(got - base).max() < 0.12, "attn_tc4"
     # different arithmetic (re-blocked softmax / re-associated products): agreement to bf16 noise
     for name, env in [("attn_tiled", {"B200RANK_ATTN": "tiled"}), ("attn_tc", {"B200RANK_ATTN": "tc"}), ("attn_regs", {"B200RANK_ATTN": "regs"}),
                       ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
