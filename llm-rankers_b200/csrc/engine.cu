@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -112,17 +113,33 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute acts on the CURRENT device, and engines on different GPUs may live in one process and be driven from different
+// host threads (include/b200rank.h): the "dynamic shared memory limit already raised" memo is per (kernel, device), not per process,
+// and guarded against concurrent first launches.
+struct SmemOptIn {
+    std::mutex mu;
+    uint64_t done = 0;   // bit d: raised on device d (a device ordinal >= 64 raises it on every launch)
+    template <typename K>
+    cudaError_t raise(K kern, int bytes) {
+        int dev = 0;
+        cudaError_t er = cudaGetDevice(&dev);
+        if (er != cudaSuccess) return er;
+        std::lock_guard<std::mutex> g(mu);
+        if (dev >= 0 && dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+        er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (er == cudaSuccess && dev >= 0 && dev < 64) done |= 1ull << dev;
+        return er;
+    }
+};
+
 // ------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI, bool TMA_EPI, int CG>
 static int launch_gemm_inst(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                             const GemmArgs& args) {
-    static bool attr_set = false;
+    static SmemOptIn smem_opt_in;
     auto kern = gemm_tcgen05_kernel<BN, EPI, TMA_EPI, CG>;
     using Cfg = GemmCfg<BN, CG>;
-    if (!attr_set) {
-        CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        attr_set = true;
-    }
+    CU_OK(smem_opt_in.raise(kern, Cfg::kSmemBytes));
     const int tiles = ((args.M + kGemmBlockM * CG - 1) / (kGemmBlockM * CG)) * ((args.N + BN - 1) / BN);
     const int grid = CG * std::min(tiles, num_sms / CG);
     cudaLaunchConfig_t cfg{};
@@ -928,23 +945,20 @@ static int attn_default_mode() {
 template <int NKB>
 static int launch_attn_tc(const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd, int H, const float* bias,
                           bf16* out, int ldo, cudaStream_t st, const CUtensorMap* tm) {
-    static bool attr_set = false;
+    static SmemOptIn smem_opt_in;
     auto kern = enc_attention_tc_kernel<NKB>;
-    if (!attr_set) {
-        CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg<NKB>::kSmemBytes));
-        attr_set = true;
-    }
+    CU_OK(smem_opt_in.raise(kern, AttnTcCfg<NKB>::kSmemBytes));
     launch_k(kern, dim3(dim3(H, nd)), dim3(kAttnTcThreads), AttnTcCfg<NKB>::kSmemBytes, st, *tm, inner, d_cu, bias, out, ldo);
     return B200RANK_OK;
 }
-static int device_sm_count() {
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    return sms;
+static int device_sm_count() {   // of the current device (test entry points without an engine; engines carry num_sms)
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 1;
 }
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
                                 int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0) {
-    static bool attr_set = false;
     if (mode == 0) mode = attn_default_mode();
     const bool persistent = (mode == 5 || mode == 6 || mode == 7);
     if (maxlen > 256 && !persistent) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
@@ -959,23 +973,21 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         const CUtensorMap* tm = &local;
         if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
         else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
-        static bool attr5 = false;
+        static SmemOptIn opt_in_split, opt_in_two_pass, opt_in_one_pass;
         static int split = -1;
         if (split < 0) split = getenv("B200RANK_ATTN_SPLIT") ? atoi(getenv("B200RANK_ATTN_SPLIT")) : 0;
         auto kern = (split || mode == 6) ? enc_attention_tc2_kernel<3, 1> : (mode == 7 ? enc_attention_tc2_kernel<3, 2> : enc_attention_tc2_kernel<3, 0>);
-        if (!attr5) {
-            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CU_OK(cudaFuncSetAttribute(enc_attention_tc2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr5 = true;
-        }
+        if (split || mode == 6) CU_OK(opt_in_split.raise(enc_attention_tc2_kernel<3, 1>, 227 * 1024));
+        else if (mode == 7) CU_OK(opt_in_one_pass.raise(enc_attention_tc2_kernel<3, 2>, 227 * 1024));
+        else CU_OK(opt_in_two_pass.raise(enc_attention_tc2_kernel<3, 0>, 227 * 1024));
         const int n_items = nd * H;
         static int spin = -1;
         if (spin < 0) spin = getenv("B200RANK_ATTN_SPIN") ? atoi(getenv("B200RANK_ATTN_SPIN")) : 0;
         if (e) prof_begin(e, "enc_attention_tc2");
         static int attn_sms = -1;   // B200RANK_ATTN_SMS=n: cap the persistent grid (leaves SMs to the decoder stream of the other query in flight)
         if (attn_sms < 0) attn_sms = getenv("B200RANK_ATTN_SMS") ? std::max(1, atoi(getenv("B200RANK_ATTN_SMS"))) : 0;
-        const int grid_cap = attn_sms > 0 ? std::min(attn_sms, device_sm_count()) : device_sm_count();
+        const int sm_count = e ? e->num_sms : device_sm_count();
+        const int grid_cap = attn_sms > 0 ? std::min(attn_sms, sm_count) : sm_count;
         CU_OK(launch_k(kern, dim3(std::min(n_items, grid_cap)), dim3(kAttnTcThreads), AttnTc2Cfg<3>::smem_bytes(H), st, *tm, inner, d_cu, bias,
                        out, ldo, H, n_items, spin, 192));
         if (e) RET_IF(post_launch(e, "enc_attention_tc2"));
@@ -995,16 +1007,16 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         return e ? post_launch(e, "enc_attention_tc") : B200RANK_OK;
     }
     if (mode == 4) {
-        static bool attr3 = false, attr4 = false;
+        static SmemOptIn opt_in3, opt_in4;
         const int nkb = maxlen <= 192 ? 3 : 4;
         const int smem = (64 + 2 * 64 * nkb) * 128 + kAttnWideBias * 4;
         if (e) prof_begin(e, "enc_attention_regs");
         const dim3 grid((maxlen + 63) / 64, H, nd);
         if (nkb == 3) {
-            if (!attr3) { CU_OK(cudaFuncSetAttribute(enc_attention_regs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr3 = true; }
+            CU_OK(opt_in3.raise(enc_attention_regs_kernel<3>, (64 + 2 * 64 * 3) * 128 + kAttnWideBias * 4));
             CU_OK(launch_k(enc_attention_regs_kernel<3>, grid, dim3(128), smem, st, qkv, ld, inner, d_cu, bias, out, ldo));
         } else {
-            if (!attr4) { CU_OK(cudaFuncSetAttribute(enc_attention_regs_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr4 = true; }
+            CU_OK(opt_in4.raise(enc_attention_regs_kernel<4>, (64 + 2 * 64 * 4) * 128 + kAttnWideBias * 4));
             CU_OK(launch_k(enc_attention_regs_kernel<4>, grid, dim3(128), smem, st, qkv, ld, inner, d_cu, bias, out, ldo));
         }
         return e ? post_launch(e, "enc_attention_regs") : B200RANK_OK;
@@ -1012,10 +1024,8 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
     if (mode == 2) {
         const int s_pad = (maxlen + 63) & ~63;
         const int smem = 3 * s_pad * 128;
-        if (!attr_set) {
-            CU_OK(cudaFuncSetAttribute(enc_attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 256 * 128));
-            attr_set = true;
-        }
+        static SmemOptIn opt_in_resident;
+        CU_OK(opt_in_resident.raise(enc_attention_resident_kernel, 3 * 256 * 128));
         if (e) prof_begin(e, "enc_attention_resident");
         launch_k(enc_attention_resident_kernel, dim3(dim3(H, nd)), dim3((s_pad / 16) * 32), smem, st, qkv, ld, inner, d_cu, bias, out, ldo, s_pad);
         return e ? post_launch(e, "enc_attention_resident") : B200RANK_OK;
@@ -1091,11 +1101,8 @@ static bool use_skinny(const b200rank_engine* e, int R) {
 template <int EPI>
 static int launch_skinny(b200rank_engine* e, const char* label, const float* x, const bf16* a, int lda, const float* ln_w, const bf16* W,
                          int ldw, int R, int n_out, int K, void* out, int ldo) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_OK(cudaFuncSetAttribute(skinny_gemv_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinnyMaxRows * 10240 * 2));
-        attr_set = true;
-    }
+    static SmemOptIn smem_opt_in;
+    CU_OK(smem_opt_in.raise(skinny_gemv_kernel<EPI>, kSkinnyMaxRows * 10240 * 2));
     if ((size_t)R * K * 2 > (size_t)kSkinnyMaxRows * 10240 * 2) return set_error(B200RANK_ERR_CAPACITY, "skinny GEMV: K=%d too long", K);
     prof_begin(e, label);
     const int grid = std::min((n_out + 7) / 8, 8 * e->num_sms);
@@ -1142,11 +1149,8 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
     const int max_len = e->staged_maxlen;
     const bool reassoc = use_reassoc_t1(e, T);
     if (reassoc) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU_OK(cudaFuncSetAttribute(cross_ctx_t1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cross_ctx_smem_bytes(240)));
-            attr_set = true;
-        }
+        static SmemOptIn smem_opt_in;
+        CU_OK(smem_opt_in.raise(cross_ctx_t1_kernel, cross_ctx_smem_bytes(240)));
     }
     for (int l = 0; l < e->Ld; ++l) {
         const LayerW& w = e->dec[l];
