@@ -17,6 +17,7 @@ _LIB_PATH = os.environ.get("B200RANK_LIB", os.path.join(os.path.dirname(_HERE), 
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
 EPI_BF16, EPI_RESID_F32, EPI_GATED_BF16, EPI_F32 = 0, 1, 2, 3
+ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CAPACITY = -1, -2, -3, -4   # include/b200rank.h: B200RANK_ERR_*
 ATTN_REL_CLAMP = 128
 ATTN_BIAS_LEN = 2 * ATTN_REL_CLAMP + 1
 
@@ -45,12 +46,15 @@ MODEL_SHAPES: Dict[str, Dict[str, int]] = {
     "flan-t5-large": dict(d_model=1024, num_heads=16, d_ff=2816, num_layers=24, num_decoder_layers=24),
     "flan-t5-xl": dict(d_model=2048, num_heads=32, d_ff=5120, num_layers=24, num_decoder_layers=24),
     "flan-t5-xxl": dict(d_model=4096, num_heads=64, d_ff=10240, num_layers=24, num_decoder_layers=24),
-    # T5 v1.0 shapes of the castorini monoT5 / duoT5 checkpoints (relu feed-forward, tied embeddings); the 3B ones use d_kv 128
-    # and are not supported by the d_kv = 64 attention kernels.
+    # T5 v1.0 shapes of the castorini monoT5 / duoT5 checkpoints (relu feed-forward, tied embeddings). The 3B ones use d_kv 128:
+    # they run on the generic-width attention of csrc/attention_wide.cuh, experimental until validated on a B200
+    # (B200RANK_EXPERIMENTAL_DKV128=1; without it construction fails with a message that says so).
     "monot5-small": dict(d_model=512, num_heads=8, d_ff=2048, num_layers=6, num_decoder_layers=6, v10=True),
     "monot5-base": dict(d_model=768, num_heads=12, d_ff=3072, num_layers=12, num_decoder_layers=12, v10=True),
     "monot5-large": dict(d_model=1024, num_heads=16, d_ff=4096, num_layers=24, num_decoder_layers=24, v10=True),
     "duot5-base": dict(d_model=768, num_heads=12, d_ff=3072, num_layers=12, num_decoder_layers=12, v10=True),
+    "monot5-3b": dict(d_model=1024, num_heads=32, d_kv=128, d_ff=16384, num_layers=24, num_decoder_layers=24, v10=True),
+    "duot5-3b": dict(d_model=1024, num_heads=32, d_kv=128, d_ff=16384, num_layers=24, num_decoder_layers=24, v10=True),
 }
 
 

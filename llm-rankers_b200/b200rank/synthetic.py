@@ -86,11 +86,15 @@ def model_cfg(name: str, vocab_size: int = 32128) -> Dict:
     shapes = dict(MODEL_SHAPES)
     shapes["t5-tiny"] = dict(d_model=128, num_heads=2, d_ff=256, num_layers=2, num_decoder_layers=2)
     shapes["t5v10-tiny"] = dict(d_model=128, num_heads=2, d_ff=256, num_layers=2, num_decoder_layers=2, v10=True)
+    # wide heads (d_kv 128, the T5-3B head shape) at toy size: the generic-width attention path against the oracle
+    shapes["t5-tiny-wide"] = dict(d_model=128, num_heads=2, d_kv=128, d_ff=256, num_layers=2, num_decoder_layers=2)
+    shapes["t5v10-tiny-wide"] = dict(d_model=128, num_heads=2, d_kv=128, d_ff=256, num_layers=2, num_decoder_layers=2, v10=True)
     if name not in shapes:
         raise KeyError(f"unknown synthetic model {name}; known: {sorted(shapes)}")
     cfg = dict(shapes[name])
     v10 = cfg.pop("v10", False)   # T5 v1.0 (monoT5 / duoT5 checkpoints): relu feed-forward, tied embeddings => scaled logits
-    cfg.update(vocab_size=vocab_size, d_kv=64, rel_buckets=32, rel_max_distance=128, layer_norm_eps=1e-6,
+    cfg.setdefault("d_kv", 64)
+    cfg.update(vocab_size=vocab_size, rel_buckets=32, rel_max_distance=128, layer_norm_eps=1e-6,
                scale_decoder_outputs=bool(v10), pad_id=0, eos_id=1)
     cfg.update(feed_forward_proj="relu" if v10 else "gated-gelu", gated_gelu=not v10, tie_word_embeddings=bool(v10))
     return cfg

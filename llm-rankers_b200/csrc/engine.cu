@@ -22,6 +22,7 @@
 #include "attention_enc.cuh"
 #include "attention_tc.cuh"
 #include "attention_dec.cuh"
+#include "attention_wide.cuh"
 #include "skinny_gemv.cuh"
 #include "cross_ctx_t1.cuh"
 #include "gemm_tcgen05.cuh"
@@ -271,6 +272,7 @@ struct b200rank_engine {
     b200rank_config cfg;
     int device = 0, num_sms = 0;
     int d = 0, inner = 0, H = 0, F = 0, V = 0, Le = 0, Ld = 0;
+    int dkv = 64;       // head width: 64 (specialised kernels) or 128 (attention_wide.cuh, experimental)
     bool gated = true;  // feed_forward_proj: gated-gelu (wi_0, wi_1) vs relu (wi)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -664,7 +666,14 @@ static int create_impl(b200rank_engine* e) {
 extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_engine** out) {
     if (!cfg || !out) return set_error(B200RANK_ERR_ARG, "null argument");
     *out = nullptr;
-    if (cfg->d_kv != 64) return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (kernels are specialised for 64)", cfg->d_kv);
+    if (cfg->d_kv != 64) {
+        // d_kv = 128 (monot5-3b / duot5-3b) runs on the generic mma.sync attention of attention_wide.cuh. That path was written without
+        // GPU time and has not been validated on a B200 yet: it stays behind B200RANK_EXPERIMENTAL_DKV128=1 until its parity test
+        // (tests/test_engine_gpu.py::test_wide_heads_vs_oracle) has passed once.
+        const bool wide_ok = cfg->d_kv == 128 && getenv("B200RANK_EXPERIMENTAL_DKV128") && atoi(getenv("B200RANK_EXPERIMENTAL_DKV128")) != 0;
+        if (!wide_ok)
+            return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (kernels are specialised for 64; 128 is experimental: B200RANK_EXPERIMENTAL_DKV128=1)", cfg->d_kv);
+    }
     if (cfg->d_model % 64 || cfg->d_ff % 128 || cfg->d_model > 4096 || cfg->vocab_size % 8)
         return set_error(B200RANK_ERR_ARG, "unsupported dims d_model=%d d_ff=%d vocab=%d", cfg->d_model, cfg->d_ff, cfg->vocab_size);
     if (cfg->num_heads <= 0 || cfg->num_layers <= 0 || cfg->num_decoder_layers <= 0)
@@ -679,6 +688,7 @@ extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_
     e->cfg = *cfg;
     e->device = device;
     e->d = cfg->d_model; e->H = cfg->num_heads; e->inner = cfg->num_heads * cfg->d_kv; e->F = cfg->d_ff; e->V = cfg->vocab_size;
+    e->dkv = cfg->d_kv;
     e->Le = cfg->num_layers; e->Ld = cfg->num_decoder_layers;
     e->gated = cfg->gated_gelu != 0;
     int r = create_impl(e);
@@ -754,7 +764,7 @@ static int derive_weights(b200rank_engine* e) {
         // W_ov[i, j] = sum_k W_o[i, k] W_v[k, j]  ==  A[M=d, K=I] . W[N=d, K=I]^T with W = W_v^T
         if (rc == B200RANK_OK) rc = gemm(e, w.wo, I, d, vt, I, (int)align_up(d, 256), d, d, I, EPI_BF16, w.wov, d, 0);
         // per-head transposed cross-attention W_k: wkT[h*d + n, m] = W_k[h*64 + m, n]
-        for (int h = 0; h < e->H && rc == B200RANK_OK; ++h) {
+        for (int h = 0; h < e->H && rc == B200RANK_OK && e->dkv == 64; ++h) {   // (the re-associated T = 1 path is d_kv = 64 only)
             const bf16* wk_h = e->wckv + ((size_t)l * 2 * I + (size_t)h * 64) * d;
             launch_k(transpose_bf16_kernel, dim3(dim3((d + 31) / 32, 2)), dim3(dim3(32, 8)), 0, e->stream, wk_h, 64, d, d, w.wkT + (size_t)h * d * 64, 64);
             rc = post_launch(e, "transpose_bf16");
@@ -1043,6 +1053,20 @@ static int ffn_in(b200rank_engine* e, const bf16* h, int h_rows, const bf16* wi,
     return gemm(e, h, d, h_rows, wi, d, F, M, F, d, EPI_RELU_BF16, g, F);
 }
 
+// Generic-width attention (attention_wide.cuh): every attention site of a d_kv = 128 model.
+template <int KIND>
+static int launch_attention_wide(b200rank_engine* e, const char* label, const bf16* q, int ldq, int T, const bf16* kv, size_t ldkv, int k_off,
+                                 int v_off, const int* cu, const float* bias, int bias_len, bf16* out, int ldo, int q_tiles, int nd) {
+    if (e->dkv != 128) return set_error(B200RANK_ERR_ARG, "attention_wide: d_kv=%d not instantiated", e->dkv);
+    static SmemOptIn smem_opt_in;
+    auto kern = attention_wide_kernel<128, KIND>;
+    CU_OK(smem_opt_in.raise(kern, AttnWideCfg<128>::kSmemBytes));
+    prof_begin(e, label);
+    CU_OK(launch_k(kern, dim3(q_tiles, e->H, nd), dim3(128), AttnWideCfg<128>::kSmemBytes, e->stream, q, ldq, T, kv, ldkv, k_off, v_off, cu, bias,
+                   bias_len, out, ldo));
+    return post_launch(e, label);
+}
+
 // Encoder over the staged batch + stacked cross-attention K|V projection of its output.
 static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
     const int n = e->staged_tokens, nd = e->staged_docs;
@@ -1053,7 +1077,11 @@ static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
         const LayerW& w = e->enc[l];
         // h = norm1(x) was produced by the previous layer's last GEMM (or the line above for layer 0)
         RET_IF(gemm(e, e->h, d, Tk, w.wqkv, d, 3 * I, n, 3 * I, d, EPI_BF16, e->qkv, 3 * I));
-        RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu_cur, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0, e->staged_minlen));
+        if (e->dkv == 64)
+            RET_IF(launch_enc_attention(e, e->qkv, 3 * I, (uint64_t)Tk, I, e->d_cu_cur, nd, e->staged_maxlen, e->H, e->bias_enc, e->ao, I, e->stream, 0, e->staged_minlen));
+        else
+            RET_IF(launch_attention_wide<ATT_ENC>(e, "enc_attention_wide", e->qkv, 3 * I, 0, e->qkv, (size_t)3 * I, I, 2 * I, e->d_cu_cur, e->bias_enc,
+                                                  kAttnBiasLen, e->ao, I, (e->staged_maxlen + 63) / 64, nd));
         RET_IF(gemm_resid_then_norm(e, e->ao, I, Tk, w.wo, I, d, n, I, e->x, w.ln2, e->h));
         RET_IF(ffn_in(e, e->h, Tk, w.wi, n, e->g));
         const bool last = (l + 1 == e->Le);  // the final layer norm lands in the slot buffer the decoder reads
@@ -1068,11 +1096,12 @@ static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
 
 // T = 1 and short documents: the decoder's cross-attention runs in re-associated form (cross_ctx_t1.cuh) and the encoder
 // skips the stacked cross-K|V projection. B200RANK_DEC_REASSOC=0 selects the reference-shaped path (K/V GEMM + attention).
-static bool use_reassoc_t1(const b200rank_engine* e, int T) {
+static bool reassoc_t1_possible(const b200rank_engine* e, int maxlen) {
     static int pref = -1;
     if (pref < 0) pref = (getenv("B200RANK_DEC_REASSOC") && atoi(getenv("B200RANK_DEC_REASSOC")) == 0) ? 0 : 1;
-    return pref && T == 1 && e->staged_maxlen <= 240 && !e->debug_simt && e->d % kCtxKC == 0;  // 240: 3-stage ring fits 227 KB
+    return pref && maxlen <= 240 && !e->debug_simt && e->d % kCtxKC == 0 && e->dkv == 64;  // 240: 3-stage ring fits 227 KB
 }
+static bool use_reassoc_t1(const b200rank_engine* e, int T) { return T == 1 && reassoc_t1_possible(e, e->staged_maxlen); }
 
 static bool cross_split_off() {   // read per call (not cached): tests flip B200RANK_CROSS_SPLIT in-process for the A/B
     const char* v = getenv("B200RANK_CROSS_SPLIT");
@@ -1161,7 +1190,10 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             RET_IF(dec_resid_proj(e, e->hd, d, w.wov, d, R));
         } else {
             RET_IF(dec_norm_proj(e, w.ln1, w.wqkv, 3 * I, R, e->qkvd, 3 * I));
-            if (dec_attn_mma(T)) {
+            if (e->dkv != 64) {
+                RET_IF(launch_attention_wide<ATT_DEC_SELF>(e, "dec_self_attention_wide", e->qkvd, 3 * I, T, e->qkvd, (size_t)3 * I, I, 2 * I, nullptr,
+                                                           e->bias_dec, kAttnRelClamp + 1, e->aod, I, (T + 63) / 64, nd));
+            } else if (dec_attn_mma(T)) {
                 prof_begin(e, "dec_self_attention_mma");
                 launch_k(dec_attention_mma_kernel<true>, dim3((T + 63) / 64, e->H, nd), dim3(128), 0, e->stream, e->qkvd, 3 * I, T, e->qkvd, (size_t)3 * I, I, 2 * I,
                          (const int*)nullptr, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
@@ -1189,6 +1221,14 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
             continue;
         }
         const int k_off = l * 2 * I, v_off = l * 2 * I + I;
+        if (e->dkv != 64) {
+            RET_IF(launch_attention_wide<ATT_CROSS>(e, "cross_attention_wide", e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, nullptr, 0,
+                                                    e->aod, I, (T + 63) / 64, nd));
+            RET_IF(dec_resid_proj(e, e->aod, I, w.wo_c, I, R));
+            RET_IF(dec_norm_ffn_in(e, w.ln2, w.wi, R));
+            RET_IF(dec_resid_proj(e, e->gd, F, w.wff, F, R));
+            continue;
+        }
         if (dec_attn_mma(T)) {
             prof_begin(e, "cross_attention_mma");
             launch_k(dec_attention_mma_kernel<false>, dim3((T + 63) / 64, e->H, nd), dim3(128), 0, e->stream, e->qd, I, T, e->ckv, ldkv, k_off, v_off,
@@ -1408,7 +1448,9 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
         }
         if (tok > e->cap_tokens) return set_error(B200RANK_ERR_CAPACITY, "%d tokens exceed max_tokens %d", tok, e->cap_tokens);
     }
-    if (maxlen > 240 || e->debug_simt) return set_error(B200RANK_ERR_ARG, "pipelined submit supports documents of at most 240 tokens");
+    // the pipelined pass skips the stacked cross-K|V projection, so it is only valid where the decoder takes the re-associated T = 1 form
+    if (!reassoc_t1_possible(e, maxlen))
+        return set_error(B200RANK_ERR_ARG, "pipelined submit supports documents of at most 240 tokens on d_kv = 64 models (re-associated T = 1 decoder)");
 
     // the stream / encoder workspace set of this slot: the ordinary ones unless B200RANK_PIPE_DUAL runs slot 1 next to slot 0
     const bool dual = e->pipe_dual && b == 1;

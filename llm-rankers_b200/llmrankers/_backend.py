@@ -121,9 +121,19 @@ class T5Backend:
         return self.engine.score_yes_no(ids, lengths, yes_id, no_id)
 
     def submit_yes_no(self, rows, yes_id: int, no_id: int):
-        """Asynchronous score_yes_no (two batches in flight, see b200rank_submit_yes_no); returns a ticket for wait_yes_no."""
+        """Asynchronous score_yes_no (two batches in flight, see b200rank_submit_yes_no); returns a ticket for wait_yes_no, or None
+        when the batch does not qualify for the pipelined pass (a document of more than 240 tokens, more documents or tokens than one
+        device pass holds, a d_kv = 128 model): b200rank_submit_yes_no validates before it enqueues anything and reports those as
+        B200RANK_ERR_ARG / B200RANK_ERR_CAPACITY, and the caller then scores the batch through the synchronous entry point (which
+        splits it into device passes and raises for arguments that are wrong in themselves)."""
+        import b200rank as br
         ids, lengths = self.pad_rows(rows, self.pad_id)
-        return self.engine.submit_yes_no(ids, lengths, yes_id, no_id)
+        try:
+            return self.engine.submit_yes_no(ids, lengths, yes_id, no_id)
+        except br.B200RankError as err:
+            if err.code in (br.ERR_ARG, br.ERR_CAPACITY):
+                return None
+            raise
 
     def wait_yes_no(self, ticket):
         return self.engine.wait_yes_no(ticket)
@@ -271,8 +281,9 @@ def _cfg_from_hf(hf: Dict) -> Dict:
     proj = hf.get("feed_forward_proj", "relu")
     if proj not in ("gated-gelu", "relu"):
         raise NotImplementedError(f"feed_forward_proj={proj!r}: gated-gelu (Flan-T5 / T5 v1.1) and relu (T5 v1.0: monoT5, duoT5) are implemented")
-    if hf["d_kv"] != 64:
-        raise NotImplementedError(f"d_kv={hf['d_kv']}: the attention kernels are specialised for 64 (the 3B T5 v1.0 checkpoints use 128)")
+    if hf["d_kv"] != 64 and not (hf["d_kv"] == 128 and os.environ.get("B200RANK_EXPERIMENTAL_DKV128", "0") not in ("", "0")):
+        raise NotImplementedError(f"d_kv={hf['d_kv']}: the attention kernels are specialised for 64; 128 (the 3B T5 v1.0 checkpoints) runs on the "
+                                  "generic-width path, experimental until validated on a B200: set B200RANK_EXPERIMENTAL_DKV128=1")
     return dict(vocab_size=hf["vocab_size"], d_model=hf["d_model"], d_kv=hf["d_kv"], num_heads=hf["num_heads"], d_ff=hf["d_ff"],
                 num_layers=hf["num_layers"], num_decoder_layers=hf.get("num_decoder_layers") or hf["num_layers"],
                 rel_buckets=hf.get("relative_attention_num_buckets", 32), rel_max_distance=hf.get("relative_attention_max_distance", 128),

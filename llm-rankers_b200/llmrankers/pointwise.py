@@ -92,13 +92,14 @@ class PointwiseLlmRanker(LlmRanker):
         template, fields_of, yes_id, no_id = spec
 
         def finish(item):
-            ticket, ranking, rows = item
+            ticket, ranking, rows, scores = item
             self.total_compare = 0
             self.total_completion_tokens = 0
             self.total_prompt_tokens = 0
             self._count_batches(rows, 1)
             if ticket is not None:
                 _, scores = self.backend.wait_yes_no(ticket)
+            if scores is not None:
                 for doc, s in zip(ranking, scores):
                     doc.score = float(s)
             return sorted(ranking, key=lambda x: x.score, reverse=True)
@@ -123,9 +124,17 @@ class PointwiseLlmRanker(LlmRanker):
                 rows = fut.result()
                 refill()
                 ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
+                scores = None
+                if rows and ticket is None:
+                    # not a pipelined batch (long documents / more than one device pass): drain what is in flight — the synchronous
+                    # entry points refuse to run next to pipelined batches — then score this query the way rerank() does
+                    if pending is not None:
+                        yield finish(pending)
+                        pending = None
+                    _, scores = self.backend.score_yes_no(rows, yes_id, no_id)
                 if pending is not None:
                     yield finish(pending)
-                pending = (ticket, ranking, rows)
+                pending = (ticket, ranking, rows, scores)
             if pending is not None:
                 yield finish(pending)
 

@@ -33,7 +33,7 @@ def build_model(cfg: Dict, weights: Dict[str, np.ndarray], threads: Optional[int
     torch.set_num_threads(threads or os.cpu_count() or 1)
     gated = bool(cfg.get("gated_gelu", True))
     tied = "lm_head.weight" not in weights
-    hf_cfg = T5Config(vocab_size=cfg["vocab_size"], d_model=cfg["d_model"], d_kv=64, d_ff=cfg["d_ff"], num_layers=cfg["num_layers"],
+    hf_cfg = T5Config(vocab_size=cfg["vocab_size"], d_model=cfg["d_model"], d_kv=cfg.get("d_kv", 64), d_ff=cfg["d_ff"], num_layers=cfg["num_layers"],
                       num_decoder_layers=cfg["num_decoder_layers"], num_heads=cfg["num_heads"],
                       feed_forward_proj="gated-gelu" if gated else "relu", tie_word_embeddings=tied, decoder_start_token_id=0)
     with torch.device("meta"):

@@ -85,6 +85,9 @@ try:
 except Exception as e:
     print("tc4 bench line unreadable:", e)
 PY
+# 6e. d_kv = 128 (monot5-3b / duot5-3b head shape) on the generic-width attention (experimental): every entry point against the oracle
+B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "wide_heads" > $OUT/${TAG}_pytest_dkv128.log 2>&1; echo "d_kv 128 tests rc=$?"
+tail -3 $OUT/${TAG}_pytest_dkv128.log
 # 7. stand-alone design probes (experiments/README.md)
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
   && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt

@@ -147,6 +147,45 @@ def test_enc_attention_onepass_vs_numpy(H, n_docs, q_scale):
         assert np.abs(out - two_pass).max() <= 0.01 * np.abs(ref).max()
 
 
+@pytest.mark.skipif(os.environ.get("B200RANK_TEST_EXPERIMENTAL") != "1",
+                    reason="d_kv = 128 (attention_wide.cuh) was written without GPU time: B200RANK_TEST_EXPERIMENTAL=1 runs it (tests/gpu_first_call.sh)")
+@pytest.mark.parametrize("shape", ["t5-tiny-wide", "t5v10-tiny-wide"])
+def test_wide_heads_vs_oracle(shape, monkeypatch):
+    """d_kv = 128 (monot5-3b / duot5-3b head shape) through every entry point against the numpy oracle, which
+    tests/test_oracle_golden.py::test_oracle_wide_heads_match_live_transformers pins to transformers at this shape: encoder
+    attention, decoder self-attention (T = 3 and T = 33) and cross-attention all run on attention_wide_kernel<128, *>."""
+    import b200rank as br
+    from b200rank.synthetic import model_cfg, synthetic_weights
+    from oracle.t5_oracle import T5Oracle, pad_batch
+    monkeypatch.setenv("B200RANK_EXPERIMENTAL_DKV128", "1")
+    cfg = model_cfg(shape, 512)
+    w = synthetic_weights(cfg, 11, lm_head_std=0.5)
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"], vocab_size=512, d_kv=128,
+                       gated_gelu=cfg["gated_gelu"], scale_decoder_outputs=cfg["scale_decoder_outputs"], max_tokens=4096, max_docs=64,
+                       max_logit_rows=512)
+    e = br.Engine(c, 0)
+    e.load_state_dict(w.items())
+    orc = T5Oracle(cfg, w)
+    rng = np.random.default_rng(5)
+    rows = [rng.integers(3, 500, size=n).tolist() + [1] for n in (9, 70, 33, 1, 190, 129, 64, 300)]
+    ids, mask = pad_batch(rows)
+    lengths = mask.sum(axis=1).astype(np.int32)
+    ids32 = ids.astype(np.int32)
+    lg, sc = e.score_yes_no(ids32, lengths, 17, 23)
+    want = orc.logits(ids, mask, np.zeros((len(rows), 1), np.int64), cols=[17, 23])[:, 0, :]
+    assert_close_logits(f"wide/{shape}/yes_no", lg, want)
+    cols = [5, 17, 23, 301]
+    got = e.logits_at(ids32, lengths, [0, 17, 301], cols, normalize=False)
+    assert_close_logits(f"wide/{shape}/logits_at", got, orc.logits_at(ids, mask, [0, 17, 301], cols, normalize=False))
+    labels = [0] + rng.integers(3, 500, size=32).tolist()
+    q = e.score_qlm(ids32, lengths, labels)
+    q_ref = orc.score_qlm(ids, mask, labels)
+    record(f"wide/{shape}/qlm", max_abs_err=float(np.abs(q - q_ref).max()), max_abs_ref=float(np.abs(q_ref).max()))
+    assert np.all(np.abs(q - q_ref) <= 0.5 + 0.01 * np.abs(q_ref))
+    new_ids = e.greedy(ids32, lengths, [0, 17], 2)
+    assert new_ids.shape == (len(rows), 2)
+
+
 def test_rel_bucket_matches_hf():
     import b200rank as br
     g = golden_npz("buckets.npz")
@@ -245,6 +284,23 @@ def test_pointwise_ranker_on_gpu(method, case, tol):
     assert [d.docid for d in out] == [d.docid for d in sorted(out, key=lambda x: x.score, reverse=True)]
     assert (r.total_compare, r.total_prompt_tokens, r.total_completion_tokens) == \
            (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
+
+
+def test_pointwise_rerank_many_with_documents_the_pipeline_declines():
+    """rerank_many on the engine with a query whose documents exceed the 240 tokens of the pipelined pass between two ordinary
+    queries: b200rank_submit_yes_no declines it (B200RANK_ERR_ARG before anything is enqueued), the query in flight is drained and
+    the long one goes through the synchronous entry point — every query must come out exactly as rerank() returns it."""
+    import copy
+    from llmrankers.pointwise import PointwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    m = golden_meta()["tiny"]
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=tiny_backend())
+    long_docs = [SearchResult(f"L{i}", 0.0, " ".join(f"w{(7 * i + j) % 1900}" for j in range(300 + 10 * i))) for i in range(3)]
+    reqs = [(m["query"], _docs(m["docs"])), ("w3 w4", long_docs), (m["query"], _docs(m["docs"][::-1])), ("w8", long_docs[:1])]
+    want = [[(d.docid, d.score) for d in r.rerank(q, copy.deepcopy(rk))] for q, rk in reqs]
+    got = [[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs])]
+    assert got == want
+    assert all(np.isfinite(s) for out in got for _, s in out)
 
 
 @pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_bubble_gen", "setwise_heap_lik", "setwise_bubble_lik"])

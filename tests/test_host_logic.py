@@ -156,6 +156,53 @@ def test_rerank_many_equals_rerank():
     assert r.total_compare == 3  # counters describe the last query (10 docs, batch_size 4)
 
 
+def test_rerank_many_falls_back_for_batches_the_pipeline_declines():
+    """b200rank_submit_yes_no only takes batches that fit the pipelined pass (documents of <= 240 tokens, one device pass); for the
+    others T5Backend.submit_yes_no returns None and rerank_many must drain the query in flight (the engine refuses synchronous calls
+    next to pipelined batches) and score the query synchronously — same results, same order of results as rerank()."""
+    from llmrankers.pointwise import PointwiseLlmRanker
+    m = golden_meta()["tiny"]
+
+    class Picky(type(backend())):
+        in_flight = 0
+
+        def submit_yes_no(self, rows, yes_id, no_id):
+            if len(rows) > 4:            # stands in for "does not fit the pipelined pass"
+                return None
+            self.in_flight += 1
+            return super().submit_yes_no(rows, yes_id, no_id)
+
+        def wait_yes_no(self, ticket):
+            self.in_flight -= 1
+            return super().wait_yes_no(ticket)
+
+        def score_yes_no(self, rows, yes_id, no_id):
+            if getattr(self, "_strict", False):
+                assert self.in_flight == 0, "synchronous call while a pipelined batch is in flight"
+            return super().score_yes_no(rows, yes_id, no_id)
+
+    b = backend()
+    b.__class__ = Picky
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=b)
+    reqs = [("w3 w4", docs_from(m["docs"][:3])), (m["query"], docs_from(m["docs"])), ("w9", []), ("w1", docs_from(m["docs"][:2])),
+            (m["query"], docs_from(m["docs"][::-1])), ("w3", docs_from(m["docs"][:4]))]
+    want = [[(d.docid, d.score) for d in r.rerank(q, copy.deepcopy(rk))] for q, rk in reqs]
+    b._strict = True
+    # OracleBackend.submit_yes_no computes through score_yes_no itself: count only the calls rerank_many makes directly
+    orig_submit = Picky.submit_yes_no
+
+    def submit(self, rows, yes_id, no_id):
+        self._strict = False
+        try:
+            return orig_submit(self, rows, yes_id, no_id)
+        finally:
+            self._strict = True
+    Picky.submit_yes_no = submit
+    got = [[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs])]
+    assert got == want
+    assert b.in_flight == 0
+
+
 # ------------------------------------------------------------------------------------------- level-parallel heap build (§8f-2)
 @pytest.mark.parametrize("n,c,k", [(100, 10, 10), (100, 3, 10), (37, 2, 5), (12, 3, 3), (5, 10, 3), (1, 3, 1), (64, 4, 64)])
 def test_batched_heap_equals_sequential_heap(n, c, k):

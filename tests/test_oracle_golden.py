@@ -173,3 +173,33 @@ def test_hf_cpu_baseline_leg_reproduces_reference_fixtures(which):
     a, _ = hf_cpu.score_yes_no(model, ids, mask, m["yes_id"], m["no_id"], batch_size=2)
     b, _ = oracle_for(which).score_yes_no(ids.astype(np.int64), mask, m["yes_id"], m["no_id"])
     np.testing.assert_allclose(a, b, atol=ATOL, rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", ["t5-tiny-wide", "t5v10-tiny-wide"])
+def test_oracle_wide_heads_match_live_transformers(shape):
+    """d_kv = 128 (the head shape of monot5-3b / duot5-3b, pointwise.py:136-186, pairwise.py:296-352): the numpy oracle against the live
+    transformers fp32 model on the same synthetic weights — yes_no logits, a 3-position decoder prefix and greedy ids. This pins the
+    checker the (experimental) generic-width attention path of the engine is held to on the GPU."""
+    import torch
+    from b200rank.synthetic import model_cfg, synthetic_weights
+    from oracle.hf_cpu import build_model
+    from oracle.t5_oracle import T5Oracle, pad_batch
+    cfg = model_cfg(shape, 512)
+    assert cfg["d_kv"] == 128
+    w = synthetic_weights(cfg, 11, lm_head_std=0.5)
+    rng = np.random.default_rng(5)
+    rows = [rng.integers(3, 500, size=n).tolist() + [1] for n in (9, 70, 33, 1)]
+    ids, mask = pad_batch(rows)
+    orc = T5Oracle(cfg, w)
+    model = build_model(cfg, w, threads=2)
+    with torch.no_grad():
+        dec = torch.tensor([[0, 17, 301]] * len(rows))
+        hf = model(input_ids=torch.tensor(ids), attention_mask=torch.tensor(mask), decoder_input_ids=dec).logits.numpy()
+    got = orc.logits(ids, mask, dec.numpy())
+    assert got.shape == hf.shape
+    assert np.abs(got - hf).max() <= 3e-4 * max(1.0, np.abs(hf).max())
+    with torch.no_grad():
+        gen = model.generate(input_ids=torch.tensor(ids), attention_mask=torch.tensor(mask), decoder_input_ids=torch.tensor([[0, 17]] * len(rows)),
+                             max_new_tokens=2, do_sample=False).numpy()
+    mine = orc.greedy(ids, mask, [0, 17], 2)
+    assert np.array_equal(mine, gen[:, 2:4])
