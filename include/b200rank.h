@@ -124,7 +124,9 @@ int b200rank_sync(b200rank_engine* e);
 /* Asynchronous form of b200rank_score_yes_no for throughput: at most two batches in flight. submit packs + copies the HOST
  * token ids and enqueues the encoder pass on the engine's main stream and the decoder pass on a second stream, so the
  * latency-bound decoder of batch i overlaps the encoder GEMMs of batch i+1 (which leave a few SMs free for it). wait blocks
- * until that batch's scores are in host memory. Each batch must fit one device pass, documents <= 240 tokens.
+ * until that batch's scores are in host memory. Each batch must fit one device pass, documents <= 240 tokens; a batch that
+ * does not qualify is refused with B200RANK_ERR_ARG / B200RANK_ERR_CAPACITY before anything is enqueued (no ticket is issued,
+ * batches in flight are unaffected): wait for the tickets in flight and score it with b200rank_score_yes_no instead.
  * (The reference's per-query loop `for qid, query, ranking in ...: ranker.rerank(query, ranking)` — run.py:184-192 — becomes
  * submit(query i+1); wait(query i).) */
 int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
