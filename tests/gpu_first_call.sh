@@ -91,4 +91,6 @@ tail -3 $OUT/${TAG}_pytest_dkv128.log
 # 7. stand-alone design probes (experiments/README.md)
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
   && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
+nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/tmem_probe experiments/tmem_probe.cu > $OUT/${TAG}_tmem_probe.txt 2>&1 \
+  && timeout 120 /tmp/tmem_probe >> $OUT/${TAG}_tmem_probe.txt 2>&1; echo "tmem_probe rc=$?"; tail -16 $OUT/${TAG}_tmem_probe.txt
 ls -la $OUT | tail -20
