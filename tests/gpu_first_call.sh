@@ -1,6 +1,8 @@
 #!/bin/bash
 # One gpurun call that re-establishes the measured state of the repo on a fresh B200 (first call of a round):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02 core'          (steps 1-6, ~15 GPU-minutes)
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02 experimental'  (steps 7, 6b-6e, ~15 GPU-minutes)
+# (no second argument: everything in one call, ~30 GPU-minutes: give gpurun --timeout 2400)
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/.
 #   1. the GPU parity suite                      -> <tag>_pytest_gpu.log, parity_report.json
 #   2. smoke()                                   -> <tag>_smoke.log
@@ -11,8 +13,10 @@
 #   7. experiments/epi_probe.cu                  -> <tag>_epi_probe.txt
 set -u
 TAG=${1:-rXX}
+PART=${2:-all}
 OUT=gpurun_out
 mkdir -p $OUT
+core_part() {
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $OUT/${TAG}_gpu.csv 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.log
 tail -3 $OUT/${TAG}_pytest_gpu.log
@@ -38,6 +42,13 @@ PY
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+}
+experimental_part() {
+# 7. stand-alone design probes (experiments/README.md)
+nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
+  && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
+nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/tmem_probe experiments/tmem_probe.cu > $OUT/${TAG}_tmem_probe.txt 2>&1 \
+  && timeout 120 /tmp/tmem_probe >> $OUT/${TAG}_tmem_probe.txt 2>&1; echo "tmem_probe rc=$?"; tail -16 $OUT/${TAG}_tmem_probe.txt
 # 6b. experimental kernel variants (compiled in round 1, not yet run): agreement test + A/B of the headline bench
 B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k variants_agree > $OUT/${TAG}_pytest_experimental.log 2>&1; echo "experimental variants rc=$?"
 tail -3 $OUT/${TAG}_pytest_experimental.log
@@ -88,9 +99,10 @@ PY
 # 6e. d_kv = 128 (monot5-3b / duot5-3b head shape) on the generic-width attention (experimental): every entry point against the oracle
 B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "wide_heads" > $OUT/${TAG}_pytest_dkv128.log 2>&1; echo "d_kv 128 tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_dkv128.log
-# 7. stand-alone design probes (experiments/README.md)
-nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
-  && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
-nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/tmem_probe experiments/tmem_probe.cu > $OUT/${TAG}_tmem_probe.txt 2>&1 \
-  && timeout 120 /tmp/tmem_probe >> $OUT/${TAG}_tmem_probe.txt 2>&1; echo "tmem_probe rc=$?"; tail -16 $OUT/${TAG}_tmem_probe.txt
+}
+case "$PART" in
+  core) core_part ;;
+  experimental) experimental_part ;;
+  *) core_part; experimental_part ;;
+esac
 ls -la $OUT | tail -20
