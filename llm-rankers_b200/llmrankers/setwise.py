@@ -223,11 +223,11 @@ class SetwiseLlmRanker(LlmRanker):
                 st["counters"][2] += sum(r[2] for r in mine)
                 if heap:
                     picks = [self._pick(r[0], inds) for r, (_, inds) in zip(mine, st["round"])]
-                else:   # bubblesort: label -> index in the window (unknown label keeps the head; beyond the window raises, :259)
+                else:
+                    # bubblesort: label -> offset from the window's head. An unknown label keeps the head; a label past the window is
+                    # applied as the reference applies it (setwise.py:252-259 indexes the whole ranking: it swaps with the element
+                    # that far down the list, and raises IndexError only past the end of the list — the generator does the same)
                     picks = [self.CHARACTERS.index(r[0]) if r[0] in self.CHARACTERS else 0 for r in mine]
-                    for b, win in zip(picks, st["round"]):
-                        if b >= len(win):
-                            raise IndexError("list index out of range")
                 try:
                     st["round"] = st["gen"].send(picks)
                     still.append(st)
