@@ -203,6 +203,79 @@ def test_rerank_many_falls_back_for_batches_the_pipeline_declines():
     assert b.in_flight == 0
 
 
+# ------------------------------------------------------------------------------------------- permutation voting (setwise.py:102-157)
+def _perm_fixture():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "golden_setwise_perm.json")) as f:
+        return json.load(f)
+
+
+def _perm_backend(g, log):
+    """The oracle-backed test backend with generate() replaced by the stand-in the fixture generator put behind the REFERENCE's
+    `self.llm.generate` (tests/golden/make_golden_setwise_perm.py::stub_generate)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_setwise_perm import stub_generate
+    b = backend()
+
+    def generate(padded_ids, dec_prefix, max_new):
+        rows = np.asarray(padded_ids).tolist()
+        assert max_new == 2 and list(dec_prefix) == [0, g["passage_id"]]
+        out = stub_generate(rows, g["passage_id"], g["label_token_ids"])
+        log.append(dict(input_ids=rows, output=out))
+        return np.asarray(out, np.int64)
+    b.generate = generate
+    return b
+
+
+def test_setwise_permutation_voting_matches_reference(capsys):
+    """num_permutation > 1: the shuffles drawn from the module RNG (seed 929), the prompt of every shuffle token for token, the vote
+    with its rejections ('X X', labels that are not in the prompt), the tie-break and the counters, compare by compare."""
+    import random
+    from llmrankers.setwise import SetwiseLlmRanker
+    g = _perm_fixture()
+    all_docs = docs_from(g["docs"])
+    by_perm = {}
+    for c in g["compares"]:
+        by_perm.setdefault(c["num_permutation"], []).append(c)
+    assert sorted(by_perm) == [2, 3, 5, 8]
+    for num_perm, compares in by_perm.items():
+        log = []
+        r = SetwiseLlmRanker(None, None, "cuda", num_child=3, k=3, scoring="generation", method="heapsort", num_permutation=num_perm,
+                             backend=_perm_backend(g, log))
+        random.seed(929)
+        for c in compares:
+            label = r.compare(g["query"], [all_docs[i] for i in c["docs"]])
+            assert log[-1]["input_ids"] == c["input_ids"], (num_perm, c["docs"])
+            assert log[-1]["output"] == c["output"]
+            assert label == c["label"], (num_perm, c["docs"])
+            check_counters(r, c)
+    capsys.readouterr()
+    assert any(c["label"] == "Unexpected voting." for c in g["compares"]) and any(len(c["label"]) == 1 for c in g["compares"])
+
+
+def test_setwise_rerank_with_permutation_voting_matches_reference(capsys):
+    import random
+    from llmrankers.setwise import SetwiseLlmRanker
+    g = _perm_fixture()
+    for c in g["reranks"]:
+        log = []
+        r = SetwiseLlmRanker(None, None, "cuda", num_child=c["num_child"], k=c["k"], scoring="generation", method=c["method"],
+                             num_permutation=c["num_permutation"], backend=_perm_backend(g, log))
+        random.seed(929)
+        if "raises" in c:
+            with pytest.raises(Exception) as ei:
+                r.rerank(g["query"], docs_from(g["docs"][:c["n"]]))
+            assert type(ei.value).__name__ == c["raises"]
+        else:
+            out = r.rerank(g["query"], docs_from(g["docs"][:c["n"]]))
+            assert [d.docid for d in out] == c["order"], c
+            assert [d.score for d in out] == c["scores"]
+        assert len(log) == c["n_generate_calls"]
+        check_counters(r, c)
+    capsys.readouterr()
+
+
 # ------------------------------------------------------------------------------------------- level-parallel heap build (§8f-2)
 @pytest.mark.parametrize("n,c,k", [(100, 10, 10), (100, 3, 10), (37, 2, 5), (12, 3, 3), (5, 10, 3), (1, 3, 1), (64, 4, 64)])
 def test_batched_heap_equals_sequential_heap(n, c, k):
