@@ -7,6 +7,7 @@ Differences, all additive: ir_datasets / pyserini are imported lazily (absent on
 `--model_name_or_path synthetic:flan-t5-large` selects seeded random weights + the synthetic tokenizer.
 """
 import argparse
+import collections
 import json
 import os
 import logging
@@ -185,17 +186,28 @@ def main(args):
     # The reference calls ranker.rerank() once per query (run.py:190). Rankers of this package that offer rerank_many (pointwise:
     # two queries in flight + tokenisation look-ahead; setwise heapsort: several queries' sorts in lockstep) yield exactly
     # rerank()'s result and counters per query, in order — B200RANK_RERANK_MANY=0 restores the one-call-per-query loop.
-    items = list(prepared())
-    n_queries = len(items)
+    # Queries are FED LAZILY: the shuffle of query i+1 is drawn when the ranker asks for it, i.e. after rerank(query i) for a
+    # ranker that works query by query — the interleaving of run.py:181-190, which matters when the ranker itself draws from the
+    # module RNG (setwise num_permutation > 1; its rerank_many falls back to one rerank() per request).
+    source = prepared()
     if world > 1:
         from b200rank.dist import shard_bounds
-        lo, hi = shard_bounds(n_queries, rank, world)
-        items = items[lo:hi]
+        items = list(source)                      # every rank draws the shuffles of all queries (one stream), then keeps its shard
+        lo, hi = shard_bounds(len(items), rank, world)
+        source = iter(items[lo:hi])
+    fed = collections.deque()
+
+    def feed():
+        for qid, query, ranking in source:
+            fed.append((qid, query))
+            yield query, ranking
+
     if hasattr(ranker, 'rerank_many') and os.environ.get('B200RANK_RERANK_MANY', '1') != '0':
-        results = ranker.rerank_many((query, ranking) for _, query, ranking in items)
+        results = ranker.rerank_many(feed())
     else:
-        results = (ranker.rerank(query, ranking) for _, query, ranking in items)
-    for (qid, query, _), result in zip(items, results):
+        results = (ranker.rerank(query, ranking) for query, ranking in feed())
+    for result in results:
+        qid, query = fed.popleft()
         reranked.append((qid, query, result))
         n_cmp += ranker.total_compare
         n_prompt += ranker.total_prompt_tokens

@@ -734,3 +734,44 @@ def test_cli_reference_data_sources_with_stub_modules(source, tmp_path, monkeypa
                 ["--query_length", "32", "--passage_length", "128", "pointwise", "--method", "yes_no", "--batch_size", "4"])
     assert [l.split("\t")[2] for l in out.read_text().splitlines()] == c["order"]
     assert f"Avg comparisons: {float(c['total_compare'])}" in capsys.readouterr().out
+
+
+# ------------------------------------------------------------------------------------------- run.py against the reference's run.py
+def _cli_fixture():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "golden_cli.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", [s["name"] for s in _cli_fixture()["scenarios"]])
+def test_cli_matches_the_reference_run_py(name, tmp_path, monkeypatch, capsys):
+    """tests/golden/golden_cli.json holds what the REFERENCE's run.py did, executed as __main__ with recording fakes for the ranker classes
+    and stand-ins for ir_datasets / pyserini (tests/golden/make_golden_cli.py): which class it built with which keywords, the exact
+    (query, [(docid, score, text)]) it handed to every rerank() — truncation, title prefix, --hits, --shuffle_ranking drawn from the
+    module RNG interleaved with the ranker's own draws — its summary prints, its TREC file, or the error it raised. llm-rankers_b200/run.py
+    must do the same under the same stand-ins."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_cli as G
+    import run as cli_mod
+    sc = next(s for s in _cli_fixture()["scenarios"] if s["name"] == name)
+    for mod_name, mod in G.stub_source_modules().items():
+        monkeypatch.setitem(sys.modules, mod_name, mod)
+    log = []
+    for names in G.RANKER_CLASSES.values():
+        for n in names:
+            monkeypatch.setattr(cli_mod, n, G.make_fake(n, log))
+    (tmp_path / "first_stage.txt").write_text("\n".join(G.RUN_LINES) + "\n")
+    save = tmp_path / "out.trec"
+    argv = ["run", "--run_path", str(tmp_path / "first_stage.txt"), "--save_path", str(save)] + sc["argv"]
+    random.seed(929)
+    if "raises" in sc:
+        with pytest.raises(Exception) as ei:
+            cli_mod.cli(argv)
+        assert [type(ei.value).__name__, str(ei.value)] == sc["raises"]
+        return
+    cli_mod.cli(argv)
+    assert log == sc["log"]
+    assert G.scrub(capsys.readouterr().out) == sc["stdout"]
+    assert save.read_text() == sc["trec"]
