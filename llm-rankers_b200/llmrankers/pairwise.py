@@ -86,6 +86,13 @@ class PairwiseLlmRanker(LlmRanker):
             res.append((txt[0] == "Passage A" and txt[1] == "Passage B", ids.shape[0] * ids.shape[1], out.shape[0] * out.shape[1]))
         return res
 
+    def _has_batched_compares(self) -> bool:
+        """True when `_compare_items` answers what this class's compare() answers (a subclass that overrides the single compare
+        without its batched twin falls back to the sequential drivers)."""
+        cls = type(self)
+        owner = lambda name: next(c for c in cls.__mro__ if name in c.__dict__)   # noqa: E731
+        return owner("_compare_items") is owner("_first_wins")
+
     def _first_wins_many(self, query: str, pairs: List) -> List[bool]:
         """`_first_wins` for several independent pairs of one query; counters as len(pairs) compare() calls."""
         res = self._compare_items([(query, a, b) for a, b in pairs])
@@ -99,7 +106,7 @@ class PairwiseLlmRanker(LlmRanker):
         sorts advancing in lockstep, every round one engine batch of all their pending pair compares (see
         SetwiseLlmRanker.rerank_many). Per-query compares, order, scores and counters are exactly rerank()'s. Other methods
         (allpair is already one large batch per query; bubblesort) and subclasses with their own compare fall back to rerank()."""
-        if self.method != "heapsort" or type(self)._first_wins is not PairwiseLlmRanker._first_wins:
+        if self.method != "heapsort" or not self._has_batched_compares():
             for query, ranking in requests:
                 yield self.rerank(query, ranking)
             return
@@ -190,7 +197,7 @@ class PairwiseLlmRanker(LlmRanker):
                              key=lambda x: x.score, reverse=True)
         elif self.method == "heapsort":
             arr = list(ranking)
-            if type(self)._first_wins is PairwiseLlmRanker._first_wins and os.environ.get("B200RANK_BATCHED_SORT", "1") != "0":
+            if self._has_batched_compares() and os.environ.get("B200RANK_BATCHED_SORT", "1") != "0":
                 binary_heap_top_k_batched(arr, self.k, lambda pairs: self._first_wins_many(query, pairs))   # level-parallel build
             else:
                 binary_heap_top_k(arr, self.k, lambda a, b: self._first_wins(query, a, b))
@@ -225,6 +232,19 @@ class DuoT5LlmRanker(PairwiseLlmRanker):
 
     def _first_wins(self, query: str, a, b) -> bool:
         return self.compare(query, [a.text, b.text])
+
+    def _compare_items(self, items: List) -> List:
+        """compare() for several independent (query, a, b) pairs in ONE engine call: the reference pads each pair to its longer
+        prompt and masks the pads (padding=True with the attention mask, pairwise.py:303-311), the engine computes on real tokens
+        only, and a row's result does not depend on its neighbours — so every verdict equals the sequential compare()'s. Returns
+        [(first_wins, prompt_tokens, completion_tokens)]; counters are left to the caller."""
+        inputs = []
+        for query, a, b in items:
+            inputs.append(DUOT5_PROMPT.format(query=query, doc1=a.text, doc2=b.text))
+            inputs.append(DUOT5_PROMPT.format(query=query, doc1=b.text, doc2=a.text))
+        rows = self.tokenizer(inputs, truncation=True)["input_ids"] if inputs else []
+        probs = self.backend.score_yes_no(rows, 1176, 6136)[1] if rows else []
+        return [(bool(probs[i] > probs[i + 1]), 2 * max(len(rows[i]), len(rows[i + 1])), 0) for i in range(0, len(rows), 2)]
 
     def rerank(self, query: str, ranking: List[SearchResult]) -> List[SearchResult]:
         if self.method != "heapsort":

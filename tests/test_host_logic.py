@@ -101,6 +101,38 @@ def test_duot5_matches_reference():
         DuoT5LlmRanker(None, None, "cuda", method="allpair", backend=v10_backend("tiny")).rerank(m["query"], docs_from(m["docs"][:3]))
 
 
+def test_duot5_batched_sequential_and_cross_query_drivers_agree(monkeypatch):
+    """DuoT5's level-parallel heap construction (one engine call per round of compares) and rerank_many (several queries in lockstep)
+    against the sequential compare-at-a-time driver the reference fixture pins: same order, scores and counters."""
+    from helpers import golden_v10_meta
+    from llmrankers.pairwise import DuoT5LlmRanker
+    meta = golden_v10_meta()
+    m, c = meta["tiny"], meta["cases"]["duo_heap"]
+    assert DuoT5LlmRanker(None, None, "cuda", method="heapsort", k=2, backend=v10_backend("tiny"))._has_batched_compares()
+    requests = [(m["query"], m["docs"][:7]), ("w3 w4", m["docs"][2:9]), (m["query"], m["docs"][:1]), ("w1 w2 w3", m["docs"][::-1]), ("w5", [])]
+    monkeypatch.setenv("B200RANK_BATCHED_SORT", "0")
+    seq = DuoT5LlmRanker(None, None, "cuda", method="heapsort", k=c["k"], backend=v10_backend("tiny"))
+    want = []
+    for q, dd in requests:
+        out = seq.rerank(q, docs_from(dd))
+        want.append(([(d.docid, d.score) for d in out], (seq.total_compare, seq.total_prompt_tokens, seq.total_completion_tokens)))
+    assert want[0][0] == list(zip(c["order"], c["scores"]))
+    monkeypatch.setenv("B200RANK_BATCHED_SORT", "1")
+    bat = DuoT5LlmRanker(None, None, "cuda", method="heapsort", k=c["k"], backend=v10_backend("tiny"))
+    calls = []
+    orig = bat.backend.score_yes_no
+    bat.backend.score_yes_no = lambda rows, y, n: (calls.append(len(rows)), orig(rows, y, n))[1]
+    for (q, dd), w in zip(requests, want):
+        out = bat.rerank(q, docs_from(dd))
+        assert ([(d.docid, d.score) for d in out], (bat.total_compare, bat.total_prompt_tokens, bat.total_completion_tokens)) == w
+    assert max(calls) > 2            # several pairs really shared an engine call
+    for window in (1, 3):
+        got = []
+        for out in bat.rerank_many([(q, docs_from(dd)) for q, dd in requests], window=window):
+            got.append(([(d.docid, d.score) for d in out], (bat.total_compare, bat.total_prompt_tokens, bat.total_completion_tokens)))
+        assert got == want
+
+
 @pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_heap_lik", "setwise_bubble_lik", "setwise_bubble_gen"])
 def test_setwise_matches_reference(case, capsys):
     from llmrankers.setwise import SetwiseLlmRanker
