@@ -246,3 +246,23 @@ def pairwise_bubble_top_k(ranking: List, k: int, first_wins: Callable[[object, o
             if not changed:
                 last_end -= 1
             cur -= 1
+
+
+def pairwise_bubble_rounds(ranking: List, k: int):
+    """pairwise_bubble_top_k as a generator of compare rounds (always one request: the passes are a dependent chain), so that the
+    bubble sorts of several queries can advance together. Yields [(lower, upper)]; expects [first_wins(lower, upper)]."""
+    k = min(k, len(ranking))
+    last_end = len(ranking) - 1
+    for i in range(k):
+        cur = last_end
+        changed = False
+        while cur > i:
+            if (yield [(ranking[cur], ranking[cur - 1])])[0]:
+                ranking[cur - 1], ranking[cur] = ranking[cur], ranking[cur - 1]
+                if not changed:
+                    changed = True
+                    if last_end != len(ranking) - 1:
+                        last_end += 1
+            if not changed:
+                last_end -= 1
+            cur -= 1

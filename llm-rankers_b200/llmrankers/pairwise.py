@@ -12,7 +12,8 @@ from itertools import combinations
 from typing import List, Optional
 
 from ._backend import T5Backend
-from ._sorting import binary_heap_top_k, binary_heap_top_k_batched, binary_heap_top_k_rounds, pairwise_bubble_top_k
+from ._sorting import (binary_heap_top_k, binary_heap_top_k_batched, binary_heap_top_k_rounds, pairwise_bubble_rounds,
+                       pairwise_bubble_top_k)
 from .rankers import LlmRanker, SearchResult
 from .setwise import _assemble
 
@@ -102,19 +103,22 @@ class PairwiseLlmRanker(LlmRanker):
         return [r[0] for r in res]
 
     def rerank_many(self, requests, window: int = 8):
-        """Extension (not in the reference): heapsort-rerank an iterable of (query, ranking) pairs with up to `window` queries'
-        sorts advancing in lockstep, every round one engine batch of all their pending pair compares (see
-        SetwiseLlmRanker.rerank_many). Per-query compares, order, scores and counters are exactly rerank()'s. Other methods
-        (allpair is already one large batch per query; bubblesort) and subclasses with their own compare fall back to rerank()."""
-        if self.method != "heapsort" or not self._has_batched_compares():
+        """Extension (not in the reference): rerank an iterable of (query, ranking) pairs (heapsort or bubblesort) with up to `window`
+        queries' sorts advancing in lockstep, every round one engine batch of all their pending pair compares (see
+        SetwiseLlmRanker.rerank_many). Per-query compares, order, scores and counters are exactly rerank()'s. allpair (already one
+        large batch per query) and subclasses with their own single compare but no batched twin fall back to rerank()."""
+        if self.method not in ("heapsort", "bubblesort") or not self._has_batched_compares():
             for query, ranking in requests:
                 yield self.rerank(query, ranking)
             return
+        heap = self.method == "heapsort"
         it = iter(requests)
         active, done, next_out, seq = [], {}, 0, 0
 
         def finish(st):
-            ranking = [SearchResult(docid=doc.docid, score=-i, text=None) for i, doc in enumerate(reversed(st["arr"]))]
+            ranking = st["arr"]
+            if heap:
+                ranking = [SearchResult(docid=doc.docid, score=-i, text=None) for i, doc in enumerate(reversed(st["arr"]))]
             done[st["seq"]] = (_assemble(ranking, st["original"], self.k), st["counters"])
 
         def admit():
@@ -125,7 +129,7 @@ class PairwiseLlmRanker(LlmRanker):
                 except StopIteration:
                     return
                 st = dict(seq=seq, query=query, original=copy.deepcopy(ranking), arr=list(ranking), counters=[0, 0, 0])
-                st["gen"] = binary_heap_top_k_rounds(st["arr"], self.k)
+                st["gen"] = binary_heap_top_k_rounds(st["arr"], self.k) if heap else pairwise_bubble_rounds(st["arr"], self.k)
                 seq += 1
                 try:
                     st["round"] = next(st["gen"])

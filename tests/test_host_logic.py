@@ -370,11 +370,12 @@ def test_pairwise_batched_and_sequential_heapsort_agree(monkeypatch):
     assert outs[0][0] == c["order"] and outs[0][2:] == (c["total_compare"], c["total_prompt_tokens"], c["total_completion_tokens"])
 
 
-def test_pairwise_rerank_many_equals_rerank():
+@pytest.mark.parametrize("sort,case", [("heapsort", "pairwise_heap"), ("bubblesort", "pairwise_bubble")])
+def test_pairwise_rerank_many_equals_rerank(sort, case):
     from llmrankers.pairwise import PairwiseLlmRanker
     meta = golden_meta()
-    m, c = meta["tiny"], meta["cases"]["pairwise_heap"]
-    mk = lambda method="heapsort": PairwiseLlmRanker(None, None, "cuda", method=method, batch_size=c["batch_size"], k=c["k"], backend=backend("tiny", True))
+    m, c = meta["tiny"], meta["cases"][case]
+    mk = lambda method=sort: PairwiseLlmRanker(None, None, "cuda", method=method, batch_size=c["batch_size"], k=c["k"], backend=backend("tiny", True))
     d12 = m["docs12"]
     requests = [(m["query"], d12[:6]), ("w7 w8", d12[4:9]), ("w1", d12[:1]), (m["query"], d12[::-1][:7]), ("w4", [])]
     want = []
