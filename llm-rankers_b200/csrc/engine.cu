@@ -206,10 +206,12 @@ static int pick_cta_group(int M, int N, int bn, int num_sms) {
     return pair_tiles >= num_sms / 2 ? 2 : 1;
 }
 
-static bool epi_pipe_pref() {
+// B200RANK_EPI_PIPE (opt-in, experimental): bit 0 = software-pipelined TMEM loads in the fp32 residual epilogue (O-proj, FFN-out),
+// bit 1 = the same in the staged bf16 epilogue (QKV projection, relu FFN-in). 1 | 2 | 3.
+static int epi_pipe_pref() {
     static int v = -1;
-    if (v < 0) v = (getenv("B200RANK_EPI_PIPE") && atoi(getenv("B200RANK_EPI_PIPE")) != 0) ? 1 : 0;
-    return v != 0;
+    if (v < 0) v = getenv("B200RANK_EPI_PIPE") ? (atoi(getenv("B200RANK_EPI_PIPE")) & 3) : 0;
+    return v;
 }
 
 // B200RANK_EPI_HINT=last|first|normal (with B200RANK_EPI_PIPE=1): L2 policy of the residual reduce-add destination lines
@@ -230,7 +232,11 @@ static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, c
                           const GemmArgs& a, int epi, int bn, bool tma_epi, int cg) {
     // the staged bf16 epilogue moves 64-column (128 B) tiles; a 32-column accumulator keeps the direct store path
     if (epi == EPI_BF16 && bn < 64) tma_epi = false;
-    if (epi == EPI_RESID_F32 && bn == 256 && tma_epi && epi_pipe_pref()) {
+    if (epi == EPI_BF16 && bn == 256 && tma_epi && (epi_pipe_pref() & 2)) {
+        return cg == 2 ? launch_gemm_inst<256, EPI_BF16_PIPE, true, 2>(st, num_sms, ta, tb, tout, a)
+                       : launch_gemm_inst<256, EPI_BF16_PIPE, true, 1>(st, num_sms, ta, tb, tout, a);
+    }
+    if (epi == EPI_RESID_F32 && bn == 256 && tma_epi && (epi_pipe_pref() & 1)) {
         // opt-in (B200RANK_EPI_PIPE=1, not yet measured on the B200): TMEM loads of the fp32 residual epilogue software-pipelined
         return cg == 2 ? launch_gemm_inst<256, EPI_RESID_F32_PIPE, true, 2>(st, num_sms, ta, tb, tout, a)
                        : launch_gemm_inst<256, EPI_RESID_F32_PIPE, true, 1>(st, num_sms, ta, tb, tout, a);

@@ -25,6 +25,8 @@ enum EpiMode : int {
     EPI_RESID_NORM = 4, // EPI_RESID_F32 with N == row width, plus: every unit owns whole 128-row blocks (all N-tiles), and once a
                         // block's adds have landed it re-reads those rows from L2 and writes norm_out = bf16(T5LayerNorm(out))
     EPI_RELU_BF16 = 5,  // host-side alias: launched as EPI_BF16 with GemmArgs::relu = 1 (out_bf16 = max(acc, 0))
+    EPI_BF16_PIPE = 7,       // EPI_BF16 (staged) with the tcgen05.ld of the next 64-column chunk in flight while the current one is packed,
+                             // staged and stored (opt-in, B200RANK_EPI_PIPE bit 1; the QKV projection runs 87 % tensor-active)
     EPI_RESID_F32_PIPE = 6,  // EPI_RESID_F32 with the tcgen05.ld of chunk c+1 in flight while chunk c is staged (opt-in, B200RANK_EPI_PIPE=1:
                              // experiments/epi_probe.cu shows the un-pipelined TMEM loads cost ~1.8 us of the ~6 us a 128 x 256 tile's epilogue takes)
 };
@@ -313,6 +315,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                         stage_close(nb * HALF + c);
+                    }
+                } else if constexpr (EPI == EPI_BF16_PIPE) {
+                    // bf16 tiles of 64 columns; two pairs of register buffers: the TMEM loads of the next 64 columns fly during the
+                    // pack + staging (two named barriers + fence + bulk store issue) of the current ones
+                    static_assert(BLOCK_N % 64 == 0, "pipelined bf16 epilogue walks 64-column chunks");
+                    uint32_t a0[32], a1[32], b0[32], b1[32];
+                    auto emit = [&](uint32_t (&r0)[32], uint32_t (&r1)[32], int c) {
+                        if (args.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                r0[j] = __float_as_uint(fmaxf(__uint_as_float(r0[j]), 0.f));
+                                r1[j] = __float_as_uint(fmaxf(__uint_as_float(r1[j]), 0.f));
+                            }
+                        }
+                        stage_open();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            put16(j, pack_bf16(__uint_as_float(r0[8 * j + 0]), __uint_as_float(r0[8 * j + 1])),
+                                  pack_bf16(__uint_as_float(r0[8 * j + 2]), __uint_as_float(r0[8 * j + 3])),
+                                  pack_bf16(__uint_as_float(r0[8 * j + 4]), __uint_as_float(r0[8 * j + 5])),
+                                  pack_bf16(__uint_as_float(r0[8 * j + 6]), __uint_as_float(r0[8 * j + 7])));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            put16(4 + j, pack_bf16(__uint_as_float(r1[8 * j + 0]), __uint_as_float(r1[8 * j + 1])),
+                                  pack_bf16(__uint_as_float(r1[8 * j + 2]), __uint_as_float(r1[8 * j + 3])),
+                                  pack_bf16(__uint_as_float(r1[8 * j + 4]), __uint_as_float(r1[8 * j + 5])),
+                                  pack_bf16(__uint_as_float(r1[8 * j + 6]), __uint_as_float(r1[8 * j + 7])));
+                        stage_close(nb * BLOCK_N + c);
+                    };
+                    tmem_ld32(taddr, a0);
+                    tmem_ld32(taddr + 32, a1);
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N; c += 128) {
+                        tmem_ld_wait();
+                        if (c + 64 < BLOCK_N) { tmem_ld32(taddr + c + 64, b0); tmem_ld32(taddr + c + 96, b1); }
+                        else { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
+                        emit(a0, a1, c);
+                        if (c + 64 < BLOCK_N) {
+                            tmem_ld_wait();
+                            if (c + 128 < BLOCK_N) { tmem_ld32(taddr + c + 128, a0); tmem_ld32(taddr + c + 160, a1); }
+                            else { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
+                            emit(b0, b1, c + 64);
+                        }
                     }
                 } else if constexpr (EPI == EPI_RESID_F32_PIPE) {
                     // fp32 tiles of 32 columns, in-L2 add; two register buffers: the TMEM load of the next chunk flies during the

@@ -61,6 +61,15 @@ try:
 except Exception as e:
     print("epi_pipe bench line unreadable:", e)
 PY
+B200RANK_EPI_PIPE=3 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe3.json 2> $OUT/${TAG}_bench_n1_epi_pipe3.err; echo "bench epi_pipe=3 (fp32 residual + bf16 epilogues pipelined) rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_epi_pipe3.json").read().strip().splitlines()[-1])
+    print("EPI_PIPE=3 docs/s", round(d["value"]), {k: v for k, v in d["roofline"]["by_kernel_ms_per_step"].items() if "epi0" in k or "epi1" in k})
+except Exception as e:
+    print("epi_pipe=3 bench line unreadable:", e)
+PY
 B200RANK_EPI_PIPE=1 B200RANK_EPI_HINT=last timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe_evict_last.json 2> $OUT/${TAG}_bench_n1_epi_pipe_evict_last.err; echo "bench epi_pipe+evict_last rc=$?"
 python - <<PY
 import json

@@ -502,7 +502,8 @@ def test_kernel_variants_agree(tmp_path):
     # variants written after the round's GPU budget was spent: compiled, never run. B200RANK_TEST_EXPERIMENTAL=1 includes them
     # (first thing to do with a fresh budget); until they have passed once they stay out of the default suite.
     if os.environ.get("B200RANK_TEST_EXPERIMENTAL") == "1":
-        for name, env in [("epi_pipe", {"B200RANK_EPI_PIPE": "1"})]:
+        for name, env in [("epi_pipe", {"B200RANK_EPI_PIPE": "1"}), ("epi_pipe_bf16", {"B200RANK_EPI_PIPE": "2"}),
+                          ("epi_pipe_both", {"B200RANK_EPI_PIPE": "3"})]:
             got = run(name, **env)
             record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
             assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
