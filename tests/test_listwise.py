@@ -195,3 +195,40 @@ def test_cli_listwise_end_to_end(case, tmp_path, monkeypatch, capsys):
     assert f"Avg comparisons: {float(c['total_compare'])}" in printed
     assert f"Avg prompt tokens: {float(c['total_prompt_tokens'])}" in printed
     assert f"Avg completion tokens: {float(c['total_completion_tokens'])}" in printed
+
+
+# ------------------------------------------------------------------------------------------- window arithmetic against the reference
+def test_sliding_windows_match_the_reference_over_a_grid():
+    """tests/golden/golden_listwise_windows.json: the reference's own rerank() loop and response handling (listwise.py:110-144, 177-195)
+    under a deterministic stand-in for compare(), 272 configurations of list size / window / step / num_repeat with partial, duplicated,
+    out-of-window, prose, junk and 'ERROR::reduce_length' responses (tests/golden/make_golden_listwise_windows.py). The drop-in class
+    must ask for the same windows in the same order and return the same ranking, scores and compare count — and, like the reference,
+    hand back the caller's own objects when num_repeat is 0."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden_listwise_windows import make_docs, response_for
+    from llmrankers.listwise import ListwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    with open(os.path.join(GOLDEN, "golden_listwise_windows.json")) as f:
+        cases = json.load(f)
+    assert len(cases) == 272 and sum(len(c["calls"]) for c in cases) == 824
+    for c in cases:
+        r = ListwiseLlmRanker(None, None, "cuda", window_size=c["window_size"], step_size=c["step_size"], scoring="generation",
+                              num_repeat=c["num_repeat"], backend=backend())
+        log = []
+
+        def compare(query, docs, c=c, log=log, r=r):
+            r.total_compare += 1
+            ids = [d.docid for d in docs]
+            log.append(ids)
+            return response_for(c["seed"], c["p_bad"], query, ids)
+        r.compare = compare
+        docs = make_docs(c["n"], SearchResult)
+        res = r.rerank(c["query"], docs)
+        assert log == c["calls"], c
+        assert [[d.docid, d.score] for d in res] == c["result"], c
+        assert (res is docs) == c["returns_input_objects"], c
+        assert [d.score for d in docs] == c["input_scores_after"], c
+        assert r.total_compare == c["total_compare"]
+        got_many = list(r.rerank_many([(c["query"], make_docs(c["n"], SearchResult))]))     # generation mode: loops over rerank()
+        assert [[d.docid, d.score] for d in got_many[0]] == c["result"], c
