@@ -808,3 +808,50 @@ def test_cli_matches_the_reference_run_py(name, tmp_path, monkeypatch, capsys):
     assert log == sc["log"]
     assert G.scrub(capsys.readouterr().out) == sc["stdout"]
     assert save.read_text() == sc["trec"]
+
+
+# ------------------------------------------------------------------------------------------- pointwise rankers over a grid
+def test_pointwise_rankers_match_the_reference_over_a_grid():
+    """tests/golden/golden_pointwise_sweep.json: the reference's PointwiseLlmRanker (yes_no, qlm) and MonoT5LlmRanker run over list sizes
+    1..33 x batch sizes 1..32 with a stand-in model whose logits are a hash of each row's real token ids
+    (tests/golden/make_golden_pointwise_sweep.py). Scores only agree if the drop-in classes hand the engine exactly the token rows the
+    reference handed the model (prompt templating over odd whitespace / newlines / empty passages); counters follow the reference's
+    per-batch accounting; the order is the reference's stable sort. The reference raises IndexError on an EMPTY ranking
+    (`tokenizer([])`); the drop-in returns [] instead — the one deliberate difference, asserted here."""
+    import json
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_pointwise_sweep as G
+    from llmrankers.pointwise import MonoT5LlmRanker, PointwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    with open(os.path.join(ROOT, "tests", "golden", "golden_pointwise_sweep.json")) as f:
+        fx = json.load(f)
+    b = backend()
+    seen_rows = []
+
+    def score_yes_no(rows, col_a, col_b):
+        seen_rows.append([len(r) for r in rows])
+        lg = torch.tensor([G.yes_no_logits(r, col_a, col_b) for r in rows], dtype=torch.float32).reshape(-1, 2)
+        return lg.numpy(), torch.softmax(lg, dim=1)[:, 0].numpy()
+
+    def score_qlm(rows, labels):
+        lg = torch.from_numpy(G.full_logits_qlm(rows, list(labels)))
+        lab = torch.tensor([list(labels)] * len(rows))
+        ce = torch.nn.CrossEntropyLoss(reduction="none")(lg.view(-1, lg.size(-1)), lab.view(-1))
+        return (-1 * ce.view(-1, lab.size(-1)).sum(dim=1)).numpy()
+    b.score_yes_no, b.score_qlm = score_yes_no, score_qlm
+    assert (b.tokenizer.encode("Yes", add_special_tokens=False)[0], b.tokenizer.encode("No", add_special_tokens=False)[0]) == (fx["yes_id"], fx["no_id"])
+    assert len(fx["cases"]) == 84
+    for c in fx["cases"]:
+        cls = MonoT5LlmRanker if c["kind"] == "monot5" else PointwiseLlmRanker
+        r = cls(None, None, "cuda", method="qlm" if c["kind"] == "qlm" else "yes_no", batch_size=c["batch_size"], backend=b)
+        docs = [SearchResult(docid=f"d{i}", score=float(c["n"] - i), text=t) for i, t in enumerate(c["texts"])]
+        out = r.rerank(c["query"], docs)
+        if "raises" in c:
+            assert c["n"] == 0 and c["raises"] == "IndexError" and out == []
+            continue
+        assert [d.docid for d in out] == [x[0] for x in c["result"]], c
+        assert np.allclose([d.score for d in out], [x[1] for x in c["result"]], rtol=1e-6, atol=1e-6), c
+        assert all(d.text is not None for d in out)           # pointwise returns the input objects, text intact (pointwise.py:125-129)
+        check_counters(r, c)
