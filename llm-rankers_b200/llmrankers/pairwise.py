@@ -186,7 +186,9 @@ class PairwiseLlmRanker(LlmRanker):
                     self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
                     self.total_completion_tokens += out.shape[0] * out.shape[1]
                     outputs.extend(out.tolist())
-            outputs = self.tokenizer.batch_decode(outputs, skip_special_tokens=True)
+            # fewer than two documents: no pairs, nothing to decode (the reference raises IndexError in tokenizer([]) here; the
+            # drop-in returns the trivial ranking)
+            outputs = self.tokenizer.batch_decode(outputs, skip_special_tokens=True) if outputs else []
             scores = defaultdict(float)
             for i in range(0, len(outputs), 2):
                 d1, d2 = doc_pairs[i // 2]

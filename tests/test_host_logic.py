@@ -855,3 +855,46 @@ def test_pointwise_rankers_match_the_reference_over_a_grid():
         assert np.allclose([d.score for d in out], [x[1] for x in c["result"]], rtol=1e-6, atol=1e-6), c
         assert all(d.text is not None for d in out)           # pointwise returns the input objects, text intact (pointwise.py:125-129)
         check_counters(r, c)
+
+
+# ------------------------------------------------------------------------------------------- pairwise allpair over a grid
+@pytest.mark.parametrize("batched", ["1", "0"])
+def test_pairwise_allpair_matches_the_reference_over_a_grid(batched, monkeypatch):
+    """tests/golden/golden_allpair_sweep.json: the reference's allpair rerank over list sizes x batch sizes x k with a stand-in generate()
+    hashing each row's non-pad token ids (tests/golden/make_golden_allpair_sweep.py): the DataLoader batch shapes, the verdict
+    aggregation (wins, conflicts, the defaultdict's insertion order deciding ties, never-scoring documents in the original-order tail),
+    scores, order and counters — with the reference batches merged into large engine calls (default) and one engine call per batch.
+    With fewer than two documents the reference raises IndexError (`tokenizer([])`); the drop-in returns the trivial ranking."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_allpair_sweep as G
+    from llmrankers.pairwise import PairwiseLlmRanker
+    from llmrankers.rankers import SearchResult
+    monkeypatch.setenv("B200RANK_BATCHED_SORT", batched)
+    with open(os.path.join(ROOT, "tests", "golden", "golden_allpair_sweep.json")) as f:
+        fx = json.load(f)
+    assert len(fx["cases"]) == 126
+    b = backend()
+    shapes = []
+
+    def generate_batches(batches, dec_prefix, max_new):
+        assert max_new == 2 and list(dec_prefix) == [0, fx["passage_id"]]
+        outs = []
+        for ids in batches:
+            shapes.append([int(ids.shape[0]), int(ids.shape[1])])
+            outs.append(np.asarray(G.stub_generate(np.asarray(ids).tolist(), fx["passage_id"], fx["a_id"], fx["b_id"], fx["junk_id"]), np.int64))
+        return outs
+    b.generate_batches = generate_batches
+    for c in fx["cases"]:
+        r = PairwiseLlmRanker(None, None, "cuda", method="allpair", batch_size=c["batch_size"], k=c["k"], backend=b)
+        docs = [SearchResult(docid=f"d{i}", score=float(c["n"] - i), text=t) for i, t in enumerate(c["texts"])]
+        del shapes[:]
+        out = r.rerank(c["query"], docs)
+        if "raises" in c:
+            assert c["n"] < 2 and c["raises"] == "IndexError"
+            assert [(d.docid, d.score) for d in out] == [(f"d{i}", -(i + 1)) for i in range(c["n"])]
+            continue
+        assert [[d.docid, d.score] for d in out] == c["result"], c
+        assert shapes == c["batches"], c
+        check_counters(r, c)
