@@ -105,6 +105,17 @@ try:
 except Exception as e:
     print("tc4 bench line unreadable:", e)
 PY
+# 6d'. everything together: pipelined epilogues + two encoder streams + one-pass attention (only meaningful if each passed above)
+B200RANK_EPI_PIPE=3 B200RANK_PIPE_DUAL=1 B200RANK_ATTN=tc4 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_all_experimental.json 2> $OUT/${TAG}_bench_n1_all_experimental.err; echo "bench all experimental rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_all_experimental.json").read().strip().splitlines()[-1])
+    print("ALL EXPERIMENTAL docs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "step_frac", round(d["roofline"]["step_frac"], 3), "clocks", d["clocks"]["sm_mhz"],
+          "parity", (d.get("parity") or {}).get("within_logit_tolerance"))
+except Exception as e:
+    print("all-experimental bench line unreadable:", e)
+PY
 # 6e. d_kv = 128 (monot5-3b / duot5-3b head shape) on the generic-width attention (experimental): every entry point against the oracle
 B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "wide_heads" > $OUT/${TAG}_pytest_dkv128.log 2>&1; echo "d_kv 128 tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_dkv128.log
