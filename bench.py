@@ -621,7 +621,14 @@ def run_engine(args):
     # prompt assembly + tokenisation of 100 never-seen documents per query on the host, then the same submit/wait pipeline.
     api_text = None
     if rank == 0 and world == 1 and not args.no_text_api:
-        api_text = text_api_docs_per_s(eng, cfg, n_queries=min(args.steps, 30))
+        try:
+            api_text = text_api_docs_per_s(eng, cfg, n_queries=min(args.steps, 30))
+        except Exception as exc:  # noqa: BLE001 - informational leg: never lose the bench line to it
+            api_text = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            try:
+                eng.drain()       # tickets the aborted pipeline left in flight would block the synchronous calls below
+            except Exception:  # noqa: BLE001
+                pass
 
     # ---- roofline for the dominant kernel: per-launch CUDA events in a separate profiled pass
     roofline = None

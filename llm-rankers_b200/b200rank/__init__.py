@@ -165,6 +165,8 @@ class Engine:
         self.cfg = cfg
         self.device = device
         self._h = C.c_void_p()
+        self._in_flight = {}      # ticket -> documents of the pipelined batches not yet waited for (see drain())
+        self._staged_n = 0
         _check(self.lib.b200rank_create(C.byref(cfg), device, C.byref(self._h)))
 
     def close(self) -> None:
@@ -281,12 +283,14 @@ class Engine:
         t = C.c_uint64()
         _check(self.lib.b200rank_submit_yes_no(self._h, _p(ids, C.c_int32), _p(lengths, C.c_int32), ids.shape[0], ids.shape[1],
                                                yes_id, no_id, C.byref(t)))
+        self._in_flight[int(t.value)] = ids.shape[0]
         return int(t.value), ids.shape[0]
 
     def submit_yes_no_staged(self, yes_id: int, no_id: int) -> Tuple[int, int]:
         """Asynchronous scoring of the batch `stage()` left in device memory (no host->device copy)."""
         t = C.c_uint64()
         _check(self.lib.b200rank_submit_yes_no(self._h, None, None, 0, 0, yes_id, no_id, C.byref(t)))
+        self._in_flight[int(t.value)] = self._staged_n
         return int(t.value), self._staged_n
 
     def wait_yes_no(self, ticket: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:
@@ -294,7 +298,17 @@ class Engine:
         logits2 = np.empty((n, 2), np.float32)
         scores = np.empty((n,), np.float32)
         _check(self.lib.b200rank_wait_yes_no(self._h, t, _p(logits2, C.c_float), _p(scores, C.c_float)))
+        self._in_flight.pop(t, None)
         return logits2, scores
+
+    def drain(self) -> int:
+        """Wait for every pipelined batch still in flight and discard its scores (after an error between submit and wait: the
+        synchronous entry points refuse to run while tickets are outstanding). Returns how many were drained."""
+        n = 0
+        for t, docs in sorted(self._in_flight.items()):
+            self.wait_yes_no((t, docs))
+            n += 1
+        return n
 
     def sync(self) -> None:
         _check(self.lib.b200rank_sync(self._h))

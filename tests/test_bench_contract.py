@@ -132,7 +132,12 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
 
     monkeypatch.setattr(br, "Engine", StandIn)
     monkeypatch.setattr(bench.ClockSampler, "run", lambda self: None)       # no nvidia-smi here
-    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=True, no_pipeline=False, hf_cuda=False)
+    # the informational text-API leg fails here (no tokenizer pipeline behind the stand-in): the headline line must survive it
+
+    def broken_text_api(*a, **k):
+        raise RuntimeError("text leg down")
+    monkeypatch.setattr(bench, "text_api_docs_per_s", broken_text_api)
+    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=False, no_pipeline=False, hf_cuda=False)
     assert bench.run_engine(args) == 0
     line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(line) == 1
@@ -140,6 +145,7 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
                 "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity"):
         assert key in d, key
+    assert d["api_text"] == {"unavailable": "RuntimeError: text leg down"}
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["dtype"] == "bf16" and d["vs_baseline"] is None
     assert d["gpu_launches"] == 3 * 438 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1200
     r = d["roofline"]
