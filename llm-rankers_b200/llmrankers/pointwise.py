@@ -118,25 +118,37 @@ class PointwiseLlmRanker(LlmRanker):
                     except StopIteration:
                         return
                     window.append((ranking, pool.submit(tokenise, query, ranking)))
-            refill()
-            while window:
-                ranking, fut = window.popleft()
-                rows = fut.result()
+            try:
                 refill()
-                ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
-                scores = None
-                if rows and ticket is None:
-                    # not a pipelined batch (long documents / more than one device pass): drain what is in flight — the synchronous
-                    # entry points refuse to run next to pipelined batches — then score this query the way rerank() does
+                while window:
+                    ranking, fut = window.popleft()
+                    rows = fut.result()
+                    refill()
+                    ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
+                    scores = None
+                    if rows and ticket is None:
+                        # not a pipelined batch (long documents / more than one device pass): drain what is in flight — the
+                        # synchronous entry points refuse to run next to pipelined batches — then score this query as rerank() does
+                        if pending is not None:
+                            item, pending = pending, None
+                            yield finish(item)
+                        _, scores = self.backend.score_yes_no(rows, yes_id, no_id)
                     if pending is not None:
-                        yield finish(pending)
-                        pending = None
-                    _, scores = self.backend.score_yes_no(rows, yes_id, no_id)
+                        item, pending = pending, (ticket, ranking, rows, scores)
+                        yield finish(item)
+                    else:
+                        pending = (ticket, ranking, rows, scores)
                 if pending is not None:
-                    yield finish(pending)
-                pending = (ticket, ranking, rows, scores)
-            if pending is not None:
-                yield finish(pending)
+                    item, pending = pending, None
+                    yield finish(item)
+            finally:
+                # the consumer stopped early or something failed between submit and wait: do not leave a ticket in flight (the
+                # engine's synchronous entry points refuse to run until every pipelined batch has been waited for)
+                if pending is not None and pending[0] is not None:
+                    try:
+                        self.backend.wait_yes_no(pending[0])
+                    except Exception:   # noqa: BLE001 - already unwinding
+                        pass
 
     def truncate(self, text, length):
         return self.tokenizer.convert_tokens_to_string(self.tokenizer.tokenize(text)[:length])

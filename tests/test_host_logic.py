@@ -235,6 +235,34 @@ def test_rerank_many_falls_back_for_batches_the_pipeline_declines():
     assert b.in_flight == 0
 
 
+def test_rerank_many_leaves_no_ticket_in_flight_when_abandoned():
+    """A consumer that stops after the first result (or an exception between submit and wait) must not leave a pipelined batch in
+    flight: the engine's synchronous entry points refuse to run until every ticket has been waited for."""
+    from llmrankers.pointwise import PointwiseLlmRanker
+    m = golden_meta()["tiny"]
+    b = backend()
+    flight = set()
+    sub, wait = b.submit_yes_no, b.wait_yes_no
+
+    def submit(rows, y, n):
+        t = sub(rows, y, n)
+        flight.add(id(t))
+        return t
+
+    def waited(t):
+        flight.discard(id(t))
+        return wait(t)
+    b.submit_yes_no, b.wait_yes_no = submit, waited
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=b)
+    reqs = [(m["query"], docs_from(m["docs"])), ("w3 w4", docs_from(m["docs"][:3])), ("w5", docs_from(m["docs"][:5]))]
+    gen = r.rerank_many(reqs)
+    first = next(gen)
+    assert len(first) == len(m["docs"]) and flight            # the second query is in flight while the first is handed out
+    gen.close()
+    assert not flight
+    assert [d.docid for d in r.rerank(m["query"], docs_from(m["docs"]))] == [d.docid for d in first]
+
+
 # ------------------------------------------------------------------------------------------- permutation voting (setwise.py:102-157)
 def _perm_fixture():
     import json
