@@ -84,11 +84,42 @@ class PointwiseLlmRanker(LlmRanker):
         same list `rerank(query, ranking)` would return for each pair, in order; counters hold the totals of the last query.
         Only the yes_no method is pipelined (the headline path); other methods fall back to rerank()."""
         spec = self._pipeline_spec()
+        from concurrent.futures import ThreadPoolExecutor
+        if spec is None and self.method == "qlm" and type(self).rerank is PointwiseLlmRanker.rerank:
+            # qlm (33 decoder positions) is not pipelined on the GPU, but the host work is: upcoming queries are tokenised on worker
+            # threads while the engine scores the current one (ctypes releases the GIL during the call) — configs[4] of BASELINE.json
+            # tokenises 1000 passages per query
+            def tokenise_qlm(query, ranking):
+                return (self._rows(QLM_PROMPT, [dict(text=doc.text) for doc in ranking]),
+                        self.tokenizer.encode(f"<pad> {query}", add_special_tokens=False))
+            it = iter(requests)
+            window = deque()
+            with ThreadPoolExecutor(max(1, tokenizer_threads)) as pool:
+                def refill_qlm():
+                    while len(window) < max(1, lookahead):
+                        try:
+                            query, ranking = next(it)
+                        except StopIteration:
+                            return
+                        window.append((ranking, pool.submit(tokenise_qlm, query, ranking)))
+                refill_qlm()
+                while window:
+                    ranking, fut = window.popleft()
+                    rows, labels = fut.result()
+                    refill_qlm()
+                    self.total_compare = 0
+                    self.total_completion_tokens = 0
+                    self.total_prompt_tokens = 0
+                    self._count_batches(rows, len(labels))
+                    scores = self.backend.score_qlm(rows, labels) if rows else []
+                    for doc, sc in zip(ranking, scores):
+                        doc.score = float(sc)
+                    yield sorted(ranking, key=lambda x: x.score, reverse=True)
+            return
         if spec is None:
             for query, ranking in requests:
                 yield self.rerank(query, ranking)
             return
-        from concurrent.futures import ThreadPoolExecutor
         template, fields_of, yes_id, no_id = spec
 
         def finish(item):

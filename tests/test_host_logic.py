@@ -177,10 +177,11 @@ def test_pointwise_sort_is_stable_and_empty_ok():
     assert r.total_compare == 2
 
 
-def test_rerank_many_equals_rerank():
+@pytest.mark.parametrize("method", ["yes_no", "qlm"])
+def test_rerank_many_equals_rerank(method):
     from llmrankers.pointwise import PointwiseLlmRanker
     m = golden_meta()["tiny"]
-    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=backend())
+    r = PointwiseLlmRanker(None, None, "cuda", method=method, batch_size=4, backend=backend())
     reqs = [(m["query"], docs_from(m["docs"])), ("w3 w4", docs_from(m["docs"][:3])), ("w9", []), (m["query"], docs_from(m["docs"][::-1]))]
     want = [[(d.docid, d.score) for d in r.rerank(q, copy.deepcopy(rk))] for q, rk in reqs]
     got = [[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs])]
