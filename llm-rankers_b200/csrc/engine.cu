@@ -335,6 +335,13 @@ struct b200rank_engine {
     bool pipe_dual = false;
     cudaStream_t stream_enc2 = nullptr;
     struct EncWs { float* x = nullptr; bf16 *h = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr; int* d_ids = nullptr; } enc_ws[2];
+    // B200RANK_DEC_GRAPH=1 (experimental, off by default): the ~250-kernel T = 1 decoder chain of the pipelined pass is captured into a
+    // CUDA graph per (slot, documents, padded longest document) on its second occurrence and replayed from the third on — one launch
+    // instead of ~250 on the host, no inter-kernel launch gaps on the device. Kernel arguments (buffers, tensor maps, grids) are fixed
+    // per key; ids / yes-no columns are uploaded outside the graph.
+    bool dec_graph = false;
+    struct DecGraph { int state = 0; cudaGraphExec_t exec = nullptr; uint64_t launches = 0; };   // 0 new, 1 seen, 2 captured, 3 never
+    std::map<std::tuple<int, int, int>, DecGraph> dec_graphs;
     int gemm_sm_cap = 0;                          // > 0: persistent GEMMs use at most this many SMs (the rest serve the other stream)
     int pipe_reserve_sms = 0;  // measured on B200 (profiles/r01_bench_n1_v10_*): capping the encoder GEMM grids does not pay off
 
@@ -519,6 +526,8 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
         for (void* p : dual)
             if (p) cudaFree(p);
     }
+    for (auto& kv : e->dec_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (e->stream_enc2) cudaStreamDestroy(e->stream_enc2);
     if (e->stream_dec) cudaStreamDestroy(e->stream_dec);
     for (int i = 0; i < 2; ++i)
@@ -650,6 +659,7 @@ static int create_impl(b200rank_engine* e) {
     e->d_cu_cur = e->d_cu;
     e->enc_ws[0].x = e->x; e->enc_ws[0].h = e->h; e->enc_ws[0].qkv = e->qkv; e->enc_ws[0].ao = e->ao; e->enc_ws[0].g = e->g;
     e->enc_ws[0].d_ids = e->d_ids;
+    e->dec_graph = getenv("B200RANK_DEC_GRAPH") && atoi(getenv("B200RANK_DEC_GRAPH")) != 0;
     e->pipe_dual = getenv("B200RANK_PIPE_DUAL") && atoi(getenv("B200RANK_PIPE_DUAL")) != 0;
     if (e->pipe_dual) {
         auto& w = e->enc_ws[1];
@@ -1502,16 +1512,51 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
         std::vector<int> dec(n_docs, e->cfg.pad_id);
         rc = upload_ints(e, e->d_dec_ids, dec);
         if (rc == B200RANK_OK) rc = upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id});
-        if (rc == B200RANK_OK) rc = run_decoder(e, 0, n_docs, 1);
+        // decoder chain + the two-column head + the score: kernels only (what a graph of this pass holds)
+        auto enqueue_decoder = [&]() -> int {
+            int r = run_decoder(e, 0, n_docs, 1);
+            if (r == B200RANK_OK) {
+                prof_begin(e, "lm_head_cols");
+                launch_k(lm_head_cols_kernel, dim3(n_docs), dim3(64), 0, e->stream, e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
+                r = post_launch(e, "lm_head_cols");
+            }
+            if (r == B200RANK_OK) {
+                prof_begin(e, "yes_no_score");
+                launch_k(yes_no_score_kernel, dim3((n_docs + 127) / 128), dim3(128), 0, e->stream, e->small_out, e->small_out2, n_docs);
+                r = post_launch(e, "yes_no_score");
+            }
+            return r;
+        };
         if (rc == B200RANK_OK) {
-            prof_begin(e, "lm_head_cols");
-            launch_k(lm_head_cols_kernel, dim3(n_docs), dim3(64), 0, e->stream, e->hd, e->d, 1, 0, e->lm_head, e->d_cols, 2, logit_scale(e), e->small_out);
-            rc = post_launch(e, "lm_head_cols");
-        }
-        if (rc == B200RANK_OK) {
-            prof_begin(e, "yes_no_score");
-            launch_k(yes_no_score_kernel, dim3((n_docs + 127) / 128), dim3(128), 0, e->stream, e->small_out, e->small_out2, n_docs);
-            rc = post_launch(e, "yes_no_score");
+            const bool try_graph = e->dec_graph && !e->profiling && !e->debug_sync && e->dec_graphs.size() < 64;
+            b200rank_engine::DecGraph* g = try_graph ? &e->dec_graphs[std::make_tuple(b, n_docs, (maxlen + 15) & ~15)] : nullptr;
+            if (g && g->state == 2) {
+                cudaError_t er = cudaGraphLaunch(g->exec, e->stream_dec);
+                if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "decoder graph launch: %s", cudaGetErrorString(er));
+                e->launches += g->launches;
+            } else if (g && g->state == 1) {
+                const uint64_t l0 = e->launches;
+                cudaGraph_t graph = nullptr;
+                cudaError_t er = cudaStreamBeginCapture(e->stream_dec, cudaStreamCaptureModeThreadLocal);
+                const int crc = (er == cudaSuccess) ? enqueue_decoder() : B200RANK_ERR_CUDA;
+                if (er == cudaSuccess) er = cudaStreamEndCapture(e->stream_dec, &graph);
+                if (crc == B200RANK_OK && er == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+                    g->state = 2;
+                    g->launches = e->launches - l0;
+                    er = cudaGraphLaunch(g->exec, e->stream_dec);
+                    if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "decoder graph launch: %s", cudaGetErrorString(er));
+                } else {            // capture is not possible here: never try this key again, run the pass the ordinary way
+                    g->state = 3;
+                    g->exec = nullptr;
+                    cudaGetLastError();
+                    e->launches = l0;
+                    rc = enqueue_decoder();
+                }
+                if (graph) cudaGraphDestroy(graph);
+            } else {
+                if (g && g->state == 0) g->state = 1;
+                rc = enqueue_decoder();
+            }
         }
         if (rc == B200RANK_OK) {
             float* ho = e->h_out_slot[b];

@@ -105,8 +105,20 @@ try:
 except Exception as e:
     print("tc4 bench line unreadable:", e)
 PY
+# 6f. CUDA graph of the pipelined decoder chain (B200RANK_DEC_GRAPH=1, experimental): bit-identity, then the A/B
+B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "decoder_graph" > $OUT/${TAG}_pytest_dec_graph.log 2>&1; echo "dec_graph tests rc=$?"
+tail -3 $OUT/${TAG}_pytest_dec_graph.log
+B200RANK_DEC_GRAPH=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_dec_graph.json 2> $OUT/${TAG}_bench_n1_dec_graph.err; echo "bench dec_graph rc=$?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_n1_dec_graph.json").read().strip().splitlines()[-1])
+    print("DEC_GRAPH docs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "clocks", d["clocks"]["sm_mhz"])
+except Exception as e:
+    print("dec_graph bench line unreadable:", e)
+PY
 # 6d'. everything together: pipelined epilogues + two encoder streams + one-pass attention (only meaningful if each passed above)
-B200RANK_EPI_PIPE=3 B200RANK_PIPE_DUAL=1 B200RANK_ATTN=tc4 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_all_experimental.json 2> $OUT/${TAG}_bench_n1_all_experimental.err; echo "bench all experimental rc=$?"
+B200RANK_EPI_PIPE=3 B200RANK_PIPE_DUAL=1 B200RANK_ATTN=tc4 B200RANK_DEC_GRAPH=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_all_experimental.json 2> $OUT/${TAG}_bench_n1_all_experimental.err; echo "bench all experimental rc=$?"
 python - <<PY
 import json
 try:

@@ -589,6 +589,38 @@ def test_pipelined_submit_wait_matches_synchronous_call():
     assert np.array_equal(e.wait_yes_no(t1)[0], want[0]) and np.array_equal(e.wait_yes_no(t2)[0], want[0])
 
 
+@pytest.mark.skipif(os.environ.get("B200RANK_TEST_EXPERIMENTAL") != "1",
+                    reason="B200RANK_DEC_GRAPH was written without GPU time: B200RANK_TEST_EXPERIMENTAL=1 runs it (tests/gpu_first_call.sh)")
+def test_decoder_graph_replay_matches_the_eager_chain(monkeypatch):
+    """B200RANK_DEC_GRAPH=1: the T = 1 decoder chain of the pipelined pass is captured on the second submit of a (slot, documents,
+    padded length) key and replayed from the third on. Every submit — eager, capturing, replayed, on both slots, with a second
+    shape interleaved — must return the bits of the synchronous call, and the launch counter must keep counting kernels."""
+    import b200rank as br
+    from b200rank.synthetic import NO_ID, YES_ID, model_cfg, synthetic_prompt_ids, synthetic_weights
+    monkeypatch.setenv("B200RANK_DEC_GRAPH", "1")
+    cfg = model_cfg("flan-t5-small")
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"], max_tokens=8192, max_docs=64)
+    e = br.Engine(c, 0)
+    e.load_state_dict(synthetic_weights(cfg, 5).items())
+    a = synthetic_prompt_ids(40, 32, 128, seed=1)
+    b = synthetic_prompt_ids(17, 32, 100, seed=2, ragged=True)
+    want_a, want_b = e.score_yes_no(*a, YES_ID, NO_ID)[0], e.score_yes_no(*b, YES_ID, NO_ID)[0]
+    order = [a, a, a, b, a, a, b, b, a, b, b, a, a]
+    launches, prev, got = [], None, []
+    for ids, lens in order:
+        l0 = e.launch_count()
+        t = e.submit_yes_no(ids, lens, YES_ID, NO_ID)
+        launches.append(e.launch_count() - l0)
+        if prev is not None:
+            got.append(e.wait_yes_no(prev)[0])
+        prev = t
+    got.append(e.wait_yes_no(prev)[0])
+    for (ids, _), g in zip(order, got):
+        assert np.array_equal(g, want_a if ids is a[0] else want_b)
+    assert len(set(l for (ids, _), l in zip(order, launches) if ids is a[0])) == 1      # a replayed graph counts its kernels
+    e.close()
+
+
 def test_large_ragged_matches_oracle_sample():
     from b200rank.synthetic import NO_ID, YES_ID, synthetic_prompt_ids
     from oracle.t5_oracle import T5Oracle
