@@ -6,7 +6,7 @@
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/.
 #   1. the GPU parity suite                      -> <tag>_pytest_gpu.log, parity_report.json
 #   2. smoke()                                   -> <tag>_smoke.log
-#   3. compute-sanitizer memcheck + racecheck of smoke() (flan-t5-small shape, every kernel family of the yes_no path)
+#   3. (last in the core part, bounded) compute-sanitizer memcheck + racecheck of smoke()
 #   4. bench.py (headline, N=1)                  -> <tag>_bench_n1.json   (never under a profiler)
 #   5. reference arm                             -> <tag>_bench_reference.json
 #   6. ncu launch list of a 2-step bench run     -> <tag>_ncu_launches.csv (per-launch times are cold-cache: compare shares)
@@ -21,11 +21,6 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --for
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.log
 tail -3 $OUT/${TAG}_pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/${TAG}_smoke.log
-for tool in memcheck racecheck; do
-  timeout 600 compute-sanitizer --tool $tool --error-exitcode 3 python __graft_entry__.py smoke > $OUT/${TAG}_sanitizer_${tool}.log 2>&1
-  echo "sanitizer $tool rc=$?" | tee -a $OUT/${TAG}_sanitizer_${tool}.log
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $OUT/${TAG}_sanitizer_${tool}.log | tail -2
-done
 timeout 900 python bench.py --steps 100 --warmup 5 --hf-cuda > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"
 python - <<PY
 import json
@@ -42,6 +37,13 @@ PY
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+# the sanitizer passes come LAST and are bounded to 5 minutes each: they are the slowest and least predictable step, and nothing above
+# may be lost to them when the call's own timeout strikes
+for tool in memcheck racecheck; do
+  timeout 300 compute-sanitizer --tool $tool --error-exitcode 3 python __graft_entry__.py smoke > $OUT/${TAG}_sanitizer_${tool}.log 2>&1
+  echo "sanitizer $tool rc=$?" | tee -a $OUT/${TAG}_sanitizer_${tool}.log
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $OUT/${TAG}_sanitizer_${tool}.log | tail -2
+done
 }
 experimental_part() {
 # 7. stand-alone design probes (experiments/README.md)
