@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call that re-establishes the measured state of the repo on a fresh B200 (first call of a round):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02 core'          (steps 1-6, ~15 GPU-minutes)
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02 experimental'  (steps 7, 6b-6e, ~15 GPU-minutes)
+#   /usr/local/graft/bin/gpurun --timeout -k 15 1500 -- 'bash tests/gpu_first_call.sh r02 core'          (steps 1-6, ~15 GPU-minutes)
+#   /usr/local/graft/bin/gpurun --timeout -k 15 1500 -- 'bash tests/gpu_first_call.sh r02 experimental'  (steps 7, 6b-6e, ~15 GPU-minutes)
 # (no second argument: everything in one call, ~30 GPU-minutes: give gpurun --timeout 2400)
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/.
 #   1. the GPU parity suite                      -> <tag>_pytest_gpu.log, parity_report.json
@@ -18,10 +18,10 @@ OUT=gpurun_out
 mkdir -p $OUT
 core_part() {
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $OUT/${TAG}_gpu.csv 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.log
+timeout -k 15 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.log
 tail -3 $OUT/${TAG}_pytest_gpu.log
-timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/${TAG}_smoke.log
-timeout 900 python bench.py --steps 100 --warmup 5 --hf-cuda > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"
+timeout -k 15 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/${TAG}_smoke.log
+timeout -k 15 900 python bench.py --steps 100 --warmup 5 --hf-cuda > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:
@@ -34,13 +34,13 @@ try:
 except Exception as e:
     print("bench line unreadable:", e)
 PY
-timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
+timeout -k 15 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
+timeout -k 15 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
 # the sanitizer passes come LAST and are bounded to 5 minutes each: they are the slowest and least predictable step, and nothing above
 # may be lost to them when the call's own timeout strikes
 for tool in memcheck racecheck; do
-  timeout 300 compute-sanitizer --tool $tool --error-exitcode 3 python __graft_entry__.py smoke > $OUT/${TAG}_sanitizer_${tool}.log 2>&1
+  timeout -k 15 300 compute-sanitizer --tool $tool --error-exitcode 3 python __graft_entry__.py smoke > $OUT/${TAG}_sanitizer_${tool}.log 2>&1
   echo "sanitizer $tool rc=$?" | tee -a $OUT/${TAG}_sanitizer_${tool}.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $OUT/${TAG}_sanitizer_${tool}.log | tail -2
 done
@@ -48,13 +48,13 @@ done
 experimental_part() {
 # 7. stand-alone design probes (experiments/README.md)
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/epi_probe experiments/epi_probe.cu > $OUT/${TAG}_epi_probe.txt 2>&1 \
-  && timeout 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
+  && timeout -k 15 120 /tmp/epi_probe >> $OUT/${TAG}_epi_probe.txt 2>&1; echo "epi_probe rc=$?"; tail -9 $OUT/${TAG}_epi_probe.txt
 nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o /tmp/tmem_probe experiments/tmem_probe.cu > $OUT/${TAG}_tmem_probe.txt 2>&1 \
-  && timeout 120 /tmp/tmem_probe >> $OUT/${TAG}_tmem_probe.txt 2>&1; echo "tmem_probe rc=$?"; tail -16 $OUT/${TAG}_tmem_probe.txt
+  && timeout -k 15 120 /tmp/tmem_probe >> $OUT/${TAG}_tmem_probe.txt 2>&1; echo "tmem_probe rc=$?"; tail -16 $OUT/${TAG}_tmem_probe.txt
 # 6b. experimental kernel variants (compiled in round 1, not yet run): agreement test + A/B of the headline bench
-B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k variants_agree > $OUT/${TAG}_pytest_experimental.log 2>&1; echo "experimental variants rc=$?"
+B200RANK_TEST_EXPERIMENTAL=1 timeout -k 15 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k variants_agree > $OUT/${TAG}_pytest_experimental.log 2>&1; echo "experimental variants rc=$?"
 tail -3 $OUT/${TAG}_pytest_experimental.log
-B200RANK_EPI_PIPE=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe.json 2> $OUT/${TAG}_bench_n1_epi_pipe.err; echo "bench epi_pipe rc=$?"
+B200RANK_EPI_PIPE=1 timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe.json 2> $OUT/${TAG}_bench_n1_epi_pipe.err; echo "bench epi_pipe rc=$?"
 python - <<PY
 import json
 try:
@@ -63,7 +63,7 @@ try:
 except Exception as e:
     print("epi_pipe bench line unreadable:", e)
 PY
-B200RANK_EPI_PIPE=3 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe3.json 2> $OUT/${TAG}_bench_n1_epi_pipe3.err; echo "bench epi_pipe=3 (fp32 residual + bf16 epilogues pipelined) rc=$?"
+B200RANK_EPI_PIPE=3 timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe3.json 2> $OUT/${TAG}_bench_n1_epi_pipe3.err; echo "bench epi_pipe=3 (fp32 residual + bf16 epilogues pipelined) rc=$?"
 python - <<PY
 import json
 try:
@@ -72,7 +72,7 @@ try:
 except Exception as e:
     print("epi_pipe=3 bench line unreadable:", e)
 PY
-B200RANK_EPI_PIPE=1 B200RANK_EPI_HINT=last timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe_evict_last.json 2> $OUT/${TAG}_bench_n1_epi_pipe_evict_last.err; echo "bench epi_pipe+evict_last rc=$?"
+B200RANK_EPI_PIPE=1 B200RANK_EPI_HINT=last timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_epi_pipe_evict_last.json 2> $OUT/${TAG}_bench_n1_epi_pipe_evict_last.err; echo "bench epi_pipe+evict_last rc=$?"
 python - <<PY
 import json
 try:
@@ -83,9 +83,9 @@ except Exception as e:
     print("epi_pipe+evict_last bench line unreadable:", e)
 PY
 # 6c. two encoder streams (B200RANK_PIPE_DUAL=1, experimental): bit-identity of the pipelined path, then the A/B
-B200RANK_PIPE_DUAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "pipelined_submit or large_yes_no" > $OUT/${TAG}_pytest_pipe_dual.log 2>&1; echo "pipe_dual tests rc=$?"
+B200RANK_PIPE_DUAL=1 timeout -k 15 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "pipelined_submit or large_yes_no" > $OUT/${TAG}_pytest_pipe_dual.log 2>&1; echo "pipe_dual tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_pipe_dual.log
-B200RANK_PIPE_DUAL=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_pipe_dual.json 2> $OUT/${TAG}_bench_n1_pipe_dual.err; echo "bench pipe_dual rc=$?"
+B200RANK_PIPE_DUAL=1 timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_pipe_dual.json 2> $OUT/${TAG}_bench_n1_pipe_dual.err; echo "bench pipe_dual rc=$?"
 python - <<PY
 import json
 try:
@@ -95,9 +95,9 @@ except Exception as e:
     print("pipe_dual bench line unreadable:", e)
 PY
 # 6d. one-pass softmax attention (B200RANK_ATTN=tc4, experimental): kernel against numpy incl. the exact-maximum redo, then the A/B
-B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "onepass" > $OUT/${TAG}_pytest_tc4.log 2>&1; echo "tc4 tests rc=$?"
+B200RANK_TEST_EXPERIMENTAL=1 timeout -k 15 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "onepass" > $OUT/${TAG}_pytest_tc4.log 2>&1; echo "tc4 tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_tc4.log
-B200RANK_ATTN=tc4 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_tc4.json 2> $OUT/${TAG}_bench_n1_tc4.err; echo "bench tc4 rc=$?"
+B200RANK_ATTN=tc4 timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_tc4.json 2> $OUT/${TAG}_bench_n1_tc4.err; echo "bench tc4 rc=$?"
 python - <<PY
 import json
 try:
@@ -108,9 +108,9 @@ except Exception as e:
     print("tc4 bench line unreadable:", e)
 PY
 # 6f. CUDA graph of the pipelined decoder chain (B200RANK_DEC_GRAPH=1, experimental): bit-identity, then the A/B
-B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "decoder_graph" > $OUT/${TAG}_pytest_dec_graph.log 2>&1; echo "dec_graph tests rc=$?"
+B200RANK_TEST_EXPERIMENTAL=1 timeout -k 15 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "decoder_graph" > $OUT/${TAG}_pytest_dec_graph.log 2>&1; echo "dec_graph tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_dec_graph.log
-B200RANK_DEC_GRAPH=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_dec_graph.json 2> $OUT/${TAG}_bench_n1_dec_graph.err; echo "bench dec_graph rc=$?"
+B200RANK_DEC_GRAPH=1 timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_dec_graph.json 2> $OUT/${TAG}_bench_n1_dec_graph.err; echo "bench dec_graph rc=$?"
 python - <<PY
 import json
 try:
@@ -120,7 +120,7 @@ except Exception as e:
     print("dec_graph bench line unreadable:", e)
 PY
 # 6d'. everything together: pipelined epilogues + two encoder streams + one-pass attention (only meaningful if each passed above)
-B200RANK_EPI_PIPE=3 B200RANK_PIPE_DUAL=1 B200RANK_ATTN=tc4 B200RANK_DEC_GRAPH=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_all_experimental.json 2> $OUT/${TAG}_bench_n1_all_experimental.err; echo "bench all experimental rc=$?"
+B200RANK_EPI_PIPE=3 B200RANK_PIPE_DUAL=1 B200RANK_ATTN=tc4 B200RANK_DEC_GRAPH=1 timeout -k 15 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-text-api > $OUT/${TAG}_bench_n1_all_experimental.json 2> $OUT/${TAG}_bench_n1_all_experimental.err; echo "bench all experimental rc=$?"
 python - <<PY
 import json
 try:
@@ -131,7 +131,7 @@ except Exception as e:
     print("all-experimental bench line unreadable:", e)
 PY
 # 6e. d_kv = 128 (monot5-3b / duot5-3b head shape) on the generic-width attention (experimental): every entry point against the oracle
-B200RANK_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "wide_heads" > $OUT/${TAG}_pytest_dkv128.log 2>&1; echo "d_kv 128 tests rc=$?"
+B200RANK_TEST_EXPERIMENTAL=1 timeout -k 15 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "wide_heads" > $OUT/${TAG}_pytest_dkv128.log 2>&1; echo "d_kv 128 tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_dkv128.log
 }
 case "$PART" in
