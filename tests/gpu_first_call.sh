@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call that re-establishes the measured state of the repo on a fresh B200 (first call of a round):
-#   /usr/local/graft/bin/gpurun --timeout -k 15 1500 -- 'bash tests/gpu_first_call.sh r02 core'          (steps 1-6, ~15 GPU-minutes)
-#   /usr/local/graft/bin/gpurun --timeout -k 15 1500 -- 'bash tests/gpu_first_call.sh r02 experimental'  (steps 7, 6b-6e, ~15 GPU-minutes)
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02 core'          (steps 1-6, ~15 GPU-minutes)
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tests/gpu_first_call.sh r02 experimental'  (steps 7, 6b-6e, ~15 GPU-minutes)
 # (no second argument: everything in one call, ~30 GPU-minutes: give gpurun --timeout 2400)
 # Writes everything under gpurun_out/<tag>_*; copy what should be judged into profiles/.
 #   1. the GPU parity suite                      -> <tag>_pytest_gpu.log, parity_report.json

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Weak-scaling run of the headline bench on N GPUs of one box (charged N x box time):
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout -k 15 900 -- 'bash tests/gpu_scaling_call.sh r02 8'
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'bash tests/gpu_scaling_call.sh r02 8'
 # Runs N = 1, 2, 4, ... up to the given count back to back, exactly as the driver launches them, and writes
 # gpurun_out/<tag>_bench_n<N>.json (+ .err). Weights are generated on rank 0 and NCCL-broadcast once; no collective in the loop.
 set -u
