@@ -690,10 +690,21 @@ extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_
         if (!wide_ok)
             return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (kernels are specialised for 64; 128 is experimental: B200RANK_EXPERIMENTAL_DKV128=1)", cfg->d_kv);
     }
-    if (cfg->d_model % 64 || cfg->d_ff % 128 || cfg->d_model > 4096 || cfg->vocab_size % 8)
+    if (cfg->d_model <= 0 || cfg->d_ff <= 0 || cfg->vocab_size <= 0 || cfg->d_model % 64 || cfg->d_ff % 128 || cfg->d_model > 4096 ||
+        cfg->d_ff > (1 << 17) || cfg->vocab_size % 8 || cfg->vocab_size > (1 << 22))
         return set_error(B200RANK_ERR_ARG, "unsupported dims d_model=%d d_ff=%d vocab=%d", cfg->d_model, cfg->d_ff, cfg->vocab_size);
-    if (cfg->num_heads <= 0 || cfg->num_layers <= 0 || cfg->num_decoder_layers <= 0)
+    if (cfg->num_heads <= 0 || cfg->num_heads > 512 || cfg->num_layers <= 0 || cfg->num_layers > 256 || cfg->num_decoder_layers <= 0 ||
+        cfg->num_decoder_layers > 256)
         return set_error(B200RANK_ERR_ARG, "bad layer/head counts");
+    // relative-position buckets: T5's formula needs an even bucket count >= 4 (half the buckets per direction, half of those exact);
+    // distances saturate at max_distance, and the bias tables of the attention kernels cover +-128 (b200rank_load_tensor re-checks)
+    if (cfg->rel_buckets < 4 || cfg->rel_buckets > 1024 || (cfg->rel_buckets & 1) || cfg->rel_max_distance < 2 || cfg->rel_max_distance > kAttnRelClamp)
+        return set_error(B200RANK_ERR_ARG, "unsupported relative attention: %d buckets, max distance %d (even bucket count >= 4, max distance 2..%d)",
+                         cfg->rel_buckets, cfg->rel_max_distance, kAttnRelClamp);
+    if (cfg->max_tokens < 0 || cfg->max_docs < 0 || cfg->max_dec_len < 0 || cfg->max_logit_rows < 0 || !(cfg->layer_norm_eps > 0.f))
+        return set_error(B200RANK_ERR_ARG, "capacities (max_tokens / max_docs / max_dec_len / max_logit_rows) must be >= 0 (0 = default) and layer_norm_eps > 0");
+    if (cfg->pad_id < 0 || cfg->pad_id >= cfg->vocab_size || cfg->eos_id < 0 || cfg->eos_id >= cfg->vocab_size)
+        return set_error(B200RANK_ERR_ARG, "pad_id / eos_id outside the vocabulary");
     int ndev = 0;
     cudaError_t err = cudaGetDeviceCount(&ndev);
     if (err != cudaSuccess || ndev <= 0)

@@ -692,6 +692,21 @@ def test_config_validation_messages():
     bad = br.make_config(128, 2, 256, 2, 2, vocab_size=2304, d_kv=128)
     assert lib.b200rank_create(ctypes.byref(bad), 0, ctypes.byref(h)) == -1
     assert b"d_kv" in lib.b200rank_last_error()
+    # every malformed configuration is refused by argument validation (B200RANK_ERR_ARG = -1) before the device is even looked at
+    ok = dict(d_model=128, num_heads=2, d_ff=256, num_layers=2, num_decoder_layers=2)
+    for bad_kw in (dict(d_model=0), dict(d_model=-64), dict(d_model=100), dict(d_model=8192), dict(d_ff=0), dict(d_ff=7), dict(num_heads=0),
+                   dict(num_layers=0), dict(num_layers=100000), dict(num_decoder_layers=-3), dict(vocab_size=0), dict(vocab_size=-8),
+                   dict(vocab_size=2 ** 31 - 8), dict(d_kv=0), dict(d_kv=32), dict(rel_buckets=0), dict(rel_buckets=33),
+                   dict(rel_max_distance=4096), dict(rel_max_distance=0), dict(max_tokens=-1), dict(max_docs=-1), dict(max_dec_len=-1),
+                   dict(max_logit_rows=-1), dict(layer_norm_eps=0.0), dict(pad_id=-1), dict(eos_id=10 ** 6)):
+        kw = dict(ok, vocab_size=2304)
+        kw.update(bad_kw)
+        cfg = br.make_config(kw.pop("d_model"), kw.pop("num_heads"), kw.pop("d_ff"), kw.pop("num_layers"), kw.pop("num_decoder_layers"), **kw)
+        assert lib.b200rank_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1, bad_kw
+        assert not h.value
+    assert lib.b200rank_create(None, 0, None) == -1
+    assert lib.b200rank_score_yes_no(None, None, None, 0, 0, 0, 0, None, None) == -1 and lib.b200rank_wait_yes_no(None, 0, None, None) == -1
+    lib.b200rank_destroy(None)      # tolerated, like free(NULL)
     assert br.rel_bucket(-200, True) == 15 and br.rel_bucket(200, True) == 31 and br.rel_bucket(-16, False) == 16
 
 
