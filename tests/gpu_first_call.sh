@@ -133,6 +133,13 @@ PY
 # 6e. d_kv = 128 (monot5-3b / duot5-3b head shape) on the generic-width attention (experimental): every entry point against the oracle
 B200RANK_TEST_EXPERIMENTAL=1 timeout -k 15 600 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "wide_heads" > $OUT/${TAG}_pytest_dkv128.log 2>&1; echo "d_kv 128 tests rc=$?"
 tail -3 $OUT/${TAG}_pytest_dkv128.log
+# 8. source-level ncu captures of the attention kernel, shipped (tc2) and one-pass (tc4): one launch each, stall reasons per line
+#    (read here with: ncu -i gpurun_out/<tag>_attn_tc2.ncu-rep --page source --csv; summarise with profiles/ncu_summarize.py)
+for variant in tc2 tc4; do
+  B200RANK_ATTN=$variant timeout -k 15 300 ncu --set full --clock-control none --import-source on -k regex:enc_attention_tc2_kernel -s 30 -c 1 -f \
+      -o $OUT/${TAG}_attn_${variant} python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_attn_${variant}.log 2>&1
+  echo "ncu attention $variant rc=$?"
+done
 }
 case "$PART" in
   core) core_part ;;
