@@ -157,6 +157,14 @@ def rel_bucket(relative_position: int, bidirectional: bool, num_buckets: int = 3
     return load_library().b200rank_rel_bucket(int(relative_position), int(bidirectional), num_buckets, max_distance)
 
 
+def is_ignored_tensor(name: str) -> bool:
+    """Checkpoint keys that carry no weight of their own: the two aliases of `shared.weight`, and the cross-attention relative bias
+    that legacy T5 v1.0 checkpoints (t5-*, the monoT5 / duoT5 `.bin` lineage) still hold although no forward reads it — transformers
+    drops it silently (`_keys_to_ignore_on_load_unexpected`, modeling_t5.py), so a local checkpoint directory must load here too."""
+    return (name in ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight")
+            or name.endswith("EncDecAttention.relative_attention_bias.weight"))
+
+
 class Engine:
     """One Flan-T5 model resident on one GPU. Mirrors what `self.llm` is to the reference rankers."""
 
@@ -191,7 +199,7 @@ class Engine:
         checkpoints) falls back to `shared.weight`, which is what transformers' tie_weights does."""
         seen_lm_head, shared = False, None
         for name, arr in tensors:
-            if name in ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight"):
+            if is_ignored_tensor(name):
                 continue
             if name == "lm_head.weight":
                 seen_lm_head = True

@@ -348,6 +348,7 @@ struct b200rank_engine {
     // pinned host staging
     int* h_ids = nullptr; int* h_cu = nullptr; float* h_out = nullptr; int* h_int = nullptr;
     int* h_small = nullptr; size_t h_small_cap = 0, h_small_off = 0;  // pinned bump buffer for small async uploads
+    bool unsynced = false;   // a synchronous-API call returned with work still enqueued on stream_main (run_yes_no_staged)
     int staged_docs = 0, staged_tokens = 0, staged_maxlen = 0;
     int staged_minlen = 0;   // shortest document of the staged pass (0 = not tracked on this path)
 
@@ -501,7 +502,7 @@ extern "C" const char* b200rank_last_error(void) { return g_last_error.c_str(); 
 extern "C" void b200rank_destroy(b200rank_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaDeviceSynchronize();
     void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
                      e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->xattn_partial, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
                      e->d_int_out, e->d_finished, e->l2_scratch};
@@ -533,7 +534,9 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     for (int i = 0; i < 2; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    // e->stream is an alias that points at stream_main / stream_dec / stream_enc2 in turn: destroy the owning handle
+    cudaStream_t main_stream = e->stream_main ? e->stream_main : e->stream;
+    if (main_stream) cudaStreamDestroy(main_stream);
     delete e;
 }
 
@@ -814,6 +817,12 @@ extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, con
     const int64_t d = e->d, I = e->inner, F = e->F, V = e->V;
     auto ident = [](int64_t r) { return r; };
     if (name == "encoder.embed_tokens.weight" || name == "decoder.embed_tokens.weight") return B200RANK_OK;  // aliases of shared.weight
+    // T5 v1.0 checkpoints (t5-*, the monoT5 / duoT5 .bin lineage) carry a cross-attention relative bias that no forward reads;
+    // transformers drops it silently (_keys_to_ignore_on_load_unexpected, modeling_t5.py), and so does this loader
+    {
+        static const std::string ignored = "EncDecAttention.relative_attention_bias.weight";
+        if (name.size() >= ignored.size() && name.compare(name.size() - ignored.size(), ignored.size(), ignored) == 0) return B200RANK_OK;
+    }
     if (e->loaded.find(name) == e->loaded.end()) return set_error(B200RANK_ERR_ARG, "unexpected tensor name %s", hf_name);
 
     int r = B200RANK_OK;
@@ -900,7 +909,16 @@ extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, con
     e->loaded[name] = true;
     bool all = true;
     for (auto& kv : e->loaded) all = all && kv.second;
-    if (all && !e->weights_ready) RET_IF(derive_weights(e));
+    // W_ov / wkT are functions of the decoder self-attention v / o and the cross-attention k weights: a reload of one of those into a
+    // live engine (checkpoint swap) must refresh them, or the T = 1 path would mix old and new weights
+    const bool feeds_derived = name.rfind("decoder.", 0) == 0 &&
+                               (name.find("SelfAttention.v.") != std::string::npos || name.find("SelfAttention.o.") != std::string::npos ||
+                                name.find("EncDecAttention.k.") != std::string::npos);
+    if (all && (!e->weights_ready || feeds_derived)) {
+        if (e->weights_ready) CU_OK(cudaDeviceSynchronize());   // nothing may still be reading the old derived weights
+        e->weights_ready = false;
+        RET_IF(derive_weights(e));
+    }
     e->weights_ready = all;
     return B200RANK_OK;
 }
@@ -1315,7 +1333,9 @@ static int check_ready(b200rank_engine* e) {
     CU_OK(cudaSetDevice(e->device));
     if (e->slot[0].busy || e->slot[1].busy)
         return set_error(B200RANK_ERR_STATE, "pipelined batches are in flight: call b200rank_wait_yes_no() for every ticket before using the synchronous API");
-    e->h_small_off = 0;
+    // the pinned bump buffer restarts only when nothing enqueued can still read it (b200rank_run_yes_no_staged returns without
+    // synchronising); otherwise it keeps advancing as a ring — upload_ints synchronises when it wraps
+    if (!e->unsynced) e->h_small_off = 0;
     e->stream = e->stream_main;
     e->enc_out_cur = e->enc_out[0];
     e->d_cu_cur = e->d_cu_slot[0];
@@ -1360,6 +1380,7 @@ static int next_group(b200rank_engine* e, const int32_t* lengths, int n_docs, in
 static int upload_ints(b200rank_engine* e, int* dst, const std::vector<int>& v) {
     if (e->h_small_off + v.size() > e->h_small_cap) {
         CU_OK(cudaStreamSynchronize(e->stream));
+        if (e->stream == e->stream_main) e->unsynced = false;
         e->h_small_off = 0;
         if (v.size() > e->h_small_cap) return set_error(B200RANK_ERR_CAPACITY, "upload of %zu ints exceeds staging", v.size());
     }
@@ -1391,6 +1412,7 @@ static int fetch_yes_no(b200rank_engine* e, float* logits2, float* scores) {
     CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * 2 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU_OK(cudaMemcpyAsync(e->h_out + 2 * (size_t)nd, e->small_out2, (size_t)nd * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU_OK(cudaStreamSynchronize(e->stream));
+    if (e->stream == e->stream_main) e->unsynced = false;
     if (logits2) memcpy(logits2, e->h_out, (size_t)nd * 2 * sizeof(float));
     if (scores) memcpy(scores, e->h_out + 2 * (size_t)nd, (size_t)nd * sizeof(float));
     return B200RANK_OK;
@@ -1425,6 +1447,7 @@ extern "C" int b200rank_stage(b200rank_engine* e, const int32_t* ids, const int3
 extern "C" int b200rank_run_yes_no_staged(b200rank_engine* e, int yes_id, int no_id) {
     RET_IF(check_ready(e));
     if (e->staged_docs <= 0) return set_error(B200RANK_ERR_STATE, "nothing staged");
+    e->unsynced = true;
     return yes_no_device(e, yes_id, no_id);
 }
 extern "C" int b200rank_fetch_yes_no(b200rank_engine* e, float* logits2, float* scores) {
@@ -1436,6 +1459,7 @@ extern "C" int b200rank_sync(b200rank_engine* e) {
     if (!e) return set_error(B200RANK_ERR_ARG, "null engine");
     CU_OK(cudaSetDevice(e->device));
     CU_OK(cudaStreamSynchronize(e->stream));
+    if (e->stream == e->stream_main) e->unsynced = false;
     return B200RANK_OK;
 }
 
@@ -1482,6 +1506,20 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
     // the stream / encoder workspace set of this slot: the ordinary ones unless B200RANK_PIPE_DUAL runs slot 1 next to slot 0
     const bool dual = e->pipe_dual && b == 1;
     cudaStream_t s_enc = dual ? e->stream_enc2 : e->stream_main;
+    if (e->unsynced) {   // a b200rank_run_yes_no_staged pass may still read the pinned bump buffer this call is about to rewrite
+        CU_OK(cudaStreamSynchronize(e->stream_main));
+        e->unsynced = false;
+    }
+    // Whatever way this function is left, the engine's "current" stream / slot pointers go back to the synchronous defaults; and if it
+    // is left on an error after work was enqueued, that work is drained first — the slot is not marked busy then, so the next submit
+    // would otherwise repack this slot's pinned staging under a copy that is still in flight.
+    struct SubmitGuard {
+        b200rank_engine* e; cudaStream_t s_enc; bool ok = false;
+        ~SubmitGuard() {
+            if (!ok) { cudaStreamSynchronize(s_enc); cudaStreamSynchronize(e->stream_dec); }
+            e->stream = e->stream_main; e->enc_out_cur = e->enc_out[0]; e->d_cu_cur = e->d_cu_slot[0]; e->gemm_sm_cap = 0;
+        }
+    } submit_guard{e, s_enc};
     struct WsGuard {   // encoder members point at the slot's set while its pass is enqueued (kernel arguments are captured at launch)
         b200rank_engine* e; bool on;
         WsGuard(b200rank_engine* e_, bool on_) : e(e_), on(on_) { if (on) use(1); }
@@ -1577,10 +1615,8 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
             if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "event record: %s", cudaGetErrorString(er));
         }
     }
-    e->stream = e->stream_main;
-    e->enc_out_cur = e->enc_out[0];
-    e->d_cu_cur = e->d_cu_slot[0];
-    if (rc != B200RANK_OK) return rc;
+    if (rc != B200RANK_OK) return rc;   // SubmitGuard drains what was enqueued and restores the synchronous defaults
+    submit_guard.ok = true;
     e->slot[b].busy = true;
     e->slot[b].ticket = e->next_ticket;
     *ticket = e->next_ticket++;

@@ -95,3 +95,39 @@ def test_missing_shard_and_empty_directory_fail_loudly(tmp_path):
         json.dump(hf, f)
     with pytest.raises(NotImplementedError, match="d_kv"):
         _load_checkpoint(str(tmp_path))
+
+
+def test_legacy_v10_bin_with_cross_attention_bias_key_loads(tmp_path):
+    """Legacy T5 v1.0 `.bin` checkpoints (t5-*, monoT5 / duoT5) carry `decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight`;
+    transformers ignores it (`_keys_to_ignore_on_load_unexpected`). Engine.load_state_dict must skip it instead of refusing the checkpoint."""
+    import torch
+    import b200rank as br
+    cfg, w = v10_model_and_weights("tiny")
+    model = _hf_model(cfg, w)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    legacy = "decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight"
+    sd[legacy] = torch.zeros(32, cfg["num_heads"])
+    model.config.save_pretrained(str(tmp_path))
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    from llmrankers._backend import _load_checkpoint
+    _, tensors = _load_checkpoint(str(tmp_path))
+    names = [n for n, _ in tensors]
+    assert legacy in names                       # the file reader passes everything through ...
+    assert br.is_ignored_tensor(legacy)          # ... and the engine loader drops what HF drops
+    assert br.is_ignored_tensor("encoder.embed_tokens.weight") and not br.is_ignored_tensor("decoder.block.0.layer.1.EncDecAttention.k.weight")
+
+    class _Recorder(br.Engine):                  # load_state_dict without a device: record what would be uploaded
+        def __init__(self):
+            self.seen = []
+        def load_tensor(self, name, arr):
+            self.seen.append(name)
+        def missing_tensors(self):
+            return []
+        def close(self):
+            pass
+        def __del__(self):
+            pass
+    rec = _Recorder()
+    rec.load_state_dict((n, np.zeros(1, np.float32)) for n in names)
+    assert legacy not in rec.seen and "shared.weight" in rec.seen
+    assert rec.seen.count("lm_head.weight") == 1   # tied checkpoint: lm_head falls back to shared
