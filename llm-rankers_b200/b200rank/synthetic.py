@@ -125,3 +125,22 @@ def synthetic_prompt_ids(n_docs: int, q_len: int = 32, p_len: int = 128, seed: i
         ids[i, : len(r)] = r
         lengths[i] = len(r)
     return ids, lengths
+
+
+def headline_query():
+    """The HEADLINE query of bench.py and of the full-size parity test: 100 documents of the BASELINE configs[1] shape (S = 184)
+    selected from a pool of random passages so that the fp32 reference's top-11 margins are further apart than bf16 arithmetic can
+    move them (tests/golden/make_headline_query.py — the selection reads the fp32 reference only). Returns
+    (ids [100,184] int32, lengths [100] int32, ref_logits [100,2] fp32 — the reference's own (yes, no) logits, meta dict).
+    Falls back to (synthetic_prompt_ids(seed 929), None, None) when the committed fixture is absent."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    p = os.path.join(root, "tests", "golden", "headline_query.npz")
+    if not os.path.exists(p):
+        ids, lengths = synthetic_prompt_ids(100, 32, 128, seed=929)
+        return ids, lengths, None, None
+    z = np.load(p)
+    with open(os.path.join(root, "tests", "golden", "headline_query_meta.json")) as f:
+        meta = json.load(f)
+    return z["ids"].astype(np.int32), z["lengths"].astype(np.int32), z["ref_logits"].astype(np.float32), meta

@@ -21,6 +21,7 @@
 #include "../../include/b200rank.h"
 #include "attention_enc.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc5.cuh"
 #include "attention_dec.cuh"
 #include "attention_wide.cuh"
 #include "skinny_gemv.cuh"
@@ -993,7 +994,7 @@ static int attn_default_mode() {
         // default: the persistent tcgen05 kernel for documents of <= 192 tokens (launch_enc_attention falls back to the mma.sync tiles
         // above that): 1.93 vs 2.32 ms per 100 documents at S=184, +3.7 % docs/s with two queries in flight
         // (profiles/r01_bench_attn_ab.txt). The first, unpipelined tcgen05 kernel ("tc") was 1.7x slower than the tiles.
-        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc3") ? 6 : (!strcmp(s, "tc4") ? 7 : 1))))));
+        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc3") ? 6 : (!strcmp(s, "tc4") ? 7 : (!strcmp(s, "tc5") ? 8 : 1)))))));
     }
     return mode;
 }
@@ -1015,13 +1016,32 @@ static int device_sm_count() {   // of the current device (test entry points wit
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
                                 int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0) {
     if (mode == 0) mode = attn_default_mode();
-    const bool persistent = (mode == 5 || mode == 6 || mode == 7);
+    const bool persistent = (mode == 5 || mode == 6 || mode == 7 || mode == 8);
     if (maxlen > 256 && !persistent) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
     // Mixed batch under the default mode: documents of <= 192 tokens still get the tcgen05 kernel (it walks only those), the longer
     // ones the mma.sync tiles (which skip the short ones) — the kernel is chosen per document, so a document's result does not
     // depend on what it is batched with.
     const bool mixed = persistent && maxlen > 192;
     if (persistent && minlen > 192) mode = 1;   // known: no document qualifies for the tcgen05 kernel
+    if (mode == 8) {
+        // persistent tcgen05 kernel, 16 softmax warps / one-pass softmax (attention_tc5.cuh)
+        CUtensorMap local;
+        const CUtensorMap* tm = &local;
+        if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
+        else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
+        static SmemOptIn opt_in_tc5;
+        CU_OK(opt_in_tc5.raise(enc_attention_tc5_kernel<3>, 227 * 1024));
+        const int n_items = nd * H;
+        if (e) prof_begin(e, "enc_attention_tc5");
+        const int sm_count = e ? e->num_sms : device_sm_count();
+        CU_OK(launch_k(enc_attention_tc5_kernel<3>, dim3(std::min(n_items, sm_count)), dim3(kAttn5Threads), AttnTc5Cfg<3>::smem_bytes(H), st, *tm, qkv, ld,
+                       inner, d_cu, bias, out, ldo, H, n_items, 192));
+        if (e) RET_IF(post_launch(e, "enc_attention_tc5"));
+        if (!mixed) return B200RANK_OK;
+        if (e) prof_begin(e, "enc_attention");
+        launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo, 192);
+        return e ? post_launch(e, "enc_attention") : B200RANK_OK;
+    }
     if (mode == 5 || mode == 6 || mode == 7) {
         // persistent tcgen05 kernel: one CTA per SM walks the (document, head) items
         CUtensorMap local;

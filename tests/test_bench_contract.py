@@ -137,7 +137,7 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
     def broken_text_api(*a, **k):
         raise RuntimeError("text leg down")
     monkeypatch.setattr(bench, "text_api_docs_per_s", broken_text_api)
-    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=False, no_pipeline=False, hf_cuda=False)
+    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=False, no_pipeline=False, hf_cuda=False, no_hf_cuda=True, no_sustained=False)
     assert bench.run_engine(args) == 0
     line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(line) == 1
@@ -156,4 +156,7 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     p = d["parity"]
     assert p["docs"] >= 2 and p["within_logit_tolerance"] is True and p["max_abs_logit_diff"] < 0.06 and 0.9 < p["kendall_tau"] <= 1.0
-    assert p["order_identical_where_ref_gap_exceeds_tolerance"] is True and "max_abs_logit_diff" in p["reference_bf16_yardstick"]
+    assert p["inversions_beyond_tolerance"] == 0 and "max_abs_logit_diff" in p["reference_bf16_yardstick"]
+    sus = d["sustained"]
+    assert sus["steps"] >= 3 and sus["value"] > 0 and 0 < sus["step_frac"] and "peak_source" in sus and "clocks" in sus
+    assert r["peak_source"].startswith(("MEASURED_PEAKS.json bf16_tflops (", "fallback burst")) and "frac_of_sustained" in r and "step_peak_source" in r

@@ -37,7 +37,8 @@ def oracle_answers():
 def check_against_oracle(text):
     lg, sc = parse(text)
     ref_lg, ref_sc = oracle_answers()
-    assert np.all(np.abs(lg - ref_lg) <= 0.06 + 0.03 * np.abs(ref_lg)), (lg, ref_lg)
+    from b200rank.tolerance import logit_tolerance
+    assert np.all(np.abs(lg - ref_lg) <= logit_tolerance(ref_lg, 0)), (lg, ref_lg)
     assert np.abs(sc - ref_sc).max() < 0.01
 
 

@@ -203,3 +203,26 @@ def test_oracle_wide_heads_match_live_transformers(shape):
                              max_new_tokens=2, do_sample=False).numpy()
     mine = orc.greedy(ids, mask, [0, 17], 2)
     assert np.array_equal(mine, gen[:, 2:4])
+
+
+def test_headline_query_fixture_reproduces_from_the_reference_arithmetic():
+    """tests/golden/headline_query.npz (the query bench.py times and the full-size GPU parity test checks all 100 documents of) holds the
+    reference's fp32 logits computed in the build container. Re-derive three of its documents — the reference's rank 1, rank 10 and its
+    last — with the transformers fp32 CPU path at full model size, and check the selection property the ordering claim rests on."""
+    from b200rank.synthetic import NO_ID, YES_ID, headline_query, model_cfg, synthetic_weights
+    from b200rank.tolerance import logit_tolerance
+    from oracle import hf_cpu
+    ids, lengths, ref, meta = headline_query()
+    assert ref is not None and ids.shape == (100, 184) and (lengths == 184).all()
+    m = ref[:, 0].astype(np.float64) - ref[:, 1]
+    order = np.argsort(-m, kind="stable")
+    assert [int(x) for x in order] == meta["order"]
+    tol = logit_tolerance(ref, 48).max(1)
+    top = order[:11]
+    assert all(m[a] - m[b] >= 2 * max(tol[a], tol[b]) - 1e-6 for a, b in zip(top[:-1], top[1:])), "top-11 reference margins must be >= 2 x tolerance apart"
+    assert all(m[top[-1]] - m[i] >= 2 * max(tol[top[-1]], tol[i]) - 1e-6 for i in order[11:])
+    cfg = model_cfg("flan-t5-large")
+    model = hf_cpu.build_model(cfg, synthetic_weights(cfg, meta["weights_seed"]))
+    pick = [int(order[0]), int(order[9]), int(order[-1])]
+    lg, _ = hf_cpu.score_yes_no(model, ids[pick].astype(np.int64), np.ones((3, 184), np.int64), YES_ID, NO_ID, 32)
+    np.testing.assert_allclose(lg, ref[pick], atol=2e-4)
