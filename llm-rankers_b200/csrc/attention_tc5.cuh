@@ -41,7 +41,7 @@ struct AttnTc5Cfg {
     static constexpr int kPBytes = NKB * 128 * 128;
     static constexpr int kWideBias = 512;                 // 511 used: index (j - i) + 255
     static constexpr int kRedBytes = 2 * 2 * 2 * 128 * 4; // partial row sums [use parity][tile slot][column half][lane]
-    static constexpr int kFixedBytes = 3 * kQKVBytes + 2 * kPBytes + 16 * 8 + 16 + kRedBytes + 1024;
+    static constexpr int kFixedBytes = 3 * kQKVBytes + 2 * kPBytes + 12 * 8 + 4 * 16 + 16 + kRedBytes + 1024;
     static constexpr int kMaxResidentHeads = (227 * 1024 - kFixedBytes) / (kWideBias * 4);
     static constexpr int smem_bytes(int H) { return kFixedBytes + (H <= kMaxResidentHeads ? (H < 2 ? 2 : H) : 2) * kWideBias * 4; }
     static constexpr int kSCol = 64 * NKB;
@@ -95,10 +95,12 @@ __device__ __noinline__ void attn_slow_row(const __nv_bfloat16* __restrict__ qkv
     }
 }
 
+// bias_wide: [H][512] fp32, bias_wide[h][w] = log2(e) * bias_h(clamp(w - 255, +-128)) (built once at weight-load time: the per-launch
+// prologue is a plain 16 B-vector copy into shared memory instead of 8 k dependent global loads).
 template <int NKB>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kAttn5Threads, 1)
 enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfloat16* __restrict__ qkv, int ld, int inner,
-                         const int* __restrict__ cu, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H,
+                         const int* __restrict__ cu, const float* __restrict__ bias_wide, __nv_bfloat16* __restrict__ out, int ldo, int H,
                          int n_items, int len_limit) {
     using Cfg = AttnTc5Cfg<NKB>;
     pdl_trigger();
@@ -109,15 +111,15 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
     uint8_t* sV = sK + Cfg::kQKVBytes;
     uint8_t* sP = sV + Cfg::kQKVBytes;                      // [2][kPBytes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
-    uint64_t* bar_qk = bars + 0;
+    uint64_t* bar_qk = bars + 0;   // Q/K of item k landed (or: the end-of-work descriptor was published)
     uint64_t* bar_v = bars + 1;
     uint64_t* qk_free = bars + 2;  // both MMA-1s of the item retired: Q/K smem reusable
     uint64_t* v_free = bars + 3;   // MMA-2s of the item retired: V smem reusable
     uint64_t* bar_s = bars + 4;    // [2] S_t ready in TMEM
-    uint64_t* bar_p = bars + 6;    // [2] P_t written to smem, S_t drained (256 arrivals)
+    uint64_t* bar_p = bars + 6;    // [2] P_t written to smem, S_t and O_t drained (256 arrivals)
     uint64_t* bar_o = bars + 8;    // [2] O_t ready in TMEM
-    uint64_t* o_free = bars + 10;  // [2] O_t drained by the epilogue (256 arrivals)
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
+    int4* sDesc = reinterpret_cast<int4*>(bars + 12);               // [4] item ring: {first token, length, head, valid}
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(sDesc + 4);
     float* sL = reinterpret_cast<float*>(tmem_base_smem + 4);       // [2 parities][2 slots][2 halves][128 lanes]
     float* sBiasW = sL + Cfg::kRedBytes / 4;                        // [H or 2][kWideBias]
     const bool bias_resident = H <= Cfg::kMaxResidentHeads;
@@ -134,45 +136,36 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
             mbar_init(&bar_s[t], 1);
             mbar_init(&bar_p[t], 256);
             mbar_init(&bar_o[t], 1);
-            mbar_init(&o_free[t], 256);
         }
         fence_barrier_init();
     }
     if (bias_resident) {
         // the bias table is a weight (written once at load time, not by the preceding kernel): it may be read before pdl_wait
-        for (int i = threadIdx.x; i < H * Cfg::kWideBias; i += kAttn5Threads) {
-            const int h = i / Cfg::kWideBias, w = i - h * Cfg::kWideBias;
-            const int rel = max(-kAttnRelClamp, min(kAttnRelClamp, w - 255));
-            sBiasW[i] = bias[h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
-        }
+        const float4* src = reinterpret_cast<const float4*>(bias_wide);
+        float4* dst = reinterpret_cast<float4*>(sBiasW);
+        for (int i = threadIdx.x; i < H * (Cfg::kWideBias / 4); i += kAttn5Threads) dst[i] = __ldg(src + i);
     }
     pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
-    const int stride = gridDim.x;
-    // documents longer than len_limit belong to the mma.sync tile kernel launched next to this one (see enc_attention_tc2_kernel)
-    auto qualify = [&](int it) {
-        while (it < n_items) {
-            const int dd = it / H;
-            if (cu[dd + 1] - cu[dd] <= len_limit) break;
-            it += stride;
-        }
-        return it;
-    };
 
+    // Every barrier above completes exactly once per item k (parity k & 1), for every item and for both tile slots: a document of at
+    // most 128 tokens simply gets no MMAs on slot 1. The TMA thread is the only role that walks cu[]: it publishes {tok0, len, head}
+    // of item k in sDesc[k & 3] before arming bar_qk(k); the MMA thread reads it after bar_qk(k), the softmax warps after bar_s(k).
+    // After the last item it publishes an invalid descriptor, which flows down the same barriers and ends the other roles.
     if (warp_idx == 0) {
         if (lane == 0) {
-            int item = qualify(blockIdx.x);
-            int doc = item < n_items ? item / H : 0;
-            int tok0 = cu[doc], tok1 = cu[doc + 1];
-            for (int k = 0; item < n_items; ++k) {
-                const int h = item - doc * H;
-                const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
-                const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];        // next item's extent: in flight during this one
-                const int nkb_used = (tok1 - tok0 + 63) >> 6;
+            const int stride = gridDim.x;
+            int k = 0;
+            for (int item = blockIdx.x; item < n_items; item += stride) {
+                const int doc = item / H, h = item - doc * H;
+                const int tok0 = cu[doc], len = cu[doc + 1] - tok0;
+                if (len > len_limit) continue;   // longer documents belong to the mma.sync tile kernel launched next to this one
+                const int nkb_used = (len + 63) >> 6;
                 if (k > 0) mbar_wait(qk_free, (k - 1) & 1);
+                sDesc[k & 3] = make_int4(tok0, len, h, 1);
                 mbar_arrive_expect_tx(bar_qk, 2 * nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b) {
                     tma_load_2d(sQ + b * 8192, &tmap_qkv, bar_qk, h * 64, tok0 + b * 64, kEvictFirst);
@@ -182,48 +175,48 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                 mbar_arrive_expect_tx(bar_v, nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b)
                     tma_load_2d(sV + b * 8192, &tmap_qkv, bar_v, 2 * inner + h * 64, tok0 + b * 64, kEvictFirst);
-                item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
+                ++k;
             }
+            if (k > 0) mbar_wait(qk_free, (k - 1) & 1);
+            sDesc[k & 3] = make_int4(0, 0, 0, 0);
+            mbar_arrive(bar_qk);
         }
     } else if (warp_idx == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(128, 64 * NKB);
             constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
-            uint32_t use0 = 0, use1 = 0;     // completed uses of tile slots 0 / 1
-            int nt_prev = 0, nkb_prev = 0;
-            int item = qualify(blockIdx.x);
-            int len = 0;
-            if (item < n_items) { const int doc = item / H; len = cu[doc + 1] - cu[doc]; }
-            // iteration k issues, per tile slot, MMA-2 of item k-1 and then MMA-1 of item k; one extra iteration drains the last item
-            for (int k = 0; item < n_items || nt_prev > 0; ++k) {
-                const bool have = item < n_items;
-                const int nitem = qualify(item + stride);
-                int nlen = 0;
-                if (have && nitem < n_items) { const int ndoc = nitem / H; nlen = cu[ndoc + 1] - cu[ndoc]; }
-                const int nt_cur = have ? (len + 127) >> 7 : 0, nkb_cur = (len + 63) >> 6;
-                if (have) { mbar_wait(bar_qk, k & 1); tc_fence_after(); }
+            int len_prev = 0;
+            for (int k = 0;; ++k) {
+                mbar_wait(bar_qk, k & 1);
+                tc_fence_after();
+                const int4 dsc = sDesc[k & 3];
+                const bool have = dsc.w != 0;
+                const int len = dsc.y;
+                const int nt = have ? (len + 127) >> 7 : 0;
+                const int nt_prev = (len_prev + 127) >> 7, nkb_prev = (len_prev + 63) >> 6;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    uint32_t& use = t == 0 ? use0 : use1;
-                    if (t < nt_prev) {
+                    if (k > 0) {
+                        // MMA-2 of item k-1: O_t = P_t . V. bar_p also says that the slot's threads are done with O_t of item k-2
+                        // (their deferred epilogue precedes their pass in program order) and with S_t of item k-1.
                         if (t == 0) mbar_wait(bar_v, (k - 1) & 1);
-                        mbar_wait(&bar_p[t], use & 1);
-                        if (use > 0) mbar_wait(&o_free[t], (use - 1) & 1);
+                        mbar_wait(&bar_p[t], (k - 1) & 1);
                         tc_fence_after();
-                        for (int kb = 0; kb < nkb_prev; ++kb) {
-                            const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP + t * Cfg::kPBytes + kb * 16384));
-                            // V block: rows = keys (the MMA K dimension), 128 B of head dims contiguous = MN-major B operand;
-                            // 16 keys per MMA = 2048 B -> +128 in (addr >> 4)
-                            const uint64_t db = make_sw128_kmajor_desc(smem_u32(sV + kb * 8192));
+                        if (t < nt_prev) {
+                            for (int kb = 0; kb < nkb_prev; ++kb) {
+                                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP + t * Cfg::kPBytes + kb * 16384));
+                                // V block: rows = keys (the MMA K dimension), 128 B of head dims contiguous = MN-major B operand;
+                                // 16 keys per MMA = 2048 B -> +128 in (addr >> 4)
+                                const uint64_t db = make_sw128_kmajor_desc(smem_u32(sV + kb * 8192));
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16(tmem_base + Cfg::kOCol0 + t * 64, da + 2 * kk, db + 128 * kk, idesc_o, (kb | kk) != 0);
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_bf16(tmem_base + Cfg::kOCol0 + t * 64, da + 2 * kk, db + 128 * kk, idesc_o, (kb | kk) != 0);
+                            }
                         }
                         umma_commit(&bar_o[t]);
-                        ++use;
-                        if (t == nt_prev - 1) umma_commit(v_free);
+                        if (t == 1) umma_commit(v_free);
                     }
-                    if (t < nt_cur) {
+                    if (t < nt) {
                         // tile slot 1 of an odd item: the A tile starts 64 query rows earlier, so that rows 128..191 of the document land on
                         // TMEM lanes 64..127 (the 64 rows below them repeat rows 64..127 and are ignored)
                         const int row0 = t * 128 - ((t == 1 && (k & 1)) ? 64 : 0);
@@ -232,166 +225,145 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             umma_bf16(tmem_base + t * Cfg::kSCol, da + 2 * kk, db + 2 * kk, idesc_s, kk != 0);
-                        umma_commit(&bar_s[t]);
-                        if (t == nt_cur - 1) umma_commit(qk_free);
                     }
+                    umma_commit(&bar_s[t]);
+                    if (t == 1 && have) umma_commit(qk_free);
                 }
-                nt_prev = nt_cur; nkb_prev = nkb_cur;
-                item = nitem; len = nlen;
+                if (!have) break;
+                len_prev = len;
             }
         }
     } else {
-        const int sw = warp_idx - 2;                  // 0..15
-        const int quarter = warp_idx & 3;             // TMEM lane quarter this warp may access
-        const int t = (sw >> 2) & 1;                  // tile slot
-        const int g = sw >> 3;                        // column half: score columns [g*kHalf, (g+1)*kHalf), output dims [32 g, 32 g + 32)
-        const int grp_tid = (((sw & 3) | (g << 2)) << 5) | lane;   // 0..255 within the eight warps of this tile slot
-        const int lane_row = quarter * 32 + lane;     // TMEM lane = row of the 128-row MMA tile
-        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol;
-        const uint32_t taddr_o = tmem_base + lane_off + Cfg::kOCol0 + t * 64 + g * 32;
-        uint8_t* prow = sP + t * Cfg::kPBytes + lane_row * 128;
-        uint32_t use = 0;
-        int h_loaded = -1;
-        int item = qualify(blockIdx.x);
-        int doc = item < n_items ? item / H : 0;
-        int tok0 = cu[doc], tok1 = cu[doc + 1];
-        // ---- deferred epilogue of the previous use of this tile slot: O_t / l -> bf16 -> global
-        bool pend = false, p_rows = false, p_row_ok = false;
-        int p_tok0 = 0, p_len = 0, p_h = 0, p_qi = 0;
-        uint32_t p_par = 0;
-        const float* p_sBq = nullptr;
-        auto epilogue = [&]() {
-            mbar_wait(&bar_o[t], p_par);
-            tc_fence_after();
-            if (p_rows) {
-                uint32_t o[32];
-                tmem_ld32(taddr_o, o);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&o_free[t]);
-                const float* lb = sL + ((p_par * 2 + t) * 2) * 128;
-                const float l = lb[lane_row] + lb[128 + lane_row];
-                if (p_row_ok) {
-                    if (l >= 7.888609e-31f && l < 1.2676506e30f) {     // [2^-100, 2^100): also false for inf / NaN
-                        const float inv = 1.f / l;
-                        uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p_tok0 + p_qi) * ldo + p_h * 64 + g * 32);
+        // Everything this role keeps across the item loop is a handful of 32-bit shared-space addresses: values derived from the
+        // thread index are cheap to recompute, a spilled one costs an L2 round trip here (210 KB of the SM's 228 KB are shared
+        // memory, so local memory does not stay in L1) — profiles/r02_attn_profile.txt.
+        // The thread's coordinates are re-derived from %tid.x (read through a volatile asm, so the compiler cannot hoist them out of
+        // the loop and then spill them) at the two places that use them.
+        auto tid_now = []() { uint32_t v; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(v)); return static_cast<int>(v); };
+        const uint32_t smem_s = smem_u32(smem);      // everything below is an offset from this one shared-space address
+        constexpr uint32_t kPOff = 3 * Cfg::kQKVBytes, kBarOff = kPOff + 2 * Cfg::kPBytes, kDescOff = kBarOff + 12 * 8,
+                           kLOff = kDescOff + 4 * 16 + 16, kBiasOff = kLOff + Cfg::kRedBytes;
+        constexpr int c0_of_g = Cfg::kHalf;
+        int4 prev = make_int4(0, 0, 0, 0);            // descriptor of the item whose epilogue is pending
+        for (int k = 0;; ++k) {
+            const int wi = tid_now() >> 5, ln = tid_now() & 31;
+            const int sw = wi - 2;                        // 0..15
+            const int quarter = wi & 3;                   // TMEM lane quarter this warp may access
+            const int t = (sw >> 2) & 1;                  // tile slot
+            const int g = sw >> 3;                        // column half: score columns [g*kHalf, (g+1)*kHalf), output dims [32 g, 32 g + 32)
+            const int lane_row = quarter * 32 + ln;       // TMEM lane = row of the 128-row MMA tile
+            const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+            const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol + g * Cfg::kHalf;
+            const uint32_t taddr_o = tmem_base + lane_off + Cfg::kOCol0 + t * 64 + g * 32;
+            const uint32_t prow_s = smem_s + kPOff + t * Cfg::kPBytes + lane_row * 128;     // this row of the P tile, k-block 0
+            const uint32_t sL_s = smem_s + kLOff + (t * 256 + lane_row) * 4;                // partial sums of this row: halves at +0 / +512 B, parity at +2048 B
+            const uint32_t sDesc_s = smem_s + kDescOff;
+            const uint32_t sBias_s = smem_s + kBiasOff;
+            const uint32_t swz = static_cast<uint32_t>(lane_row & 7);
+            // ---- deferred epilogue of item k-1 on this slot: O_t / l -> bf16 -> global. It comes BEFORE the wait on S_t(k): MMA-2(k-1, t)
+            // was issued ahead of MMA-1(k, t), and passing bar_o licenses the writes into P_t below.
+            if (prev.w) {
+                const int kp = k - 1;
+                mbar_wait(&bar_o[t], kp & 1);
+                tc_fence_after();
+                const int shift = (t == 1 && (kp & 1)) ? 64 : 0;
+                const int qi = t * 128 + lane_row - shift;
+                const int len = prev.y;
+                if (quarter * 32 >= shift && (t * 128 + quarter * 32 - shift) < len) {     // warp-uniform: this warp owns real query rows
+                    uint32_t o[32];
+                    tmem_ld32(taddr_o, o);
+                    const uint32_t la = sL_s + (kp & 1) * 2048;
+                    const float l = ld_shared_f32(la) + ld_shared_f32(la + 512);
+                    tmem_ld_wait();
+                    if (qi < len) {
+                        if (l >= 7.888609e-31f && l < 1.2676506e30f) {     // [2^-100, 2^100): also false for inf / NaN
+                            const float inv = 1.f / l;
+                            uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(prev.x + qi) * ldo + prev.z * 64 + g * 32);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 v;
-                            v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-                            v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-                            v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-                            v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-                            dst[i] = v;
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 v;
+                                v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                                v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                                v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                                v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                                dst[i] = v;
+                            }
+                        } else {
+                            const float* sBq = sBiasW + (bias_resident ? prev.z : t) * Cfg::kWideBias + (255 - qi);
+                            attn_slow_row(qkv, ld, inner, prev.x, len, qi, prev.z, g, sBq, out, ldo);
                         }
-                    } else {
-                        attn_slow_row(qkv, ld, inner, p_tok0, p_len, p_qi, p_h, g, p_sBq, out, ldo);
                     }
                 }
-            } else {
-                mbar_arrive(&o_free[t]);
             }
-        };
-        for (int k = 0; item < n_items; ++k) {
-            const int h = item - doc * H;
-            const int len = tok1 - tok0, my_tok0 = tok0;
-            const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
-            const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
-            item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
-            if (t >= ((len + 127) >> 7)) continue;
-            const int ncols = ((len + 63) >> 6) * 64;
+            mbar_wait(&bar_s[t], k & 1);
+            tc_fence_after();
+            const int4 dsc = ld_shared_v4_s32(sDesc_s + (k & 3) * 16);
+            if (!dsc.w) break;
+            const int len = dsc.y, h = dsc.z;
             const int shift = (t == 1 && (k & 1)) ? 64 : 0;       // see the MMA issuer
             const int qi = t * 128 + lane_row - shift;            // query row of this thread (0..255 whatever the lane)
-            const bool row_ok = lane_row >= shift && qi < len;
             const bool rows = quarter * 32 >= shift && (t * 128 + quarter * 32 - shift) < len;   // warp-uniform: some real query row
-            float* sB = sBiasW + (bias_resident ? h : t) * Cfg::kWideBias;
-            if (!bias_resident && h != h_loaded) {
-                // the previous window may still be needed by a pending slow-row epilogue of this group: run the epilogues first
-                if (pend) { epilogue(); pend = false; }
-                named_bar_sync(1 + t, 256);               // every warp of the slot's group is past its reads of the old window
-                for (int i = grp_tid; i < 511; i += 256) {
-                    const int rel = max(-kAttnRelClamp, min(kAttnRelClamp, i - 255));
-                    sB[i] = bias[h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
-                }
+            if (!bias_resident && (!prev.w || h != prev.z)) {     // the slot's window holds the previous item's head
+                named_bar_sync(1 + t, 256);               // every warp of the slot is past its reads of the old window (incl. slow rows)
+                const int grp_tid = (((sw & 3) | (g << 2)) << 5) | ln;
+                for (int i = grp_tid; i < Cfg::kWideBias; i += 256) sBiasW[t * Cfg::kWideBias + i] = __ldg(bias_wide + h * Cfg::kWideBias + i);
                 named_bar_sync(1 + t, 256);
-                h_loaded = h;
             }
-            const uint32_t sBrow = smem_u32(sB) + (255 - qi) * 4;   // [sBrow + 4 j] = log2(e) * bias(j - qi)
-            // the epilogue of the previous use comes BEFORE the wait on S_t: MMA-2(k-1, t) was issued ahead of MMA-1(k, t), so O_t is the
-            // older result; draining it overlaps MMA-1 and licenses the writes into P_t below
-            if (pend) { epilogue(); pend = false; }
-            mbar_wait(&bar_s[t], use & 1);
-            tc_fence_after();
-            float l = 0.f;
             if (rows) {
-                const int c0 = g * Cfg::kHalf;
-                const int c_hi = min(ncols, c0 + Cfg::kHalf);               // columns this thread must fill in the P tile
-                const int nch = len > c0 ? (min(len, c0 + Cfg::kHalf) - c0 + 15) >> 4 : 0;   // 16-column chunks that hold real keys
-                float l4[4] = {0.f, 0.f, 0.f, 0.f};
-                // 16 keys = 32 B = two 16 B chunks of the 128B-swizzled K-major P tile (k-block c / 64)
-                auto store_p = [&](const uint32_t (&packed)[8], int c) {
-                    uint8_t* kblk = prow + (c >> 6) * 16384;
-                    const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        st_shared_v4(kblk + (((chunk0 + i) ^ (lane_row & 7)) << 4), packed[4 * i], packed[4 * i + 1], packed[4 * i + 2],
-                                     packed[4 * i + 3]);
+                const int c0 = g * c0_of_g;
+                // [sBrow + 4 c] = log2(e) * bias(c0 + c - qi)
+                const uint32_t sBrow = sBias_s + ((bias_resident ? h : t) * Cfg::kWideBias + 255 - qi + c0) * 4;
+                const int n_real = min(len - c0, Cfg::kHalf);                   // my columns that hold real keys (may be <= 0)
+                const int n_fill = min(((len + 63) & ~63) - c0, Cfg::kHalf);    // my columns of the P tile the MMA will read
+                float l0 = 0.f, l1 = 0.f;
+                // 16 keys = 32 B = two 16 B chunks of the 128B-swizzled K-major P tile (k-block (c0 + c) / 64)
+                auto store_p = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7, int c) {
+                    const int cc = c0 + c;
+                    const uint32_t kblk = prow_s + (cc >> 6) * 16384;
+                    const uint32_t chunk0 = static_cast<uint32_t>(cc & 63) >> 3;     // even: chunk0 ^ swz and (chunk0 + 1) ^ swz differ in bit 0 only
+                    st_shared_v4_addr(kblk + ((chunk0 ^ swz) << 4), a0, a1, a2, a3);
+                    st_shared_v4_addr(kblk + (((chunk0 + 1) ^ swz) << 4), a4, a5, a6, a7);
                 };
-                auto chunk_p = [&](const uint32_t (&r)[16], int c) {
-                    uint32_t packed[8];
-                    if (c + 16 <= len) {
-#pragma unroll
-                        for (int e = 0; e < 16; e += 2) {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e))));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e + 1))));
-                            l4[(e >> 1) & 3] += p0 + p1;
-                            packed[e >> 1] = pack_bf16(p0, p1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; e += 2) {
-                            float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e))));
-                            float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e + 1))));
-                            p0 = (c + e < len) ? p0 : 0.f;
-                            p1 = (c + e + 1 < len) ? p1 : 0.f;
-                            l4[(e >> 1) & 3] += p0 + p1;
-                            packed[e >> 1] = pack_bf16(p0, p1);
-                        }
-                    }
-                    store_p(packed, c);
-                };
-                {
-                    // TMEM loads double-buffered in registers: chunk i+1 is in flight while chunk i is turned into P
-                    uint32_t ra[16], rb[16];
-                    if (nch > 0) tmem_ld16(taddr_s + c0, ra);
+                int c = 0;
+                // full chunks: no masking in the inner loop (LDS, FFMA, MUFU.EX2, FADD, half an F2FP per column)
 #pragma unroll 1
-                    for (int i = 0; i < nch; i += 2) {
-                        tmem_ld_wait();
-                        if (i + 1 < nch) tmem_ld16(taddr_s + c0 + 16 * (i + 1), rb);
-                        chunk_p(ra, c0 + 16 * i);
-                        if (i + 1 < nch) {
-                            tmem_ld_wait();
-                            if (i + 2 < nch) tmem_ld16(taddr_s + c0 + 16 * (i + 2), ra);
-                            chunk_p(rb, c0 + 16 * (i + 1));
-                        }
+                for (; c + 16 <= n_real; c += 16) {
+                    uint32_t r[16], pk[8];
+                    tmem_ld16(taddr_s + c, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e))));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e + 1))));
+                        if (e & 2) l1 += p0 + p1; else l0 += p0 + p1;
+                        pk[e >> 1] = pack_bf16(p0, p1);
                     }
+                    store_p(pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7], c);
                 }
-                {
-                    const uint32_t zeros[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                    for (int c = c0 + 16 * nch; c < c_hi; c += 16) store_p(zeros, c);
+                if (c < n_real) {       // the chunk that holds the document's last keys: columns past them contribute p = 0
+                    uint32_t r[16], pk[8];
+                    tmem_ld16(taddr_s + c, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e))));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (c + e + 1))));
+                        p0 = (c + e < n_real) ? p0 : 0.f;
+                        p1 = (c + e + 1 < n_real) ? p1 : 0.f;
+                        l0 += p0 + p1;
+                        pk[e >> 1] = pack_bf16(p0, p1);
+                    }
+                    store_p(pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7], c);
+                    c += 16;
                 }
-                l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-                sL[(((use & 1) * 2 + t) * 2 + g) * 128 + lane_row] = l;
+                for (c = max(c, 0); c < n_fill; c += 16) store_p(0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, c);
+                st_shared_f32(sL_s + (k & 1) * 2048 + g * 512, l0 + l1);
             }
-            tc_fence_before();      // TMEM reads of S_t are complete before MMA-1 of the next use overwrites it
+            tc_fence_before();      // TMEM reads of S_t (and of O_t in the epilogue above) are complete before the MMAs overwrite them
             fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&bar_p[t]);
-            pend = true; p_rows = rows; p_row_ok = row_ok; p_tok0 = my_tok0; p_len = len; p_h = h; p_qi = qi; p_par = use & 1;
-            p_sBq = sB + (255 - qi);
-            ++use;
+            prev = dsc;
         }
-        if (pend) epilogue();
     }
     tc_fence_before();
     __syncthreads();

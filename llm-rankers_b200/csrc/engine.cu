@@ -293,6 +293,7 @@ struct b200rank_engine {
     bf16* lm_head = nullptr;     // [V, d]
     float *enc_final_ln = nullptr, *dec_final_ln = nullptr;
     float *bias_enc = nullptr;   // [H][257]
+    float *bias_enc_wide = nullptr;  // [H][512]: log2(e) * bias(clamp(w - 255)), the shared-memory window image of attention_tc5.cuh
     float *bias_dec = nullptr;   // [H][129]
     bf16* wckv = nullptr;        // [Ld * 2 * inner, d]  (k rows then v rows per decoder layer)
     std::vector<LayerW> enc, dec;
@@ -582,6 +583,7 @@ static int create_impl(b200rank_engine* e) {
     reserve((void**)&e->enc_final_ln, d * 4);
     reserve((void**)&e->dec_final_ln, d * 4);
     reserve((void**)&e->bias_enc, (size_t)e->H * kAttnBiasLen * 4);
+    reserve((void**)&e->bias_enc_wide, (size_t)e->H * 512 * 4);
     reserve((void**)&e->bias_dec, (size_t)e->H * (kAttnRelClamp + 1) * 4);
     reserve((void**)&e->wckv, (size_t)e->Ld * 2 * I * d * 2);
     e->enc.resize(e->Le);
@@ -809,6 +811,17 @@ static int derive_weights(b200rank_engine* e) {
     return B200RANK_OK;
 }
 
+// [H][257] position-bias table -> [H][512] shared-memory window image of the tcgen05 attention kernel: entry w = log2(e) * bias(clamp(w - 255))
+static std::vector<float> widen_enc_bias(const float* table, int H) {
+    std::vector<float> wide((size_t)H * 512, 0.f);
+    for (int h = 0; h < H; ++h)
+        for (int w = 0; w < 511; ++w) {
+            const int rel = std::max(-kAttnRelClamp, std::min(kAttnRelClamp, w - 255));
+            wide[(size_t)h * 512 + w] = table[(size_t)h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
+        }
+    return wide;
+}
+
 extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, const void* data, int dtype, int64_t rows,
                                     int64_t cols) {
     if (!e || !hf_name || !data) return set_error(B200RANK_ERR_ARG, "null argument");
@@ -864,6 +877,8 @@ extern "C" int b200rank_load_tensor(b200rank_engine* e, const char* hf_name, con
                         t[(size_t)h * kAttnBiasLen + dlt + kAttnRelClamp] =
                             src_at(data, dtype, (size_t)b200rank_rel_bucket(dlt, 1, nb, md) * e->H + h);
                 CU_OK(cudaMemcpy(e->bias_enc, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+                std::vector<float> wide = widen_enc_bias(t.data(), e->H);
+                CU_OK(cudaMemcpy(e->bias_enc_wide, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
             } else {
                 const int len = kAttnRelClamp + 1;
                 std::vector<float> t((size_t)e->H * len);
@@ -1014,7 +1029,8 @@ static int device_sm_count() {   // of the current device (test entry points wit
     return sms > 0 ? sms : 1;
 }
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
-                                int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0) {
+                                int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0,
+                                const float* bias_wide = nullptr) {
     if (mode == 0) mode = attn_default_mode();
     const bool persistent = (mode == 5 || mode == 6 || mode == 7 || mode == 8);
     if (maxlen > 256 && !persistent) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
@@ -1034,8 +1050,10 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         const int n_items = nd * H;
         if (e) prof_begin(e, "enc_attention_tc5");
         const int sm_count = e ? e->num_sms : device_sm_count();
+        const float* bw = e ? e->bias_enc_wide : bias_wide;
+        if (!bw) return set_error(B200RANK_ERR_ARG, "tc5 attention needs the widened bias table");
         CU_OK(launch_k(enc_attention_tc5_kernel<3>, dim3(std::min(n_items, sm_count)), dim3(kAttn5Threads), AttnTc5Cfg<3>::smem_bytes(H), st, *tm, qkv, ld,
-                       inner, d_cu, bias, out, ldo, H, n_items, 192));
+                       inner, d_cu, bw, out, ldo, H, n_items, 192));
         if (e) RET_IF(post_launch(e, "enc_attention_tc5"));
         if (!mixed) return B200RANK_OK;
         if (e) prof_begin(e, "enc_attention");
@@ -1948,8 +1966,15 @@ extern "C" int b200rank_test_enc_attention(int device, const void* qkv_bf16, con
     CU_OK(cudaMemcpy(dcu, cu_seqlens, (n_docs + 1) * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(dbias, bias, (size_t)num_heads * kAttnBiasLen * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemset(dout, 0, (size_t)tokens * inner * 2));
-    int rc = launch_enc_attention(nullptr, dq, 3 * inner, qrows, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, mode);
+    float* dwide = nullptr;
+    {
+        std::vector<float> wide = widen_enc_bias(bias, num_heads);
+        CU_OK(cudaMalloc((void**)&dwide, wide.size() * 4));
+        CU_OK(cudaMemcpy(dwide, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
+    }
+    int rc = launch_enc_attention(nullptr, dq, 3 * inner, qrows, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, mode, 0, dwide);
     cudaError_t err = cudaDeviceSynchronize();
+    cudaFree(dwide);
     if (rc != B200RANK_OK) { cudaFree(dq); cudaFree(dout); cudaFree(dcu); cudaFree(dbias); return rc; }
     if (err != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "enc_attention kernel failed: %s", cudaGetErrorString(err));
     else cudaMemcpy(out_bf16, dout, (size_t)tokens * inner * 2, cudaMemcpyDeviceToHost);
