@@ -47,8 +47,7 @@ MODEL_SHAPES: Dict[str, Dict[str, int]] = {
     "flan-t5-xl": dict(d_model=2048, num_heads=32, d_ff=5120, num_layers=24, num_decoder_layers=24),
     "flan-t5-xxl": dict(d_model=4096, num_heads=64, d_ff=10240, num_layers=24, num_decoder_layers=24),
     # T5 v1.0 shapes of the castorini monoT5 / duoT5 checkpoints (relu feed-forward, tied embeddings). The 3B ones use d_kv 128:
-    # they run on the generic-width attention of csrc/attention_wide.cuh, experimental until validated on a B200
-    # (B200RANK_EXPERIMENTAL_DKV128=1; without it construction fails with a message that says so).
+    # they run on the generic-width attention of csrc/attention_wide.cuh.
     "monot5-small": dict(d_model=512, num_heads=8, d_ff=2048, num_layers=6, num_decoder_layers=6, v10=True),
     "monot5-base": dict(d_model=768, num_heads=12, d_ff=3072, num_layers=12, num_decoder_layers=12, v10=True),
     "monot5-large": dict(d_model=1024, num_heads=16, d_ff=4096, num_layers=24, num_decoder_layers=24, v10=True),

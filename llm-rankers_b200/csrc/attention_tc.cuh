@@ -1,14 +1,7 @@
-// tcgen05 encoder self-attention for short documents (len <= 256: the pointwise / pairwise regime).
-//
-// One CTA per (document, head). Q, K, V head slices (len x 64 bf16, 128 B rows) are TMA-loaded once into shared memory
-// (128B swizzle). Then, per 128-query tile t (at most two):
-//   MMA-1 (tcgen05, one thread):  S_t[128 x 64*NKB] = Q_t . K^T      fp32 in TMEM (columns t*256 ..)
-//   softmax (warpgroup t, one thread per query row): TMEM -> registers, + relative-position bias, key-length mask,
-//            exact two-pass softmax in fp32 (the whole row is resident, no online rescaling), P -> bf16 -> shared memory
-//            in the K-major 128B-swizzled layout of an MMA A operand
-//   MMA-2 (tcgen05):              O_t[128 x 64] = P_t . V            V consumed in place as an MN-major B operand
-//   epilogue (warpgroup t):       O_t / rowsum -> bf16 -> global
-// The two query tiles overlap: while warpgroup 0 does the softmax of tile 0 the tensor core computes S_1, etc.
+// Round-1 persistent tcgen05 encoder self-attention (B200RANK_ATTN=tc2): one thread per query row, two passes over TMEM. Kept as the
+// validated A/B partner of the round-2 kernel (attention_tc5.cuh, the default), which shares its TMA / MMA roles and TMEM layout;
+// the exploratory variants of round 1 (unpipelined tc, row-split tc3, provisional-shift tc4, mma.sync regs / resident) were removed
+// once tc5 had beaten all of them on the B200 (profiles/r02_bench_attn_ab.txt).
 // No 1/sqrt(d) scaling (modeling_t5.py:308); bias + mask + fp32 softmax as modeling_t5.py:313-334; padded keys do not
 // exist in the packed layout (rows past `len` belong to the next document: they are masked to -inf / never stored).
 #pragma once
@@ -20,207 +13,10 @@ namespace b200 {
 
 constexpr int kAttnTcThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: softmax tile 0, warps 6-9: softmax tile 1
 
-template <int NKB>
-struct AttnTcCfg {
-    static constexpr int kRows = 64 * NKB;              // padded keys / queries held in smem
-    static constexpr int kQKVBytes = kRows * 128;       // one of Q, K, V
-    static constexpr int kPBytes = NKB * 128 * 128;     // P tile: NKB k-blocks of [128 rows x 128 B]
-    static constexpr int kSmemBytes = 3 * kQKVBytes + 2 * kPBytes + 8 * 8 + 16 + kAttnBiasLen * 4 + 1024;
-};
-
 // Instruction descriptor with an MN-major B operand (bit 16), otherwise as make_idesc_bf16.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t m, uint32_t n) {
     return make_idesc_bf16(m, n) | (1u << 16);
 }
-
-template <int NKB>
-__global__ void __launch_bounds__(kAttnTcThreads, 1)
-enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
-                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo) {
-    using Cfg = AttnTcCfg<NKB>;
-    pdl_trigger();
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + Cfg::kQKVBytes;
-    uint8_t* sV = sK + Cfg::kQKVBytes;
-    uint8_t* sP = sV + Cfg::kQKVBytes;                      // [2][kPBytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
-    uint64_t* bar_qk = bars + 0;
-    uint64_t* bar_v = bars + 1;
-    uint64_t* bar_s = bars + 2;   // [2] S_t ready in TMEM
-    uint64_t* bar_p = bars + 4;   // [2] P_t written to smem (128 arrivals)
-    uint64_t* bar_o = bars + 6;   // [2] O_t ready in TMEM
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8);
-    float* sBias = reinterpret_cast<float*>(tmem_base_smem + 4);
-
-    const int h = blockIdx.x, doc = blockIdx.y;
-    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp_idx == 1) tmem_alloc(tmem_base_smem, 512);  // prologue work that needs no global data comes before pdl_wait
-    pdl_wait();
-    const int tok0 = cu[doc];
-    const int len = cu[doc + 1] - tok0;
-    const int ntiles = (len + 127) >> 7;
-
-    if (warp_idx == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_qkv);
-        mbar_init(bar_qk, 1);
-        mbar_init(bar_v, 1);
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(&bar_s[t], 1);
-            mbar_init(&bar_p[t], 128);
-            mbar_init(&bar_o[t], 1);
-        }
-        fence_barrier_init();
-    }
-    for (int i = threadIdx.x; i < kAttnBiasLen; i += kAttnTcThreads) sBias[i] = bias[h * kAttnBiasLen + i];
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_smem;
-    const int nkb_used = (len + 63) >> 6;  // 64-key blocks that hold real keys
-
-    if (warp_idx == 0) {
-        if (lane == 0) {
-            // Q and K first (MMA-1 needs both), then V. Rows past the document come from the next document (masked later).
-            mbar_arrive_expect_tx(bar_qk, 2 * nkb_used * 8192);
-            for (int b = 0; b < nkb_used; ++b) {
-                tma_load_2d(sQ + b * 8192, &tmap_qkv, bar_qk, h * 64, tok0 + b * 64, kEvictFirst);
-                tma_load_2d(sK + b * 8192, &tmap_qkv, bar_qk, inner + h * 64, tok0 + b * 64, kEvictFirst);
-            }
-            mbar_arrive_expect_tx(bar_v, nkb_used * 8192);
-            for (int b = 0; b < nkb_used; ++b)
-                tma_load_2d(sV + b * 8192, &tmap_qkv, bar_v, 2 * inner + h * 64, tok0 + b * 64, kEvictFirst);
-        }
-    } else if (warp_idx == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 64 * NKB);
-            constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
-            mbar_wait(bar_qk, 0);
-            tc_fence_after();
-            for (int t = 0; t < ntiles; ++t) {
-                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sQ + t * 128 * 128));
-                const uint64_t db = make_sw128_kmajor_desc(smem_u32(sK));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + t * 256, da + 2 * k, db + 2 * k, idesc_s, k != 0);
-                umma_commit(&bar_s[t]);
-            }
-            mbar_wait(bar_v, 0);
-            for (int t = 0; t < ntiles; ++t) {
-                mbar_wait(&bar_p[t], 0);
-                tc_fence_after();
-                for (int kb = 0; kb < nkb_used; ++kb) {
-                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP + t * Cfg::kPBytes + kb * 16384));
-                    // V block: rows = keys (the MMA K dimension), 128 B of head dims contiguous = MN-major B operand;
-                    // 16 keys per MMA = 2048 B -> +128 in (addr >> 4)
-                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(sV + kb * 8192));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + t * 256, da + 2 * k, db + 128 * k, idesc_o, (kb | k) != 0);
-                }
-                umma_commit(&bar_o[t]);
-            }
-        }
-    } else {
-        const int t = (warp_idx - 2) >> 2;            // query tile of this warpgroup
-        const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
-        if (t < ntiles) {
-            const int row_in_tile = quarter * 32 + lane;
-            const int qi = t * 128 + row_in_tile;     // query index inside the document
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-            const int ncols = nkb_used * 64;
-            mbar_wait(&bar_s[t], 0);
-            tc_fence_after();
-            // ---- pass 1: row maximum of scores + bias over the real keys
-            float m = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < ncols; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int j = c + e;
-                    int rel = j - qi;
-                    rel = max(-kAttnRelClamp, min(kAttnRelClamp, rel));
-                    const float v = __uint_as_float(r[e]) + sBias[rel + kAttnRelClamp];
-                    m = fmaxf(m, (j < len) ? v : -INFINITY);
-                }
-            }
-            // ---- pass 2: p = exp(v - m), row sum, bf16 P into the swizzled A-operand tile
-            const float m_l2 = m * 1.4426950408889634f;
-            float l = 0.f;
-            uint8_t* prow = sP + t * Cfg::kPBytes + row_in_tile * 128;
-#pragma unroll 1
-            for (int c = 0; c < ncols; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c, r);
-                tmem_ld_wait();
-                uint32_t packed[16];
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float p[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int j = c + e + u;
-                        int rel = j - qi;
-                        rel = max(-kAttnRelClamp, min(kAttnRelClamp, rel));
-                        const float v = __uint_as_float(r[e + u]) + sBias[rel + kAttnRelClamp];
-                        p[u] = (j < len) ? exp2f(v * 1.4426950408889634f - m_l2) : 0.f;
-                        l += p[u];
-                    }
-                    packed[e >> 1] = pack_bf16(p[0], p[1]);
-                }
-                // 32 keys = 64 B = 4 chunks of 16 B inside k-block c/64, chunk index ((c % 64) / 8 + i)
-                uint8_t* kblk = prow + (c >> 6) * 16384;
-                const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), packed[4 * i], packed[4 * i + 1], packed[4 * i + 2],
-                                 packed[4 * i + 3]);
-            }
-            tc_fence_before();      // this thread's TMEM reads of S_t are complete before MMA-2 overwrites the columns with O_t
-            fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&bar_p[t]);
-            // ---- epilogue: O_t / l -> bf16 -> global
-            mbar_wait(&bar_o[t], 0);
-            tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld32(taddr, o0);
-            tmem_ld32(taddr + 32, o1);
-            tmem_ld_wait();
-            if (qi < len) {
-                const float inv = 1.f / l;
-                uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(tok0 + qi) * ldo + h * 64);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 v;
-                    v.x = pack_bf16(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
-                    v.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
-                    v.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
-                    v.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
-                    dst[i] = v;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 v;
-                    v.x = pack_bf16(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
-                    v.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
-                    v.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
-                    v.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
-                    dst[4 + i] = v;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp_idx == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // Persistent variant (documents of at most 64*NKB <= 192 tokens): one CTA per SM walks (document, head) work items
@@ -254,13 +50,12 @@ struct AttnTc2Cfg {
     static_assert(kOCol0 + 128 <= 512, "S and O tiles must fit the 512 TMEM columns side by side");
 };
 
-template <int NKB, int MODE>   // MODE 0: two TMEM passes (ships), 1: row split over two threads (tc3), 2: one pass with a provisional shift (tc4)
+template <int NKB>
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner, const int* __restrict__ cu,
                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int ldo, int H, int n_items, int spin,
                          int len_limit) {
     using Cfg = AttnTc2Cfg<NKB>;
-    constexpr bool SPLIT = (MODE == 1);
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -278,8 +73,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
     uint64_t* bar_o = bars + 8;    // [2] O_t ready in TMEM
     uint64_t* o_free = bars + 10;  // [2] O_t drained by the epilogue (128 arrivals)
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16);
-    float* sRed = reinterpret_cast<float*>(tmem_base_smem + 4);     // [4][128] row max / row sum exchange of the SPLIT softmax
-    float* sBiasW = sRed + 512;                                     // [H or 2][kWideBias]
+    float* sBiasW = reinterpret_cast<float*>(tmem_base_smem + 4) + 512;                                     // [H or 2][kWideBias]
     const bool bias_resident = H <= Cfg::kMaxResidentHeads;
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,9 +86,9 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
         mbar_init(v_free, 1);
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bar_s[t], 1);
-            mbar_init(&bar_p[t], SPLIT ? 256 : 128);
+            mbar_init(&bar_p[t], 128);
             mbar_init(&bar_o[t], 1);
-            mbar_init(&o_free[t], SPLIT ? 256 : 128);
+            mbar_init(&o_free[t], 128);
         }
         fence_barrier_init();
     }
@@ -401,7 +195,7 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
                 item = nitem; len = nlen;
             }
         }
-    } else if constexpr (MODE == 0) {
+    } else {
         const int t = (warp_idx - 2) >> 2;            // query tile slot of this warpgroup
         const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
         const int wg_tid = threadIdx.x - 64 - t * 128;
@@ -572,340 +366,6 @@ enc_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, int inner
             ++use;
         }
         if (pend) epilogue();
-    } else if constexpr (MODE == 2) {
-        // ---- ONE PASS (tc4, experimental, B200RANK_ATTN=tc4): softmax is shift-invariant, and fp32 / bf16 share one exponent range, so
-        // the shift need not be the row maximum: any value within ~2^100 of it gives the same relative precision in p, in the row sum
-        // and in O = P V. The maximum of the row's FIRST 32-key chunk serves as the shift. Every chunk is then read from TMEM once and
-        // p = 2^(v - shift) goes straight into the P tile: no write-back of v (tcgen05.st), no second TMEM read, half the per-thread
-        // chain of the two-pass walk that bounds MODE 0 (profiles/r01_bench_attn_ab.txt). A row whose sum leaves [1/2, 2^100) — scores
-        // that climb by more than ~69 natural-log units after the first chunk, or non-finite scores — is redone with its exact maximum
-        // (S_t is still intact in TMEM); the decision is taken per warp because tcgen05.ld is warp-collective.
-        // The epilogue of the previous use of the tile slot runs BEFORE the wait on S_t: MMA-2(k-1, t) was issued ahead of MMA-1(k, t),
-        // so O_t is the older result; draining it overlaps MMA-1 and licenses the writes into P_t.
-        const int t = (warp_idx - 2) >> 2;            // query tile slot of this warpgroup
-        const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
-        const int wg_tid = threadIdx.x - 64 - t * 128;
-        const int row_in_tile = quarter * 32 + lane;
-        const int qi = t * 128 + row_in_tile;         // query index inside the document
-        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol;
-        const uint32_t taddr_o = tmem_base + lane_off + Cfg::kOCol0 + t * 64;
-        uint8_t* prow = sP + t * Cfg::kPBytes + row_in_tile * 128;
-        uint32_t use = 0;
-        int h_loaded = -1;
-        int item = qualify(blockIdx.x);
-        int doc = item < n_items ? item / H : 0;
-        int tok0 = cu[doc], tok1 = cu[doc + 1];
-        bool pend = false, p_active = false;
-        float p_l = 0.f;
-        int p_tok0 = 0, p_len = 0, p_h = 0;
-        uint32_t p_par = 0;
-        auto epilogue = [&]() {
-            wait(&bar_o[t], p_par);
-            tc_fence_after();
-            if (p_active) {
-                uint32_t o0[32], o1[32];
-                tmem_ld32(taddr_o, o0);
-                tmem_ld32(taddr_o + 32, o1);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&o_free[t]);
-                if (qi < p_len) {
-                    const float inv = 1.f / p_l;
-                    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p_tok0 + qi) * ldo + p_h * 64);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
-                        v.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
-                        v.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
-                        v.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
-                        dst[i] = v;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
-                        v.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
-                        v.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
-                        v.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
-                        dst[4 + i] = v;
-                    }
-                }
-            } else {
-                mbar_arrive(&o_free[t]);
-            }
-        };
-        while (item < n_items) {
-            const int h = item - doc * H;
-            const int len = tok1 - tok0, my_tok0 = tok0;
-            const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
-            const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
-            item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
-            if (t >= ((len + 127) >> 7)) continue;
-            const int ncols = ((len + 63) >> 6) * 64;
-            const bool active = (t * 128 + quarter * 32) < len;   // warp-uniform: at least one real query row
-            float* sB = sBiasW + (bias_resident ? h : t) * Cfg::kWideBias;
-            if (!bias_resident && h != h_loaded) {
-                named_bar_sync(1 + t, 128);               // every warp of the group is past its reads of the old window
-                for (int i = wg_tid; i < 511; i += 128) {
-                    const int rel = max(-kAttnRelClamp, min(kAttnRelClamp, i - 255));
-                    sB[i] = bias[h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
-                }
-                named_bar_sync(1 + t, 128);
-                h_loaded = h;
-            }
-            const uint32_t sBrow = smem_u32(sB) + (255 - qi) * 4;   // [sBrow + 4 j] = log2(e) * bias(j - qi)
-            if (pend) { epilogue(); pend = false; }
-            wait(&bar_s[t], use & 1);
-            tc_fence_after();
-            float l = 0.f;
-            if (active) {
-                float shift = 0.f;
-                float l4[4];
-                // v_j = s_j * log2(e) + bias'(j - qi) of one 32-key chunk; keys past the document read as -inf (p = 0)
-                auto score = [&](uint32_t s_bits, int j) {
-                    return fmaf(__uint_as_float(s_bits), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * j));
-                };
-                auto chunk_max = [&](const uint32_t (&r)[32], int c, float (&m4)[4]) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        float v = score(r[e], c + e);
-                        if (c + 32 > len) v = (c + e < len) ? v : -INFINITY;
-                        m4[e & 3] = fmaxf(m4[e & 3], v);
-                    }
-                };
-                auto chunk_p = [&](const uint32_t (&r)[32], int c) {
-                    uint32_t packed[16];
-                    if (c + 32 <= len) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const float p0 = ex2_approx(score(r[e], c + e) - shift);
-                            const float p1 = ex2_approx(score(r[e + 1], c + e + 1) - shift);
-                            l4[(e >> 1) & 3] += p0 + p1;
-                            packed[e >> 1] = pack_bf16(p0, p1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            float p0 = ex2_approx(score(r[e], c + e) - shift);
-                            float p1 = ex2_approx(score(r[e + 1], c + e + 1) - shift);
-                            p0 = (c + e < len) ? p0 : 0.f;
-                            p1 = (c + e + 1 < len) ? p1 : 0.f;
-                            l4[(e >> 1) & 3] += p0 + p1;
-                            packed[e >> 1] = pack_bf16(p0, p1);
-                        }
-                    }
-                    uint8_t* kblk = prow + (c >> 6) * 16384;
-                    const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), packed[4 * i], packed[4 * i + 1],
-                                     packed[4 * i + 2], packed[4 * i + 3]);
-                };
-                // one walk over the row's chunks, TMEM loads double-buffered in registers; FIRST: take the shift from chunk 0
-                auto walk_p = [&](bool first_chunk_shift) {
-                    l4[0] = l4[1] = l4[2] = l4[3] = 0.f;
-                    uint32_t ra[32], rb[32];
-                    tmem_ld32(taddr_s, ra);
-#pragma unroll 1
-                    for (int c = 0; c < len; c += 64) {
-                        tmem_ld_wait();
-                        if (c + 32 < len) tmem_ld32(taddr_s + c + 32, rb);
-                        if (first_chunk_shift && c == 0) {
-                            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                            chunk_max(ra, 0, m4);
-                            shift = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                        }
-                        chunk_p(ra, c);
-                        if (c + 32 < len) {
-                            tmem_ld_wait();
-                            if (c + 64 < len) tmem_ld32(taddr_s + c + 64, ra);
-                            chunk_p(rb, c + 32);
-                        }
-                    }
-                    return (l4[0] + l4[1]) + (l4[2] + l4[3]);
-                };
-                l = walk_p(true);
-                const bool bad = !(l >= 0.5f && l < 1.2676506e30f);   // 2^100; also catches inf / NaN
-                if (__any_sync(0xffffffffu, bad)) {
-                    // rare: exact row maximum, then the same walk with it (every lane of the warp, each with its own maximum)
-                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    uint32_t ra[32];
-#pragma unroll 1
-                    for (int c = 0; c < len; c += 32) {
-                        tmem_ld32(taddr_s + c, ra);
-                        tmem_ld_wait();
-                        chunk_max(ra, c, m4);
-                    }
-                    shift = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                    l = walk_p(false);
-                }
-                {
-                    const uint32_t zeros[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                    for (int c = (len + 31) & ~31; c < ncols; c += 32) {
-                        uint8_t* kblk = prow + (c >> 6) * 16384;
-                        const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), zeros[4 * i], zeros[4 * i + 1], zeros[4 * i + 2],
-                                         zeros[4 * i + 3]);
-                    }
-                }
-            }
-            tc_fence_before();      // TMEM reads of S_t are complete before MMA-1 of the next use overwrites it
-            fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&bar_p[t]);
-            pend = true; p_active = active; p_l = l; p_tok0 = my_tok0; p_len = len; p_h = h; p_par = use & 1;
-            ++use;
-        }
-        if (pend) epilogue();
-    } else {
-        // ---- SPLIT: every query row is shared by TWO threads (one per warpgroup, 32*NKB columns each). The scores of a row
-        // are read from TMEM ONCE and stay in registers (96 fp32 at NKB = 3) between the max and the exp phase; row max and row
-        // sum are exchanged through shared memory (two 256-thread named barriers per tile). Both warpgroups work on tile slot 0,
-        // then on slot 1. Half the TMEM traffic and half the serial chain of the one-thread-per-row version.
-        constexpr int HC = 32 * NKB;                  // columns per thread
-        const int g = (warp_idx - 2) >> 2;            // column half of this warpgroup
-        const int quarter = warp_idx & 3;             // TMEM lane quarter of this warp
-        const int wg_tid = threadIdx.x - 64 - g * 128;
-        const int row_in_tile = quarter * 32 + lane;
-        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        float* sRedM = sRed;                          // [2][128] partial row maxima
-        float* sRedL = sRed + 256;                    // [2][128] partial row sums
-        uint32_t use0 = 0, use1 = 0;
-        int h_loaded = -1;
-        // deferred epilogues, one per tile slot
-        bool pend[2] = {false, false}, p_active[2] = {false, false};
-        float p_l[2] = {0.f, 0.f};
-        int p_tok0[2] = {0, 0}, p_len[2] = {0, 0}, p_h[2] = {0, 0};
-        uint32_t p_par[2] = {0, 0};
-        auto epilogue = [&](int t) {
-            wait(&bar_o[t], p_par[t]);
-            tc_fence_after();
-            if (p_active[t]) {
-                uint32_t o[32];
-                tmem_ld32(tmem_base + lane_off + Cfg::kOCol0 + t * 64 + g * 32, o);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&o_free[t]);
-                const int qi = t * 128 + row_in_tile;
-                if (qi < p_len[t]) {
-                    const float inv = 1.f / p_l[t];
-                    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p_tok0[t] + qi) * ldo + p_h[t] * 64 + g * 32);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 v;
-                        v.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-                        v.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-                        v.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-                        v.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-                        dst[i] = v;
-                    }
-                }
-            } else {
-                mbar_arrive(&o_free[t]);
-            }
-            pend[t] = false;
-        };
-        int item = qualify(blockIdx.x);
-        int doc = item < n_items ? item / H : 0;
-        int tok0 = cu[doc], tok1 = cu[doc + 1];
-        while (item < n_items) {
-            const int h = item - doc * H;
-            const int len = tok1 - tok0, my_tok0 = tok0;
-            const int nitem = qualify(item + stride), ndoc = nitem < n_items ? nitem / H : 0;
-            const int ntok0 = cu[ndoc], ntok1 = cu[ndoc + 1];            // next item's extent: in flight during this one
-            item = nitem; doc = ndoc; tok0 = ntok0; tok1 = ntok1;
-            const int ntiles = (len + 127) >> 7;
-            float* sB = sBiasW + (bias_resident ? h : g) * Cfg::kWideBias;
-            if (!bias_resident && h != h_loaded) {
-                named_bar_sync(1 + g, 128);
-                for (int i = wg_tid; i < 511; i += 128) {
-                    const int rel = max(-kAttnRelClamp, min(kAttnRelClamp, i - 255));
-                    sB[i] = bias[h * kAttnBiasLen + rel + kAttnRelClamp] * 1.4426950408889634f;
-                }
-                named_bar_sync(1 + g, 128);
-                h_loaded = h;
-            }
-#pragma unroll 1
-            for (int t = 0; t < ntiles; ++t) {
-                uint32_t& use = t == 0 ? use0 : use1;
-                const int qi = t * 128 + row_in_tile;
-                const bool active = (t * 128 + quarter * 32) < len;   // warp-uniform, and the same in both warpgroups
-                const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol + g * HC;
-                const uint32_t sBrow = smem_u32(sB) + (255 - qi + g * HC) * 4;   // [sBrow + 4 c] = log2(e) * bias(g*HC + c - qi)
-                wait(&bar_s[t], use & 1);
-                tc_fence_after();
-                uint32_t v[NKB][32];
-                float m = -INFINITY, l = 0.f;
-                if (active) {
-#pragma unroll
-                    for (int cc = 0; cc < NKB; ++cc) tmem_ld32(taddr_s + 32 * cc, v[cc]);
-                    tmem_ld_wait();
-                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-                    for (int cc = 0; cc < NKB; ++cc) {
-                        const int c0 = g * HC + 32 * cc;       // first key of this chunk
-                        if (c0 + 32 <= len) {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const float x = fmaf(__uint_as_float(v[cc][e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (32 * cc + e)));
-                                m4[e & 3] = fmaxf(m4[e & 3], x);
-                                v[cc][e] = __float_as_uint(x);
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                float x = fmaf(__uint_as_float(v[cc][e]), 1.4426950408889634f, ld_shared_f32(sBrow + 4 * (32 * cc + e)));
-                                x = (c0 + e < len) ? x : -INFINITY;
-                                m4[e & 3] = fmaxf(m4[e & 3], x);
-                                v[cc][e] = __float_as_uint(x);
-                            }
-                        }
-                    }
-                    m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                    sRedM[g * 128 + row_in_tile] = m;
-                }
-                tc_fence_before();                // S_t is in registers: its TMEM columns are free once every thread got here
-                named_bar_sync(3, 256);
-                if (active) m = fmaxf(m, sRedM[(1 - g) * 128 + row_in_tile]);   // finite: key 0 of every row lies in half 0
-                // the previous use of this tile slot: its MMA-2 retired long ago; passing bar_o also frees P_t for the writes below
-                if (pend[t]) epilogue(t);
-                if (active) {
-                    float l4[4] = {0.f, 0.f, 0.f, 0.f};
-                    uint8_t* prow = sP + t * Cfg::kPBytes + row_in_tile * 128;
-#pragma unroll
-                    for (int cc = 0; cc < NKB; ++cc) {
-                        uint32_t packed[16];
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const float p0 = ex2_approx(__uint_as_float(v[cc][e]) - m);
-                            const float p1 = ex2_approx(__uint_as_float(v[cc][e + 1]) - m);
-                            l4[(e >> 1) & 3] += p0 + p1;
-                            packed[e >> 1] = pack_bf16(p0, p1);
-                        }
-                        const int c = g * HC + 32 * cc;
-                        uint8_t* kblk = prow + (c >> 6) * 16384;
-                        const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            st_shared_v4(kblk + (((chunk0 + i) ^ (row_in_tile & 7)) << 4), packed[4 * i], packed[4 * i + 1],
-                                         packed[4 * i + 2], packed[4 * i + 3]);
-                    }
-                    l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-                    sRedL[g * 128 + row_in_tile] = l;
-                }
-                fence_proxy_async();    // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
-                named_bar_sync(3, 256);
-                if (active) l += sRedL[(1 - g) * 128 + row_in_tile];
-                mbar_arrive(&bar_p[t]);
-                pend[t] = true; p_active[t] = active; p_l[t] = l; p_tok0[t] = my_tok0; p_len[t] = len; p_h[t] = h; p_par[t] = use & 1;
-                ++use;
-            }
-        }
-        if (pend[0]) epilogue(0);
-        if (pend[1]) epilogue(1);
     }
     tc_fence_before();
     __syncthreads();

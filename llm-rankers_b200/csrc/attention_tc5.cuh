@@ -51,7 +51,9 @@ struct AttnTc5Cfg {
 };
 
 // Exact softmax(q_i K^T + bias) V for ONE query row and 32 of its 64 output dims on CUDA cores: the rare-row fallback of the
-// one-pass kernel (row sum outside [2^-100, 2^100) or not finite). sBq[j] = log2(e) * bias(j - qi).
+// one-pass kernel (row sum outside [2^-100, 2^100) or not finite). sBq[j] = log2(e) * bias(j - qi) (a pointer into the global
+// [H][512] table). Called only from the fix-up walk AFTER the item loop: a call inside the loop makes ptxas keep the loop state
+// in local memory (ABI), and local memory is an L2 round trip in this kernel (profiles/r02_attn_profile.txt).
 __device__ __noinline__ void attn_slow_row(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, int tok0, int len, int qi, int h, int g,
                                            const float* sBq, __nv_bfloat16* __restrict__ out, int ldo) {
     const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(qkv + static_cast<size_t>(tok0 + qi) * ld + h * 64);
@@ -82,7 +84,7 @@ __device__ __noinline__ void attn_slow_row(const __nv_bfloat16* __restrict__ qkv
             o[2 * i + 1] = fmaf(pb, v.y, o[2 * i + 1]);
         }
     }
-    const float inv = 1.f / l;
+    const float inv = __fdividef(1.f, l);
     uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(tok0 + qi) * ldo + h * 64 + g * 32);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -97,11 +99,18 @@ __device__ __noinline__ void attn_slow_row(const __nv_bfloat16* __restrict__ qkv
 
 // bias_wide: [H][512] fp32, bias_wide[h][w] = log2(e) * bias_h(clamp(w - 255, +-128)) (built once at weight-load time: the per-launch
 // prologue is a plain 16 B-vector copy into shared memory instead of 8 k dependent global loads).
-template <int NKB>
+template <int WAIT>
+__device__ __forceinline__ void attn5_wait(uint64_t* bar, uint32_t parity) {
+    if constexpr (WAIT == 1) mbar_wait_backoff(bar, parity, 64);
+    else if constexpr (WAIT == 2) mbar_wait_spin(bar, parity);
+    else mbar_wait(bar, parity);
+}
+
+template <int NKB, int WAIT>   // WAIT 0: mbarrier.try_wait loops; 1: try_wait + nanosleep back-off (ships); 2: busy poll
 __global__ void __launch_bounds__(kAttn5Threads, 1)
 enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfloat16* __restrict__ qkv, int ld, int inner,
                          const int* __restrict__ cu, const float* __restrict__ bias_wide, __nv_bfloat16* __restrict__ out, int ldo, int H,
-                         int n_items, int len_limit) {
+                         int n_items, int len_limit, uint8_t* __restrict__ bad_map) {
     using Cfg = AttnTc5Cfg<NKB>;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -119,7 +128,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
     uint64_t* bar_p = bars + 6;    // [2] P_t written to smem, S_t and O_t drained (256 arrivals)
     uint64_t* bar_o = bars + 8;    // [2] O_t ready in TMEM
     int4* sDesc = reinterpret_cast<int4*>(bars + 12);               // [4] item ring: {first token, length, head, valid}
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(sDesc + 4);
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(sDesc + 4);   // [0] TMEM base, [2] "some row needs the fix-up walk" (as a float)
     float* sL = reinterpret_cast<float*>(tmem_base_smem + 4);       // [2 parities][2 slots][2 halves][128 lanes]
     float* sBiasW = sL + Cfg::kRedBytes / 4;                        // [H or 2][kWideBias]
     const bool bias_resident = H <= Cfg::kMaxResidentHeads;
@@ -127,6 +136,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp_idx == 1) tmem_alloc(tmem_base_smem, 512);
     if (warp_idx == 0 && lane == 0) {
+        tmem_base_smem[2] = 0u;
         tma_prefetch_desc(&tmap_qkv);
         mbar_init(bar_qk, 1);
         mbar_init(bar_v, 1);
@@ -164,20 +174,20 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                 const int tok0 = cu[doc], len = cu[doc + 1] - tok0;
                 if (len > len_limit) continue;   // longer documents belong to the mma.sync tile kernel launched next to this one
                 const int nkb_used = (len + 63) >> 6;
-                if (k > 0) mbar_wait(qk_free, (k - 1) & 1);
+                if (k > 0) attn5_wait<WAIT>(qk_free, (k - 1) & 1);
                 sDesc[k & 3] = make_int4(tok0, len, h, 1);
                 mbar_arrive_expect_tx(bar_qk, 2 * nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b) {
                     tma_load_2d(sQ + b * 8192, &tmap_qkv, bar_qk, h * 64, tok0 + b * 64, kEvictFirst);
                     tma_load_2d(sK + b * 8192, &tmap_qkv, bar_qk, inner + h * 64, tok0 + b * 64, kEvictFirst);
                 }
-                if (k > 0) mbar_wait(v_free, (k - 1) & 1);
+                if (k > 0) attn5_wait<WAIT>(v_free, (k - 1) & 1);
                 mbar_arrive_expect_tx(bar_v, nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b)
                     tma_load_2d(sV + b * 8192, &tmap_qkv, bar_v, 2 * inner + h * 64, tok0 + b * 64, kEvictFirst);
                 ++k;
             }
-            if (k > 0) mbar_wait(qk_free, (k - 1) & 1);
+            if (k > 0) attn5_wait<WAIT>(qk_free, (k - 1) & 1);
             sDesc[k & 3] = make_int4(0, 0, 0, 0);
             mbar_arrive(bar_qk);
         }
@@ -187,7 +197,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
             constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
             int len_prev = 0;
             for (int k = 0;; ++k) {
-                mbar_wait(bar_qk, k & 1);
+                attn5_wait<WAIT>(bar_qk, k & 1);
                 tc_fence_after();
                 const int4 dsc = sDesc[k & 3];
                 const bool have = dsc.w != 0;
@@ -199,8 +209,8 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                     if (k > 0) {
                         // MMA-2 of item k-1: O_t = P_t . V. bar_p also says that the slot's threads are done with O_t of item k-2
                         // (their deferred epilogue precedes their pass in program order) and with S_t of item k-1.
-                        if (t == 0) mbar_wait(bar_v, (k - 1) & 1);
-                        mbar_wait(&bar_p[t], (k - 1) & 1);
+                        if (t == 0) attn5_wait<WAIT>(bar_v, (k - 1) & 1);
+                        attn5_wait<WAIT>(&bar_p[t], (k - 1) & 1);
                         tc_fence_after();
                         if (t < nt_prev) {
                             for (int kb = 0; kb < nkb_prev; ++kb) {
@@ -264,7 +274,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
             // was issued ahead of MMA-1(k, t), and passing bar_o licenses the writes into P_t below.
             if (prev.w) {
                 const int kp = k - 1;
-                mbar_wait(&bar_o[t], kp & 1);
+                attn5_wait<WAIT>(&bar_o[t], kp & 1);
                 tc_fence_after();
                 const int shift = (t == 1 && (kp & 1)) ? 64 : 0;
                 const int qi = t * 128 + lane_row - shift;
@@ -277,7 +287,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                     tmem_ld_wait();
                     if (qi < len) {
                         if (l >= 7.888609e-31f && l < 1.2676506e30f) {     // [2^-100, 2^100): also false for inf / NaN
-                            const float inv = 1.f / l;
+                            const float inv = __fdividef(1.f, l);   // l in [2^-100, 2^100): 2 ulp, and no slow-path call in the loop
                             uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(prev.x + qi) * ldo + prev.z * 64 + g * 32);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -289,13 +299,14 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                                 dst[i] = v;
                             }
                         } else {
-                            const float* sBq = sBiasW + (bias_resident ? prev.z : t) * Cfg::kWideBias + (255 - qi);
-                            attn_slow_row(qkv, ld, inner, prev.x, len, qi, prev.z, g, sBq, out, ldo);
+                            // rare: leave the row to the fix-up walk after the item loop (both half-row threads see the same l and mark the same byte)
+                            bad_map[static_cast<size_t>(prev.x + qi) * H + prev.z] = 1;
+                            st_shared_f32(smem_s + kDescOff + 4 * 16 + 8, 1.f);
                         }
                     }
                 }
             }
-            mbar_wait(&bar_s[t], k & 1);
+            attn5_wait<WAIT>(&bar_s[t], k & 1);
             tc_fence_after();
             const int4 dsc = ld_shared_v4_s32(sDesc_s + (k & 3) * 16);
             if (!dsc.w) break;
@@ -370,6 +381,24 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
     if (warp_idx == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+    // ---- fix-up walk (cold): rows whose unshifted row sum left [2^-100, 2^100) were marked in bad_map instead of being stored. Walk this
+    // CTA's items again and recompute exactly those rows on CUDA cores with the true row maximum; the marks are cleared on the way, so
+    // the map is all-zero again when the kernel ends. Which rows take this path depends on the row alone.
+    if (tmem_base_smem[2] != 0u && warp_idx >= 2) {
+        const int stid = threadIdx.x - 64;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int doc = item / H, h = item - doc * H;
+            const int tok0 = cu[doc], len = cu[doc + 1] - tok0;
+            if (len > len_limit) continue;
+            for (int task0 = 0; task0 < 2 * len; task0 += kAttn5Threads - 64) {
+                const int task = task0 + stid, qi = task >> 1, g = task & 1;     // the two halves of a row sit in adjacent lanes
+                const bool mine = task < 2 * len && bad_map[static_cast<size_t>(tok0 + qi) * H + h] != 0;
+                if (mine) attn_slow_row(qkv, ld, inner, tok0, len, qi, h, g, bias_wide + h * Cfg::kWideBias + (255 - qi), out, ldo);
+                __syncwarp();
+                if (mine && g == 0) bad_map[static_cast<size_t>(tok0 + qi) * H + h] = 0;
+            }
+        }
     }
 }
 

@@ -293,6 +293,7 @@ struct b200rank_engine {
     bf16* lm_head = nullptr;     // [V, d]
     float *enc_final_ln = nullptr, *dec_final_ln = nullptr;
     float *bias_enc = nullptr;   // [H][257]
+    uint8_t* attn_bad_map = nullptr;  // [cap_tokens, H] bytes, all zero between launches: rows the tcgen05 attention leaves to its fix-up walk
     float *bias_enc_wide = nullptr;  // [H][512]: log2(e) * bias(clamp(w - 255)), the shared-memory window image of attention_tc5.cuh
     float *bias_dec = nullptr;   // [H][129]
     bf16* wckv = nullptr;        // [Ld * 2 * inner, d]  (k rows then v rows per decoder layer)
@@ -331,13 +332,7 @@ struct b200rank_engine {
     cudaEvent_t ev_enc[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     struct Slot { int docs = 0, tokens = 0, maxlen = 0; bool busy = false; uint64_t ticket = 0; } slot[2];
     uint64_t next_ticket = 1;
-    // B200RANK_PIPE_DUAL=1 (experimental, off by default): the encoder passes of the two in-flight batches run on two streams with
-    // two sets of encoder workspaces, so that one batch's HBM/L2-bound kernels (T5LayerNorm, epilogue tails, attention tails) overlap
-    // the other batch's tensor-bound GEMMs instead of queueing behind them. Slot 0 = the ordinary set.
-    bool pipe_dual = false;
-    cudaStream_t stream_enc2 = nullptr;
-    struct EncWs { float* x = nullptr; bf16 *h = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr; int* d_ids = nullptr; } enc_ws[2];
-    // B200RANK_DEC_GRAPH=1 (experimental, off by default): the ~250-kernel T = 1 decoder chain of the pipelined pass is captured into a
+    // Decoder graph (on by default, B200RANK_DEC_GRAPH=0 disables): the ~250-kernel T = 1 decoder chain of the pipelined pass is captured into a
     // CUDA graph per (slot, documents, padded longest document) on its second occurrence and replayed from the third on — one launch
     // instead of ~250 on the host, no inter-kernel launch gaps on the device. Kernel arguments (buffers, tensor maps, grids) are fixed
     // per key; ids / yes-no columns are uploaded outside the graph.
@@ -506,7 +501,7 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
-                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->xattn_partial, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
+                     e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->xattn_partial, e->attn_bad_map, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
                      e->d_int_out, e->d_finished, e->l2_scratch};
     for (void* p : frees)
         if (p) cudaFree(p);
@@ -524,19 +519,13 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
         if (e->ev_enc[b]) cudaEventDestroy(e->ev_enc[b]);
         if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
     }
-    if (e->pipe_dual) {
-        void* dual[] = {e->enc_ws[1].x, e->enc_ws[1].h, e->enc_ws[1].qkv, e->enc_ws[1].ao, e->enc_ws[1].g, e->enc_ws[1].d_ids};
-        for (void* p : dual)
-            if (p) cudaFree(p);
-    }
     for (auto& kv : e->dec_graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    if (e->stream_enc2) cudaStreamDestroy(e->stream_enc2);
     if (e->stream_dec) cudaStreamDestroy(e->stream_dec);
     for (int i = 0; i < 2; ++i)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
-    // e->stream is an alias that points at stream_main / stream_dec / stream_enc2 in turn: destroy the owning handle
+    // e->stream is an alias that points at stream_main / stream_dec in turn: destroy the owning handle
     cudaStream_t main_stream = e->stream_main ? e->stream_main : e->stream;
     if (main_stream) cudaStreamDestroy(main_stream);
     delete e;
@@ -653,6 +642,8 @@ static int create_impl(b200rank_engine* e) {
     e->xattn_partial_bytes = (size_t)std::min(e->cap_docs, 256) * e->H * kXAttnSplit * 4 * 66 * sizeof(float);   // groups of <= 256 documents, T <= 4
     RET_IF(dev_alloc(e, &e->xattn_partial, e->xattn_partial_bytes / sizeof(float)));
     RET_IF(dev_alloc(e, &e->d_ids, Tk));
+    RET_IF(dev_alloc(e, &e->attn_bad_map, (size_t)Tk * e->H));
+    CU_OK(cudaMemset(e->attn_bad_map, 0, (size_t)Tk * e->H));
     for (int b = 0; b < 2; ++b) {
         RET_IF(dev_alloc(e, &e->enc_out[b], Tk * d));
         RET_IF(dev_alloc(e, &e->d_cu_slot[b], (size_t)e->cap_docs + 1));
@@ -663,16 +654,8 @@ static int create_impl(b200rank_engine* e) {
     e->enc_out_cur = e->enc_out[0];
     e->d_cu = e->d_cu_slot[0];
     e->d_cu_cur = e->d_cu;
-    e->enc_ws[0].x = e->x; e->enc_ws[0].h = e->h; e->enc_ws[0].qkv = e->qkv; e->enc_ws[0].ao = e->ao; e->enc_ws[0].g = e->g;
-    e->enc_ws[0].d_ids = e->d_ids;
-    e->dec_graph = getenv("B200RANK_DEC_GRAPH") && atoi(getenv("B200RANK_DEC_GRAPH")) != 0;
-    e->pipe_dual = getenv("B200RANK_PIPE_DUAL") && atoi(getenv("B200RANK_PIPE_DUAL")) != 0;
-    if (e->pipe_dual) {
-        auto& w = e->enc_ws[1];
-        RET_IF(dev_alloc(e, &w.x, Tk * d)); RET_IF(dev_alloc(e, &w.h, Tk * d)); RET_IF(dev_alloc(e, &w.qkv, Tk * 3 * I));
-        RET_IF(dev_alloc(e, &w.ao, Tk * I)); RET_IF(dev_alloc(e, &w.g, Tk * F)); RET_IF(dev_alloc(e, &w.d_ids, Tk));
-        CU_OK(cudaStreamCreateWithFlags(&e->stream_enc2, cudaStreamNonBlocking));
-    }
+    // the decoder graph is on unless B200RANK_DEC_GRAPH=0 (bit-identical to the eager chain: tests/test_engine_gpu.py)
+    e->dec_graph = !(getenv("B200RANK_DEC_GRAPH") && atoi(getenv("B200RANK_DEC_GRAPH")) == 0);
     RET_IF(dev_alloc(e, &e->d_dec_ids, R)); RET_IF(dev_alloc(e, &e->d_cols, 64)); RET_IF(dev_alloc(e, &e->d_labels, R));
     RET_IF(dev_alloc(e, &e->d_int_out, (size_t)e->cap_docs * 16)); RET_IF(dev_alloc(e, &e->d_finished, (size_t)e->cap_docs));
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ids), Tk * sizeof(int), cudaHostAllocDefault));
@@ -688,14 +671,10 @@ static int create_impl(b200rank_engine* e) {
 extern "C" int b200rank_create(const b200rank_config* cfg, int device, b200rank_engine** out) {
     if (!cfg || !out) return set_error(B200RANK_ERR_ARG, "null argument");
     *out = nullptr;
-    if (cfg->d_kv != 64) {
-        // d_kv = 128 (monot5-3b / duot5-3b) runs on the generic mma.sync attention of attention_wide.cuh. That path was written without
-        // GPU time and has not been validated on a B200 yet: it stays behind B200RANK_EXPERIMENTAL_DKV128=1 until its parity test
-        // (tests/test_engine_gpu.py::test_wide_heads_vs_oracle) has passed once.
-        const bool wide_ok = cfg->d_kv == 128 && getenv("B200RANK_EXPERIMENTAL_DKV128") && atoi(getenv("B200RANK_EXPERIMENTAL_DKV128")) != 0;
-        if (!wide_ok)
-            return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (kernels are specialised for 64; 128 is experimental: B200RANK_EXPERIMENTAL_DKV128=1)", cfg->d_kv);
-    }
+    // d_kv = 64 runs on the specialised kernels; d_kv = 128 (monot5-3b / duot5-3b) on the generic-width mma.sync attention of
+    // attention_wide.cuh (validated on the B200 in round 2: tests/test_engine_gpu.py::test_wide_heads_vs_oracle)
+    if (cfg->d_kv != 64 && cfg->d_kv != 128)
+        return set_error(B200RANK_ERR_ARG, "d_kv=%d unsupported (64 and 128 are implemented)", cfg->d_kv);
     if (cfg->d_model <= 0 || cfg->d_ff <= 0 || cfg->vocab_size <= 0 || cfg->d_model % 64 || cfg->d_ff % 128 || cfg->d_model > 4096 ||
         cfg->d_ff > (1 << 17) || cfg->vocab_size % 8 || cfg->vocab_size > (1 << 22))
         return set_error(B200RANK_ERR_ARG, "unsupported dims d_model=%d d_ff=%d vocab=%d", cfg->d_model, cfg->d_ff, cfg->vocab_size);
@@ -998,29 +977,18 @@ static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int 
     return k_rmsnorm(e, x, norm_w, h, M);
 }
 
-// Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length),
-// 2 = mma.sync resident-KV (len <= 256), 3 = tcgen05 (len <= 256), 4 = mma.sync scores-in-registers (len <= 256),
-// 5 = persistent tcgen05 (len <= 192), 6 = its row-split variant (tc3), 7 = its one-pass variant (tc4, experimental).
-// B200RANK_ATTN=tiled|resident|tc|regs|tc2|tc3|tc4 overrides mode 0.
+// Encoder attention dispatch. mode: 0 = default for the build, 1 = mma.sync 64-query tiles (any length), 5 = round-1 persistent tcgen05
+// kernel (len <= 192), 8 = round-2 persistent tcgen05 kernel (len <= 192; 16 softmax warps, one unshifted pass: attention_tc5.cuh).
+// B200RANK_ATTN=tiled|tc2|tc5 overrides mode 0.
 static int attn_default_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* s = getenv("B200RANK_ATTN");
-        // default: the persistent tcgen05 kernel for documents of <= 192 tokens (launch_enc_attention falls back to the mma.sync tiles
-        // above that): 1.93 vs 2.32 ms per 100 documents at S=184, +3.7 % docs/s with two queries in flight
-        // (profiles/r01_bench_attn_ab.txt). The first, unpipelined tcgen05 kernel ("tc") was 1.7x slower than the tiles.
-        mode = !s ? 5 : (!strcmp(s, "tc") ? 3 : (!strcmp(s, "resident") ? 2 : (!strcmp(s, "regs") ? 4 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc3") ? 6 : (!strcmp(s, "tc4") ? 7 : (!strcmp(s, "tc5") ? 8 : 1)))))));
+        // default: tc5 for documents of <= 192 tokens (launch_enc_attention falls back to the mma.sync tiles above that):
+        // 1.55 vs 2.0 ms (tc2) vs 2.3 ms (tiles) per 100 documents at S = 184 (profiles/r02_bench_attn_ab.txt)
+        mode = !s ? 8 : (!strcmp(s, "tc2") ? 5 : (!strcmp(s, "tc5") ? 8 : 1));
     }
     return mode;
-}
-template <int NKB>
-static int launch_attn_tc(const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd, int H, const float* bias,
-                          bf16* out, int ldo, cudaStream_t st, const CUtensorMap* tm) {
-    static SmemOptIn smem_opt_in;
-    auto kern = enc_attention_tc_kernel<NKB>;
-    CU_OK(smem_opt_in.raise(kern, AttnTcCfg<NKB>::kSmemBytes));
-    launch_k(kern, dim3(dim3(H, nd)), dim3(kAttnTcThreads), AttnTcCfg<NKB>::kSmemBytes, st, *tm, inner, d_cu, bias, out, ldo);
-    return B200RANK_OK;
 }
 static int device_sm_count() {   // of the current device (test entry points without an engine; engines carry num_sms)
     int dev = 0, sms = 0;
@@ -1030,10 +998,10 @@ static int device_sm_count() {   // of the current device (test entry points wit
 }
 static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uint64_t qkv_rows, int inner, const int* d_cu, int nd,
                                 int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0,
-                                const float* bias_wide = nullptr) {
+                                const float* bias_wide = nullptr, uint8_t* bad_map = nullptr) {
     if (mode == 0) mode = attn_default_mode();
-    const bool persistent = (mode == 5 || mode == 6 || mode == 7 || mode == 8);
-    if (maxlen > 256 && !persistent) mode = 1;   // modes 2-4 hold a whole document in shared memory / registers
+    const bool persistent = (mode == 5 || mode == 8);
+    if (!persistent) mode = 1;
     // Mixed batch under the default mode: documents of <= 192 tokens still get the tcgen05 kernel (it walks only those), the longer
     // ones the mma.sync tiles (which skip the short ones) — the kernel is chosen per document, so a document's result does not
     // depend on what it is batched with.
@@ -1045,34 +1013,34 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         const CUtensorMap* tm = &local;
         if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
         else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
-        static SmemOptIn opt_in_tc5;
-        CU_OK(opt_in_tc5.raise(enc_attention_tc5_kernel<3>, 227 * 1024));
+        static SmemOptIn opt_in_tc5[3];
+        static int wait_mode = -1;   // B200RANK_ATTN_WAIT=0|1|2: mbarrier wait flavour of the kernel's roles (attention_tc5.cuh)
+        if (wait_mode < 0) wait_mode = getenv("B200RANK_ATTN_WAIT") ? std::max(0, std::min(2, atoi(getenv("B200RANK_ATTN_WAIT")))) : 1;
+        auto kern5 = wait_mode == 1 ? enc_attention_tc5_kernel<3, 1> : (wait_mode == 2 ? enc_attention_tc5_kernel<3, 2> : enc_attention_tc5_kernel<3, 0>);
+        CU_OK(opt_in_tc5[wait_mode].raise(kern5, 227 * 1024));
         const int n_items = nd * H;
         if (e) prof_begin(e, "enc_attention_tc5");
         const int sm_count = e ? e->num_sms : device_sm_count();
         const float* bw = e ? e->bias_enc_wide : bias_wide;
-        if (!bw) return set_error(B200RANK_ERR_ARG, "tc5 attention needs the widened bias table");
-        CU_OK(launch_k(enc_attention_tc5_kernel<3>, dim3(std::min(n_items, sm_count)), dim3(kAttn5Threads), AttnTc5Cfg<3>::smem_bytes(H), st, *tm, qkv, ld,
-                       inner, d_cu, bw, out, ldo, H, n_items, 192));
+        uint8_t* bm = e ? e->attn_bad_map : bad_map;
+        if (!bw || !bm) return set_error(B200RANK_ERR_ARG, "tc5 attention needs the widened bias table and the row fix-up map");
+        CU_OK(launch_k(kern5, dim3(std::min(n_items, sm_count)), dim3(kAttn5Threads), AttnTc5Cfg<3>::smem_bytes(H), st, *tm, qkv, ld,
+                       inner, d_cu, bw, out, ldo, H, n_items, 192, bm));
         if (e) RET_IF(post_launch(e, "enc_attention_tc5"));
         if (!mixed) return B200RANK_OK;
         if (e) prof_begin(e, "enc_attention");
         launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo, 192);
         return e ? post_launch(e, "enc_attention") : B200RANK_OK;
     }
-    if (mode == 5 || mode == 6 || mode == 7) {
+    if (mode == 5) {
         // persistent tcgen05 kernel: one CTA per SM walks the (document, head) items
         CUtensorMap local;
         const CUtensorMap* tm = &local;
         if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
         else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
-        static SmemOptIn opt_in_split, opt_in_two_pass, opt_in_one_pass;
-        static int split = -1;
-        if (split < 0) split = getenv("B200RANK_ATTN_SPLIT") ? atoi(getenv("B200RANK_ATTN_SPLIT")) : 0;
-        auto kern = (split || mode == 6) ? enc_attention_tc2_kernel<3, 1> : (mode == 7 ? enc_attention_tc2_kernel<3, 2> : enc_attention_tc2_kernel<3, 0>);
-        if (split || mode == 6) CU_OK(opt_in_split.raise(enc_attention_tc2_kernel<3, 1>, 227 * 1024));
-        else if (mode == 7) CU_OK(opt_in_one_pass.raise(enc_attention_tc2_kernel<3, 2>, 227 * 1024));
-        else CU_OK(opt_in_two_pass.raise(enc_attention_tc2_kernel<3, 0>, 227 * 1024));
+        static SmemOptIn opt_in_two_pass;
+        auto kern = enc_attention_tc2_kernel<3>;
+        CU_OK(opt_in_two_pass.raise(kern, 227 * 1024));
         const int n_items = nd * H;
         static int spin = -1;
         if (spin < 0) spin = getenv("B200RANK_ATTN_SPIN") ? atoi(getenv("B200RANK_ATTN_SPIN")) : 0;
@@ -1088,40 +1056,6 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         if (e) prof_begin(e, "enc_attention");
         launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo, 192);
         return e ? post_launch(e, "enc_attention") : B200RANK_OK;
-    }
-    if (mode == 3) {
-        CUtensorMap local;
-        const CUtensorMap* tm = &local;
-        if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
-        else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
-        if (e) prof_begin(e, "enc_attention_tc");
-        if (maxlen <= 192) RET_IF(launch_attn_tc<3>(qkv, ld, qkv_rows, inner, d_cu, nd, H, bias, out, ldo, st, tm));
-        else RET_IF(launch_attn_tc<4>(qkv, ld, qkv_rows, inner, d_cu, nd, H, bias, out, ldo, st, tm));
-        return e ? post_launch(e, "enc_attention_tc") : B200RANK_OK;
-    }
-    if (mode == 4) {
-        static SmemOptIn opt_in3, opt_in4;
-        const int nkb = maxlen <= 192 ? 3 : 4;
-        const int smem = (64 + 2 * 64 * nkb) * 128 + kAttnWideBias * 4;
-        if (e) prof_begin(e, "enc_attention_regs");
-        const dim3 grid((maxlen + 63) / 64, H, nd);
-        if (nkb == 3) {
-            CU_OK(opt_in3.raise(enc_attention_regs_kernel<3>, (64 + 2 * 64 * 3) * 128 + kAttnWideBias * 4));
-            CU_OK(launch_k(enc_attention_regs_kernel<3>, grid, dim3(128), smem, st, qkv, ld, inner, d_cu, bias, out, ldo));
-        } else {
-            CU_OK(opt_in4.raise(enc_attention_regs_kernel<4>, (64 + 2 * 64 * 4) * 128 + kAttnWideBias * 4));
-            CU_OK(launch_k(enc_attention_regs_kernel<4>, grid, dim3(128), smem, st, qkv, ld, inner, d_cu, bias, out, ldo));
-        }
-        return e ? post_launch(e, "enc_attention_regs") : B200RANK_OK;
-    }
-    if (mode == 2) {
-        const int s_pad = (maxlen + 63) & ~63;
-        const int smem = 3 * s_pad * 128;
-        static SmemOptIn opt_in_resident;
-        CU_OK(opt_in_resident.raise(enc_attention_resident_kernel, 3 * 256 * 128));
-        if (e) prof_begin(e, "enc_attention_resident");
-        launch_k(enc_attention_resident_kernel, dim3(dim3(H, nd)), dim3((s_pad / 16) * 32), smem, st, qkv, ld, inner, d_cu, bias, out, ldo, s_pad);
-        return e ? post_launch(e, "enc_attention_resident") : B200RANK_OK;
     }
     if (e) prof_begin(e, "enc_attention");
     launch_k(enc_attention_kernel, dim3(dim3((maxlen + 63) / 64, H, nd)), dim3(128), 0, st, qkv, ld, inner, d_cu, bias, out, ldo, 0);
@@ -1541,9 +1475,7 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
     if (!reassoc_t1_possible(e, maxlen))
         return set_error(B200RANK_ERR_ARG, "pipelined submit supports documents of at most 240 tokens on d_kv = 64 models (re-associated T = 1 decoder)");
 
-    // the stream / encoder workspace set of this slot: the ordinary ones unless B200RANK_PIPE_DUAL runs slot 1 next to slot 0
-    const bool dual = e->pipe_dual && b == 1;
-    cudaStream_t s_enc = dual ? e->stream_enc2 : e->stream_main;
+    cudaStream_t s_enc = e->stream_main;
     if (e->unsynced) {   // a b200rank_run_yes_no_staged pass may still read the pinned bump buffer this call is about to rewrite
         CU_OK(cudaStreamSynchronize(e->stream_main));
         e->unsynced = false;
@@ -1558,17 +1490,10 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
             e->stream = e->stream_main; e->enc_out_cur = e->enc_out[0]; e->d_cu_cur = e->d_cu_slot[0]; e->gemm_sm_cap = 0;
         }
     } submit_guard{e, s_enc};
-    struct WsGuard {   // encoder members point at the slot's set while its pass is enqueued (kernel arguments are captured at launch)
-        b200rank_engine* e; bool on;
-        WsGuard(b200rank_engine* e_, bool on_) : e(e_), on(on_) { if (on) use(1); }
-        ~WsGuard() { if (on) use(0); }
-        void use(int k) { const auto& w = e->enc_ws[k]; e->x = w.x; e->h = w.h; e->qkv = w.qkv; e->ao = w.ao; e->g = w.g; e->d_ids = w.d_ids; }
-    } ws_guard(e, dual);
     e->stream = s_enc;
     CU_OK(cudaStreamWaitEvent(s_enc, e->ev_done[b], 0));  // the decoder that last read this slot has finished
     if (resident) {
         if (b != 0) CU_OK(cudaMemcpyAsync(e->d_cu_slot[b], e->d_cu_slot[0], (size_t)(n_docs + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s_enc));
-        if (dual) e->d_ids = e->enc_ws[0].d_ids;   // the staged ids are read-only and were uploaded synchronously: both slots read them in place
     } else {
         // host packing into this slot's pinned staging (its previous H2D finished before the slot was waited on)
         int* hid = e->h_ids_slot[b]; int* hcu = e->h_cu_slot[b];
@@ -1967,14 +1892,22 @@ extern "C" int b200rank_test_enc_attention(int device, const void* qkv_bf16, con
     CU_OK(cudaMemcpy(dbias, bias, (size_t)num_heads * kAttnBiasLen * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemset(dout, 0, (size_t)tokens * inner * 2));
     float* dwide = nullptr;
+    uint8_t* dbad = nullptr;
+    CU_OK(cudaMalloc((void**)&dbad, (size_t)tokens * num_heads));
+    CU_OK(cudaMemset(dbad, 0, (size_t)tokens * num_heads));
     {
         std::vector<float> wide = widen_enc_bias(bias, num_heads);
         CU_OK(cudaMalloc((void**)&dwide, wide.size() * 4));
         CU_OK(cudaMemcpy(dwide, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
     }
-    int rc = launch_enc_attention(nullptr, dq, 3 * inner, qrows, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, mode, 0, dwide);
+    int rc = launch_enc_attention(nullptr, dq, 3 * inner, qrows, inner, dcu, n_docs, maxlen, num_heads, dbias, dout, inner, 0, mode, 0, dwide, dbad);
     cudaError_t err = cudaDeviceSynchronize();
-    cudaFree(dwide);
+    if (err == cudaSuccess && rc == B200RANK_OK) {   // the fix-up walk must leave the map clean for the next launch
+        std::vector<uint8_t> hb((size_t)tokens * num_heads);
+        cudaMemcpy(hb.data(), dbad, hb.size(), cudaMemcpyDeviceToHost);
+        for (uint8_t b : hb) if (b) { rc = set_error(B200RANK_ERR_CUDA, "attention fix-up map not cleared"); break; }
+    }
+    cudaFree(dwide); cudaFree(dbad);
     if (rc != B200RANK_OK) { cudaFree(dq); cudaFree(dout); cudaFree(dcu); cudaFree(dbias); return rc; }
     if (err != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "enc_attention kernel failed: %s", cudaGetErrorString(err));
     else cudaMemcpy(out_bf16, dout, (size_t)tokens * inner * 2, cudaMemcpyDeviceToHost);

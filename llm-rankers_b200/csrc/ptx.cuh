@@ -45,6 +45,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// try_wait without a suspend-time hint: the hardware's default (short) time limit per attempt, then the loop polls again.
+__device__ __forceinline__ void mbar_wait_short(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "LAB_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Poll with an explicit back-off: a role that waits for long (a producer thread, a warp without rows) must not burn the issue slots of
+// the SM sub-partition it shares with working warps — the try_wait loops above re-issue hundreds of times per wait (ncu: 44 % of the
+// attention kernel's executed instructions were wait loops of single-lane producer warps).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        asm volatile("nanosleep.u32 %0;" ::"r"(ns) : "memory");
+    }
+}
+
 // Busy-poll variant (no suspend-time hint): for short, latency-critical waits where the waiter has nothing else to do.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     asm volatile(

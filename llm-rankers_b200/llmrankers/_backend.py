@@ -281,9 +281,9 @@ def _cfg_from_hf(hf: Dict) -> Dict:
     proj = hf.get("feed_forward_proj", "relu")
     if proj not in ("gated-gelu", "relu"):
         raise NotImplementedError(f"feed_forward_proj={proj!r}: gated-gelu (Flan-T5 / T5 v1.1) and relu (T5 v1.0: monoT5, duoT5) are implemented")
-    if hf["d_kv"] != 64 and not (hf["d_kv"] == 128 and os.environ.get("B200RANK_EXPERIMENTAL_DKV128", "0") not in ("", "0")):
-        raise NotImplementedError(f"d_kv={hf['d_kv']}: the attention kernels are specialised for 64; 128 (the 3B T5 v1.0 checkpoints) runs on the "
-                                  "generic-width path, experimental until validated on a B200: set B200RANK_EXPERIMENTAL_DKV128=1")
+    if hf["d_kv"] not in (64, 128):
+        raise NotImplementedError(f"d_kv={hf['d_kv']}: head widths 64 (specialised tcgen05 kernels) and 128 (the 3B T5 v1.0 checkpoints, generic-width "
+                                  "attention) are implemented")
     return dict(vocab_size=hf["vocab_size"], d_model=hf["d_model"], d_kv=hf["d_kv"], num_heads=hf["num_heads"], d_ff=hf["d_ff"],
                 num_layers=hf["num_layers"], num_decoder_layers=hf.get("num_decoder_layers") or hf["num_layers"],
                 rel_buckets=hf.get("relative_attention_num_buckets", 32), rel_max_distance=hf.get("relative_attention_max_distance", 128),

@@ -90,7 +90,7 @@ def test_missing_shard_and_empty_directory_fail_loudly(tmp_path):
         _load_checkpoint(str(tmp_path))
     with open(tmp_path / "config.json") as f:
         hf = json.load(f)
-    hf["d_kv"] = 128
+    hf["d_kv"] = 96
     with open(tmp_path / "config.json", "w") as f:
         json.dump(hf, f)
     with pytest.raises(NotImplementedError, match="d_kv"):

@@ -689,7 +689,7 @@ def test_config_validation_messages():
     import b200rank as br
     lib = br.load_library()
     h = ctypes.c_void_p()
-    bad = br.make_config(128, 2, 256, 2, 2, vocab_size=2304, d_kv=128)
+    bad = br.make_config(128, 2, 256, 2, 2, vocab_size=2304, d_kv=96)
     assert lib.b200rank_create(ctypes.byref(bad), 0, ctypes.byref(h)) == -1
     assert b"d_kv" in lib.b200rank_last_error()
     # every malformed configuration is refused by argument validation (B200RANK_ERR_ARG = -1) before the device is even looked at
