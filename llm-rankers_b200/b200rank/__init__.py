@@ -75,9 +75,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        raise B200RankError(-2, f"{_LIB_PATH} not found — run `python __graft_entry__.py build` (no CPU fallback)")
-    lib = C.CDLL(_LIB_PATH)
+    # B200RANK_LIB=<path>: load another build of the same ABI (same-box A/B of kernel changes: tests/gpu_call_ab.sh); default in-tree
+    path = os.environ.get("B200RANK_LIB") or _LIB_PATH
+    if not os.path.exists(path):
+        raise B200RankError(-2, f"{path} not found — run `python __graft_entry__.py build` (no CPU fallback)")
+    lib = C.CDLL(path)
     i32p, f32p, vp = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p
     lib.b200rank_version.restype = C.c_char_p
     lib.b200rank_last_error.restype = C.c_char_p

@@ -207,51 +207,16 @@ static int pick_cta_group(int M, int N, int bn, int num_sms) {
     return pair_tiles >= num_sms / 2 ? 2 : 1;
 }
 
-// B200RANK_EPI_PIPE (opt-in, experimental): bit 0 = software-pipelined TMEM loads in the fp32 residual epilogue (O-proj, FFN-out),
-// bit 1 = the same in the staged bf16 epilogue (QKV projection, relu FFN-in). 1 | 2 | 3.
-static int epi_pipe_pref() {
-    static int v = -1;
-    if (v < 0) v = getenv("B200RANK_EPI_PIPE") ? (atoi(getenv("B200RANK_EPI_PIPE")) & 3) : 0;
-    return v;
-}
-
-// B200RANK_EPI_HINT=last|first|normal (with B200RANK_EPI_PIPE=1): L2 policy of the residual reduce-add destination lines
-static unsigned long long epi_l2_hint() {
-    static int init = 0;
-    static unsigned long long v = 0;
-    if (!init) {
-        const char* s = getenv("B200RANK_EPI_HINT");
-        if (s && !strcmp(s, "last")) v = kEvictLast;
-        else if (s && !strcmp(s, "first")) v = kEvictFirst;
-        else if (s && !strcmp(s, "normal")) v = kEvictNormal;
-        init = 1;
-    }
-    return v;
-}
-
 static int launch_gemm_tc(cudaStream_t st, int num_sms, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                           const GemmArgs& a, int epi, int bn, bool tma_epi, int cg) {
     // the staged bf16 epilogue moves 64-column (128 B) tiles; a 32-column accumulator keeps the direct store path
     if (epi == EPI_BF16 && bn < 64) tma_epi = false;
-    if (epi == EPI_BF16 && bn == 256 && tma_epi && (epi_pipe_pref() & 2)) {
-        return cg == 2 ? launch_gemm_inst<256, EPI_BF16_PIPE, true, 2>(st, num_sms, ta, tb, tout, a)
-                       : launch_gemm_inst<256, EPI_BF16_PIPE, true, 1>(st, num_sms, ta, tb, tout, a);
-    }
-    if (epi == EPI_RESID_F32 && bn == 256 && tma_epi && (epi_pipe_pref() & 1)) {
-        // opt-in (B200RANK_EPI_PIPE=1, not yet measured on the B200): TMEM loads of the fp32 residual epilogue software-pipelined
-        return cg == 2 ? launch_gemm_inst<256, EPI_RESID_F32_PIPE, true, 2>(st, num_sms, ta, tb, tout, a)
-                       : launch_gemm_inst<256, EPI_RESID_F32_PIPE, true, 1>(st, num_sms, ta, tb, tout, a);
-    }
     if (cg == 2) {
 #define GEMM_CG2(EPI) \
     if (bn == 256 && epi == EPI && tma_epi) return launch_gemm_inst<256, EPI, true, 2>(st, num_sms, ta, tb, tout, a);
-        GEMM_CG2(EPI_BF16) GEMM_CG2(EPI_RESID_F32) GEMM_CG2(EPI_GATED_BF16) GEMM_CG2(EPI_F32) GEMM_CG2(EPI_RESID_NORM)
+        GEMM_CG2(EPI_BF16) GEMM_CG2(EPI_RESID_F32) GEMM_CG2(EPI_GATED_BF16) GEMM_CG2(EPI_F32)
 #undef GEMM_CG2
         return set_error(B200RANK_ERR_ARG, "no cta_group::2 GEMM instantiation for block_n=%d epi=%d tma_epi=%d", bn, epi, (int)tma_epi);
-    }
-    if (epi == EPI_RESID_NORM) {
-        if (bn == 256 && tma_epi) return launch_gemm_inst<256, EPI_RESID_NORM, true, 1>(st, num_sms, ta, tb, tout, a);
-        return set_error(B200RANK_ERR_ARG, "fused residual+norm GEMM needs block_n 256 and the staged epilogue");
     }
 #define GEMM_CASE(BN, EPI)                                                                              \
     if (bn == BN && epi == EPI)                                                                         \
@@ -416,13 +381,12 @@ static int post_launch(b200rank_engine* e, const char* what) {
 
 // acc[M,N] = A[M,K] . W[N,K]^T with fused epilogue. a_rows/w_rows: row capacity of the operands (TMA bounds).
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn, const float* norm_w, bf16* norm_out, int n_per_batch, int a_cols) {
+                int K, int epi, void* out, int ldo, int force_bn, int n_per_batch, int a_cols) {
     if (M <= 0) return B200RANK_OK;
     if (N % 8 != 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0)
         return set_error(B200RANK_ERR_ARG, "gemm dims must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     const int relu = (epi == EPI_RELU_BF16);
     int bn = force_bn ? force_bn : pick_block_n(M, N, K, relu ? EPI_BF16 : epi, e->num_sms);
-    if (epi == EPI_RESID_NORM) bn = 256;
     char label[96];
     if (e->profiling) snprintf(label, sizeof label, "gemm_tcgen05<bn%d,epi%d> M%d N%d K%d", bn, epi, M, N, K);  // cta group: pick_cta_group
     prof_begin(e, label);
@@ -431,7 +395,7 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
         if (n_per_batch) return set_error(B200RANK_ERR_ARG, "block-diagonal GEMM has no CUDA-core debug variant");
         const int n_out = epi == EPI_GATED_BF16 ? N / 2 : N;
         dim3 blk(32, 8), grd((n_out + 31) / 32, (M + 7) / 8);
-        gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi == EPI_RESID_NORM ? EPI_RESID_F32 : epi, 256, out, ldo);
+        gemm_simt_debug_kernel<<<grd, blk, 0, e->stream>>>(A, lda, W, ldw, M, N, K, epi, 256, out, ldo);
         return post_launch(e, "gemm_simt_debug");
     }
     if (relu) epi = EPI_BF16;
@@ -444,12 +408,12 @@ static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf
     ta = *cached;
     RET_IF(engine_tmap(e, W, w_rows, K, ldw, bn / cg, 0, &cached));
     tb = *cached;
-    const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32 || epi == EPI_RESID_NORM);
+    const bool out_f32 = (epi == EPI_RESID_F32 || epi == EPI_F32);
     const int n_out = (epi == EPI_GATED_BF16) ? N / 2 : N;
     // the output map carries the LIVE row count so TMA clips the ragged last M-tile
     RET_IF(engine_tmap(e, out, M, n_out, ldo, kGemmBlockM, out_f32 ? 2 : 1, &cached));
     tout = *cached;
-    GemmArgs args{M, N, K, out, ldo, norm_w, norm_out, e->cfg.layer_norm_eps, n_per_batch, relu, epi_l2_hint()};
+    GemmArgs args{M, N, K, out, ldo, n_per_batch, relu};
     const int sms = (e->gemm_sm_cap > 0 && bn == 256 && M > 1024) ? std::min(e->gemm_sm_cap, e->num_sms) : e->num_sms;
     RET_IF(launch_gemm_tc(e->stream, sms, ta, tb, tout, args, epi, bn, !e->direct_epi, cg));
     return post_launch(e, "gemm_tcgen05");
@@ -756,7 +720,7 @@ static int shape_check(const char* name, int64_t rows, int64_t cols, int64_t er,
 }
 
 static int gemm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int N,
-                int K, int epi, void* out, int ldo, int force_bn = 0, const float* norm_w = nullptr, bf16* norm_out = nullptr,
+                int K, int epi, void* out, int ldo, int force_bn = 0,
                 int n_per_batch = 0, int a_cols = 0);
 
 // Derived weights, computed once on the device when the last tensor arrives (they live in the arena, so the NCCL
@@ -959,20 +923,11 @@ static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h
     return post_launch(e, label);
 }
 
-// x += A.W^T, then h = bf16(T5LayerNorm(x) * norm_w). Fused into one launch (EPI_RESID_NORM: row-block-owning units re-read
-// their finished rows from L2) when there are enough 128*CG-row blocks to occupy the machine; otherwise GEMM + rmsnorm kernel.
-static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n);
+// x += A.W^T (in-L2 reduce-add epilogue), then h = bf16(T5LayerNorm(x) * norm_w) as a kernel of its own: fusing the norm into the GEMM
+// (row-owning units re-reading their finished rows from L2) measured slower on the B200 in round 1 and was removed in round 2.
 static int gemm_resid_then_norm(b200rank_engine* e, const bf16* A, int lda, int a_rows, const bf16* W, int ldw, int w_rows, int M, int K,
                                 float* x, const float* norm_w, bf16* h) {
     const int d = e->d;
-    static int fuse_pref = -1;
-    // default OFF: measured slower than GEMM + rmsnorm on B200 in round 1 (profiles/r01_bench_n1_v6*.json); B200RANK_FUSE_NORM=1 enables it
-    if (fuse_pref < 0) fuse_pref = (getenv("B200RANK_FUSE_NORM") && atoi(getenv("B200RANK_FUSE_NORM")) != 0) ? 1 : 0;
-    const int cg = pick_cta_group(M, d, 256, e->num_sms);
-    const int row_blocks = (M + 128 * cg - 1) / (128 * cg);
-    const int units = e->num_sms / cg;
-    const bool fuse = fuse_pref && !e->direct_epi && !e->debug_simt && d % 256 == 0 && row_blocks * 10 >= units * 6;
-    if (fuse) return gemm(e, A, lda, a_rows, W, ldw, w_rows, M, d, K, EPI_RESID_NORM, x, d, 0, norm_w, h);
     RET_IF(gemm(e, A, lda, a_rows, W, ldw, w_rows, M, d, K, EPI_RESID_F32, x, d));
     return k_rmsnorm(e, x, norm_w, h, M);
 }
@@ -1225,13 +1180,13 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         if (reassoc) {
             // cross_ctx_t1.cuh: scores = (W_k,h^T q_h) . e_j and out_h = W_v,h (sum_j p_j e_j): no K/V projection of the encoder
             const int HD = e->H * d, dcap = (int)align_up(e->cap_docs, 128);
-            RET_IF(gemm(e, e->qd, I, cap, w.wkT, 64, HD, R, HD, 64, EPI_BF16, e->qp, HD, 0, nullptr, nullptr, /*n_per_batch=*/d, /*a_cols=*/I));
+            RET_IF(gemm(e, e->qd, I, cap, w.wkT, 64, HD, R, HD, 64, EPI_BF16, e->qp, HD, 0, /*n_per_batch=*/d, /*a_cols=*/I));
             const int s_pad = (max_len + 15) & ~15;
             prof_begin(e, "cross_ctx_t1");
             launch_k(cross_ctx_t1_kernel, dim3(nd), dim3(kCtxThreads), cross_ctx_smem_bytes(s_pad), e->stream, e->qp, e->enc_out_cur, e->d_cu_cur + doc0, e->ctxb, e->H, d, s_pad);
             RET_IF(post_launch(e, "cross_ctx_t1"));
             const bf16* wv_l = e->wckv + ((size_t)l * 2 * I + I) * d;
-            RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, nullptr, nullptr, /*n_per_batch=*/64, /*a_cols=*/HD));
+            RET_IF(gemm(e, e->ctxb, HD, dcap, wv_l, d, I, R, I, d, EPI_BF16, e->aod, I, /*force_bn=*/32, /*n_per_batch=*/64, /*a_cols=*/HD));
             RET_IF(dec_resid_proj(e, e->aod, I, w.wo_c, I, R));
             RET_IF(dec_norm_ffn_in(e, w.ln2, w.wi, R));
             RET_IF(dec_resid_proj(e, e->gd, F, w.wff, F, R));
@@ -1854,7 +1809,7 @@ extern "C" int b200rank_test_gemm(int device, const void* a_bf16, const void* w_
         rc = make_tmap(&ta, dA, Mp, K, K, kGemmBlockM);
         if (rc == B200RANK_OK) rc = make_tmap(&tb, dW, Np, K, K, bn / cg);
         if (rc == B200RANK_OK) rc = make_tmap(&tout, dO, M, n_out, n_out, kGemmBlockM, out_elem == 4 ? 2 : 1);
-        GemmArgs args{M, N, K, dO, n_out, nullptr, nullptr, 0.f, 0, 0, 0ull};
+        GemmArgs args{M, N, K, dO, n_out, 0, 0};
         if (rc == B200RANK_OK) rc = launch_gemm_tc(0, prop.multiProcessorCount, ta, tb, tout, args, epi, bn, !direct, cg);
     }
     if (rc == B200RANK_OK) {

@@ -22,28 +22,17 @@ enum EpiMode : int {
     EPI_RESID_F32 = 1,  // out_f32[m, n]            += acc              (residual stream, in place)
     EPI_GATED_BF16 = 2, // out_bf16[m, n/2 ...]      = gelu_new(acc[:, :BN/2]) * acc[:, BN/2:]  per N-tile
     EPI_F32 = 3,        // out_f32[m, n]             = acc
-    EPI_RESID_NORM = 4, // EPI_RESID_F32 with N == row width, plus: every unit owns whole 128-row blocks (all N-tiles), and once a
-                        // block's adds have landed it re-reads those rows from L2 and writes norm_out = bf16(T5LayerNorm(out))
     EPI_RELU_BF16 = 5,  // host-side alias: launched as EPI_BF16 with GemmArgs::relu = 1 (out_bf16 = max(acc, 0))
-    EPI_BF16_PIPE = 7,       // EPI_BF16 (staged) with the tcgen05.ld of the next 64-column chunk in flight while the current one is packed,
-                             // staged and stored (opt-in, B200RANK_EPI_PIPE bit 1; the QKV projection runs 87 % tensor-active)
-    EPI_RESID_F32_PIPE = 6,  // EPI_RESID_F32 with the tcgen05.ld of chunk c+1 in flight while chunk c is staged (opt-in, B200RANK_EPI_PIPE=1:
-                             // experiments/epi_probe.cu shows the un-pipelined TMEM loads cost ~1.8 us of the ~6 us a 128 x 256 tile's epilogue takes)
 };
 
 struct GemmArgs {
     int M, N, K;   // N counts accumulator columns (= weight rows); K is the contraction length
     void* out;     // bf16* or float* depending on the epilogue
     int ldo;       // leading dimension of out, in elements
-    // EPI_RESID_NORM only: fused T5LayerNorm (modeling_t5.py:55-68) of the updated residual rows
-    const float* norm_w;        // [N]
-    __nv_bfloat16* norm_out;    // [M, N] bf16, leading dimension N
-    float norm_eps;
     // Block-diagonal GEMM (n_per_batch > 0): column block b = n / n_per_batch of the output contracts A[:, b*K : (b+1)*K]
     // with W rows of that block, i.e. out[:, b-th block] = A_b . W_b^T for per-head weight slices (decoder T=1 fast path).
     int n_per_batch;
     int relu;      // EPI_BF16 only: out = max(acc, 0) (T5 v1.0 DenseReluDense, modeling_t5.py:88-103)
-    unsigned long long l2_hint;  // EPI_RESID_F32_PIPE only (experimental): L2 cache policy of the reduce-add destination, 0 = none
 };
 
 constexpr int kGemmBlockM = 128;
@@ -70,6 +59,10 @@ struct GemmCfg {
 //                  performs x += acc inside L2 so the SMs never read the residual stream.
 // TMA_EPI = false: per-thread 16 B global stores straight from registers (round-1 bring-up path, kept for bisecting
 //                  with B200RANK_GEMM_DIRECT_EPI=1).
+// Tried on the B200 in round 2 and dropped (same-box A/B, profiles/r02_gemm_epilogue_ab.txt): software-pipelined TMEM loads in the
+// epilogues (no change) and TWO epilogue warpgroups splitting the tile's columns (slower: O-projection 1.10 -> 1.23 ms per step, one
+// ring stage less) — the residual-epilogue GEMMs are not bound by epilogue threads but by L2: operand tiles at 64 B/clk/SM plus the
+// read-modify-write of the fp32 residual in L2.
 // CG = 2: the kernel runs as clusters of two CTAs (cta_group::2). One tcgen05.mma then covers 256 x BLOCK_N: each CTA keeps
 //         its own 128 accumulator rows in its own TMEM and stages its own 128 rows of A but only HALF of the B tile — the
 //         tensor core reads the other half from the peer's shared memory. That halves the L2->SM and shared-memory traffic
@@ -110,21 +103,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int tiles_n = (args.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (args.K + kGemmBlockK - 1) / kGemmBlockK;
-    constexpr bool kRowOwner = (EPI == EPI_RESID_NORM);
-    constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_NORM || EPI == EPI_RESID_F32_PIPE);
-    // it-th tile of this unit -> (m-block, n-block). Default: tiles round-robin over units, n fastest. Row-owner mode: a unit
-    // takes whole m-blocks (all n-tiles back to back) so that it alone completes rows.
+    constexpr bool kResid = (EPI == EPI_RESID_F32);
+    // it-th tile of this unit -> (m-block, n-block): tiles round-robin over units, n fastest
     auto get_tile = [&](int it, int& mb, int& nb) -> bool {
-        if constexpr (kRowOwner) {
-            mb = unit + (it / tiles_n) * num_units;
-            nb = it % tiles_n;
-            return mb < tiles_m;
-        } else {
-            const int tile = unit + it * num_units;
-            mb = tile / tiles_n;
-            nb = tile % tiles_n;
-            return tile < num_tiles;
-        }
+        const int tile = unit + it * num_units;
+        mb = tile / tiles_n;
+        nb = tile % tiles_n;
+        return tile < num_tiles;
     };
 
     if (warp_idx == 0 && lane == 0) {
@@ -251,10 +236,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     named_bar_sync(1, 128);
                     if (issuer) {
                         const void* src = smem_stage + stage_sel * (kGemmBlockM * 128);
-                        if constexpr (EPI == EPI_RESID_F32_PIPE) {
-                            if (args.l2_hint) tma_reduce_add_2d_hint(&tmap_out, src, out_col0, m0, args.l2_hint);
-                            else tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
-                        } else if constexpr (kResid) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
+                        if constexpr (kResid) tma_reduce_add_2d(&tmap_out, src, out_col0, m0);
                         else tma_store_2d(&tmap_out, src, out_col0, m0);
                         tma_store_commit();
                     }
@@ -315,71 +297,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                         stage_close(nb * HALF + c);
-                    }
-                } else if constexpr (EPI == EPI_BF16_PIPE) {
-                    // bf16 tiles of 64 columns; two pairs of register buffers: the TMEM loads of the next 64 columns fly during the
-                    // pack + staging (two named barriers + fence + bulk store issue) of the current ones
-                    static_assert(BLOCK_N % 64 == 0, "pipelined bf16 epilogue walks 64-column chunks");
-                    uint32_t a0[32], a1[32], b0[32], b1[32];
-                    auto emit = [&](uint32_t (&r0)[32], uint32_t (&r1)[32], int c) {
-                        if (args.relu) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                r0[j] = __float_as_uint(fmaxf(__uint_as_float(r0[j]), 0.f));
-                                r1[j] = __float_as_uint(fmaxf(__uint_as_float(r1[j]), 0.f));
-                            }
-                        }
-                        stage_open();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            put16(j, pack_bf16(__uint_as_float(r0[8 * j + 0]), __uint_as_float(r0[8 * j + 1])),
-                                  pack_bf16(__uint_as_float(r0[8 * j + 2]), __uint_as_float(r0[8 * j + 3])),
-                                  pack_bf16(__uint_as_float(r0[8 * j + 4]), __uint_as_float(r0[8 * j + 5])),
-                                  pack_bf16(__uint_as_float(r0[8 * j + 6]), __uint_as_float(r0[8 * j + 7])));
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            put16(4 + j, pack_bf16(__uint_as_float(r1[8 * j + 0]), __uint_as_float(r1[8 * j + 1])),
-                                  pack_bf16(__uint_as_float(r1[8 * j + 2]), __uint_as_float(r1[8 * j + 3])),
-                                  pack_bf16(__uint_as_float(r1[8 * j + 4]), __uint_as_float(r1[8 * j + 5])),
-                                  pack_bf16(__uint_as_float(r1[8 * j + 6]), __uint_as_float(r1[8 * j + 7])));
-                        stage_close(nb * BLOCK_N + c);
-                    };
-                    tmem_ld32(taddr, a0);
-                    tmem_ld32(taddr + 32, a1);
-#pragma unroll 1
-                    for (int c = 0; c < BLOCK_N; c += 128) {
-                        tmem_ld_wait();
-                        if (c + 64 < BLOCK_N) { tmem_ld32(taddr + c + 64, b0); tmem_ld32(taddr + c + 96, b1); }
-                        else { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
-                        emit(a0, a1, c);
-                        if (c + 64 < BLOCK_N) {
-                            tmem_ld_wait();
-                            if (c + 128 < BLOCK_N) { tmem_ld32(taddr + c + 128, a0); tmem_ld32(taddr + c + 160, a1); }
-                            else { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
-                            emit(b0, b1, c + 64);
-                        }
-                    }
-                } else if constexpr (EPI == EPI_RESID_F32_PIPE) {
-                    // fp32 tiles of 32 columns, in-L2 add; two register buffers: the TMEM load of the next chunk flies during the
-                    // shared-memory staging (two named barriers + fence + bulk reduce issue) of the current one
-                    static_assert(BLOCK_N % 64 == 0, "pipelined fp32 epilogue walks pairs of 32-column chunks");
-                    uint32_t ra[32], rb[32];
-                    tmem_ld32(taddr, ra);
-#pragma unroll 1
-                    for (int c = 0; c < BLOCK_N; c += 64) {
-                        tmem_ld_wait();
-                        tmem_ld32(taddr + c + 32, rb);
-                        stage_open();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) put16(j, ra[4 * j + 0], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
-                        stage_close(nb * BLOCK_N + c);
-                        tmem_ld_wait();
-                        if (c + 64 < BLOCK_N) tmem_ld32(taddr + c + 64, ra);
-                        else { tc_fence_before(); release_acc(&tmem_empty_bar[acc]); }
-                        stage_open();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) put16(j, rb[4 * j + 0], rb[4 * j + 1], rb[4 * j + 2], rb[4 * j + 3]);
-                        stage_close(nb * BLOCK_N + c + 32);
                     }
                 } else {  // fp32 tiles of 32 columns: plain store (EPI_F32) or in-L2 add (EPI_RESID_F32)
 #pragma unroll 1
@@ -480,87 +397,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                     x.w = __uint_as_float(r[j + 3]);
                                     *reinterpret_cast<float4*>(out + col0 + j) = x;
                                 }
-                            }
-                        }
-                    }
-                }
-            }
-            if constexpr (kRowOwner && TMA_EPI) {
-                if (nb == tiles_n - 1) {
-                    // All N-tiles of this unit's rows [m0, m0+128) are issued. Wait until the bulk reduce-adds have been performed
-                    // (wait_group without .read), then normalise the rows straight out of L2: one warp per row, row in registers.
-                    if (threadIdx.x == 64) tma_store_wait<0>();
-                    named_bar_sync(1, 128);
-                    const int d = args.N;
-                    const int nvec = d >> 2;
-                    const int ew = warp_idx - 2;  // 0..3: this warp normalises rows ew*32 .. ew*32+31 of the block
-                    const float4* wv = reinterpret_cast<const float4*>(args.norm_w);
-                    const float* xbase = reinterpret_cast<const float*>(args.out);
-                    if (nvec <= 256) {
-                        // d <= 1024: four rows per step, whole rows held in registers (32 independent 16 B loads per lane in flight)
-                        for (int r4 = 0; r4 < 32; r4 += 4) {
-                            float4 v[4][8];
-                            float ss[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int row = m0 + ew * 32 + r4 + q;
-                                const float4* src = reinterpret_cast<const float4*>(xbase + static_cast<size_t>(min(row, args.M - 1)) * args.ldo);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int idx = lane + i * 32;
-                                    v[q][i] = (idx < nvec) ? __ldcg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                }
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) ss[q] += v[q][i].x * v[q][i].x + v[q][i].y * v[q][i].y + v[q][i].z * v[q][i].z + v[q][i].w * v[q][i].w;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) ss[q] += __shfl_xor_sync(0xffffffffu, ss[q], o);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int row = m0 + ew * 32 + r4 + q;
-                                if (row < args.M) {
-                                    const float r = rsqrtf(ss[q] / static_cast<float>(d) + args.norm_eps);
-                                    uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const int idx = lane + i * 32;
-                                        if (idx < nvec) {
-                                            const float4 gw = __ldg(wv + idx);
-                                            uint2 o2;
-                                            o2.x = pack_bf16(v[q][i].x * r * gw.x, v[q][i].y * r * gw.y);
-                                            o2.y = pack_bf16(v[q][i].z * r * gw.z, v[q][i].w * r * gw.w);
-                                            dst[idx] = o2;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    } else {
-                        for (int rr = ew * 32; rr < ew * 32 + 32; ++rr) {   // wide models: two passes over the L2-resident row
-                            const int row = m0 + rr;
-                            if (row >= args.M) break;
-                            const float4* src = reinterpret_cast<const float4*>(xbase + static_cast<size_t>(row) * args.ldo);
-                            float ss = 0.f;
-#pragma unroll 8
-                            for (int idx = lane; idx < nvec; idx += 32) {
-                                const float4 v = __ldcg(src + idx);
-                                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-                            }
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                            const float r = rsqrtf(ss / static_cast<float>(d) + args.norm_eps);
-                            uint2* dst = reinterpret_cast<uint2*>(args.norm_out + static_cast<size_t>(row) * d);
-#pragma unroll 8
-                            for (int idx = lane; idx < nvec; idx += 32) {
-                                const float4 v = __ldcg(src + idx);
-                                const float4 gw = __ldg(wv + idx);
-                                uint2 o2;
-                                o2.x = pack_bf16(v.x * r * gw.x, v.y * r * gw.y);
-                                o2.y = pack_bf16(v.z * r * gw.z, v.w * r * gw.w);
-                                dst[idx] = o2;
                             }
                         }
                     }

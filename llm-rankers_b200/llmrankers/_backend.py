@@ -290,3 +290,113 @@ def _cfg_from_hf(hf: Dict) -> Dict:
                 layer_norm_eps=hf.get("layer_norm_epsilon", 1e-6), gated_gelu=proj == "gated-gelu",
                 scale_decoder_outputs=bool(hf.get("tie_word_embeddings", True)), pad_id=hf.get("pad_token_id", 0),
                 eos_id=hf.get("eos_token_id", 1))
+
+
+class ShardedBackend:
+    """Document-level sharding across the GPUs of one box (north_star: "candidate (query, passage) prompts shard
+    embarrassingly across the 8 GPUs ... no collective inside the scoring loop").
+
+    Wraps the T5Backend of THIS rank (one process per GPU, torch.distributed already initialised) and presents the same interface to
+    the rankers. Every rank runs the same host program on the same inputs, so every scoring call sees the same flattened list of
+    prompt rows on all ranks; the wrapper scores the contiguous slice [lo, hi) of that list on its own GPU and concatenates the
+    ranks' results in rank order with ONE host-side all-gather of the (tiny) result arrays per call — the engine's device passes
+    contain no collective. A row's result does not depend on what it is batched with (tests/test_engine_gpu.py: batch-composition
+    invariance, bit-exact), so the gathered result equals the single-GPU result bit for bit, and every rank holds the complete
+    answer: sort drivers, counters and output assembly proceed identically everywhere; rank 0 writes the run file.
+
+    Where it pays: one query with many prompts — pairwise allpair (`pairwise.py:169-219`: n(n-1) = 9900 prompts for 100 hits),
+    pointwise over 1000 hits (`pointwise.py:41-82`) — is strong-scaled over the GPUs. Sort-based methods issue short dependent
+    batches (one compare = one prompt); for those run.py shards QUERIES instead (`B200RANK_SHARD=queries`)."""
+
+    def __init__(self, inner: "T5Backend", group=None):
+        import torch.distributed as dist
+        self.inner, self.group = inner, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def __getattr__(self, name):           # tokenizer, cfg, engine, pad_id, eos_id, assembler, prompt_rows, pad_rows, ...
+        return getattr(self.inner, name)
+
+    # -- plumbing
+    def _bounds(self, n: int) -> Tuple[int, int]:
+        from b200rank.dist import shard_bounds
+        return shard_bounds(n, self.rank, self.world)
+
+    def _gather(self, local):
+        """Per-rank Python objects in rank order (small numpy arrays: pickled through torch.distributed, gloo or nccl)."""
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, local, group=self.group)
+        return parts
+
+    def _cat(self, local: np.ndarray, tail_shape=()) -> np.ndarray:
+        parts = [p for p in self._gather(np.ascontiguousarray(local)) if p.shape[0]]
+        return np.concatenate(parts, axis=0) if parts else np.zeros((0,) + tuple(tail_shape), local.dtype)
+
+    # -- the scoring calls, sharded
+    def score_yes_no(self, rows, yes_id: int, no_id: int):
+        lo, hi = self._bounds(len(rows))
+        if hi > lo:
+            lg, sc = self.inner.score_yes_no(rows[lo:hi], yes_id, no_id)
+        else:
+            lg, sc = np.zeros((0, 2), np.float32), np.zeros((0,), np.float32)
+        both = self._cat(np.concatenate([np.asarray(lg, np.float32).reshape(-1, 2), np.asarray(sc, np.float32).reshape(-1, 1)], axis=1), (3,))
+        return both[:, :2].copy(), both[:, 2].copy()
+
+    def submit_yes_no(self, rows, yes_id: int, no_id: int):
+        """Pipelined form: this rank's slice goes through the engine's submit (or, if the slice does not qualify for the pipelined pass,
+        is scored synchronously right away); the all-gather happens in wait_yes_no. The decision to pipeline at all is taken on the
+        whole row list, which every rank sees, so all ranks take the same path."""
+        lo, hi = self._bounds(len(rows))
+        ticket, ready = None, None
+        if hi > lo:
+            ticket = self.inner.submit_yes_no(rows[lo:hi], yes_id, no_id)
+            if ticket is None:
+                ready = self.inner.score_yes_no(rows[lo:hi], yes_id, no_id)
+        else:
+            ready = (np.zeros((0, 2), np.float32), np.zeros((0,), np.float32))
+        return ("sharded", ticket, ready)
+
+    def wait_yes_no(self, ticket):
+        _, t, ready = ticket
+        lg, sc = ready if t is None else self.inner.wait_yes_no(t)
+        both = self._cat(np.concatenate([np.asarray(lg, np.float32).reshape(-1, 2), np.asarray(sc, np.float32).reshape(-1, 1)], axis=1), (3,))
+        return both[:, :2].copy(), both[:, 2].copy()
+
+    def score_qlm(self, rows, labels: Sequence[int]) -> np.ndarray:
+        lo, hi = self._bounds(len(rows))
+        local = np.asarray(self.inner.score_qlm(rows[lo:hi], labels), np.float32) if hi > lo else np.zeros((0,), np.float32)
+        return self._cat(local)
+
+    def label_probs(self, rows, dec_prefix: Sequence[int], cols: Sequence[int]) -> np.ndarray:
+        lo, hi = self._bounds(len(rows))
+        local = (np.asarray(self.inner.label_probs(rows[lo:hi], dec_prefix, cols), np.float32) if hi > lo
+                 else np.zeros((0, len(cols)), np.float32))
+        return self._cat(local, (len(cols),))
+
+    def generate_rows(self, rows, dec_prefix: Sequence[int], max_new: int) -> List[np.ndarray]:
+        lo, hi = self._bounds(len(rows))
+        local = self.inner.generate_rows(rows[lo:hi], dec_prefix, max_new) if hi > lo else []
+        return [x for part in self._gather(list(local)) for x in part]
+
+    def generate_batches(self, batches, dec_prefix: Sequence[int], max_new: int) -> List[np.ndarray]:
+        """Whole reference batches are the unit (a batch's padding / early-stopping semantics are per batch): batches [lo, hi) here."""
+        lo, hi = self._bounds(len(batches))
+        local = self.inner.generate_batches(batches[lo:hi], dec_prefix, max_new) if hi > lo else []
+        return [x for part in self._gather(list(local)) for x in part]
+
+    def generate(self, padded_ids: np.ndarray, dec_prefix: Sequence[int], max_new: int) -> np.ndarray:
+        """One padded batch is not split (its early-stopping length depends on all of its rows, and compare batches are one or two
+        prompts): every rank computes it — identical bits — and no communication is needed."""
+        return self.inner.generate(padded_ids, dec_prefix, max_new)
+
+
+def shard_mode(ranker_kind: str, method: str) -> str:
+    """'docs' or 'queries': how run.py / bench.py split work over ranks (B200RANK_SHARD overrides). Document-level sharding for the
+    rankers whose per-query work is one big independent prompt list (pointwise yes_no / qlm, MonoT5, pairwise allpair); query-level
+    sharding for the sort drivers (heapsort / bubblesort / sliding windows), whose compares are short dependent batches."""
+    forced = os.environ.get("B200RANK_SHARD", "").lower()
+    if forced in ("docs", "queries"):
+        return forced
+    if ranker_kind == "pointwise" or (ranker_kind == "pairwise" and method == "allpair"):
+        return "docs"
+    return "queries"

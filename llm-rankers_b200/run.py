@@ -161,6 +161,63 @@ def _dist_setup(args):
     return dist.get_rank(), world
 
 
+def flat_document_pieces(rankings, batch_size, rank, world):
+    """Document-level sharding of a pointwise run ("shard the concatenated (query, doc) list, not queries"): the
+    documents of ALL queries form one list, cut into `world` contiguous, equally long slices; a query that straddles a cut is
+    scored in two pieces on two GPUs. Cuts fall on multiples of `batch_size` inside a query, so the reference's DataLoader batches —
+    and with them its per-batch counters (pointwise.py:64-70,106-115) — are exactly those of the unsharded run. Returns this rank's
+    pieces [(query index, start, stop)] in order; the slices of all ranks tile the list."""
+    units, total = [], 0                       # (query index, start, stop) of every reference batch
+    for qi, ranking in enumerate(rankings):
+        for s0 in range(0, len(ranking), batch_size):
+            units.append((qi, s0, min(s0 + batch_size, len(ranking))))
+            total += units[-1][2] - s0
+    lo_doc, hi_doc = total * rank // world, total * (rank + 1) // world
+    pieces, seen = [], 0
+    for qi, s0, s1 in units:                   # a batch belongs to the rank whose slice holds its first document
+        if lo_doc <= seen < hi_doc:
+            if pieces and pieces[-1][0] == qi and pieces[-1][2] == s0:
+                pieces[-1] = (qi, pieces[-1][1], s1)
+            else:
+                pieces.append((qi, s0, s1))
+        seen += s1 - s0
+    return pieces
+
+
+def main_pointwise_flat(args, ranker, first_stage, rank, world):
+    """--pointwise under torchrun with document-level sharding: every rank scores its slice of the flattened (query, document) list
+    through the ranker's own rerank_many (two batches in flight per GPU), the (index, score) pairs and counters are gathered ONCE at
+    the end, and rank 0 applies every query's final sort. No collective inside the scoring loop."""
+    from b200rank.dist import gather_lists
+    items = list(first_stage)
+    pieces = flat_document_pieces([r for _, _, r in items], ranker.batch_size, rank, world)
+    tic = time.time()
+    requests = [(items[qi][1], items[qi][2][s0:s1]) for qi, s0, s1 in pieces]
+    local = []
+    many = hasattr(ranker, 'rerank_many') and os.environ.get('B200RANK_RERANK_MANY', '1') != '0'
+    results = ranker.rerank_many(iter(requests)) if many else (ranker.rerank(q, r) for q, r in requests)
+    for (qi, s0, s1), (_, sub), _ in zip(pieces, requests, results):
+        local.append((qi, s0, [float(d.score) for d in sub], ranker.total_compare, ranker.total_prompt_tokens, ranker.total_completion_tokens))
+    toc = time.time()
+    gathered = gather_lists(local)
+    import torch.distributed as dist
+    dist.barrier()
+    if rank != 0:
+        return
+    n_cmp = n_prompt = n_completion = 0
+    for qi, s0, scores, c, pt, ct in gathered:
+        for doc, sc in zip(items[qi][2][s0:s0 + len(scores)], scores):
+            doc.score = sc
+        n_cmp, n_prompt, n_completion = n_cmp + c, n_prompt + pt, n_completion + ct
+    # the ranker's own final step (pointwise.py:82,127): a stable descending sort over the query's hits in their input order
+    reranked = [(qid, query, sorted(ranking, key=lambda x: x.score, reverse=True)) for qid, query, ranking in items]
+    print(f'Avg comparisons: {n_cmp / len(reranked)}')
+    print(f'Avg prompt tokens: {n_prompt / len(reranked)}')
+    print(f'Avg completion tokens: {n_completion / len(reranked)}')
+    print(f'Avg time per query: {(toc - tic) / len(reranked)}')
+    write_run_file(args.run.save_path, reranked, 'LLMRankers')
+
+
 def main(args):
     rank, world = _dist_setup(args)
     ranker = build_ranker(args)
@@ -190,7 +247,20 @@ def main(args):
     # ranker that works query by query — the interleaving of run.py:181-190, which matters when the ranker itself draws from the
     # module RNG (setwise num_permutation > 1; its rerank_many falls back to one rerank() per request).
     source = prepared()
+    # How work is split over the ranks (llmrankers/_backend.py::shard_mode, B200RANK_SHARD=docs|queries): document level for the rankers
+    # whose per-query work is one independent prompt list, query level for the sort drivers.
+    mode = 'queries'
     if world > 1:
+        from llmrankers._backend import ShardedBackend, shard_mode
+        kind = 'pointwise' if args.pointwise else 'pairwise' if args.pairwise else 'setwise' if args.setwise else 'listwise'
+        sub = getattr(args, kind)
+        mode = shard_mode(kind, getattr(sub, 'method', '') or '')
+        if mode == 'docs' and kind == 'pointwise' and hasattr(ranker, 'batch_size'):
+            return main_pointwise_flat(args, ranker, source, rank, world)
+        if mode == 'docs' and hasattr(ranker, 'backend'):
+            # pairwise allpair: every rank walks all queries; each query's n(n-1) prompts are split over the GPUs inside the backend
+            ranker.backend = ShardedBackend(ranker.backend)
+    if world > 1 and mode == 'queries':
         from b200rank.dist import shard_bounds
         items = list(source)                      # every rank draws the shuffles of all queries (one stream), then keeps its shard
         lo, hi = shard_bounds(len(items), rank, world)
@@ -213,7 +283,12 @@ def main(args):
         n_prompt += ranker.total_prompt_tokens
         n_completion += ranker.total_completion_tokens
     toc = time.time()
-    if world > 1:
+    if world > 1 and mode == 'docs':
+        import torch.distributed as dist
+        dist.barrier()
+        if rank != 0:       # every rank holds the complete, identical result: rank 0 reports it
+            return
+    elif world > 1:
         import torch.distributed as dist
         from b200rank.dist import gather_lists
         reranked = gather_lists(reranked)                       # rank order == file order (contiguous shards)

@@ -64,7 +64,9 @@ def assert_same_order_within_tol(name, docids, got_scores, ref_scores, tol):
 
 # ---------------------------------------------------------------------------------------- kernels
 @pytest.mark.parametrize("M,N,K,epi", [(128, 256, 64, 3), (1000, 1024, 1024, 0), (1000, 1024, 1024, 1), (777, 512, 2816, 1),
-                                       (1000, 1024, 1024, 2), (100, 3072, 1024, 0), (300, 32128, 512, 3)])
+                                       (1000, 1024, 1024, 2), (100, 3072, 1024, 0), (300, 32128, 512, 3),
+                                       # enough 256-row tiles for CTA pairs (cta_group::2) with both epilogue warpgroups, ragged last tile
+                                       (5001, 1024, 1024, 1), (4999, 1536, 512, 0), (4900, 2048, 512, 2), (4870, 1024, 256, 3)])
 def test_gemm_vs_numpy(M, N, K, epi):
     import b200rank as br
     rng = np.random.default_rng(M + N + K + epi)
@@ -498,13 +500,8 @@ def test_kernel_variants_agree(tmp_path):
 
     base = run("default")
     assert np.all(np.isfinite(base))
-    for name, env in [("cg1", {"B200RANK_GEMM_CG": "1"}), ("fused_norm", {"B200RANK_FUSE_NORM": "1"}),
-                      ("direct_epi", {"B200RANK_GEMM_DIRECT_EPI": "1"}), ("rmsnorm_fwd", {"B200RANK_RMSNORM_REV": "0"}),
-                      ("pdl_off", {"B200RANK_PDL": "0"})]:
-        got = run(name, **env)
-        record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
-        assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
-    for name, env in [("epi_pipe", {"B200RANK_EPI_PIPE": "1"}), ("epi_pipe_bf16", {"B200RANK_EPI_PIPE": "2"}), ("epi_pipe_both", {"B200RANK_EPI_PIPE": "3"})]:
+    for name, env in [("cg1", {"B200RANK_GEMM_CG": "1"}), ("direct_epi", {"B200RANK_GEMM_DIRECT_EPI": "1"}), ("rmsnorm_fwd", {"B200RANK_RMSNORM_REV": "0"}),
+                      ("pdl_off", {"B200RANK_PDL": "0"}), ("dec_graph_off", {"B200RANK_DEC_GRAPH": "0"})]:
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
