@@ -342,7 +342,18 @@ def cli(argv=None):
     chosen = vars(args)
     if chosen['run'] is None or sum(v is not None for v in chosen.values()) != 2:
         raise ValueError('Need to set --run and can only set one of --pointwise, --pairwise, --setwise, --listwise')
-    main(args)
+    try:
+        main(args)
+    finally:
+        # leave the rendezvous in an orderly way: a rank that exits while its peers are still inside a collective (or with the
+        # process group's threads alive) aborts the interpreter on some backends
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                try:
+                    dist.barrier()
+                finally:
+                    dist.destroy_process_group()
 
 
 if __name__ == '__main__':
