@@ -361,6 +361,62 @@ def text_api_docs_per_s(eng, cfg, n_queries):
             "tokenizer_threads": 4, "what": "strings -> prompt assembly + tokenisation (host threads) -> submit/wait pipeline -> sorted SearchResults"}
 
 
+def dist_init():
+    """(rank, world, local, dist module or None): joins the torchrun rendezvous when WORLD_SIZE > 1 (NCCL, one rank per GPU)."""
+    rank, world, local = dist_env()
+    if world == 1:
+        return rank, world, local, None
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"           # stdout carries exactly one JSON line
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def load_and_broadcast(eng, cfg, rank, world, local, dist, tweak=None):
+    """Rank 0 builds the seeded synthetic weights and uploads them; the device weight arena then goes to every other rank in ONE NCCL
+    broadcast (the system's only collective outside result gathering). Returns timing / size of both steps."""
+    from b200rank.synthetic import synthetic_weights
+    t0 = time.time()
+    if rank == 0:
+        w = synthetic_weights(cfg, SEED)
+        if tweak is not None:
+            tweak(w)
+        eng.load_state_dict(w.items())
+        del w
+    t_load = time.time() - t0
+    info = {"weights_load_s": round(t_load, 2)}
+    if dist is not None:
+        import torch
+        from b200rank.dist import arena_as_tensor
+        arena = arena_as_tensor(eng, local)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(arena, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        if rank != 0:
+            eng.mark_weights_loaded()
+        ms = e0.elapsed_time(e1)
+        info["broadcast"] = {"bytes": int(arena.numel()), "ms": round(ms, 2), "GB_per_s": round(arena.numel() / (ms * 1e-3) / 1e9, 1),
+                             "what": "torch.distributed.broadcast of the device weight arena over NCCL / NVLink, CUDA events on rank 0 (first use of the communicator included)"}
+    return info
+
+
+def max_over_ranks_f(x, dist, local):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_setwise(args):
     """Secondary workload (BASELINE configs[2]): SetwiseLlmRanker heapsort, flan-t5-large, num_child 10, k 10,
     100 hits/query, generation scoring — through the drop-in Python API on TEXT. A compare prompt holds 11 passages x 128 words + the
@@ -438,108 +494,154 @@ def run_setwise(args):
 
 
 def run_qlm(args):
-    """Secondary workload (BASELINE configs[4] shape on one GPU, SURVEY.md §8d cfg5 at flan-t5-large): pointwise qlm — S = 144
-    (p128 + 16 template ids), labels T = 33 (`<pad>` + 32 query ids), 100 hits per step, through b200rank_score_qlm with HOST
-    buffers (pack + H2D + encoder + 33-position decoder + full-vocab log-softmax + D2H inside the timed region)."""
+    """Secondary workload (BASELINE configs[4]): pointwise qlm — S = 144 (p128 + 16 template ids), labels T = 33
+    (`<pad>` + 32 query ids), `--hits` documents per query (default 100; configs[4] says 1000), model `--model` (default flan-t5-large;
+    configs[4] says flan-t5-xxl). N = 1: b200rank_score_qlm with HOST buffers (pack + H2D + encoder + 33-position decoder + full-vocab
+    log-softmax + D2H inside the timed region). N > 1 (torchrun): ONE query's documents are split contiguously over the ranks
+    (document-level sharding, strong scaling), weights NCCL-broadcast once, scores gathered once per query; value = whole-job docs/s."""
     import b200rank as br
-    from b200rank.synthetic import model_cfg, synthetic_weights
+    from b200rank.dist import shard_bounds
+    from b200rank.synthetic import model_cfg
+    rank, world, local, dist = dist_init()
     model = args.model or MODEL
+    hits = args.hits or HITS
     cfg = model_cfg(model)
-    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
-                       max_tokens=HITS * 160, max_docs=128, max_dec_len=40, max_logit_rows=HITS * 40)
-    eng = br.Engine(c, 0)
-    t_w = time.time()
-    eng.load_state_dict(synthetic_weights(cfg, SEED).items())
-    t_w = time.time() - t_w
-    rng = np.random.default_rng(SEED)
     S, T = P_LEN + 16, Q_LEN + 1
-    ids = rng.integers(3, 32000, size=(HITS, S)).astype(np.int32)
+    lo, hi = shard_bounds(hits, rank, world)
+    n_local = hi - lo
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
+                       max_tokens=max(n_local, 1) * 160, max_docs=max(128, n_local), max_dec_len=40, max_logit_rows=min(max(n_local, 1), 128) * 40)
+    eng = br.Engine(c, local)
+    load = load_and_broadcast(eng, cfg, rank, world, local, dist)
+    rng = np.random.default_rng(SEED)
+    ids = rng.integers(3, 32000, size=(hits, S)).astype(np.int32)
     ids[:, -1] = 1
-    lengths = np.full((HITS,), S, np.int32)
+    lengths = np.full((hits,), S, np.int32)
     labels = [0] + rng.integers(3, 32000, size=Q_LEN).tolist()
+
+    def step():
+        local_scores = eng.score_qlm(ids[lo:hi], lengths[lo:hi], labels) if n_local else np.zeros((0,), np.float32)
+        if dist is None:
+            return local_scores
+        from b200rank.dist import all_gather_variable
+        return all_gather_variable(np.asarray(local_scores, np.float32))
+
     for _ in range(max(args.warmup, 3)):
-        sc = eng.score_qlm(ids, lengths, labels)
+        sc = step()
     eng.sync()
     steps = max(5, min(args.steps, 30))
-    eng.profile(True)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        sc = eng.score_qlm(ids, lengths, labels)
-    eng.sync()
-    dt = time.perf_counter() - t0
-    rep = eng.profile_report()
-    eng.profile(False)
+    rep = None
+    if world == 1:
+        eng.profile(True)
+        for _ in range(steps):
+            sc = step()
+        eng.sync()
+        rep = eng.profile_report()
+        eng.profile(False)
+    if dist is not None:
+        dist.barrier()
     t1 = time.perf_counter()
     for _ in range(steps):
-        sc = eng.score_qlm(ids, lengths, labels)
+        sc = step()
     eng.sync()
-    dt = time.perf_counter() - t1          # timed without the per-launch profiling events
+    dt = max_over_ranks_f(time.perf_counter() - t1, dist, local)          # timed without the per-launch profiling events
     dm, I, F, V = cfg["d_model"], cfg["num_heads"] * 64, cfg["d_ff"], cfg["vocab_size"]     # SURVEY.md §8d formula
     gf = (cfg["num_layers"] * (8 * dm * I * S + 6 * dm * F * S + 4 * S * S * I) + cfg["num_decoder_layers"] * 4 * dm * I * S
           + cfg["num_decoder_layers"] * (8 * dm * I * T + 4 * T * T * I + 4 * dm * I * T + 4 * T * S * I + 6 * dm * F * T)
           + 2 * dm * V * T) / 1e9
-    peak, _ = load_peaks()
-    line = {"metric": f"docs scored/sec, pointwise qlm ({model}, S 144, T 33)", "value": HITS * steps / dt, "unit": "docs/s", "n_gpus": 1,
-            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{model} pointwise qlm, 100 hits/step, S 144, labels T 33 (BASELINE configs[4] shape, 1 GPU)",
-                       "algorithmic_gflop_per_doc": gf, "weights_load_s": round(t_w, 1)},
-            "step_frac": HITS * steps / dt * gf * 1e9 / (peak * 1e12), "finite_scores": bool(np.isfinite(sc).all()),
-            "by_kernel_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:14]}}
-    print(json.dumps(line))
+    peak, peak_src = peak_for_region(dt)
+    if rank == 0:
+        import hashlib
+        value = hits * steps / dt
+        line = {"metric": f"docs scored/sec, pointwise qlm ({model}, S 144, T 33)", "value": value, "unit": "docs/s", "n_gpus": world,
+                "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{model} pointwise qlm, {hits} hits/step, S 144, labels T 33 (BASELINE configs[4] shape)",
+                           "parallelism": f"dp{world}: the documents of ONE query split contiguously over the ranks, weights NCCL-broadcast once, "
+                                          "scores all-gathered once per query (host side); no collective inside the scoring pass",
+                           "algorithmic_gflop_per_doc": gf, **load},
+                "step_frac": value / world * gf * 1e9 / (peak * 1e12), "step_peak_source": peak_src, "finite_scores": bool(np.isfinite(sc).all()),
+                "scores_sha1": hashlib.sha1(np.ascontiguousarray(sc, np.float32).tobytes()).hexdigest()[:16]}
+        if rep is not None:
+            line["by_kernel_ms_per_step"] = {k: round(v["ms"] / steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:14]}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
     eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
     return 0
 
 
 def run_pairwise(args):
     """Secondary workload (BASELINE configs[3]): PairwiseLlmRanker allpair, flan-t5-xl, batch_size 2 (the
-    reference default), through the drop-in Python API on TEXT; 24 hits/query (552 prompts of S ~ 320) instead of 100 (9900 prompts)
-    to keep the run short. Reports prompts/s with the reference's DataLoader batches merged into large engine calls (default)
-    against one engine call per reference batch (B200RANK_BATCHED_SORT=0); outputs are identical."""
+    reference default), through the drop-in Python API on TEXT; `--hits` documents per query (default 24 -> 552 prompts of S ~ 320 to
+    keep a 1-GPU run short; configs[3] says 100 -> 9900 prompts). N = 1 also reports the reference's one-call-per-DataLoader-batch
+    loop (B200RANK_BATCHED_SORT=0; outputs identical). N > 1 (torchrun): the n(n-1) prompts of ONE query are split over the ranks
+    inside the backend (llmrankers/_backend.py::ShardedBackend: whole reference batches per rank, one host-side gather per engine
+    call) — strong scaling; every rank assembles all prompt rows (host work is replicated and inside the timed region)."""
     import b200rank as br
-    from b200rank.synthetic import model_cfg, synthetic_tokenizer, synthetic_weights
-    from llmrankers._backend import T5Backend
+    from b200rank.synthetic import model_cfg, synthetic_tokenizer
+    from llmrankers._backend import ShardedBackend, T5Backend
     from llmrankers.pairwise import PairwiseLlmRanker
     from llmrankers.rankers import SearchResult
-    model, hits = "flan-t5-xl", 24
+    rank, world, local, dist = dist_init()
+    model, hits = args.model or "flan-t5-xl", args.hits or 24
     cfg = model_cfg(model)
     tok = synthetic_tokenizer()
-    w = synthetic_weights(cfg, SEED)
     lab = [tok.convert_tokens_to_ids("\u2581" + c) for c in "AB"]
-    w["lm_head.weight"][lab] *= 30.0   # label-favouring lm_head: generation emits "Passage A/B"
+
+    def tweak(w):
+        w["lm_head.weight"][lab] *= 30.0   # label-favouring lm_head: generation emits "Passage A/B"
     c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
                        max_tokens=32768, max_docs=256, max_dec_len=8, max_logit_rows=256)
-    eng = br.Engine(c, 0)
-    eng.load_state_dict(w.items())
-    del w
+    eng = br.Engine(c, local)
+    load = load_and_broadcast(eng, cfg, rank, world, local, dist, tweak)
     be = T5Backend(eng, tok, cfg)
+    if dist is not None:
+        be = ShardedBackend(be)
     rng = np.random.default_rng(SEED)
     words = rng.integers(0, 2000, size=(hits + 1, P_LEN))
     query = " ".join(f"w{int(x)}" for x in words[hits, :Q_LEN])
     docs = [SearchResult(docid=str(i), score=0.0, text=" ".join(f"w{int(x)}" for x in words[i])) for i in range(hits)]
     res = {}
-    for mode, flag in (("merged", "1"), ("per_batch", "0")):
+    modes = (("merged", "1"), ("per_batch", "0")) if world == 1 and hits <= 32 else (("merged", "1"),)
+    for mode, flag in modes:
         os.environ["B200RANK_BATCHED_SORT"] = flag
         r = PairwiseLlmRanker(None, None, "cuda", method="allpair", batch_size=2, k=10, backend=be)
         r.rerank(query, list(docs[:6]))   # warm-up
         eng.sync()
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
         out = r.rerank(query, list(docs))
         eng.sync()
-        dt = time.perf_counter() - t0
+        dt = max_over_ranks_f(time.perf_counter() - t0, dist, local)
         res[mode] = dict(s=dt, prompts=hits * (hits - 1), order=[d.docid for d in out], tokens=r.total_prompt_tokens, compares=r.total_compare)
-    assert res["merged"]["order"] == res["per_batch"]["order"] and res["merged"]["tokens"] == res["per_batch"]["tokens"]
-    m, b = res["merged"], res["per_batch"]
-    line = {"metric": "prompts/sec, pairwise allpair (flan-t5-xl, batch_size 2, generation)", "value": m["prompts"] / m["s"], "unit": "prompts/s",
-            "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": m["s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"flan-t5-xl pairwise allpair, {hits} hits/query -> {m['prompts']} prompts, batch_size 2, text API (BASELINE configs[3] at reduced hits)",
-                       "padded_prompt_tokens": m["tokens"], "reference_batches": m["compares"]},
-            "per_reference_batch": {"value": b["prompts"] / b["s"], "ms_per_step": b["s"] * 1e3,
-                                    "what": "B200RANK_BATCHED_SORT=0: one engine call per DataLoader batch of 2, as the reference loops (same outputs)"},
-            "speedup_from_merged_batches": b["s"] / m["s"]}
-    print(json.dumps(line))
+    m = res["merged"]
+    if rank == 0:
+        import hashlib
+        line = {"metric": f"prompts/sec, pairwise allpair ({model}, batch_size 2, generation)", "value": m["prompts"] / m["s"], "unit": "prompts/s",
+                "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": m["s"] * 1e3, "higher_is_better": True,
+                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{model} pairwise allpair, {hits} hits/query -> {m['prompts']} prompts, batch_size 2, text API (BASELINE configs[3]"
+                                       + (")" if hits == 100 else " at reduced hits)"),
+                           "parallelism": f"dp{world}: the prompts of ONE query split over the ranks (whole reference batches), weights NCCL-broadcast once, "
+                                          "generated ids gathered per engine call (host side)",
+                           "padded_prompt_tokens": m["tokens"], "reference_batches": m["compares"], **load},
+                "order_sha1": hashlib.sha1(",".join(m["order"]).encode()).hexdigest()[:16]}
+        if "per_batch" in res:
+            b = res["per_batch"]
+            assert m["order"] == b["order"] and m["tokens"] == b["tokens"]
+            line["per_reference_batch"] = {"value": b["prompts"] / b["s"], "ms_per_step": b["s"] * 1e3,
+                                           "what": "B200RANK_BATCHED_SORT=0: one engine call per DataLoader batch of 2, as the reference loops (same outputs)"}
+            line["speedup_from_merged_batches"] = b["s"] / m["s"]
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
     eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
     return 0
 
 
@@ -833,7 +935,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise", "qlm"],
                     help="pointwise = the headline (BASELINE configs[1], default); setwise / pairwise = configs[2] / configs[3] through the text API, 1 GPU")
-    ap.add_argument("--model", default=None, help="qlm workload only: synthetic model shape (default flan-t5-large; BASELINE configs[4] is flan-t5-xxl)")
+    ap.add_argument("--model", default=None, help="qlm / pairwise workloads: synthetic model shape (qlm: default flan-t5-large, BASELINE configs[4] is flan-t5-xxl; "
+                                                   "pairwise: default flan-t5-xl)")
+    ap.add_argument("--hits", type=int, default=0, help="qlm / pairwise workloads: documents per query (qlm: default 100, configs[4] says 1000; pairwise: default 24, configs[3] says 100)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")
@@ -845,18 +949,17 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.gpus > 1 and dist_env()[1] == 1:
+        # convenience: re-launch under torchrun when asked for N > 1 directly (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     if args.workload == "setwise":
         return run_setwise(args)
     if args.workload == "pairwise":
         return run_pairwise(args)
     if args.workload == "qlm":
         return run_qlm(args)
-    rank, world, _ = dist_env()
-    if args.gpus > 1 and world == 1:
-        # convenience: re-launch under torchrun when asked for N > 1 directly
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-               "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
-        return subprocess.call(cmd)
     return run_engine(args)
 
 
