@@ -762,7 +762,8 @@ def run_engine(args):
     # the synchronous single-stream path must give the same bits
     eng.run_yes_no_staged(YES_ID, NO_ID)
     lg_sync, _ = eng.fetch_yes_no()
-    assert np.array_equal(lg_sync, logits_dev), "pipelined and synchronous passes disagree"
+    debug_skip = os.environ.get("B200RANK_DEBUG_SKIP_DECODER", "0") not in ("", "0")    # measurement switch: scores are garbage then
+    assert debug_skip or np.array_equal(lg_sync, logits_dev), "pipelined and synchronous passes disagree"
 
     # ---- e2e: HOST buffers through the C-ABI (submit/wait), wall clock; pack + H2D + compute + D2H inside the timed region
     run_steps(max(args.warmup, 3), lambda: eng.submit_yes_no(ids, lengths, YES_ID, NO_ID))
@@ -772,7 +773,7 @@ def run_engine(args):
     eng.sync()
     e2e_s = max_over_ranks(time.perf_counter() - w0)
     e2e_value = world * HITS * args.steps / e2e_s
-    assert np.array_equal(lg, logits_dev), "e2e and device-resident passes disagree"
+    assert debug_skip or np.array_equal(lg, logits_dev), "e2e and device-resident passes disagree"
     h2d = n_tok * 4 + (HITS + 1) * 4 + HITS * 4 + 2 * 4  # packed ids + cu_seqlens + decoder ids + (yes,no) ids
     d2h = HITS * 3 * 4                                   # (yes, no) logits + P(yes) per document
 

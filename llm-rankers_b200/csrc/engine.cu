@@ -1481,6 +1481,10 @@ extern "C" int b200rank_submit_yes_no(b200rank_engine* e, const int32_t* ids, co
         if (rc == B200RANK_OK) rc = upload_ints(e, e->d_cols, std::vector<int>{yes_id, no_id});
         // decoder chain + the two-column head + the score: kernels only (what a graph of this pass holds)
         auto enqueue_decoder = [&]() -> int {
+            // measurement switch (never set in production: the scores are then garbage): how fast do the encoder passes run back to
+            // back when no decoder chain competes for SMs at their kernel boundaries? ("decoder interference")
+            static const bool skip = getenv("B200RANK_DEBUG_SKIP_DECODER") && atoi(getenv("B200RANK_DEBUG_SKIP_DECODER")) != 0;
+            if (skip) return B200RANK_OK;
             int r = run_decoder(e, 0, n_docs, 1);
             if (r == B200RANK_OK) {
                 prof_begin(e, "lm_head_cols");

@@ -332,6 +332,13 @@ class ShardedBackend:
         parts = [p for p in self._gather(np.ascontiguousarray(local)) if p.shape[0]]
         return np.concatenate(parts, axis=0) if parts else np.zeros((0,) + tuple(tail_shape), local.dtype)
 
+    # -- for callers that shard their HOST work too (PairwiseLlmRanker allpair): which reference batches are this rank's, and a gather
+    def shard_batches(self, n_batches: int) -> Tuple[int, int]:
+        return self._bounds(n_batches)
+
+    def gather_objects(self, local):
+        return self._gather(local)
+
     # -- the scoring calls, sharded
     def score_yes_no(self, rows, yes_id: int, no_id: int):
         lo, hi = self._bounds(len(rows))

@@ -170,22 +170,37 @@ class PairwiseLlmRanker(LlmRanker):
         self.total_prompt_tokens = 0
         if self.method == "allpair":
             doc_pairs = list(combinations(ranking, 2))
-            fields = []
-            for d1, d2 in doc_pairs:
-                fields.append(dict(query=query, doc1=d1.text, doc2=d2.text))
-                fields.append(dict(query=query, doc1=d2.text, doc2=d1.text))
-            rows = self.backend.prompt_rows(self.prompt, fields) if fields else []
+
+            def field(r):      # prompt row r: pair r // 2 in the order (d1, d2) for even r, (d2, d1) for odd r (pairwise.py:169-174)
+                d1, d2 = doc_pairs[r >> 1]
+                return dict(query=query, doc1=d1.text, doc2=d2.text) if r % 2 == 0 else dict(query=query, doc1=d2.text, doc2=d1.text)
+            n_rows = 2 * len(doc_pairs)
+            n_batches = (n_rows + self.batch_size - 1) // self.batch_size
+            # Under document-level sharding (ShardedBackend) this rank assembles, pads and generates only ITS contiguous range of the
+            # reference's DataLoader batches — host work shards with the GPU work — and the per-batch outputs and counters are gathered
+            # once per query. A batch's result does not depend on which rank or engine call it lands in.
+            sharded = hasattr(self.backend, "shard_batches")
+            b_lo, b_hi = self.backend.shard_batches(n_batches) if sharded else (0, n_batches)
+            be = self.backend.inner if sharded else self.backend
+            r_lo, r_hi = b_lo * self.batch_size, min(b_hi * self.batch_size, n_rows)
+            rows = be.prompt_rows(self.prompt, [field(r) for r in range(r_lo, r_hi)]) if r_hi > r_lo else []
             outputs = []
             # the reference's DataLoader batches (batch_size rows, padded to the batch's longest), many of them per engine call
-            batches = [self.backend.pad_rows(rows[i:i + self.batch_size], self.backend.pad_id)[0] for i in range(0, len(rows), self.batch_size)]
+            batches = [be.pad_rows(rows[i:i + self.batch_size], be.pad_id)[0] for i in range(0, len(rows), self.batch_size)]
             per_call = max(1, 4096 // max(1, self.batch_size)) if os.environ.get("B200RANK_BATCHED_SORT", "1") != "0" else 1
             for c0 in range(0, len(batches), per_call):
                 chunk = batches[c0:c0 + per_call]
-                for ids, out in zip(chunk, self.backend.generate_batches(chunk, self.decoder_input_ids, 2)):
+                for ids, out in zip(chunk, be.generate_batches(chunk, self.decoder_input_ids, 2)):
                     self.total_compare += 1
                     self.total_prompt_tokens += ids.shape[0] * ids.shape[1]
                     self.total_completion_tokens += out.shape[0] * out.shape[1]
                     outputs.extend(out.tolist())
+            if sharded:
+                parts = self.backend.gather_objects((outputs, self.total_compare, self.total_prompt_tokens, self.total_completion_tokens))
+                outputs = [o for part in parts for o in part[0]]
+                self.total_compare = sum(part[1] for part in parts)
+                self.total_prompt_tokens = sum(part[2] for part in parts)
+                self.total_completion_tokens = sum(part[3] for part in parts)
             # fewer than two documents: no pairs, nothing to decode (the reference raises IndexError in tokenizer([]) here; the
             # drop-in returns the trivial ranking)
             outputs = self.tokenizer.batch_decode(outputs, skip_special_tokens=True) if outputs else []
