@@ -1,29 +1,41 @@
-// Persistent tcgen05 encoder self-attention, round-2 design ("tc5"): 16 softmax warps, two threads per query row, ONE pass over
-// TMEM with no shift, for documents of <= 192 tokens (modeling_t5.py:308-334: scores + position bias + mask -> fp32 softmax -> P.V;
-// no 1/sqrt(d) scaling in T5).
+// Persistent tcgen05 encoder self-attention, round-2 design ("tc5", the default): 16 softmax warps, two threads per query row, ONE
+// pass over TMEM with no shift, P handed to the second MMA through tensor memory; for documents of <= 192 tokens
+// (modeling_t5.py:308-334: scores + position bias + mask -> fp32 softmax -> P.V; no 1/sqrt(d) scaling in T5).
 //
-// What the round-1 kernel (enc_attention_tc2_kernel, attention_tc.cuh) was bound by, measured on the B200
-// (profiles/r02_attn_profile.txt): 8 softmax warps, one thread per 192-column row, two passes through TMEM. ncu: issue slots 31 %
-// busy, tensor pipe 12 %, the six warps that own real rows at S = 184 execute ~1550 instructions per item at an IPC of 0.12 —
-// a per-thread latency chain (TMEM load ~53 clk dependent, LDS 29 clk, MUFU, the FADD/FMNMX chains), not a throughput limit:
-// experiments/tmem_probe.cu shows the TMEM read rate still growing at 16 warps (960 B/clk/SM vs 300-600 with 4-8 warps).
-// So this kernel buys thread-level parallelism and sheds instructions:
-//   * 18 warps: warp 0 TMA, warp 1 MMA issue + TMEM allocation, warps 2..17 softmax. A softmax warp is (quarter q = warp_idx & 3:
-//     the 32 TMEM lanes it may touch, tile slot t, column half g): a query row's 192 score columns are shared by two threads
-//     (96 columns = three 32-column tcgen05.ld chunks each), twelve of the sixteen warps own real rows at S = 184.
-//   * ONE pass, NO shift: softmax is shift-invariant and fp32 / bf16 share one exponent range, so p = 2^v (v = log2(e) s + bias')
-//     is as precise as 2^(v - max) as long as the row maximum lies within +-100 (powers of two — natural-log scores within +-69).
-//     No row maximum, no write-back of v, no second TMEM read, no cross-thread dependency ahead of the P tile: per column
-//     LDS (bias), FFMA, MUFU.EX2, FADD (row sum), half an F2FP. The two threads of a row exchange their partial sums through
-//     shared memory for the deferred epilogue. A row whose total sum leaves [2^-100, 2^100) or is not finite — scores beyond
-//     +-69, which trained T5 checkpoints do not produce but the contract must survive — is recomputed exactly by its two threads
-//     on CUDA cores from Q/K/V in global memory (attn_slow_row: two-pass softmax with the true maximum), so the result is always
-//     the exact softmax; tests/test_engine_gpu.py drives that path with scores in the hundreds.
+// What the round-1 kernel (enc_attention_tc2_kernel, attention_tc.cuh) was bound by, measured on the B200 (profiles/r02_attn_profile.txt):
+// 8 softmax warps, one thread per 192-column row, two passes through TMEM; ncu: issue slots 31 % busy, tensor pipe 12 %, the six
+// warps that own real rows at S = 184 run at an IPC of 0.12 — per-thread latency chains, spilled loop state that is an L2 round trip
+// away (210 KB of the SM's 228 KB were shared memory, so local memory does not stay in L1), and cu[] look-ups in every role.
+// experiments/tmem_probe.cu: the TMEM read rate keeps growing to 16 warps (960 B/clk/SM vs 300-600 with 4-8 warps). So:
+//   * 18 warps: warp 0 TMA, warp 1 MMA issue + TMEM allocation, warps 2..17 softmax. A softmax warp is (quarter q = warp_idx & 3: the 32
+//     TMEM lanes it may touch, tile slot t, column half g): a query row's 192 score columns are shared by two threads (96 columns =
+//     six 16-column tcgen05.ld chunks each); twelve of the sixteen warps own real rows at S = 184.
+//   * ONE pass, NO shift: softmax is shift-invariant and fp32 / bf16 share one exponent range, so p = 2^v (v = log2(e) s + bias') is as
+//     precise as 2^(v - max) while the row maximum lies within +-100 (powers of two: natural-log scores within +-69). No row
+//     maximum, no write-back of v, no second TMEM read, no dependency between the two threads of a row ahead of P: per column
+//     LDS (bias), FFMA, MUFU.EX2, FADD (row sum), half an F2FP. The two threads leave their partial sums in shared memory for the
+//     deferred epilogue. A row whose total sum leaves [2^-100, 2^100) or is not finite — scores beyond +-69, which trained T5
+//     checkpoints do not produce but the contract must survive — is NOT stored: its byte in a global bad-row map is set, and after
+//     the item loop the CTA walks its items again and recomputes exactly the marked rows on CUDA cores with the true maximum
+//     (attn_slow_row), clearing the map. The result is always the exact softmax (tests drive this with scores in the hundreds),
+//     and the hot loop contains no call (a call in the loop made ptxas keep the loop state in local memory).
+//   * P through tensor memory: each thread writes the bf16 P of its 16-key chunk back into the S_t columns it has just read
+//     (tcgen05.st; two bf16 per column, always behind its own read pointer) and MMA-2 reads its A operand from tensor memory
+//     (tcgen05.mma [d], [a_tmem], b_desc). No P tile in shared memory (96 KB), no proxy fence, and the N = 64 MMA-2 no longer
+//     competes with the softmax warps' bias loads for the 128 B/clk shared-memory port.
+//   * the TMA thread is the only role that walks cu[]: it publishes {first token, length, head} of item k in a 4-entry shared-memory
+//     ring before arming the item's load barrier; the other roles read the ring after a barrier they wait on anyway. Every barrier
+//     completes exactly once per item (parity k & 1), for both tile slots — a short document simply gets no MMAs on slot 1 — and
+//     an invalid descriptor after the last item ends all roles.
 //   * the second query tile of a 129..192-token document has at most 64 real rows: on odd items the MMA's A descriptor starts 64
 //     rows earlier, so those rows land on TMEM lanes 64..127 (warps of quarters 2, 3) instead of lanes 0..63 — over two items
 //     every SM sub-partition gets the same softmax work instead of quarters 0, 1 doing twice that of 2, 3.
-// Roles, barriers, TMEM columns (S_t at t*192, O_t at 384 + 64 t) and the item pipeline (TMA one item ahead; per tile slot MMA-2 of
-// item k then MMA-1 of item k+1; epilogue of item k deferred to the start of item k+1) are those of enc_attention_tc2_kernel.
+//   * nothing derived from the thread index lives across the item loop (re-derived from %tid.x each iteration; shared-memory
+//     accesses are explicit ld/st.shared on 32-bit addresses): zero local-memory traffic inside the loop.
+// TMEM columns: S_t at t*192 (P_t inside it), O_t at 384 + 64 t. Item pipeline: TMA one item ahead; per tile slot MMA-2 of item k
+// then MMA-1 of item k+1; epilogue of item k deferred to the start of item k+1. B200, 100 documents x 16 heads, S = 184:
+// 2.00 ms per step (tc2) -> 1.44 ms; ncu in profiles/r02_attn_profile.txt. Tried and dropped on the way: splitting S_t into
+// independently pipelined key halves (more barriers, Q read twice: slower), busy-poll / plain try_wait loops (no change).
 // A document's result is a function of the document alone (lane placement does not enter the arithmetic): bit-identical across
 // batch compositions, like every other kernel of the path.
 #pragma once
@@ -38,12 +50,11 @@ template <int NKB>
 struct AttnTc5Cfg {
     static constexpr int kRows = 64 * NKB;
     static constexpr int kQKVBytes = kRows * 128;
-    static constexpr int kPBytes = NKB * 128 * 128;
     static constexpr int kWideBias = 512;                 // 511 used: index (j - i) + 255
     static constexpr int kRedBytes = 2 * 2 * 2 * 128 * 4; // partial row sums [use parity][tile slot][column half][lane]
-    static constexpr int kFixedBytes = 3 * kQKVBytes + 2 * kPBytes + 12 * 8 + 4 * 16 + 16 + kRedBytes + 1024;
-    static constexpr int kMaxResidentHeads = (227 * 1024 - kFixedBytes) / (kWideBias * 4);
-    static constexpr int smem_bytes(int H) { return kFixedBytes + (H <= kMaxResidentHeads ? (H < 2 ? 2 : H) : 2) * kWideBias * 4; }
+    static constexpr int kFixedBytes = 3 * kQKVBytes + 12 * 8 + 4 * 16 + 16 + kRedBytes + 1024;
+    static constexpr int kMaxHeads = (227 * 1024 - kFixedBytes) / (kWideBias * 4);     // 71: every T5 size (xxl has 64 heads)
+    static constexpr int smem_bytes(int H) { return kFixedBytes + H * kWideBias * 4; }
     static constexpr int kSCol = 64 * NKB;
     static constexpr int kOCol0 = 2 * 64 * NKB;
     static constexpr int kHalf = 32 * NKB;                // score columns per thread
@@ -99,14 +110,16 @@ __device__ __noinline__ void attn_slow_row(const __nv_bfloat16* __restrict__ qkv
 
 // bias_wide: [H][512] fp32, bias_wide[h][w] = log2(e) * bias_h(clamp(w - 255, +-128)) (built once at weight-load time: the per-launch
 // prologue is a plain 16 B-vector copy into shared memory instead of 8 k dependent global loads).
-template <int WAIT>
-__device__ __forceinline__ void attn5_wait(uint64_t* bar, uint32_t parity) {
-    if constexpr (WAIT == 1) mbar_wait_backoff(bar, parity, 64);
-    else if constexpr (WAIT == 2) mbar_wait_spin(bar, parity);
-    else mbar_wait(bar, parity);
-}
+// All roles wait with try_wait + a 64 ns back-off (plain try_wait loops and busy polling measured the same on the B200; the back-off
+// keeps single-lane producer warps from burning the issue slots of the sub-partition they share with softmax warps).
+__device__ __forceinline__ void attn5_wait(uint64_t* bar, uint32_t parity) { mbar_wait_backoff(bar, parity, 64); }
 
-template <int NKB, int WAIT>   // WAIT 0: mbarrier.try_wait loops; 1: try_wait + nanosleep back-off (ships); 2: busy poll
+// P_t never touches shared memory: every thread writes the bf16 P of its keys back into tensor memory with tcgen05.st, into the S_t
+// columns it has just read (keys [96 g, 96 g + 96) -> columns 96 g .. 96 g + 47 of S_t, two bf16 per column), and MMA-2 takes its A
+// operand from tensor memory (tcgen05.mma with [a_tmem]): no st.shared of P, no shared-memory read of P by the tensor core (the
+// N = 64 MMA-2 was shared-memory bound on its 4 KB A operand), no proxy fence; 1.54 -> 1.44 ms per step against the shared-memory
+// version (profiles/r02_bench_attn_ab.txt). The bias windows of all heads (H <= 71) are resident in the shared memory this frees.
+template <int NKB>
 __global__ void __launch_bounds__(kAttn5Threads, 1)
 enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __nv_bfloat16* __restrict__ qkv, int ld, int inner,
                          const int* __restrict__ cu, const float* __restrict__ bias_wide, __nv_bfloat16* __restrict__ out, int ldo, int H,
@@ -118,8 +131,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + Cfg::kQKVBytes;
     uint8_t* sV = sK + Cfg::kQKVBytes;
-    uint8_t* sP = sV + Cfg::kQKVBytes;                      // [2][kPBytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::kQKVBytes);
     uint64_t* bar_qk = bars + 0;   // Q/K of item k landed (or: the end-of-work descriptor was published)
     uint64_t* bar_v = bars + 1;
     uint64_t* qk_free = bars + 2;  // both MMA-1s of the item retired: Q/K smem reusable
@@ -130,8 +142,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
     int4* sDesc = reinterpret_cast<int4*>(bars + 12);               // [4] item ring: {first token, length, head, valid}
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(sDesc + 4);   // [0] TMEM base, [2] "some row needs the fix-up walk" (as a float)
     float* sL = reinterpret_cast<float*>(tmem_base_smem + 4);       // [2 parities][2 slots][2 halves][128 lanes]
-    float* sBiasW = sL + Cfg::kRedBytes / 4;                        // [H or 2][kWideBias]
-    const bool bias_resident = H <= Cfg::kMaxResidentHeads;
+    float* sBiasW = sL + Cfg::kRedBytes / 4;                        // [H][kWideBias]
 
     const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp_idx == 1) tmem_alloc(tmem_base_smem, 512);
@@ -149,7 +160,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
         }
         fence_barrier_init();
     }
-    if (bias_resident) {
+    {
         // the bias table is a weight (written once at load time, not by the preceding kernel): it may be read before pdl_wait
         const float4* src = reinterpret_cast<const float4*>(bias_wide);
         float4* dst = reinterpret_cast<float4*>(sBiasW);
@@ -174,20 +185,20 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                 const int tok0 = cu[doc], len = cu[doc + 1] - tok0;
                 if (len > len_limit) continue;   // longer documents belong to the mma.sync tile kernel launched next to this one
                 const int nkb_used = (len + 63) >> 6;
-                if (k > 0) attn5_wait<WAIT>(qk_free, (k - 1) & 1);
+                if (k > 0) attn5_wait(qk_free, (k - 1) & 1);
                 sDesc[k & 3] = make_int4(tok0, len, h, 1);
                 mbar_arrive_expect_tx(bar_qk, 2 * nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b) {
                     tma_load_2d(sQ + b * 8192, &tmap_qkv, bar_qk, h * 64, tok0 + b * 64, kEvictFirst);
                     tma_load_2d(sK + b * 8192, &tmap_qkv, bar_qk, inner + h * 64, tok0 + b * 64, kEvictFirst);
                 }
-                if (k > 0) attn5_wait<WAIT>(v_free, (k - 1) & 1);
+                if (k > 0) attn5_wait(v_free, (k - 1) & 1);
                 mbar_arrive_expect_tx(bar_v, nkb_used * 8192);
                 for (int b = 0; b < nkb_used; ++b)
                     tma_load_2d(sV + b * 8192, &tmap_qkv, bar_v, 2 * inner + h * 64, tok0 + b * 64, kEvictFirst);
                 ++k;
             }
-            if (k > 0) attn5_wait<WAIT>(qk_free, (k - 1) & 1);
+            if (k > 0) attn5_wait(qk_free, (k - 1) & 1);
             sDesc[k & 3] = make_int4(0, 0, 0, 0);
             mbar_arrive(bar_qk);
         }
@@ -197,7 +208,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
             constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
             int len_prev = 0;
             for (int k = 0;; ++k) {
-                attn5_wait<WAIT>(bar_qk, k & 1);
+                attn5_wait(bar_qk, k & 1);
                 tc_fence_after();
                 const int4 dsc = sDesc[k & 3];
                 const bool have = dsc.w != 0;
@@ -209,18 +220,20 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                     if (k > 0) {
                         // MMA-2 of item k-1: O_t = P_t . V. bar_p also says that the slot's threads are done with O_t of item k-2
                         // (their deferred epilogue precedes their pass in program order) and with S_t of item k-1.
-                        if (t == 0) attn5_wait<WAIT>(bar_v, (k - 1) & 1);
-                        attn5_wait<WAIT>(&bar_p[t], (k - 1) & 1);
+                        if (t == 0) attn5_wait(bar_v, (k - 1) & 1);
+                        attn5_wait(&bar_p[t], (k - 1) & 1);
                         tc_fence_after();
                         if (t < nt_prev) {
                             for (int kb = 0; kb < nkb_prev; ++kb) {
-                                const uint64_t da = make_sw128_kmajor_desc(smem_u32(sP + t * Cfg::kPBytes + kb * 16384));
                                 // V block: rows = keys (the MMA K dimension), 128 B of head dims contiguous = MN-major B operand;
                                 // 16 keys per MMA = 2048 B -> +128 in (addr >> 4)
                                 const uint64_t db = make_sw128_kmajor_desc(smem_u32(sV + kb * 8192));
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    umma_bf16(tmem_base + Cfg::kOCol0 + t * 64, da + 2 * kk, db + 128 * kk, idesc_o, (kb | kk) != 0);
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    const int key0 = kb * 64 + kk * 16;          // P of keys [key0, key0 + 16): 8 columns inside S_t
+                                    const int pcol = key0 < Cfg::kHalf ? (key0 >> 1) : Cfg::kHalf + ((key0 - Cfg::kHalf) >> 1);
+                                    umma_bf16_ts(tmem_base + Cfg::kOCol0 + t * 64, tmem_base + t * Cfg::kSCol + pcol, db + 128 * kk, idesc_o, (kb | kk) != 0);
+                                }
                             }
                         }
                         umma_commit(&bar_o[t]);
@@ -251,7 +264,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
         // the loop and then spill them) at the two places that use them.
         auto tid_now = []() { uint32_t v; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(v)); return static_cast<int>(v); };
         const uint32_t smem_s = smem_u32(smem);      // everything below is an offset from this one shared-space address
-        constexpr uint32_t kPOff = 3 * Cfg::kQKVBytes, kBarOff = kPOff + 2 * Cfg::kPBytes, kDescOff = kBarOff + 12 * 8,
+        constexpr uint32_t kBarOff = 3 * Cfg::kQKVBytes, kDescOff = kBarOff + 12 * 8,
                            kLOff = kDescOff + 4 * 16 + 16, kBiasOff = kLOff + Cfg::kRedBytes;
         constexpr int c0_of_g = Cfg::kHalf;
         int4 prev = make_int4(0, 0, 0, 0);            // descriptor of the item whose epilogue is pending
@@ -265,16 +278,14 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
             const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
             const uint32_t taddr_s = tmem_base + lane_off + t * Cfg::kSCol + g * Cfg::kHalf;
             const uint32_t taddr_o = tmem_base + lane_off + Cfg::kOCol0 + t * 64 + g * 32;
-            const uint32_t prow_s = smem_s + kPOff + t * Cfg::kPBytes + lane_row * 128;     // this row of the P tile, k-block 0
             const uint32_t sL_s = smem_s + kLOff + (t * 256 + lane_row) * 4;                // partial sums of this row: halves at +0 / +512 B, parity at +2048 B
             const uint32_t sDesc_s = smem_s + kDescOff;
             const uint32_t sBias_s = smem_s + kBiasOff;
-            const uint32_t swz = static_cast<uint32_t>(lane_row & 7);
             // ---- deferred epilogue of item k-1 on this slot: O_t / l -> bf16 -> global. It comes BEFORE the wait on S_t(k): MMA-2(k-1, t)
             // was issued ahead of MMA-1(k, t), and passing bar_o licenses the writes into P_t below.
             if (prev.w) {
                 const int kp = k - 1;
-                attn5_wait<WAIT>(&bar_o[t], kp & 1);
+                attn5_wait(&bar_o[t], kp & 1);
                 tc_fence_after();
                 const int shift = (t == 1 && (kp & 1)) ? 64 : 0;
                 const int qi = t * 128 + lane_row - shift;
@@ -306,7 +317,7 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                     }
                 }
             }
-            attn5_wait<WAIT>(&bar_s[t], k & 1);
+            attn5_wait(&bar_s[t], k & 1);
             tc_fence_after();
             const int4 dsc = ld_shared_v4_s32(sDesc_s + (k & 3) * 16);
             if (!dsc.w) break;
@@ -314,26 +325,16 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
             const int shift = (t == 1 && (k & 1)) ? 64 : 0;       // see the MMA issuer
             const int qi = t * 128 + lane_row - shift;            // query row of this thread (0..255 whatever the lane)
             const bool rows = quarter * 32 >= shift && (t * 128 + quarter * 32 - shift) < len;   // warp-uniform: some real query row
-            if (!bias_resident && (!prev.w || h != prev.z)) {     // the slot's window holds the previous item's head
-                named_bar_sync(1 + t, 256);               // every warp of the slot is past its reads of the old window (incl. slow rows)
-                const int grp_tid = (((sw & 3) | (g << 2)) << 5) | ln;
-                for (int i = grp_tid; i < Cfg::kWideBias; i += 256) sBiasW[t * Cfg::kWideBias + i] = __ldg(bias_wide + h * Cfg::kWideBias + i);
-                named_bar_sync(1 + t, 256);
-            }
             if (rows) {
                 const int c0 = g * c0_of_g;
                 // [sBrow + 4 c] = log2(e) * bias(c0 + c - qi)
-                const uint32_t sBrow = sBias_s + ((bias_resident ? h : t) * Cfg::kWideBias + 255 - qi + c0) * 4;
+                const uint32_t sBrow = sBias_s + (h * Cfg::kWideBias + 255 - qi + c0) * 4;
                 const int n_real = min(len - c0, Cfg::kHalf);                   // my columns that hold real keys (may be <= 0)
                 const int n_fill = min(((len + 63) & ~63) - c0, Cfg::kHalf);    // my columns of the P tile the MMA will read
                 float l0 = 0.f, l1 = 0.f;
-                // 16 keys = 32 B = two 16 B chunks of the 128B-swizzled K-major P tile (k-block (c0 + c) / 64)
+                // keys c0 + c .. + 15 of this row -> 8 packed columns right behind the thread's read pointer in its own half of S_t
                 auto store_p = [&](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7, int c) {
-                    const int cc = c0 + c;
-                    const uint32_t kblk = prow_s + (cc >> 6) * 16384;
-                    const uint32_t chunk0 = static_cast<uint32_t>(cc & 63) >> 3;     // even: chunk0 ^ swz and (chunk0 + 1) ^ swz differ in bit 0 only
-                    st_shared_v4_addr(kblk + ((chunk0 ^ swz) << 4), a0, a1, a2, a3);
-                    st_shared_v4_addr(kblk + (((chunk0 + 1) ^ swz) << 4), a4, a5, a6, a7);
+                    tmem_st8(taddr_s + (c >> 1), a0, a1, a2, a3, a4, a5, a6, a7);
                 };
                 int c = 0;
                 // full chunks: no masking in the inner loop (LDS, FFMA, MUFU.EX2, FADD, half an F2FP per column)
@@ -370,8 +371,8 @@ enc_attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __n
                 for (c = max(c, 0); c < n_fill; c += 16) store_p(0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, c);
                 st_shared_f32(sL_s + (k & 1) * 2048 + g * 512, l0 + l1);
             }
-            tc_fence_before();      // TMEM reads of S_t (and of O_t in the epilogue above) are complete before the MMAs overwrite them
-            fence_proxy_async();    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tmem_st_wait();         // this thread's P columns have landed in tensor memory
+            tc_fence_before();      // ... and its TMEM reads of S_t (and of O_t in the epilogue above) are complete before the MMAs touch them
             mbar_arrive(&bar_p[t]);
             prev = dsc;
         }

@@ -955,6 +955,7 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
                                 int maxlen, int H, const float* bias, bf16* out, int ldo, cudaStream_t st, int mode, int minlen = 0,
                                 const float* bias_wide = nullptr, uint8_t* bad_map = nullptr) {
     if (mode == 0) mode = attn_default_mode();
+    if (mode == 8 && H > AttnTc5Cfg<3>::kMaxHeads) mode = 1;   // the bias windows of all heads must fit in shared memory (71 heads; T5-11B has 64)
     const bool persistent = (mode == 5 || mode == 8);
     if (!persistent) mode = 1;
     // Mixed batch under the default mode: documents of <= 192 tokens still get the tcgen05 kernel (it walks only those), the longer
@@ -968,11 +969,9 @@ static int launch_enc_attention(b200rank_engine* e, const bf16* qkv, int ld, uin
         const CUtensorMap* tm = &local;
         if (e) RET_IF(engine_tmap(e, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0, &tm));
         else RET_IF(make_tmap(&local, qkv, qkv_rows, (uint64_t)ld, (uint64_t)ld, 64, 0));
-        static SmemOptIn opt_in_tc5[3];
-        static int wait_mode = -1;   // B200RANK_ATTN_WAIT=0|1|2: mbarrier wait flavour of the kernel's roles (attention_tc5.cuh)
-        if (wait_mode < 0) wait_mode = getenv("B200RANK_ATTN_WAIT") ? std::max(0, std::min(2, atoi(getenv("B200RANK_ATTN_WAIT")))) : 1;
-        auto kern5 = wait_mode == 1 ? enc_attention_tc5_kernel<3, 1> : (wait_mode == 2 ? enc_attention_tc5_kernel<3, 2> : enc_attention_tc5_kernel<3, 0>);
-        CU_OK(opt_in_tc5[wait_mode].raise(kern5, 227 * 1024));
+        static SmemOptIn opt_in_tc5;
+        auto kern5 = enc_attention_tc5_kernel<3>;
+        CU_OK(opt_in_tc5.raise(kern5, 227 * 1024));
         const int n_items = nd * H;
         if (e) prof_begin(e, "enc_attention_tc5");
         const int sm_count = e ? e->num_sms : device_sm_count();
