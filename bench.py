@@ -510,7 +510,7 @@ def run_qlm(args):
     lo, hi = shard_bounds(hits, rank, world)
     n_local = hi - lo
     c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
-                       max_tokens=max(n_local, 1) * 160, max_docs=max(128, n_local), max_dec_len=40, max_logit_rows=min(max(n_local, 1), 128) * 40)
+                       max_tokens=max(n_local, 1) * 160, max_docs=max(128, n_local), max_dec_len=40, max_logit_rows=min(max(n_local, 1), int(os.environ.get("B200RANK_BENCH_QLM_PASS_DOCS", "512"))) * 40)
     eng = br.Engine(c, local)
     load = load_and_broadcast(eng, cfg, rank, world, local, dist)
     rng = np.random.default_rng(SEED)

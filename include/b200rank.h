@@ -57,7 +57,7 @@ typedef struct b200rank_config {
     int32_t max_tokens;            /* encoder-token capacity of one device pass (0 = default 32768) */
     int32_t max_docs;              /* documents per device pass (0 = default 1024) */
     int32_t max_dec_len;           /* longest decoder sequence (0 = default 64; hard limit 64) */
-    int32_t max_logit_rows;        /* rows of the full-vocabulary logits scratch (0 = default 4096) */
+    int32_t max_logit_rows;        /* rows of the full-vocabulary logits scratch (0 = default 16384) */
 } b200rank_config;
 
 typedef struct b200rank_engine b200rank_engine;

@@ -591,7 +591,7 @@ static int create_impl(b200rank_engine* e) {
     e->cap_docs = c.max_docs > 0 ? c.max_docs : 1024;
     e->cap_T = c.max_dec_len > 0 ? c.max_dec_len : 64;
     if (e->cap_T > 64) return set_error(B200RANK_ERR_ARG, "max_dec_len %d > 64 unsupported", e->cap_T);
-    e->cap_logit_rows = (int)align_up(c.max_logit_rows > 0 ? c.max_logit_rows : 4096, 128);
+    e->cap_logit_rows = (int)align_up(c.max_logit_rows > 0 ? c.max_logit_rows : 16384, 128);   // qlm: 496 documents x 33 label positions per device pass
     e->cap_rows = (int)align_up(std::max(e->cap_docs, e->cap_logit_rows), 128);
     const size_t Tk = e->cap_tokens, R = e->cap_rows;
     RET_IF(dev_alloc(e, &e->x, Tk * d)); RET_IF(dev_alloc(e, &e->h, Tk * d));
