@@ -573,6 +573,54 @@ def run_qlm(args):
     return 0
 
 
+def run_monot5(args):
+    """Secondary workload: MonoT5-style pointwise scoring — T5 v1.0 (relu feed-forward, tied embeddings), yes/no =
+    true/false logits at decoder position 0 — on a synthetic model of the shape `--model` (default monot5-3b: d_kv 128, 32 heads,
+    d_ff 16384, i.e. the head width that runs on the generic-width attention of csrc/attention_wide.cuh instead of the tcgen05
+    kernels), `--hits` documents of S = 184 per step through the synchronous b200rank_score_yes_no with HOST buffers."""
+    import b200rank as br
+    from b200rank.synthetic import model_cfg, synthetic_prompt_ids, synthetic_weights
+    model, hits = args.model or "monot5-3b", args.hits or HITS
+    cfg = model_cfg(model)
+    c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"], d_kv=cfg["d_kv"],
+                       gated_gelu=cfg["gated_gelu"], scale_decoder_outputs=cfg["scale_decoder_outputs"],
+                       max_tokens=hits * (Q_LEN + P_LEN + 24) + 256, max_docs=max(128, hits), max_logit_rows=256)
+    eng = br.Engine(c, 0)
+    t_w = time.time()
+    eng.load_state_dict(synthetic_weights(cfg, SEED).items())
+    t_w = time.time() - t_w
+    ids, lengths = synthetic_prompt_ids(hits, Q_LEN, P_LEN, seed=SEED)
+    for _ in range(max(args.warmup, 3)):
+        lg, sc = eng.score_yes_no(ids, lengths, 1176, 6136)      # 'true' / 'false' ids of the T5 vocabulary (pointwise.py:170-171)
+    steps = max(5, min(args.steps, 30))
+    eng.profile(True)
+    for _ in range(steps):
+        eng.score_yes_no(ids, lengths, 1176, 6136)
+    rep = eng.profile_report()
+    eng.profile(False)
+    eng.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lg, sc = eng.score_yes_no(ids, lengths, 1176, 6136)
+    dt = time.perf_counter() - t0
+    S = Q_LEN + P_LEN + 24
+    d, I, F, V = cfg["d_model"], cfg["num_heads"] * cfg["d_kv"], cfg["d_ff"], cfg["vocab_size"]
+    gf = (cfg["num_layers"] * (8 * d * I * S + 4 * d * F * S + 4 * S * S * I) + cfg["num_decoder_layers"] * 4 * d * I * S
+          + cfg["num_decoder_layers"] * (8 * d * I + 4 * d * I + 4 * S * I + 4 * d * F) + 2 * d * V) / 1e9      # SURVEY.md §8d with an ungated feed-forward
+    peak, peak_src = peak_for_region(dt)
+    value = hits * steps / dt
+    line = {"metric": f"docs scored/sec, MonoT5-style yes/no ({model}, q32/p128)", "value": value, "unit": "docs/s", "n_gpus": 1, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{model} (T5 v1.0, d_kv {cfg['d_kv']}) pointwise true/false, {hits} hits/step, S {S}, T 1, synchronous call with host buffers",
+                       "algorithmic_gflop_per_doc": gf, "weights_load_s": round(t_w, 1)},
+            "step_frac": value * gf * 1e9 / (peak * 1e12), "step_peak_source": peak_src, "finite_scores": bool(np.isfinite(sc).all()),
+            "by_kernel_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
+    print(json.dumps(line))
+    eng.close()
+    return 0
+
+
 def run_pairwise(args):
     """Secondary workload (BASELINE configs[3]): PairwiseLlmRanker allpair, flan-t5-xl, batch_size 2 (the
     reference default), through the drop-in Python API on TEXT; `--hits` documents per query (default 24 -> 552 prompts of S ~ 320 to
@@ -934,7 +982,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise", "qlm"],
+    ap.add_argument("--workload", default="pointwise", choices=["pointwise", "setwise", "pairwise", "qlm", "monot5"],
                     help="pointwise = the headline (BASELINE configs[1], default); setwise / pairwise = configs[2] / configs[3] through the text API, 1 GPU")
     ap.add_argument("--model", default=None, help="qlm / pairwise workloads: synthetic model shape (qlm: default flan-t5-large, BASELINE configs[4] is flan-t5-xxl; "
                                                    "pairwise: default flan-t5-xl)")
@@ -961,6 +1009,8 @@ def main():
         return run_pairwise(args)
     if args.workload == "qlm":
         return run_qlm(args)
+    if args.workload == "monot5":
+        return run_monot5(args)
     return run_engine(args)
 
 
