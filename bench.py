@@ -938,7 +938,10 @@ def run_engine(args):
                       against="tests/golden/headline_query.npz: fp32 transformers logits of all 100 documents of the headline query (committed fixture)",
                       tolerance=tolerance.describe(n_layers))
         if live is not None:
-            parity["live_check"] = live
+            # the live re-derivation covers the first 32 documents: its logit agreement is what it adds (top-k of a 32-document
+            # subset of this query is not separated by construction and says nothing)
+            parity["live_check"] = {k: live[k] for k in ("against", "docs", "max_abs_logit_diff", "mean_abs_logit_diff", "within_logit_tolerance",
+                                                         "inversions_beyond_tolerance", "max_abs_score_diff", "reference_bf16_yardstick") if k in live}
 
     hf_cuda = None
     if rank == 0 and world == 1 and not args.no_hf_cuda:
