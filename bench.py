@@ -910,7 +910,8 @@ def run_engine(args):
         # Launch times come from event pairs around each launch and include the inter-kernel gap, so this is a lower bound
         # (ncu, kernel alone: 17.5-19.2 us per launch = 5.9 TB/s, profiles/r01_ncu_summary_final.txt).
         if "rmsnorm" in rep:
-            rows_per_step = (2 * cfg["num_layers"] + 1) * n_tok
+            # (2 per encoder layer: the norm before block 0 rides on the embedding gather and the final one closes the last layer)
+            rows_per_step = rep["rmsnorm"]["n"] / prof_steps * n_tok
             nbytes = rows_per_step * cfg["d_model"] * 6.0
             hbm_peak, hbm_src = load_hbm_peak()
             gbs = nbytes / (rep["rmsnorm"]["ms"] / prof_steps * 1e-3) / 1e9

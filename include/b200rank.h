@@ -109,7 +109,10 @@ int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const int32_t* le
 
 /* Replaces `self.llm.generate(input_ids, decoder_input_ids=prefix, max_new_tokens=n)` (greedy, eos/pad from
  * the config) — llmrankers/setwise.py:93-95, pairwise.py:97-99,196-200. new_ids: [n_docs][max_new]; after a
- * row emits eos the remaining positions hold pad (transformers/generation/utils.py:2797). */
+ * row emits eos the remaining positions hold pad (transformers/generation/utils.py:2797). 1 <= max_new <= 64 and
+ * prefix_len + max_new - 1 <= max_dec_len. Like the library's cached loop (generation/utils.py:2762-2804) a call keeps a
+ * self-attention K/V cache: the prefix runs once, then one decoder position per generated token (B200RANK_KV_CACHE=0
+ * re-runs the growing prefix instead; identical tokens for the rankers' two-token prefix). */
 int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
                     const int32_t* dec_prefix, int prefix_len, int max_new, int32_t* new_ids);
 

@@ -239,6 +239,8 @@ struct LayerW {
 };
 
 constexpr int kXAttnSplit = 8;   // key splits of the 2-4-position cross-attention (fixed: see run_decoder)
+constexpr int kGreedyMaxNew = 64;  // b200rank_greedy: new tokens per call (bounded by max_dec_len as well)
+constexpr int kKvCacheRows = 4096; // (document, position) rows of the greedy self-attention K/V cache
 
 struct b200rank_engine {
     b200rank_config cfg;
@@ -274,6 +276,10 @@ struct b200rank_engine {
     float* logits = nullptr;       // [cap_logit_rows, V]
     float* small_out = nullptr;    // [cap_rows * 32] generic fp32 results
     float* small_out2 = nullptr;   // [cap_docs * 32]
+    // self-attention K/V cache of greedy decoding (allocated on the first b200rank_greedy call): [Ld][kvc_rows][q | k | v] bf16, the row of
+    // (document, decoder position) = document * (prefix_len + max_new) + position. The q third is where the step's fused q|k|v
+    // projection lands (one GEMM, no copy); only k and v of earlier positions are read back.
+    bf16* kvc = nullptr; int kvc_rows = 0;
     float* xattn_partial = nullptr;  // key-split cross-attention partials: [docs][H][nsplit][T][66] fp32 (few documents, long prompts)
     size_t xattn_partial_bytes = 0;
     int* d_ids = nullptr;          // [cap_tokens]
@@ -281,7 +287,7 @@ struct b200rank_engine {
     int* d_dec_ids = nullptr;      // [cap_rows]
     int* d_cols = nullptr;         // [64]
     int* d_labels = nullptr;       // [cap_rows]
-    int* d_int_out = nullptr;      // [cap_docs * 16]: new ids | argmax scratch
+    int* d_int_out = nullptr;      // [cap_docs * (kGreedyMaxNew + 1)]: new ids | argmax scratch
     int* d_finished = nullptr;     // [cap_docs]
     uint8_t* l2_scratch = nullptr; size_t l2_scratch_bytes = 0;
     size_t workspace_bytes = 0;
@@ -466,7 +472,7 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
     cudaDeviceSynchronize();
     void* frees[] = {e->arena, e->x, e->h, e->qkv, e->ao, e->g, e->ckv, e->xd, e->hd, e->qkvd, e->aod, e->qd, e->gd, e->hlast,
                      e->logits, e->qp, e->ctxb, e->small_out, e->small_out2, e->xattn_partial, e->attn_bad_map, e->d_ids, e->d_dec_ids, e->d_cols, e->d_labels,
-                     e->d_int_out, e->d_finished, e->l2_scratch};
+                     e->d_int_out, e->d_finished, e->l2_scratch, e->kvc};
     for (void* p : frees)
         if (p) cudaFree(p);
     if (e->h_ids) cudaFreeHost(e->h_ids);
@@ -504,15 +510,16 @@ static int create_impl(b200rank_engine* e) {
         return set_error(B200RANK_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", e->device, prop.major,
                          prop.minor);
     e->num_sms = prop.multiProcessorCount;
-    CU_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    e->stream_main = e->stream;
     {
-        // Decoder stream priority: equal to the main stream by default. Measured on B200 (profiles/r01_bench_n1_v11_*): giving the
-        // short decoder kernels the HIGHEST priority costs ~4 % (they cut into the encoder GEMM waves); B200RANK_PIPE_PRIORITY=1 selects it.
+        // Stream priorities: equal by default. Measured on B200 (profiles/r01_bench_n1_v11_*): giving the short decoder kernels the
+        // HIGHEST priority costs ~4 % (they cut into the encoder GEMM waves); B200RANK_PIPE_PRIORITY=1 selects it, =2 the opposite
+        // (encoder stream above the decoder stream: the chain only takes SMs no encoder CTA is waiting for).
         int prio_lo = 0, prio_hi = 0;
         CU_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        const bool hi = getenv("B200RANK_PIPE_PRIORITY") && atoi(getenv("B200RANK_PIPE_PRIORITY")) != 0;
-        CU_OK(cudaStreamCreateWithPriority(&e->stream_dec, cudaStreamNonBlocking, hi ? prio_hi : prio_lo));
+        const int mode = getenv("B200RANK_PIPE_PRIORITY") ? atoi(getenv("B200RANK_PIPE_PRIORITY")) : 0;
+        CU_OK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, mode == 2 ? prio_hi : prio_lo));
+        e->stream_main = e->stream;
+        CU_OK(cudaStreamCreateWithPriority(&e->stream_dec, cudaStreamNonBlocking, mode == 1 ? prio_hi : prio_lo));
     }
     for (int b = 0; b < 2; ++b) {
         CU_OK(cudaEventCreateWithFlags(&e->ev_enc[b], cudaEventDisableTiming));
@@ -621,11 +628,11 @@ static int create_impl(b200rank_engine* e) {
     // the decoder graph is on unless B200RANK_DEC_GRAPH=0 (bit-identical to the eager chain: tests/test_engine_gpu.py)
     e->dec_graph = !(getenv("B200RANK_DEC_GRAPH") && atoi(getenv("B200RANK_DEC_GRAPH")) == 0);
     RET_IF(dev_alloc(e, &e->d_dec_ids, R)); RET_IF(dev_alloc(e, &e->d_cols, 64)); RET_IF(dev_alloc(e, &e->d_labels, R));
-    RET_IF(dev_alloc(e, &e->d_int_out, (size_t)e->cap_docs * 16)); RET_IF(dev_alloc(e, &e->d_finished, (size_t)e->cap_docs));
+    RET_IF(dev_alloc(e, &e->d_int_out, (size_t)e->cap_docs * (kGreedyMaxNew + 1))); RET_IF(dev_alloc(e, &e->d_finished, (size_t)e->cap_docs));
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_ids), Tk * sizeof(int), cudaHostAllocDefault));
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_cu), ((size_t)e->cap_docs + 1) * sizeof(int), cudaHostAllocDefault));
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_out), (size_t)e->cap_docs * 64 * sizeof(float), cudaHostAllocDefault));
-    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_int), (size_t)e->cap_docs * 8 * sizeof(int), cudaHostAllocDefault));
+    CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_int), (size_t)e->cap_docs * kGreedyMaxNew * sizeof(int), cudaHostAllocDefault));
     e->h_small_cap = 4 * R + 4096;
     CU_OK(cudaHostAlloc(reinterpret_cast<void**>(&e->h_small), e->h_small_cap * sizeof(int), cudaHostAllocDefault));
     CU_OK(cudaStreamSynchronize(e->stream));
@@ -909,6 +916,23 @@ static int k_embed(b200rank_engine* e, const int* ids, float* x, int n) {
     prof_begin(e, "embed"); launch_k(embed_kernel, dim3((n + 7) / 8), dim3(256), 0, e->stream, ids, e->emb, x, n, e->d, e->V);
     return post_launch(e, "embed");
 }
+// x = E[ids], h = T5LayerNorm(x; w) in one pass over the rows (B200RANK_FUSE_EMBED_NORM=0: the two kernels, bit-identical)
+static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n);
+static int k_embed_norm(b200rank_engine* e, const int* ids, float* x, const float* w, bf16* h, int n) {
+    if (n <= 0) return B200RANK_OK;
+    static int fuse = -1;
+    if (fuse < 0) fuse = (getenv("B200RANK_FUSE_EMBED_NORM") && atoi(getenv("B200RANK_FUSE_EMBED_NORM")) == 0) ? 0 : 1;
+    if (!fuse) {
+        RET_IF(k_embed(e, ids, x, n));
+        return k_rmsnorm(e, x, w, h, n);
+    }
+    const int grid = (n + 7) / 8;
+    prof_begin(e, "embed_norm");
+    if (e->d <= 1024) launch_k(embed_norm_kernel<8>, dim3(grid), dim3(256), 0, e->stream, ids, (const float*)e->emb, x, w, h, n, e->d, e->V, e->cfg.layer_norm_eps);
+    else if (e->d <= 2048) launch_k(embed_norm_kernel<16>, dim3(grid), dim3(256), 0, e->stream, ids, (const float*)e->emb, x, w, h, n, e->d, e->V, e->cfg.layer_norm_eps);
+    else launch_k(embed_norm_kernel<32>, dim3(grid), dim3(256), 0, e->stream, ids, (const float*)e->emb, x, w, h, n, e->d, e->V, e->cfg.layer_norm_eps);
+    return post_launch(e, "embed_norm");
+}
 static int k_rmsnorm(b200rank_engine* e, const float* x, const float* w, bf16* h, int n) {
     if (n <= 0) return B200RANK_OK;
     const int grid = (n + 7) / 8;
@@ -1042,8 +1066,7 @@ static int launch_attention_wide(b200rank_engine* e, const char* label, const bf
 static int run_encoder(b200rank_engine* e, bool need_ckv = true) {
     const int n = e->staged_tokens, nd = e->staged_docs;
     const int d = e->d, I = e->inner, F = e->F, Tk = e->cap_tokens;
-    RET_IF(k_embed(e, e->d_ids, e->x, n));
-    RET_IF(k_rmsnorm(e, e->x, e->enc[0].ln1, e->h, n));
+    RET_IF(k_embed_norm(e, e->d_ids, e->x, e->enc[0].ln1, e->h, n));
     for (int l = 0; l < e->Le; ++l) {
         const LayerW& w = e->enc[l];
         // h = norm1(x) was produced by the previous layer's last GEMM (or the line above for layer 0)
@@ -1112,10 +1135,11 @@ static int launch_skinny(b200rank_engine* e, const char* label, const float* x, 
 }
 
 // out_bf16[R, N] = T5LayerNorm(xd; ln_w) . W^T   (W: [N, d])
-static int dec_norm_proj(b200rank_engine* e, const float* ln_w, const bf16* W, int N, int R, bf16* out, int ldo) {
+// normed: hd already holds the normed rows (block 0, where the embedding kernel produced them)
+static int dec_norm_proj(b200rank_engine* e, const float* ln_w, const bf16* W, int N, int R, bf16* out, int ldo, bool normed = false) {
     const int d = e->d;
     if (use_skinny(e, R)) return launch_skinny<SK_BF16>(e, "skinny_norm_proj", e->xd, nullptr, 0, ln_w, W, d, R, N, d, out, ldo);
-    RET_IF(k_rmsnorm(e, e->xd, ln_w, e->hd, R));
+    if (!normed) RET_IF(k_rmsnorm(e, e->xd, ln_w, e->hd, R));
     return gemm(e, e->hd, d, e->cap_rows, W, d, N, R, N, d, EPI_BF16, out, ldo);
 }
 
@@ -1137,14 +1161,62 @@ static int dec_norm_ffn_in(b200rank_engine* e, const float* ln_w, const bf16* wi
     return ffn_in(e, e->hd, e->cap_rows, wi, R, e->gd);
 }
 
+// Cross-attention of 1-4 decoder positions per document (generation / likelihood prefixes, KV-cached greedy steps). The keys of every
+// (document, head) are ALWAYS split 8 ways (CTA z takes the 128-key chunks z, z+8, ...; flash-decoding partials + exact log-sum-exp
+// merge): a setwise compare (1 document, 1.5 k keys) otherwise runs on 16 CTAs of a 148-SM GPU, 100 us per layer. The split is a
+// function of the document alone — not of how many documents share the pass, nor of how many positions are in flight — so a row's
+// result stays bit-identical across batch compositions (what lets rerank_many / the level-parallel heaps reproduce rerank()
+// exactly) and between a re-run prefix and a cached step. The last launch's post_launch is left to the caller.
+static int cross_attention_short(b200rank_engine* e, int doc0, int nd, int T, size_t ldkv, int k_off, int v_off) {
+    const int I = e->inner;
+    if (!cross_split_off()) {
+        const int group = (int)(e->xattn_partial_bytes / ((size_t)e->H * kXAttnSplit * T * 66 * sizeof(float)));
+        for (int g0 = 0; g0 < nd; g0 += group) {
+            const int gn = std::min(group, nd - g0);
+            if (g0) prof_begin(e, "cross_attention");
+            cross_attention_kernel<4, 128><<<dim3(e->H, gn, kXAttnSplit), 128, 0, e->stream>>>(e->qd + (size_t)g0 * T * I, I, T, e->ckv, ldkv, k_off, v_off,
+                                                                                                e->d_cu_cur + doc0 + g0, e->aod + (size_t)g0 * T * I, I, e->xattn_partial);
+            RET_IF(post_launch(e, "cross_attention"));
+            prof_begin(e, "cross_attention_combine");
+            cross_attention_combine_kernel<<<dim3(e->H, gn), 64, 0, e->stream>>>(e->xattn_partial, kXAttnSplit, T, e->aod + (size_t)g0 * T * I, I);
+            if (g0 + gn < nd) RET_IF(post_launch(e, "cross_attention_combine"));
+        }
+    } else {
+        cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
+    }
+    return B200RANK_OK;
+}
+
+// ---- greedy decoding with a self-attention K/V cache (generation/utils.py:2762-2804 runs one cached step per new token)
+// B200RANK_KV_CACHE=0 selects the cache-less loop (the growing prefix re-run per step); read per call so that the GPU tests can
+// compare the two in one process.
+static bool kv_cache_off() {
+    const char* v = getenv("B200RANK_KV_CACHE");
+    return v && atoi(v) == 0;
+}
+static bf16* kvc_layer(const b200rank_engine* e, int l) { return e->kvc + (size_t)l * e->kvc_rows * 3 * e->inner; }
+
+// k | v of the prefix rows (qkv workspace, row = doc * T + t) -> cache rows doc * row_stride + t (columns [inner, 3 inner))
+__global__ void kv_cache_fill_kernel(const bf16* __restrict__ qkv, int ld, int inner, int T, bf16* __restrict__ cache, int row_stride, int n_rows) {
+    pdl_trigger();
+    pdl_wait();
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)r * ld + inner);
+    uint4* dst = reinterpret_cast<uint4*>(cache + ((size_t)(r / T) * row_stride + (r % T)) * ld + inner);
+    for (int i = threadIdx.x; i < 2 * inner / 8; i += blockDim.x) dst[i] = src[i];
+}
+
 // Decoder over documents [doc0, doc0+nd) with T positions each; dec ids in d_dec_ids[nd*T].
 // Leaves the final-normed hidden states in hd[nd*T, d].
-static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
+// kv_stride > 0 (first step of a KV-cached greedy call): the self-attention k | v rows of the T prefix positions are also written to
+// the cache, row stride kv_stride per document, for run_decoder_cached_step to attend to.
+static int run_decoder(b200rank_engine* e, int doc0, int nd, int T, int kv_stride = 0) {
     const int R = nd * T;
     const int d = e->d, I = e->inner, F = e->F, cap = e->cap_rows;
     if (R > cap) return set_error(B200RANK_ERR_CAPACITY, "decoder rows %d exceed capacity %d", R, cap);
     if (T > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "decoder length %d exceeds max_dec_len %d", T, e->cap_T);
-    RET_IF(k_embed(e, e->d_dec_ids, e->xd, R));
+    RET_IF(k_embed_norm(e, e->d_dec_ids, e->xd, e->dec[0].ln1, e->hd, R));   // block 0's first norm rides on the embedding gather
     const size_t ldkv = (size_t)e->Ld * 2 * I;
     const int max_len = e->staged_maxlen;
     const bool reassoc = use_reassoc_t1(e, T);
@@ -1157,10 +1229,20 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         if (T == 1) {
             // one decoder position: softmax over a single key is 1, so the block is x += W_o W_v norm(x) (derive_weights).
             // Input and output are both xd, so the norm stays a kernel of its own (a fused norm would race with the adds).
-            RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
+            if (l > 0) RET_IF(k_rmsnorm(e, e->xd, w.ln1, e->hd, R));
+            // the fused W_o W_v product never forms k and v: project them for the cache from the same normed rows (the k | v rows
+            // of Wqkv; a GEMM row does not depend on the tile shape, so these are the values a re-run prefix would compute)
+            if (kv_stride)
+                RET_IF(gemm(e, e->hd, d, cap, w.wqkv + (size_t)I * d, d, 2 * I, R, 2 * I, d, EPI_BF16, kvc_layer(e, l) + I, kv_stride * 3 * I));
             RET_IF(dec_resid_proj(e, e->hd, d, w.wov, d, R));
         } else {
-            RET_IF(dec_norm_proj(e, w.ln1, w.wqkv, 3 * I, R, e->qkvd, 3 * I));
+            RET_IF(dec_norm_proj(e, w.ln1, w.wqkv, 3 * I, R, e->qkvd, 3 * I, /*normed=*/l == 0));
+            // k | v of the prefix go to the cache: inside the CUDA-core attention kernel for short prefixes, by a copy otherwise
+            if (kv_stride && (e->dkv != 64 || dec_attn_mma(T))) {
+                prof_begin(e, "kv_cache_fill");
+                launch_k(kv_cache_fill_kernel, dim3(R), dim3(128), 0, e->stream, (const bf16*)e->qkvd, 3 * I, I, T, kvc_layer(e, l), kv_stride, R);
+                RET_IF(post_launch(e, "kv_cache_fill"));
+            }
             if (e->dkv != 64) {
                 RET_IF(launch_attention_wide<ATT_DEC_SELF>(e, "dec_self_attention_wide", e->qkvd, 3 * I, T, e->qkvd, (size_t)3 * I, I, 2 * I, nullptr,
                                                            e->bias_dec, kAttnRelClamp + 1, e->aod, I, (T + 63) / 64, nd));
@@ -1170,7 +1252,8 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
                          (const int*)nullptr, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
                 RET_IF(post_launch(e, "dec_self_attention_mma"));
             } else {
-                prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+                prof_begin(e, "dec_self_attention"); dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qkvd, 3 * I, I, T, 0, T, e->bias_dec, kAttnRelClamp + 1, e->aod, I,
+                                                                                                          kv_stride ? kvc_layer(e, l) : nullptr, kv_stride);
                 RET_IF(post_launch(e, "dec_self_attention"));
             }
             RET_IF(dec_resid_proj(e, e->aod, I, w.wo, I, R));
@@ -1216,26 +1299,7 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
         else if (T == 1 && e->H % 4 == 0 && max_len <= 2048)
             cross_attention_t1_kernel<64><<<dim3(e->H / 4, nd), 128, 0, e->stream>>>(e->qd, I, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
         else if (T <= 4) {
-            // Generation / likelihood prefixes (2-4 decoder positions). The keys of every (document, head) are ALWAYS split 8 ways
-            // (CTA z takes the 128-key chunks z, z+8, ...; flash-decoding partials + exact log-sum-exp merge): a setwise compare
-            // (1 document, 1.5 k keys) otherwise runs on 16 CTAs of a 148-SM GPU, 100 us per layer. The split is a function of the
-            // document alone — not of how many documents share the pass — so a row's result stays bit-identical across batch
-            // compositions (what lets rerank_many / the level-parallel heaps reproduce rerank() exactly).
-            if (!cross_split_off()) {
-                const int group = (int)(e->xattn_partial_bytes / ((size_t)e->H * kXAttnSplit * T * 66 * sizeof(float)));
-                for (int g0 = 0; g0 < nd; g0 += group) {
-                    const int gn = std::min(group, nd - g0);
-                    if (g0) prof_begin(e, "cross_attention");
-                    cross_attention_kernel<4, 128><<<dim3(e->H, gn, kXAttnSplit), 128, 0, e->stream>>>(e->qd + (size_t)g0 * T * I, I, T, e->ckv, ldkv, k_off, v_off,
-                                                                                                        e->d_cu_cur + doc0 + g0, e->aod + (size_t)g0 * T * I, I, e->xattn_partial);
-                    RET_IF(post_launch(e, "cross_attention"));
-                    prof_begin(e, "cross_attention_combine");
-                    cross_attention_combine_kernel<<<dim3(e->H, gn), 64, 0, e->stream>>>(e->xattn_partial, kXAttnSplit, T, e->aod + (size_t)g0 * T * I, I);
-                    if (g0 + gn < nd) RET_IF(post_launch(e, "cross_attention_combine"));
-                }
-            } else {
-                cross_attention_kernel<4, 128><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
-            }
+            RET_IF(cross_attention_short(e, doc0, nd, T, ldkv, k_off, v_off));
         }
         else
             cross_attention_kernel<40, 64><<<dim3(e->H, nd), 128, 0, e->stream>>>(e->qd, I, T, e->ckv, ldkv, k_off, v_off, e->d_cu_cur + doc0, e->aod, I);
@@ -1248,8 +1312,52 @@ static int run_decoder(b200rank_engine* e, int doc0, int nd, int T) {
     return B200RANK_OK;
 }
 
+// One NEW decoder position per document (position pos >= 1; its token in d_dec_ids[nd]) against the self-attention K/V cache that
+// run_decoder(kv_stride) and the earlier steps filled. Per layer: the fused q|k|v projection of the new row lands in the cache row
+// of (document, pos) — the output tensor map strides by a document's kv_stride rows — the generalised dec_self_attention_kernel
+// attends that row's q to the k/v of positions 0..pos, and cross-attention runs with one query row per document. Every kernel and
+// every per-row summation order is the one the cache-less loop uses for the same position, so the generated tokens are identical.
+// Leaves the final-normed hidden states of the new rows in hd[nd, d].
+static int run_decoder_cached_step(b200rank_engine* e, int doc0, int nd, int pos, int kv_stride) {
+    const int R = nd;
+    const int I = e->inner, F = e->F;
+    const size_t ldkv = (size_t)e->Ld * 2 * I;
+    RET_IF(k_embed_norm(e, e->d_dec_ids, e->xd, e->dec[0].ln1, e->hd, R));
+    for (int l = 0; l < e->Ld; ++l) {
+        const LayerW& w = e->dec[l];
+        bf16* cache = kvc_layer(e, l);
+        RET_IF(dec_norm_proj(e, w.ln1, w.wqkv, 3 * I, R, cache + (size_t)pos * 3 * I, kv_stride * 3 * I, /*normed=*/l == 0));
+        prof_begin(e, "dec_self_attention");
+        dec_self_attention_kernel<<<dim3(e->H, nd), 128, 0, e->stream>>>(cache, 3 * I, I, kv_stride, pos, 1, e->bias_dec, kAttnRelClamp + 1, e->aod, I);
+        RET_IF(post_launch(e, "dec_self_attention"));
+        RET_IF(dec_resid_proj(e, e->aod, I, w.wo, I, R));
+        RET_IF(dec_norm_proj(e, w.ln_c, w.wq_c, I, R, e->qd, I));
+        prof_begin(e, "cross_attention");
+        RET_IF(cross_attention_short(e, doc0, nd, 1, ldkv, l * 2 * I, l * 2 * I + I));
+        RET_IF(post_launch(e, "cross_attention"));
+        RET_IF(dec_resid_proj(e, e->aod, I, w.wo_c, I, R));
+        RET_IF(dec_norm_ffn_in(e, w.ln2, w.wi, R));
+        RET_IF(dec_resid_proj(e, e->gd, F, w.wff, F, R));
+    }
+    RET_IF(k_rmsnorm(e, e->xd, e->dec_final_ln, e->hd, R));
+    return B200RANK_OK;
+}
+
 static float logit_scale(const b200rank_engine* e) {
     return e->cfg.scale_decoder_outputs ? 1.0f / std::sqrt(static_cast<float>(e->d)) : 1.0f;
+}
+
+// Full-vocabulary row reductions (log-prob of a label / argmax / softmax gather): the register-resident single-pass kernel when the
+// row fits (V <= 32768, a multiple of 4, 16 B-aligned rows), the multi-pass kernel otherwise. B200RANK_VOCAB_ROW=multipass forces the latter.
+static int k_vocab_row(b200rank_engine* e, const char* what, int rows, int mode, const int* labels, const int* cols, int ncols, float* out_f, int* out_i) {
+    static int regs = -1;
+    if (regs < 0) regs = (getenv("B200RANK_VOCAB_ROW") && !strcmp(getenv("B200RANK_VOCAB_ROW"), "multipass")) ? 0 : 1;
+    prof_begin(e, "vocab_row");
+    if (regs && e->V % 4 == 0 && e->V <= 32768)
+        launch_k(vocab_row_regs_kernel<8>, dim3(rows), dim3(1024), 0, e->stream, (const float*)e->logits, e->V, (size_t)e->V, mode, logit_scale(e), labels, cols, ncols, out_f, out_i);
+    else
+        launch_k(vocab_row_kernel, dim3(rows), dim3(256), 0, e->stream, (const float*)e->logits, e->V, (size_t)e->V, mode, logit_scale(e), labels, cols, ncols, out_f, out_i);
+    return post_launch(e, what);
 }
 
 // ------------------------------------------------------------------ staging
@@ -1583,8 +1691,7 @@ extern "C" int b200rank_score_qlm(b200rank_engine* e, const int32_t* ids, const 
         RET_IF(upload_ints(e, e->d_labels, lab));
         RET_IF(run_decoder(e, 0, nd, T));
         RET_IF(gemm(e, e->hd, e->d, e->cap_rows, e->lm_head, e->d, e->V, R, e->V, e->d, EPI_F32, e->logits, e->V));
-        prof_begin(e, "vocab_row"); launch_k(vocab_row_kernel, dim3(R), dim3(256), 0, e->stream, e->logits, e->V, (size_t)e->V, 0, logit_scale(e), e->d_labels, nullptr, 0, e->small_out, nullptr);
-        RET_IF(post_launch(e, "vocab_row_logprob"));
+        RET_IF(k_vocab_row(e, "vocab_row_logprob", R, 0, e->d_labels, nullptr, 0, e->small_out, nullptr));
         prof_begin(e, "sum_rows"); launch_k(sum_rows_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, e->small_out, T, e->small_out2, nd);
         RET_IF(post_launch(e, "sum_rows"));
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out2, (size_t)nd * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
@@ -1626,8 +1733,7 @@ extern "C" int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const 
             prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
             RET_IF(post_launch(e, "gather_rows"));
             RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
-            prof_begin(e, "vocab_row"); launch_k(vocab_row_kernel, dim3(nd), dim3(256), 0, e->stream, e->logits, e->V, (size_t)e->V, 2, logit_scale(e), nullptr, e->d_cols, ncols, e->small_out, nullptr);
-            RET_IF(post_launch(e, "vocab_row_softmax_gather"));
+            RET_IF(k_vocab_row(e, "vocab_row_softmax_gather", nd, 2, nullptr, e->d_cols, ncols, e->small_out, nullptr));
         }
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * ncols * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
         CU_OK(cudaStreamSynchronize(e->stream));
@@ -1652,24 +1758,35 @@ __global__ void greedy_update_kernel(const int* __restrict__ argmax, int* __rest
     new_ids[i * max_new + step] = tok;
     if (t_write < t_stride) dec_rows[i * t_stride + t_write] = tok;
 }
-// expand dec rows [nd, t_stride] -> contiguous [nd, T] ids for this step
-__global__ void dec_rows_to_ids_kernel(const int* __restrict__ dec_rows, int t_stride, int T, int* __restrict__ dec_ids, int nd) {
+// expand dec rows [nd, t_stride] -> contiguous [nd, T] ids for this step: positions t0 .. t0 + T - 1 of every document
+__global__ void dec_rows_to_ids_kernel(const int* __restrict__ dec_rows, int t_stride, int t0, int T, int* __restrict__ dec_ids, int nd) {
     pdl_trigger();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd * T) return;
-    dec_ids[i] = dec_rows[(i / T) * t_stride + (i % T)];
+    dec_ids[i] = dec_rows[(i / T) * t_stride + t0 + (i % T)];
 }
 
 extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int32_t* lengths, int n_docs, int stride,
                                const int32_t* dec_prefix, int prefix_len, int max_new, int32_t* new_ids) {
     RET_IF(check_ready(e));
-    if (!ids || !lengths || !dec_prefix || !new_ids || n_docs < 0 || stride <= 0 || prefix_len <= 0 || max_new <= 0 || max_new > 8)
-        return set_error(B200RANK_ERR_ARG, "bad arguments (max_new must be 1..8)");
+    if (!ids || !lengths || !dec_prefix || !new_ids || n_docs < 0 || stride <= 0 || prefix_len <= 0 || max_new <= 0 || max_new > kGreedyMaxNew)
+        return set_error(B200RANK_ERR_ARG, "bad arguments (max_new must be 1..%d)", kGreedyMaxNew);
     const int Tmax = prefix_len + max_new - 1;  // longest decoder input actually run
     if (Tmax > e->cap_T) return set_error(B200RANK_ERR_CAPACITY, "prefix+new %d exceeds max_dec_len %d", Tmax, e->cap_T);
     const int t_stride = prefix_len + max_new;
-    const int doc_limit = std::min(std::min(e->cap_docs, e->cap_rows / t_stride), e->cap_logit_rows);
+    // Self-attention K/V cache (the cached loop of generation/utils.py:2762-2804): step 0 runs the prefix and fills the cache, every
+    // later step runs ONE new position per document, so the decoder work of a call is linear in the tokens generated. The cached
+    // kernel holds <= 64 positions and 64-wide heads; anything else (and B200RANK_KV_CACHE=0) re-runs the growing prefix per step.
+    const bool cached = !kv_cache_off() && max_new > 1 && e->dkv == 64 && Tmax <= 64;
+    if (cached && !e->kvc) {
+        e->kvc_rows = getenv("B200RANK_KV_CACHE_ROWS") ? std::max(128, atoi(getenv("B200RANK_KV_CACHE_ROWS"))) : kKvCacheRows;
+        RET_IF(dev_alloc(e, &e->kvc, (size_t)e->Ld * e->kvc_rows * 3 * e->inner));
+    }
+    int doc_limit = std::min(std::min(e->cap_docs, e->cap_rows / t_stride), e->cap_logit_rows);
+    if (cached) doc_limit = std::min(doc_limit, e->kvc_rows / t_stride);
+    if (doc_limit <= 0) return set_error(B200RANK_ERR_CAPACITY, "prefix+new %d leaves no room for a document (decoder rows %d)", t_stride, e->cap_rows);
+    int* d_argmax = e->d_int_out + (size_t)e->cap_docs * kGreedyMaxNew;  // behind the new ids
     int d0 = 0;
     while (d0 < n_docs) {
         int d1 = 0;
@@ -1683,18 +1800,24 @@ extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int
         RET_IF(upload_ints(e, e->d_labels, rows));
         CU_OK(cudaMemsetAsync(e->d_finished, 0, (size_t)nd * sizeof(int), e->stream));
         for (int step = 0; step < max_new; ++step) {
-            const int T = prefix_len + step;
-            // No KV cache: the decoder prefix is re-run (<= prefix_len + max_new - 1 positions; negligible next to
-            // the encoder pass) — token-for-token the same greedy choice as the cached loop in generation/utils.py:2762-2804.
-            prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd * T + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, T, e->d_dec_ids, nd);
-            RET_IF(post_launch(e, "dec_rows_to_ids"));
-            RET_IF(run_decoder(e, 0, nd, T));
-            prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
-            RET_IF(post_launch(e, "gather_rows"));
-            RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
-            int* d_argmax = e->d_int_out + (size_t)e->cap_docs * 8;  // second half of the int scratch
-            prof_begin(e, "vocab_row"); launch_k(vocab_row_kernel, dim3(nd), dim3(256), 0, e->stream, e->logits, e->V, (size_t)e->V, 1, logit_scale(e), nullptr, nullptr, 0, nullptr, d_argmax);
-            RET_IF(post_launch(e, "vocab_row_argmax"));
+            const int T = prefix_len + step;   // decoder positions so far; the new token is written at position T
+            const bf16* h_last = nullptr;
+            if (cached && step > 0) {
+                prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, T - 1, 1, e->d_dec_ids, nd);
+                RET_IF(post_launch(e, "dec_rows_to_ids"));
+                RET_IF(run_decoder_cached_step(e, 0, nd, T - 1, t_stride));
+                h_last = e->hd;
+            } else {
+                // cache-less loop: the decoder prefix is re-run — token-for-token the same greedy choice
+                prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd * T + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, 0, T, e->d_dec_ids, nd);
+                RET_IF(post_launch(e, "dec_rows_to_ids"));
+                RET_IF(run_decoder(e, 0, nd, T, cached ? t_stride : 0));
+                prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
+                RET_IF(post_launch(e, "gather_rows"));
+                h_last = e->hlast;
+            }
+            RET_IF(gemm(e, h_last, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
+            RET_IF(k_vocab_row(e, "vocab_row_argmax", nd, 1, nullptr, nullptr, 0, nullptr, d_argmax));
             prof_begin(e, "greedy_update"); launch_k(greedy_update_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
                                                                           t_stride, step, max_new, e->cfg.eos_id, e->cfg.pad_id);
             RET_IF(post_launch(e, "greedy_update"));

@@ -78,13 +78,66 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
     }
 }
 
-// Decoder self-attention for a short prefix (T <= 64), causal, with the unidirectional
+// Embedding gather fused with the first T5LayerNorm of the stack (SURVEY K1 + K2 of block 0): one warp per token reads the fp32 table
+// row once, writes the residual stream x and h = bf16(x * rsqrt(mean(x^2) + eps) * w). Same per-lane summation order as
+// rmsnorm_kernel, so the pair (embed_kernel, rmsnorm_kernel) and this kernel produce identical bits.
+template <int MAX_VEC>
+__global__ void embed_norm_kernel(const int* __restrict__ ids, const float* __restrict__ table, float* __restrict__ x,
+                                  const float* __restrict__ w, __nv_bfloat16* __restrict__ h, int n_tokens, int d, int vocab, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    const int warps_per_block = blockDim.x >> 5;
+    const int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (t >= n_tokens) return;
+    const int lane = threadIdx.x & 31;
+    int id = ids[t];
+    if (id < 0 || id >= vocab) id = 0;
+    const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(id) * d);
+    float4* dx = reinterpret_cast<float4*>(x + static_cast<size_t>(t) * d);
+    const int nvec = d / 4;
+    float4 v[MAX_VEC];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            v[i] = __ldg(src + idx);
+            dx[idx] = v[i];
+            ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+    }
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss / static_cast<float>(d) + eps);
+    const float4* wv = reinterpret_cast<const float4*>(w);
+    uint2* dst = reinterpret_cast<uint2*>(h + static_cast<size_t>(t) * d);
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            const float4 g = __ldg(wv + idx);
+            uint2 o;
+            o.x = pack_bf16(v[i].x * r * g.x, v[i].y * r * g.y);
+            o.y = pack_bf16(v[i].z * r * g.z, v[i].w * r * g.w);
+            dst[idx] = o;
+        }
+    }
+}
+
+// Decoder self-attention for a short prefix (<= 64 positions), causal, with the unidirectional
 // relative-position bias (modeling_t5.py:236-251, 308-334; no 1/sqrt(d) scaling).
-// grid (H, n_docs); qkv rows = doc*T + t, layout [q | k | v] each `inner` wide; head dim 64.
-// bias: [H][bias_len] indexed by (i - j) clamped to bias_len-1.
-__global__ void dec_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, int T,
+// grid (H, n_docs); rows are [q | k | v], each `inner` wide, head dim 64; row of (doc, position p) = doc * doc_rows + p.
+// The Tq queries of a document sit at positions q_pos0 .. q_pos0 + Tq - 1 and attend to the keys at positions 0 .. own position:
+//   whole prefix (qlm / likelihood / first greedy step):  doc_rows = Tq = T, q_pos0 = 0, rows in the qkv workspace;
+//   KV-cached greedy step (generation/utils.py:2762-2804): doc_rows = row stride of the cache, Tq = 1, q_pos0 = number of cached
+//   positions — the rows of the earlier positions were written by the earlier steps' projections (engine.cu, run_decoder_cached_step).
+// A query's arithmetic is the same whichever way it is reached, so the cached step is bit-identical to re-running the prefix.
+// Output rows are dense: doc * Tq + local query index. bias: [H][bias_len] indexed by (i - j) clamped to bias_len-1.
+// kv_out != nullptr (first step of a cached greedy call): the k | v values read are also copied to the cache, whose rows have the same
+// [q | k | v] layout and kv_out_doc_rows rows per document.
+__global__ void dec_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int inner, int doc_rows, int q_pos0, int Tq,
                                           const float* __restrict__ bias, int bias_len,
-                                          __nv_bfloat16* __restrict__ out, int ldo) {
+                                          __nv_bfloat16* __restrict__ out, int ldo,
+                                          __nv_bfloat16* __restrict__ kv_out = nullptr, int kv_out_doc_rows = 0) {
     pdl_trigger();
     pdl_wait();
     constexpr int D = 64;
@@ -95,15 +148,22 @@ __global__ void dec_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
     __shared__ float sP[4][MAXT];
     const int h = blockIdx.x, doc = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const __nv_bfloat16* base = qkv + static_cast<size_t>(doc) * T * ld + h * D;
+    const int T = q_pos0 + Tq;   // keys in play
+    const __nv_bfloat16* base = qkv + static_cast<size_t>(doc) * doc_rows * ld + h * D;
+    __nv_bfloat16* cbase = kv_out ? kv_out + static_cast<size_t>(doc) * kv_out_doc_rows * ld + h * D : nullptr;
     for (int idx = threadIdx.x; idx < T * D; idx += blockDim.x) {
         const int j = idx / D, dd = idx % D;
-        sK[j][dd] = __bfloat162float(base[static_cast<size_t>(j) * ld + inner + dd]);
-        sV[j][dd] = __bfloat162float(base[static_cast<size_t>(j) * ld + 2 * inner + dd]);
+        const __nv_bfloat16 kb = base[static_cast<size_t>(j) * ld + inner + dd], vb = base[static_cast<size_t>(j) * ld + 2 * inner + dd];
+        sK[j][dd] = __bfloat162float(kb);
+        sV[j][dd] = __bfloat162float(vb);
+        if (cbase) {
+            cbase[static_cast<size_t>(j) * ld + inner + dd] = kb;
+            cbase[static_cast<size_t>(j) * ld + 2 * inner + dd] = vb;
+        }
     }
     __syncthreads();
     const float* hb = bias + static_cast<size_t>(h) * bias_len;
-    for (int i = warp; i < T; i += 4) {
+    for (int i = q_pos0 + warp; i < T; i += 4) {
         sQ[warp][lane] = __bfloat162float(base[static_cast<size_t>(i) * ld + lane]);
         sQ[warp][lane + 32] = __bfloat162float(base[static_cast<size_t>(i) * ld + lane + 32]);
         __syncwarp();
@@ -139,7 +199,7 @@ __global__ void dec_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv,
             const int dd = lane + 32 * r;
             float acc = 0.f;
             for (int j = 0; j <= i; ++j) acc += sP[warp][j] * sV[j][dd];
-            out[(static_cast<size_t>(doc) * T + i) * ldo + h * D + dd] = __float2bfloat16(acc * inv);
+            out[(static_cast<size_t>(doc) * Tq + (i - q_pos0)) * ldo + h * D + dd] = __float2bfloat16(acc * inv);
         }
         __syncwarp();
     }
@@ -496,6 +556,89 @@ __global__ void vocab_row_kernel(const float* __restrict__ logits, int V, size_t
     __syncthreads();
     float sum = 0.f;
     for (int i = tid; i < V; i += blockDim.x) sum += expf(row[i] * scale - m);
+    sum = warp_sum(sum);
+    if (lane == 0) s_val[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        sum = lane < nwarps ? s_val[lane] : 0.f;
+        sum = warp_sum(sum);
+        if (lane == 0) s_val[0] = sum;
+    }
+    __syncthreads();
+    sum = s_val[0];
+    if (mode == 0) {
+        if (tid == 0) out_f[r] = row[labels[r]] * scale - m - logf(sum);
+    } else {
+        for (int c = tid; c < ncols; c += blockDim.x) out_f[static_cast<size_t>(r) * ncols + c] = expf(row[cols[c]] * scale - m) / sum;
+    }
+}
+
+// The same reductions with the row read from memory ONCE: 1024 threads hold the scaled row in registers (MAXV float4 each, i.e.
+// V <= 4096 * MAXV), so the maximum, the sum of exponentials and the gathers are one streaming pass over the 128 KB row instead of
+// two or three (qlm reads 5 k such rows per device pass). Argmax ties resolve to the first index exactly as above.
+template <int MAXV>
+__global__ void __launch_bounds__(1024)
+vocab_row_regs_kernel(const float* __restrict__ logits, int V, size_t ld, int mode, float scale,
+                      const int* __restrict__ labels, const int* __restrict__ cols, int ncols,
+                      float* __restrict__ out_f, int* __restrict__ out_i) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float s_val[32];
+    __shared__ int s_idx[32];
+    const int r = blockIdx.x;
+    const float* row = logits + static_cast<size_t>(r) * ld;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int nvec = V >> 2;
+    float4 v[MAXV];
+    float m = -INFINITY;
+    int mi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = tid + i * 1024;
+        if (idx < nvec) {
+            float4 t = __ldcs(row4 + idx);
+            t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+            v[i] = t;
+            if (t.x > m) { m = t.x; mi = 4 * idx; }
+            if (t.y > m) { m = t.y; mi = 4 * idx + 1; }
+            if (t.z > m) { m = t.z; mi = 4 * idx + 2; }
+            if (t.w > m) { m = t.w; mi = 4 * idx + 3; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    if (lane == 0) { s_val[warp] = m; s_idx[warp] = mi; }
+    __syncthreads();
+    if (warp == 0) {
+        m = lane < nwarps ? s_val[lane] : -INFINITY;
+        mi = lane < nwarps ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+        }
+        if (lane == 0) { s_val[0] = m; s_idx[0] = mi; }
+    }
+    __syncthreads();
+    m = s_val[0];
+    mi = s_idx[0];
+    if (mode == 1) {
+        if (tid == 0) out_i[r] = mi;
+        return;
+    }
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = tid + i * 1024;
+        if (idx < nvec) sum += expf(v[i].x - m) + expf(v[i].y - m) + expf(v[i].z - m) + expf(v[i].w - m);
+    }
     sum = warp_sum(sum);
     if (lane == 0) s_val[warp] = sum;
     __syncthreads();

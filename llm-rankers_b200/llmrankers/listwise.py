@@ -6,8 +6,9 @@
     last prefix position gathered at the label tokens A..W, labels sorted by probability -> "[i]>[j]>..." — one `logits_at` call
     on the engine, the same forward as SetwiseLlmRanker's likelihood mode;
   * scoring='generation' (listwise.py:246-256): the RankGPT completion prompt, truncated like `tokenizer(..., truncation=True)`,
-    then free-form greedy decoding `self.llm.generate(input_ids)` — run here as chunks of the engine's `greedy` entry point
-    (<= 8 new tokens per call, the decoder prefix grows between calls) until </s> or the default generation budget.
+    then free-form greedy decoding `self.llm.generate(input_ids)` — the engine's `greedy` entry point with its self-attention K/V
+    cache (one call covers the default budget; longer budgets continue in chunks of GREEDY_CHUNK new tokens whose decoder prefix
+    is what has been generated) until </s> or the generation budget.
 The response parser (`clean_response` / `remove_duplicate` / `receive_permutation`, listwise.py:110-144) is host logic and is pinned
 to the reference by fixtures (tests/golden/make_golden_listwise.py).
 
@@ -82,6 +83,7 @@ def _window_positions(n: int, window_size: int, step_size: int):
 
 
 class ListwiseLlmRanker(LlmRanker):
+    GREEDY_CHUNK = 32   # new tokens per b200rank_greedy call (the engine takes up to 64 decoder positions)
     CHARACTERS = ["A", "B", "C", "D", "E", "F", "G", "H", "I", "J", "K", "L",
                   "M", "N", "O", "P", "Q", "R", "S", "T", "U", "V", "W"]
 
@@ -128,7 +130,9 @@ class ListwiseLlmRanker(LlmRanker):
         budget = int(os.environ.get("B200RANK_LISTWISE_MAX_NEW", DEFAULT_MAX_NEW_TOKENS))
         out = [self.backend.pad_id]
         while len(out) - 1 < budget:
-            chunk = min(8, budget - (len(out) - 1))          # b200rank_greedy takes at most 8 new tokens per call
+            # one engine call per GREEDY_CHUNK new tokens: b200rank_greedy keeps a self-attention K/V cache inside a call (one decoder
+            # position per step); a further chunk re-encodes the prompt and re-runs what has been generated as its prefix
+            chunk = min(self.GREEDY_CHUNK, budget - (len(out) - 1))
             got = self.backend.generate_rows([row], out, chunk)[0].tolist()
             new = got[len(out):]
             out = got

@@ -20,7 +20,12 @@ def main(out_path, model="flan-t5-base", n_docs=96):
     e.load_state_dict(synthetic_weights(cfg, 5).items())
     ids, lengths = synthetic_prompt_ids(n_docs, 32, 128, seed=11, ragged=True)
     lg, sc = e.score_yes_no(ids, lengths, YES_ID, NO_ID)
-    np.savez(out_path, logits=lg, scores=sc)
+    # the other entry points on a few documents: full-vocabulary reductions (qlm log-probs, label softmax, greedy argmax)
+    k = min(16, n_docs)
+    qlm = e.score_qlm(ids[:k], lengths[:k], [71, 272, 205, 309, 262, 377, 350, 1])
+    probs = e.logits_at(ids[:k], lengths[:k], [0, 5], [71, 272, 205, 309], normalize=True)
+    new = e.greedy(ids[:k], lengths[:k], [0, 5], 3)
+    np.savez(out_path, logits=lg, scores=sc, qlm=qlm, probs=probs, greedy=new)
 
 
 if __name__ == "__main__":

@@ -480,6 +480,76 @@ def test_greedy_vs_golden(case):
     assert n_skipped <= max(1, n_tok // 20)
 
 
+def _ragged_prompts(rng, n, lo, hi, vocab):
+    lens = rng.integers(lo, hi + 1, size=n)
+    ids = np.zeros((n, int(lens.max())), np.int32)
+    for i, L in enumerate(lens):
+        ids[i, :L] = rng.integers(3, vocab - 1, size=L)
+        ids[i, L - 1] = 1
+    return ids, lens.astype(np.int32)
+
+
+def test_greedy_kv_cache_is_bit_identical_to_the_rerun_prefix(monkeypatch):
+    """b200rank_greedy keeps a self-attention K/V cache (generation/utils.py:2762-2804 runs one cached step per token). With the
+    decoder prefix `<pad> Passage` of the setwise / pairwise rankers every position goes through the same kernels and per-row
+    summation orders whether it is a cached step or part of a re-run prefix, so the tokens of the two loops must be IDENTICAL —
+    ragged documents, several device passes worth of rows, full flan-t5-large and the tiny fixture model."""
+    rng = np.random.default_rng(77)
+    for which in ("tiny", "large"):
+        if which == "tiny":
+            e = engine_for("tiny", label_favouring=True)
+            vocab = model_and_weights("tiny", True)[0]["vocab_size"]
+            ids, lengths = _ragged_prompts(rng, 37, 5, 300, vocab)
+        else:
+            e = large_engine()[0]
+            ids, lengths = _ragged_prompts(rng, 9, 40, 1500, 32000)
+        for prefix, max_new in (([0, 5], 2), ([0, 5], 3), ([0, 5, 71], 2)):
+            monkeypatch.setenv("B200RANK_KV_CACHE", "0")
+            rerun = e.greedy(ids, lengths, prefix, max_new)
+            monkeypatch.setenv("B200RANK_KV_CACHE", "1")
+            cached = e.greedy(ids, lengths, prefix, max_new)
+            assert np.array_equal(cached, rerun), (which, prefix, max_new, np.argwhere(cached != rerun)[:4])
+        # a cached row does not depend on its batch either
+        alone = e.greedy(ids[2:3], lengths[2:3], [0, 5], 3)
+        assert np.array_equal(alone[0], e.greedy(ids, lengths, [0, 5], 3)[2])
+    record("variant/greedy_kv_cache", identical=True)
+
+
+def test_greedy_kv_cache_long_generation_vs_oracle(monkeypatch):
+    """Twenty cached steps from the bare decoder start token (the free-form generation shape: step 0 is the T = 1 pass whose fused
+    W_o W_v block never forms k / v, so the cache gets them from the extra projection) against the fp32 oracle's greedy loop: every
+    token must agree until the first step whose top-2 margin in the oracle is inside the logit tolerance."""
+    rng = np.random.default_rng(78)
+    cfg = model_and_weights("tiny", True)[0]
+    ids, lengths = _ragged_prompts(rng, 12, 8, 120, cfg["vocab_size"])
+    for favouring in (True, False):   # boosted label rows of lm_head give decisive steps, the plain random model many near ties
+        e = engine_for("tiny", label_favouring=favouring)
+        orc = oracle_for("tiny", label_favouring=favouring)
+        n_tok = near = same = total = 0
+        for prefix, max_new in (([0], 20), ([0, 5], 12), ([0, 5, 9, 11, 13, 17], 10)):   # the last prefix takes the tensor-core prefix kernels + the copy into the cache
+            got = e.greedy(ids, lengths, prefix, max_new)
+            monkeypatch.setenv("B200RANK_KV_CACHE", "0")
+            rerun = e.greedy(ids, lengths, prefix, max_new)   # beyond 4 positions the re-run prefix takes the mma.sync kernels: same tokens up to near ties
+            monkeypatch.delenv("B200RANK_KV_CACHE")
+            same += int((got == rerun).sum()); total += got.size
+            for b in range(ids.shape[0]):
+                row = ids[b:b + 1, :lengths[b]].astype(np.int64)
+                want = orc.greedy(row, np.ones_like(row), prefix, max_new)[0]
+                for s in range(max_new):
+                    if got[b, s] != want[s]:
+                        dec = np.concatenate([np.asarray(prefix), want[:s]])[None]
+                        lg = orc.logits(row, np.ones_like(row), dec)[0, -1]
+                        top = np.sort(lg)[::-1]
+                        assert top[0] - top[1] <= 2 * (LOGIT_ATOL + LOGIT_RTOL * abs(top[0])), (favouring, prefix, b, s, got[b], want)
+                        near += 1
+                        break
+                    n_tok += 1
+        record(f"api/greedy_kv_cache_long/label_favouring={favouring}", tokens_agreeing=n_tok, sequences=36, near_tie_stops=near,
+               tokens_equal_to_rerun_prefix=same, tokens=total)
+        if favouring:   # (the plain random model leaves the oracle only a handful of decisive steps: recorded, not gated)
+            assert n_tok >= 300 and same >= 0.9 * total   # the check must actually reach the late steps
+
+
 # ---------------------------------------------------------------------------------------- kernel variants
 def test_kernel_variants_agree(tmp_path):
     """The optional kernel variants are re-schedulings of the same arithmetic: CTA-pair (cta_group::2) vs single-CTA GEMM
@@ -496,10 +566,23 @@ def test_kernel_variants_agree(tmp_path):
         full.update(env)
         p = subprocess.run([sys.executable, runner, out], env=full, capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, p.stderr[-2000:]
-        return np.load(out)["logits"]
+        z = np.load(out)
+        extras[name] = {k: z[k] for k in ("qlm", "probs", "greedy")}
+        return z["logits"]
 
+    extras = {}
     base = run("default")
     assert np.all(np.isfinite(base))
+    # round-2 additions: embedding gather fused with block 0's first norm (bit-exact re-scheduling, every entry point) and the
+    # register-resident single-pass vocabulary reductions (same maxima / argmax; the sum of exponentials is taken in another order)
+    got = run("embed_norm_unfused", B200RANK_FUSE_EMBED_NORM="0")
+    assert np.array_equal(got, base) and all(np.array_equal(extras["embed_norm_unfused"][k], extras["default"][k]) for k in extras["default"])
+    run("vocab_row_multipass", B200RANK_VOCAB_ROW="multipass")
+    a, b = extras["vocab_row_multipass"], extras["default"]
+    assert np.array_equal(a["greedy"], b["greedy"])
+    np.testing.assert_allclose(a["qlm"], b["qlm"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(a["probs"], b["probs"], rtol=1e-5, atol=1e-9)
+    record("variant/vocab_row_multipass", max_abs_qlm_diff=float(np.abs(a["qlm"] - b["qlm"]).max()))
     for name, env in [("cg1", {"B200RANK_GEMM_CG": "1"}), ("direct_epi", {"B200RANK_GEMM_DIRECT_EPI": "1"}), ("rmsnorm_fwd", {"B200RANK_RMSNORM_REV": "0"}),
                       ("pdl_off", {"B200RANK_PDL": "0"}), ("dec_graph_off", {"B200RANK_DEC_GRAPH": "0"})]:
         got = run(name, **env)

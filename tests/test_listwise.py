@@ -93,13 +93,16 @@ def test_listwise_prompt_tokens_and_generated_ids_match_the_recorded_calls(case)
 
 
 def test_generation_budget_and_eos_stop(monkeypatch):
-    """Chunked free-form decoding: the budget is honoured across the 8-token chunks of the greedy entry point, and an </s> ends it."""
+    """Chunked free-form decoding: the budget is honoured within one call of the greedy entry point and across chunks (8-token
+    chunks here, so that the default budget spans three calls), and an </s> ends it."""
     m = meta()
     c = m["cases"]["listwise_gen"]
     r = ranker(c)
+    one_call = r._generate_free(r._generation_row(m["query"], docs_from(m["docs12"][:3])))
+    r.GREEDY_CHUNK = 8
     row = r._generation_row(m["query"], docs_from(m["docs12"][:3]))
     full = r._generate_free(row)
-    assert len(full) == 21 and full[0] == 0
+    assert len(full) == 21 and full[0] == 0 and full == one_call
     for budget in (1, 7, 8, 9, 16, 19):
         monkeypatch.setenv("B200RANK_LISTWISE_MAX_NEW", str(budget))
         assert r._generate_free(row) == full[:budget + 1]
