@@ -318,11 +318,12 @@ def run_reference(args):
     return 0
 
 
-def workload_config(world, sample_docs=None):
+def workload_config(world, sample_docs=None, queries_per_step=1):
     return {
         "workload": f"{MODEL} pointwise yes_no, {HITS} hits/query, batch_size 32 (one device pass), q_len {Q_LEN} p_len {P_LEN} -> S {Q_LEN + P_LEN + 24}, T 1 (BASELINE configs[1])",
-        "docs_per_step_per_gpu": HITS if sample_docs is None else sample_docs,
-        "global_docs_per_step": (HITS if sample_docs is None else sample_docs) * world,
+        "queries_per_step": queries_per_step,
+        "docs_per_step_per_gpu": HITS * queries_per_step if sample_docs is None else sample_docs,
+        "global_docs_per_step": (HITS * queries_per_step if sample_docs is None else sample_docs) * world,
         "parallelism": f"dp{world} (queries sharded across ranks, weights NCCL-broadcast once at load, no collective in the loop)",
         "pipeline": "two queries in flight per GPU (submit/wait): decoder pass of query i on a second stream overlaps the encoder GEMMs of query i+1",
         "weights": f"seeded random init (numpy PCG64 seed {SEED}), bf16 on device",
@@ -708,8 +709,10 @@ def run_engine(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = model_cfg(MODEL)
+    QPS = max(1, getattr(args, "queries_per_step", 1))   # queries merged into one device pass (= one step)
+    DOCS = HITS * QPS
     c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
-                       max_tokens=HITS * (Q_LEN + P_LEN + 24) + 256, max_docs=128, max_logit_rows=256)
+                       max_tokens=DOCS * (Q_LEN + P_LEN + 24) + 256, max_docs=max(128, DOCS), max_logit_rows=256)
     eng = br.Engine(c, local)
     t_load = time.time()
     if rank == 0:
@@ -731,6 +734,11 @@ def run_engine(args):
 
     # every rank scores its own query (different token ids), 100 hits each; rank 0's is the committed headline query
     ids, lengths, fixture_logits = bench_query(rank)
+    if QPS > 1:   # further queries of the same shape ride in the same device pass (a document's result does not depend on its batch)
+        parts = [(ids, lengths)] + [synthetic_prompt_ids(HITS, Q_LEN, P_LEN, seed=SEED + 1000 * q + rank) for q in range(1, QPS)]
+        width = max(p[0].shape[1] for p in parts)
+        ids = np.concatenate([np.pad(p[0], ((0, 0), (0, width - p[0].shape[1]))) for p in parts]).astype(np.int32)
+        lengths = np.concatenate([p[1] for p in parts]).astype(np.int32)
     n_tok = int(lengths.sum())
 
     def barrier():
@@ -785,7 +793,7 @@ def run_engine(args):
     sampler.stop()
     clocks = sampler.summary(t0, t1)
     ms = max_over_ranks(ms)
-    value = world * HITS * args.steps / (ms * 1e-3)
+    value = world * DOCS * args.steps / (ms * 1e-3)
     # ---- sustained: the same loop for >= 3 s, so that the power-capped steady state (what MEASURED_PEAKS' sustained cuBLAS figure was
     # taken in) has a matching numerator next to the short driver-sized region above
     sustained = None
@@ -803,7 +811,7 @@ def run_engine(args):
         ts1 = time.time()
         s_sampler.stop()
         sus_peak, sus_src = peak_for_region(ms_sus * 1e-3)
-        sus_value = world * HITS * n_sus / (ms_sus * 1e-3)
+        sus_value = world * DOCS * n_sus / (ms_sus * 1e-3)
         sustained = {"value": sus_value, "unit": "docs/s", "steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus,
                      "step_frac": (sus_value / world) * GF_PER_DOC * 1e9 / (sus_peak * 1e12), "peak": sus_peak, "peak_source": sus_src,
                      "clocks": s_sampler.summary(ts0, ts1)}
@@ -820,10 +828,14 @@ def run_engine(args):
     lg, sc = run_steps(args.steps, lambda: eng.submit_yes_no(ids, lengths, YES_ID, NO_ID))
     eng.sync()
     e2e_s = max_over_ranks(time.perf_counter() - w0)
-    e2e_value = world * HITS * args.steps / e2e_s
+    e2e_value = world * DOCS * args.steps / e2e_s
     assert debug_skip or np.array_equal(lg, logits_dev), "e2e and device-resident passes disagree"
-    h2d = n_tok * 4 + (HITS + 1) * 4 + HITS * 4 + 2 * 4  # packed ids + cu_seqlens + decoder ids + (yes,no) ids
-    d2h = HITS * 3 * 4                                   # (yes, no) logits + P(yes) per document
+    if QPS > 1 and not debug_skip:   # batch-composition invariance, checked where it is relied on: the headline query alone gives the same bits
+        lg1, _ = eng.score_yes_no(ids[:HITS], lengths[:HITS], YES_ID, NO_ID)
+        assert np.array_equal(lg1, np.asarray(logits_dev)[:HITS]), "a merged pass changed the headline query's logits"
+    h2d = n_tok * 4 + (DOCS + 1) * 4 + DOCS * 4 + 2 * 4  # packed ids + cu_seqlens + decoder ids + (yes,no) ids
+    d2h = DOCS * 3 * 4                                   # (yes, no) logits + P(yes) per document
+    logits_dev, scores_dev = np.asarray(logits_dev)[:HITS], np.asarray(scores_dev)[:HITS]   # the headline query: what the parity legs below compare
 
     # ---- informational: the same workload through the drop-in Python API with TEXT (llmrankers PointwiseLlmRanker.rerank_many):
     # prompt assembly + tokenisation of 100 never-seen documents per query on the host, then the same submit/wait pipeline.
@@ -898,7 +910,7 @@ def run_engine(args):
             # all gemm_tcgen05 launches of a step together (264 launches incl. the small decoder GEMMs)
             "all_gemm": {"achieved": agg_achieved, "frac": agg_achieved / peak, "launches_per_step": gemm_n,
                          "executed_gflop_per_step": flops / 1e9,
-                         "algorithmic_gflop_per_step": gemm_gflop_per_doc(cfg, Q_LEN + P_LEN + 24) * HITS,
+                         "algorithmic_gflop_per_step": gemm_gflop_per_doc(cfg, Q_LEN + P_LEN + 24) * DOCS,
                          "share_of_step": gemm_ms / all_ms if all_ms else None},
             # whole path: the reference's algorithmic 136.1 GF/doc at the measured docs/s, against the peak matching the timed region
             "step_frac": (value / world) * GF_PER_DOC * 1e9 / (step_peak * 1e12), "step_peak": step_peak, "step_peak_source": step_peak_src,
@@ -966,7 +978,7 @@ def run_engine(args):
             "metric": f"docs scored/sec ({MODEL} q32/p128, pointwise yes_no)", "value": value, "unit": "docs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks,
+            "config": workload_config(world, queries_per_step=QPS), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "docs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": launches, "sustained": sustained, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "api_text": api_text, "hf_cuda": hf_cuda,
             "weights_load_s": round(t_load, 2), "sample_scores": [float(x) for x in scores_dev[:4]],
@@ -991,6 +1003,8 @@ def main():
     ap.add_argument("--model", default=None, help="qlm / pairwise workloads: synthetic model shape (qlm: default flan-t5-large, BASELINE configs[4] is flan-t5-xxl; "
                                                    "pairwise: default flan-t5-xl)")
     ap.add_argument("--hits", type=int, default=0, help="qlm / pairwise workloads: documents per query (qlm: default 100, configs[4] says 1000; pairwise: default 24, configs[3] says 100)")
+    ap.add_argument("--queries-per-step", type=int, default=int(os.environ.get("B200RANK_BENCH_QUERIES_PER_STEP", "1")),
+                    help="headline workload: queries (100 hits each) merged into one device pass = one step; the first is the committed headline query")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch in flight (wait right after submit) instead of two")
