@@ -7,14 +7,17 @@
 
 Workload (BASELINE.json configs[1]): flan-t5-large, pointwise yes_no, 100 hits per query, q_len 32 / p_len 128
 (S = 184 encoder tokens, T = 1 decoder token), synthetic token ids + seeded random-init weights of that architecture.
-A step = one query's 100 candidate documents through the whole hot path (the reference's 4 batches of 32/32/32/4,
-which the engine runs as one device pass — bit-identical, tests/test_engine_gpu.py). With N GPUs every rank scores its
-own query per step (prompts shard embarrassingly; weights are NCCL-broadcast once at load) => weak scaling.
+A step = one device pass of the whole hot path over the 100 candidate documents of each of `--queries-per-step` queries
+(default 2 => 200 documents; the first is the committed headline query). The reference loops over batches of 32/32/32/4 of one
+query; the engine's per-document results do not depend on what shares the pass (bit-identical, tests/test_engine_gpu.py, and
+asserted here against the headline query scored alone), so batches — and queries — are merged to amortise the ~250-launch
+decoder chain (same-box A/B: profiles/r02_bench_queries_per_step_ab.txt). With N GPUs every rank scores its own queries per step
+(prompts shard embarrassingly; weights are NCCL-broadcast once at load) => weak scaling.
 
 `value`  : device-resident inputs, K steps timed with CUDA events on the engine streams, max over ranks.
 `e2e`    : the same K steps through the C-ABI calls a host makes (b200rank_submit_yes_no / _wait_yes_no: HOST token ids in,
            HOST scores out; packing, H2D, compute, D2H inside the timed region), wall clock, max over ranks.
-Both keep two queries in flight per GPU (--no-pipeline: one), like a host loop `submit(i+1); wait(i)`.
+Both keep two passes in flight per GPU (--no-pipeline: one), like a host loop `submit(i+1); wait(i)`.
 `roofline`: the dominant kernel (the gemm_tcgen05_kernel instantiation with the largest share of the step): 2*M*N*K per launch /
            its average launch duration, measured live with per-launch CUDA events in a separate profiled pass; peak from
            MEASURED_PEAKS.json; `traffic` = its DRAM bytes per launch from the committed ncu capture; `all_gemm` = the same
@@ -709,7 +712,7 @@ def run_engine(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = model_cfg(MODEL)
-    QPS = max(1, getattr(args, "queries_per_step", 1))   # queries merged into one device pass (= one step)
+    QPS = max(1, getattr(args, "queries_per_step", 2))   # queries merged into one device pass (= one step)
     DOCS = HITS * QPS
     c = br.make_config(cfg["d_model"], cfg["num_heads"], cfg["d_ff"], cfg["num_layers"], cfg["num_decoder_layers"],
                        max_tokens=DOCS * (Q_LEN + P_LEN + 24) + 256, max_docs=max(128, DOCS), max_logit_rows=256)
@@ -1003,7 +1006,7 @@ def main():
     ap.add_argument("--model", default=None, help="qlm / pairwise workloads: synthetic model shape (qlm: default flan-t5-large, BASELINE configs[4] is flan-t5-xxl; "
                                                    "pairwise: default flan-t5-xl)")
     ap.add_argument("--hits", type=int, default=0, help="qlm / pairwise workloads: documents per query (qlm: default 100, configs[4] says 1000; pairwise: default 24, configs[3] says 100)")
-    ap.add_argument("--queries-per-step", type=int, default=int(os.environ.get("B200RANK_BENCH_QUERIES_PER_STEP", "1")),
+    ap.add_argument("--queries-per-step", type=int, default=int(os.environ.get("B200RANK_BENCH_QUERIES_PER_STEP", "2")),
                     help="headline workload: queries (100 hits each) merged into one device pass = one step; the first is the committed headline query")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-api", action="store_true", help="skip the informational strings -> rerank_many measurement")

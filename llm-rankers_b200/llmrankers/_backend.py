@@ -41,6 +41,10 @@ def generate_mask_mode() -> str:
 
 
 class T5Backend:
+    # a document's logits are bit-identical whatever else shares its device pass (tests/test_engine_gpu.py): callers may
+    # merge the documents of several queries into one pass (PointwiseLlmRanker.rerank_many)
+    batch_invariant = True
+
     def __init__(self, engine, tokenizer, cfg: Dict):
         self.engine = engine
         self.tokenizer = tokenizer

@@ -6,9 +6,9 @@ descending sort. Replaced: tokenise -> DataLoader(4 worker forks) -> padded HF f
 becomes one tokenizer call, one C-ABI call for the whole candidate list (the engine packs real tokens and splits
 device passes itself; per-document results do not depend on batch composition) and one D2H copy.
 """
-from typing import List, Optional
-
+import os
 from collections import deque
+from typing import List, Optional
 
 from ._backend import T5Backend
 from .rankers import LlmRanker, SearchResult
@@ -77,10 +77,11 @@ class PointwiseLlmRanker(LlmRanker):
         return (YES_NO_PROMPT, lambda query, doc: dict(text=doc.text, query=query),
                 self.tokenizer.encode("Yes", add_special_tokens=False)[0], self.tokenizer.encode("No", add_special_tokens=False)[0])
 
-    def rerank_many(self, requests, tokenizer_threads: int = 4, lookahead: int = 8):
+    def rerank_many(self, requests, tokenizer_threads: int = 4, lookahead: int = 8, queries_per_pass: Optional[int] = None):
         """Extension (not in the reference): rerank an iterable of (query, ranking) pairs as a pipeline. Upcoming queries are
         tokenised on `tokenizer_threads` worker threads (the Rust tokenizer releases the GIL), up to `lookahead` queries ahead, and
-        two queries are in flight on the GPU — query i+1's encoder pass runs while query i's decoder pass finishes. Yields the
+        two device passes are in flight on the GPU — pass i+1's encoder runs while pass i's decoder chain finishes — each holding the
+        documents of up to `queries_per_pass` consecutive queries (default B200RANK_QUERIES_PER_PASS = 2). Yields the
         same list `rerank(query, ranking)` would return for each pair, in order; counters hold the totals of the last query.
         Only the yes_no method is pipelined (the headline path); other methods fall back to rerank()."""
         spec = self._pipeline_spec()
@@ -121,26 +122,46 @@ class PointwiseLlmRanker(LlmRanker):
                 yield self.rerank(query, ranking)
             return
         template, fields_of, yes_id, no_id = spec
+        # Several queries per device pass: the decoder chain of a pass (~250 small launches next to the following pass's encoder GEMMs)
+        # costs about the same for 100 documents as for 400, so merging consecutive queries amortises it (B200: +3 % docs/s at two
+        # queries per pass, profiles/r02_bench_queries_per_step_ab.txt). It rests on the engine's batch-composition invariance — a
+        # document's logits are bit-identical whatever shares its pass — so only backends that state it (`batch_invariant`) merge.
+        if queries_per_pass is None:
+            queries_per_pass = int(os.environ.get("B200RANK_QUERIES_PER_PASS", "2"))
+        if not getattr(self.backend, "batch_invariant", False):
+            queries_per_pass = 1
+        group_size = [max(1, queries_per_pass)]
 
         def finish(item):
-            ticket, ranking, rows, scores = item
-            self.total_compare = 0
-            self.total_completion_tokens = 0
-            self.total_prompt_tokens = 0
-            self._count_batches(rows, 1)
+            ticket, members, scores = item
             if ticket is not None:
                 _, scores = self.backend.wait_yes_no(ticket)
-            if scores is not None:
-                for doc, s in zip(ranking, scores):
-                    doc.score = float(s)
-            return sorted(ranking, key=lambda x: x.score, reverse=True)
+            out, off = [], 0
+            for ranking, rows in members:
+                self.total_compare = 0
+                self.total_completion_tokens = 0
+                self.total_prompt_tokens = 0
+                self._count_batches(rows, 1)
+                if scores is not None:
+                    for doc, s in zip(ranking, scores[off:off + len(rows)]):
+                        doc.score = float(s)
+                off += len(rows)
+                out.append(sorted(ranking, key=lambda x: x.score, reverse=True))
+            return out
 
         def tokenise(query, ranking):
             return self._rows(template, [fields_of(query, doc) for doc in ranking])
 
+        class _Ready:   # a tokenised query handed back to the window
+            def __init__(self, rows):
+                self.rows = rows
+
+            def result(self):
+                return self.rows
+
         it = iter(requests)
         window = deque()   # (ranking, future of rows), in request order
-        pending = None     # (ticket, ranking, rows) of the query whose decoder pass is still running
+        pending = None     # (ticket, [(ranking, rows)], scores) of the pass whose decoder chain is still running
         with ThreadPoolExecutor(max(1, tokenizer_threads)) as pool:
             def refill():
                 while len(window) < max(1, lookahead):
@@ -152,26 +173,37 @@ class PointwiseLlmRanker(LlmRanker):
             try:
                 refill()
                 while window:
-                    ranking, fut = window.popleft()
-                    rows = fut.result()
-                    refill()
+                    members = []
+                    while window and len(members) < group_size[0]:
+                        ranking, fut = window.popleft()
+                        members.append((ranking, fut.result()))
+                        refill()
+                    rows = [r for _, rs in members for r in rs]
                     ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
+                    if rows and ticket is None and len(members) > 1:
+                        # the merged pass was declined (capacity of one device pass, or a long document in one of the queries): hand the
+                        # other queries back and go on one query per pass
+                        for ranking, rs in reversed(members[1:]):
+                            window.appendleft((ranking, _Ready(rs)))
+                        members, group_size[0] = members[:1], 1
+                        rows = members[0][1]
+                        ticket = self.backend.submit_yes_no(rows, yes_id, no_id) if rows else None
                     scores = None
                     if rows and ticket is None:
                         # not a pipelined batch (long documents / more than one device pass): drain what is in flight — the
                         # synchronous entry points refuse to run next to pipelined batches — then score this query as rerank() does
                         if pending is not None:
                             item, pending = pending, None
-                            yield finish(item)
+                            yield from finish(item)
                         _, scores = self.backend.score_yes_no(rows, yes_id, no_id)
                     if pending is not None:
-                        item, pending = pending, (ticket, ranking, rows, scores)
-                        yield finish(item)
+                        item, pending = pending, (ticket, members, scores)
+                        yield from finish(item)
                     else:
-                        pending = (ticket, ranking, rows, scores)
+                        pending = (ticket, members, scores)
                 if pending is not None:
                     item, pending = pending, None
-                    yield finish(item)
+                    yield from finish(item)
             finally:
                 # the consumer stopped early or something failed between submit and wait: do not leave a ticket in flight (the
                 # engine's synchronous entry points refuse to run until every pipelined batch has been waited for)

@@ -7,6 +7,8 @@ from llmrankers._backend import T5Backend, generate_mask_mode
 
 
 class OracleBackend(T5Backend):
+    batch_invariant = False   # numpy's BLAS results depend on the batch shape in the last bits: no merged passes where tests compare exactly
+
     def __init__(self, oracle, tokenizer, cfg):
         super().__init__(engine=None, tokenizer=tokenizer, cfg=cfg)
         self.oracle = oracle

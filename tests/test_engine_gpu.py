@@ -310,6 +310,25 @@ def test_pointwise_rerank_many_with_documents_the_pipeline_declines():
     assert all(np.isfinite(s) for out in got for _, s in out)
 
 
+def test_pointwise_rerank_many_merged_passes_equal_rerank():
+    """Several queries per device pass (PointwiseLlmRanker.rerank_many, queries_per_pass): on the engine every query must come out with
+    EXACTLY the scores, order and counters of rerank() — the batch-composition invariance the merge relies on, through the public API."""
+    import copy
+    from llmrankers.pointwise import PointwiseLlmRanker
+    m = golden_meta()["tiny"]
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=tiny_backend())
+    reqs = [(m["query"], _docs(m["docs"])), ("w3 w4", _docs(m["docs"][:3])), ("w9", []), (m["query"], _docs(m["docs"][::-1])),
+            ("w1 w7", _docs(m["docs"][2:9])), ("w5", _docs(m["docs"][:1])), ("w11 w23", _docs(m["docs"][4:]))]
+    want, counters = [], []
+    for q, rk in reqs:
+        want.append([(d.docid, d.score) for d in r.rerank(q, copy.deepcopy(rk))] if rk else [])
+        counters.append((r.total_compare, r.total_prompt_tokens, r.total_completion_tokens))
+    for qpp in (1, 2, 3, 7):
+        got = [[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs], queries_per_pass=qpp)]
+        assert got == want, qpp
+        assert (r.total_compare, r.total_prompt_tokens, r.total_completion_tokens) == counters[-1]
+
+
 @pytest.mark.parametrize("case", ["setwise_heap_gen", "setwise_bubble_gen", "setwise_heap_lik", "setwise_bubble_lik"])
 def test_setwise_ranker_on_gpu(case):
     from llmrankers.setwise import SetwiseLlmRanker

@@ -189,6 +189,47 @@ def test_rerank_many_equals_rerank(method):
     assert r.total_compare == 3  # counters describe the last query (10 docs, batch_size 4)
 
 
+def test_rerank_many_merges_queries_into_passes():
+    """queries_per_pass: consecutive queries share one submit (backends that state batch-composition invariance only), every query gets
+    its own scores / order / counters back, and a declined merged pass falls back to one query per pass for good."""
+    from llmrankers.pointwise import PointwiseLlmRanker
+    m = golden_meta()["tiny"]
+
+    class Merging(type(backend())):
+        batch_invariant = True
+        calls = []
+        max_rows = 10 ** 6
+
+        def submit_yes_no(self, rows, yes_id, no_id):
+            if len(rows) > self.max_rows:
+                self.calls.append(("declined", len(rows)))
+                return None
+            self.calls.append(("submit", len(rows)))
+            return super().submit_yes_no(rows, yes_id, no_id)
+
+    b = backend()
+    b.__class__ = Merging
+    r = PointwiseLlmRanker(None, None, "cuda", method="yes_no", batch_size=4, backend=b)
+    reqs = [(m["query"], docs_from(m["docs"])), ("w3 w4", docs_from(m["docs"][:3])), ("w9", []), (m["query"], docs_from(m["docs"][::-1])),
+            ("w1", docs_from(m["docs"][:2]))]
+    want = [[(d.docid, d.score) for d in r.rerank(q, copy.deepcopy(rk))] for q, rk in reqs]
+
+    def check(got):
+        assert [[d for d, _ in q] for q in got] == [[d for d, _ in q] for q in want]
+        for g, w in zip(got, want):
+            np.testing.assert_allclose([s for _, s in g], [s for _, s in w], rtol=0, atol=1e-5)   # the numpy stand-in is not bit-invariant
+    for qpp, expect in ((2, [("submit", 13), ("submit", 10), ("submit", 2)]), (3, [("submit", 13), ("submit", 12)]), (1, None)):
+        Merging.calls = []
+        check([[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs], queries_per_pass=qpp)])
+        if expect is not None:
+            assert Merging.calls == expect
+    assert r.total_compare == 1   # counters describe the last query (2 docs, batch_size 4)
+    # a merged pass that does not fit: the first query goes alone, the others are handed back in order, no further merging
+    Merging.calls, Merging.max_rows = [], 12
+    check([[(d.docid, d.score) for d in out] for out in r.rerank_many([(q, copy.deepcopy(rk)) for q, rk in reqs], queries_per_pass=2)])
+    assert Merging.calls == [("declined", 13), ("submit", 10), ("submit", 3), ("submit", 10), ("submit", 2)]
+
+
 def test_rerank_many_falls_back_for_batches_the_pipeline_declines():
     """b200rank_submit_yes_no only takes batches that fit the pipelined pass (documents of <= 240 tokens, one device pass); for the
     others T5Backend.submit_yes_no returns None and rerank_many must drain the query in flight (the engine refuses synchronous calls
