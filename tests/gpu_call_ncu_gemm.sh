@@ -5,9 +5,10 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tests/gpu_call_ncu_gemm.sh r02n'
 set -u
 TAG=${1:-r02n}; OUT=gpurun_out; mkdir -p $OUT
-timeout -k 15 420 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:gemm_tcgen05_kernel<256' -s 40 -c 8 -f -o $OUT/${TAG}_gemm \
+timeout -k 15 420 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:gemm_tcgen05_kernel<\(int\)256' -s 40 -c 8 -f -o $OUT/${TAG}_gemm \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-text-api --no-hf-cuda --no-sustained > $OUT/${TAG}_ncu_gemm.log 2>&1; echo "ncu rc=$?"
 ls -la $OUT/${TAG}_gemm.ncu-rep
+[ "${2:-}" = "ncu-only" ] && exit 0
 timeout -k 15 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hf-cuda > $OUT/${TAG}_bench_steps20.json 2> $OUT/${TAG}_bench_steps20.err; echo "bench rc=$?"
 python - <<PY
 import json
