@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -310,6 +311,9 @@ struct b200rank_engine {
     bool dec_graph = false;
     struct DecGraph { int state = 0; cudaGraphExec_t exec = nullptr; uint64_t launches = 0; };   // 0 new, 1 seen, 2 captured, 3 never
     std::map<std::tuple<int, int, int>, DecGraph> dec_graphs;
+    // the same for the decoder steps of the synchronous generation / likelihood entry points (b200rank_greedy, b200rank_logits_at): one
+    // graph per (entry point, documents, decoder shape, step); a setwise / pairwise sort replays the same few shapes for every compare
+    std::map<std::array<int, 8>, DecGraph> step_graphs;
     int gemm_sm_cap = 0;                          // > 0: persistent GEMMs use at most this many SMs (the rest serve the other stream)
     int pipe_reserve_sms = 0;  // measured on B200 (profiles/r01_bench_n1_v10_*): capping the encoder GEMM grids does not pay off
 
@@ -490,6 +494,8 @@ extern "C" void b200rank_destroy(b200rank_engine* e) {
         if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
     }
     for (auto& kv : e->dec_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& kv : e->step_graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (e->stream_dec) cudaStreamDestroy(e->stream_dec);
     for (int i = 0; i < 2; ++i)
@@ -1347,6 +1353,50 @@ static float logit_scale(const b200rank_engine* e) {
     return e->cfg.scale_decoder_outputs ? 1.0f / std::sqrt(static_cast<float>(e->d)) : 1.0f;
 }
 
+// Runs `enqueue` (kernel launches on e->stream with arguments that are a function of `key` alone — no copies, no synchronisation) as a
+// CUDA graph: eagerly on the key's first occurrence, captured on the second, replayed from then on. One host call instead of ~280, no
+// launch gaps on the device; the kernels and their order are the eager ones, so the results are bit-identical. B200RANK_DEC_GRAPH=0,
+// profiling and B200RANK_DEBUG_SYNC run everything eagerly; so does a key that arrives when 256 graphs exist already.
+template <class F>
+static int run_as_graph(b200rank_engine* e, const std::array<int, 8>& key, F&& enqueue) {
+    b200rank_engine::DecGraph* g = nullptr;
+    if (e->dec_graph && !e->profiling && !e->debug_sync) {
+        auto it = e->step_graphs.find(key);
+        if (it != e->step_graphs.end()) g = &it->second;
+        else if (e->step_graphs.size() < 256) g = &e->step_graphs[key];
+    }
+    if (g && g->state == 2) {
+        cudaError_t er = cudaGraphLaunch(g->exec, e->stream);
+        if (er != cudaSuccess) return set_error(B200RANK_ERR_CUDA, "decoder step graph launch: %s", cudaGetErrorString(er));
+        e->launches += g->launches;
+        return B200RANK_OK;
+    }
+    if (g && g->state == 1) {
+        const uint64_t l0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        cudaError_t er = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+        const int crc = (er == cudaSuccess) ? enqueue() : B200RANK_ERR_CUDA;
+        if (er == cudaSuccess) er = cudaStreamEndCapture(e->stream, &graph);
+        int rc = B200RANK_OK;
+        if (crc == B200RANK_OK && er == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+            g->state = 2;
+            g->launches = e->launches - l0;
+            er = cudaGraphLaunch(g->exec, e->stream);
+            if (er != cudaSuccess) rc = set_error(B200RANK_ERR_CUDA, "decoder step graph launch: %s", cudaGetErrorString(er));
+        } else {            // capture is not possible here: never try this key again, run the step the ordinary way
+            g->state = 3;
+            g->exec = nullptr;
+            cudaGetLastError();
+            e->launches = l0;
+            rc = enqueue();
+        }
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (g && g->state == 0) g->state = 1;
+    return enqueue();
+}
+
 // Full-vocabulary row reductions (log-prob of a label / argmax / softmax gather): the register-resident single-pass kernel when the
 // row fits (V <= 32768, a multiple of 4, 16 B-aligned rows), the multi-pass kernel otherwise. B200RANK_VOCAB_ROW=multipass forces the latter.
 static int k_vocab_row(b200rank_engine* e, const char* what, int rows, int mode, const int* labels, const int* cols, int ncols, float* out_f, int* out_i) {
@@ -1725,16 +1775,18 @@ extern "C" int b200rank_logits_at(b200rank_engine* e, const int32_t* ids, const 
         for (int i = 0; i < nd; ++i) std::copy(dec_prefix, dec_prefix + T, dec.begin() + (size_t)i * T);
         RET_IF(upload_ints(e, e->d_dec_ids, dec));
         RET_IF(upload_ints(e, e->d_cols, std::vector<int>(cols, cols + ncols)));
-        RET_IF(run_decoder(e, 0, nd, T));
-        if (!normalize) {
-            prof_begin(e, "lm_head_cols"); launch_k(lm_head_cols_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
-            RET_IF(post_launch(e, "lm_head_cols"));
-        } else {
+        auto enqueue_pass = [&]() -> int {
+            RET_IF(run_decoder(e, 0, nd, T));
+            if (!normalize) {
+                prof_begin(e, "lm_head_cols"); launch_k(lm_head_cols_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->lm_head, e->d_cols, ncols, logit_scale(e), e->small_out);
+                return post_launch(e, "lm_head_cols");
+            }
             prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
             RET_IF(post_launch(e, "gather_rows"));
             RET_IF(gemm(e, e->hlast, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
-            RET_IF(k_vocab_row(e, "vocab_row_softmax_gather", nd, 2, nullptr, e->d_cols, ncols, e->small_out, nullptr));
-        }
+            return k_vocab_row(e, "vocab_row_softmax_gather", nd, 2, nullptr, e->d_cols, ncols, e->small_out, nullptr);
+        };
+        RET_IF(run_as_graph(e, {2, nd, T, ncols, normalize ? 1 : 0, T == 1 ? ((e->staged_maxlen + 15) & ~15) : 0, 0, cross_split_off() ? 1 : 0}, enqueue_pass));
         CU_OK(cudaMemcpyAsync(e->h_out, e->small_out, (size_t)nd * ncols * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
         CU_OK(cudaStreamSynchronize(e->stream));
         memcpy(out + (size_t)d0 * ncols, e->h_out, (size_t)nd * ncols * sizeof(float));
@@ -1801,26 +1853,31 @@ extern "C" int b200rank_greedy(b200rank_engine* e, const int32_t* ids, const int
         CU_OK(cudaMemsetAsync(e->d_finished, 0, (size_t)nd * sizeof(int), e->stream));
         for (int step = 0; step < max_new; ++step) {
             const int T = prefix_len + step;   // decoder positions so far; the new token is written at position T
-            const bf16* h_last = nullptr;
-            if (cached && step > 0) {
-                prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, T - 1, 1, e->d_dec_ids, nd);
-                RET_IF(post_launch(e, "dec_rows_to_ids"));
-                RET_IF(run_decoder_cached_step(e, 0, nd, T - 1, t_stride));
-                h_last = e->hd;
-            } else {
-                // cache-less loop: the decoder prefix is re-run — token-for-token the same greedy choice
-                prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd * T + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, 0, T, e->d_dec_ids, nd);
-                RET_IF(post_launch(e, "dec_rows_to_ids"));
-                RET_IF(run_decoder(e, 0, nd, T, cached ? t_stride : 0));
-                prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
-                RET_IF(post_launch(e, "gather_rows"));
-                h_last = e->hlast;
-            }
-            RET_IF(gemm(e, h_last, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
-            RET_IF(k_vocab_row(e, "vocab_row_argmax", nd, 1, nullptr, nullptr, 0, nullptr, d_argmax));
-            prof_begin(e, "greedy_update"); launch_k(greedy_update_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
-                                                                          t_stride, step, max_new, e->cfg.eos_id, e->cfg.pad_id);
-            RET_IF(post_launch(e, "greedy_update"));
+            auto enqueue_step = [&]() -> int {
+                const bf16* h_last = nullptr;
+                if (cached && step > 0) {
+                    prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, T - 1, 1, e->d_dec_ids, nd);
+                    RET_IF(post_launch(e, "dec_rows_to_ids"));
+                    RET_IF(run_decoder_cached_step(e, 0, nd, T - 1, t_stride));
+                    h_last = e->hd;
+                } else {
+                    // cache-less loop: the decoder prefix is re-run — token-for-token the same greedy choice
+                    prof_begin(e, "dec_rows_to_ids"); launch_k(dec_rows_to_ids_kernel, dim3((nd * T + 255) / 256), dim3(256), 0, e->stream, e->d_labels, t_stride, 0, T, e->d_dec_ids, nd);
+                    RET_IF(post_launch(e, "dec_rows_to_ids"));
+                    RET_IF(run_decoder(e, 0, nd, T, cached ? t_stride : 0));
+                    prof_begin(e, "gather_rows"); launch_k(gather_rows_kernel, dim3(nd), dim3(128), 0, e->stream, e->hd, e->d, T, T - 1, e->hlast, nd);
+                    RET_IF(post_launch(e, "gather_rows"));
+                    h_last = e->hlast;
+                }
+                RET_IF(gemm(e, h_last, e->d, e->cap_rows, e->lm_head, e->d, e->V, nd, e->V, e->d, EPI_F32, e->logits, e->V));
+                RET_IF(k_vocab_row(e, "vocab_row_argmax", nd, 1, nullptr, nullptr, 0, nullptr, d_argmax));
+                prof_begin(e, "greedy_update"); launch_k(greedy_update_kernel, dim3((nd + 127) / 128), dim3(128), 0, e->stream, d_argmax, e->d_labels, e->d_finished, e->d_int_out, nd, T,
+                                                                              t_stride, step, max_new, e->cfg.eos_id, e->cfg.pad_id);
+                return post_launch(e, "greedy_update");
+            };
+            // every launch argument of a step follows from (documents, prefix, budget, step) — token ids, lengths and finished flags are
+            // read on the device — plus the longest document where one decoder position selects its kernels by it
+            RET_IF(run_as_graph(e, {1, nd, prefix_len, max_new, step, T == 1 ? ((e->staged_maxlen + 15) & ~15) : 0, cached ? 1 : 0, cross_split_off() ? 1 : 0}, enqueue_step));
         }
         CU_OK(cudaMemcpyAsync(e->h_int, e->d_int_out, (size_t)nd * max_new * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CU_OK(cudaStreamSynchronize(e->stream));

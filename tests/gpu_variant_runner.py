@@ -23,8 +23,11 @@ def main(out_path, model="flan-t5-base", n_docs=96):
     # the other entry points on a few documents: full-vocabulary reductions (qlm log-probs, label softmax, greedy argmax)
     k = min(16, n_docs)
     qlm = e.score_qlm(ids[:k], lengths[:k], [71, 272, 205, 309, 262, 377, 350, 1])
-    probs = e.logits_at(ids[:k], lengths[:k], [0, 5], [71, 272, 205, 309], normalize=True)
-    new = e.greedy(ids[:k], lengths[:k], [0, 5], 3)
+    # three times each: the decoder steps of these entry points run eagerly on a shape's first occurrence, are captured into a CUDA graph
+    # on the second and replayed from the third on — what is saved is the replayed result
+    for _ in range(3):
+        probs = e.logits_at(ids[:k], lengths[:k], [0, 5], [71, 272, 205, 309], normalize=True)
+        new = e.greedy(ids[:k], lengths[:k], [0, 5], 3)
     np.savez(out_path, logits=lg, scores=sc, qlm=qlm, probs=probs, greedy=new)
 
 

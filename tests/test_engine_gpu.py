@@ -534,6 +534,43 @@ def test_greedy_kv_cache_is_bit_identical_to_the_rerun_prefix(monkeypatch):
     record("variant/greedy_kv_cache", identical=True)
 
 
+def test_decoder_step_graphs_replay_the_eager_steps(monkeypatch):
+    """The decoder steps of b200rank_greedy / b200rank_logits_at run eagerly on a shape's first occurrence, are captured into a CUDA graph
+    on the second and replayed afterwards (keyed by entry point, documents, decoder shape, step). Eager, capturing and replayed calls —
+    two shapes interleaved, the cache-less loop and the unsplit cross-attention as further keys — must return identical results, and
+    the launch counter must keep counting kernels."""
+    e = engine_for("tiny", label_favouring=True)
+    rng = np.random.default_rng(91)
+    vocab = model_and_weights("tiny", True)[0]["vocab_size"]
+    a = _ragged_prompts(rng, 7, 20, 260, vocab)
+    b = _ragged_prompts(rng, 3, 300, 900, vocab)
+    cols = [39, 40, 41, 42, 43]
+
+    def run(x):
+        l0 = e.launch_count()
+        out = (e.greedy(x[0], x[1], [0, 4], 4), e.greedy(x[0], x[1], [0], 3), e.logits_at(x[0], x[1], [0, 4], cols, normalize=True),
+               e.logits_at(x[0], x[1], [0, 4, 39], cols, normalize=False))
+        return out, e.launch_count() - l0
+    first = {}
+    for name, x in (("a", a), ("b", b), ("a", a), ("a", a), ("b", b), ("b", b), ("a", a), ("b", b)):
+        out, launches = run(x)
+        if name not in first:
+            first[name] = (out, launches)
+        assert launches == first[name][1], (name, launches, first[name][1])
+        for got, want in zip(out, first[name][0]):
+            assert np.array_equal(got, want), name
+    for env in ({"B200RANK_KV_CACHE": "0"}, {"B200RANK_CROSS_SPLIT": "0"}):      # other keys: their graphs must not be confused with the default ones
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ref = [run(a)[0] for _ in range(3)]
+        for r in ref[1:]:
+            assert all(np.array_equal(x, y) for x, y in zip(r, ref[0]))
+        for k in env:
+            monkeypatch.delenv(k)
+        out, _ = run(a)
+        assert all(np.array_equal(x, y) for x, y in zip(out, first["a"][0]))
+
+
 def test_greedy_kv_cache_long_generation_vs_oracle(monkeypatch):
     """Twenty cached steps from the bare decoder start token (the free-form generation shape: step 0 is the T = 1 pass whose fused
     W_o W_v block never forms k / v, so the cache gets them from the extra projection) against the fp32 oracle's greedy loop: every
@@ -607,6 +644,8 @@ def test_kernel_variants_agree(tmp_path):
         got = run(name, **env)
         record("variant/" + name, max_abs_diff=float(np.abs(got - base).max()))
         assert np.array_equal(got, base), (name, float(np.abs(got - base).max()))
+        # ... and so must the generation / likelihood / qlm entry points (dec_graph_off: eager decoder steps vs the replayed step graphs)
+        assert all(np.array_equal(extras[name][k], extras["default"][k]) for k in extras["default"]), name
     # different arithmetic (re-blocked softmax / re-associated products): agreement to bf16 noise
     for name, env in [("attn_tiled", {"B200RANK_ATTN": "tiled"}), ("attn_tc2", {"B200RANK_ATTN": "tc2"}), ("dec_reference_shaped", {"B200RANK_DEC_REASSOC": "0"})]:
         got = run(name, **env)
