@@ -32,7 +32,7 @@ except Exception as e:
     print("bench line unreadable:", e)
 PY
 timeout -k 15 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; echo "reference rc=$?"
-timeout -k 15 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
+timeout -k 15 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/${TAG}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-text-api > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
 # the sanitizer passes come LAST and are bounded to 5 minutes each: they are the slowest and least predictable step, and nothing above
 # may be lost to them when the call's own timeout strikes

@@ -6,6 +6,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from helpers import ROOT
 
 
@@ -42,7 +44,8 @@ def test_engine_arm_fails_loudly_without_a_gpu():
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)   # no CPU fallback behind the bench either
 
 
-def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
+@pytest.mark.parametrize("qps", [1, 2])
+def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys, qps):
     """run_engine end to end on CPU: b200rank.Engine is replaced by a stand-in that answers with the transformers fp32 forward (+ noise of
     bf16 size) and reports a canned per-kernel profile, so every leg that shapes the JSON line runs — value / e2e / launches / roofline
     (dominant kernel, traffic lookup, HBM entry) / cpu_baseline / parity (incl. the bf16 yardstick and Kendall tau) / text API. This is a
@@ -77,14 +80,24 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
             self.model = hf_cpu.build_model(model_cfg(bench.MODEL), dict(items), threads=4)
 
         def _score(self, ids, lengths, yes_id, no_id):
+            # per-document cache: like the engine, a document's result does not depend on what shares its pass (the bench scores the same
+            # queries over and over, and checks a merged pass against the headline query scored alone)
             self.n_launch += 438
-            key = (np.asarray(ids).tobytes(), np.asarray(lengths).tobytes(), yes_id, no_id)
-            if key not in self.cache:       # the bench scores the same query over and over: one real forward is enough here
-                mask = (np.arange(ids.shape[1])[None] < np.asarray(lengths)[:, None]).astype(np.int64)
-                lg, _ = hf_cpu.score_yes_no(self.model, np.asarray(ids, np.int64) * mask, mask, yes_id, no_id, 32)
+            ids, lengths = np.asarray(ids), np.asarray(lengths)
+            keys = [(ids[i, :lengths[i]].tobytes(), yes_id, no_id) for i in range(len(lengths))]
+            todo = [i for i, k in enumerate(keys) if k not in self.cache]
+            if todo:
+                sub, ln = ids[todo], lengths[todo]
+                mask = (np.arange(sub.shape[1])[None] < ln[:, None]).astype(np.int64)
+                lg, _ = hf_cpu.score_yes_no(self.model, np.asarray(sub, np.int64) * mask, mask, yes_id, no_id, 32)
                 lg = (lg + np.random.default_rng(0).normal(0, 0.01, lg.shape)).astype(np.float32)
-                self.cache[key] = (lg, (np.exp(lg[:, 0]) / np.exp(lg).sum(1)).astype(np.float32))
-            return self.cache[key]
+                for i, row in zip(todo, lg):
+                    self.cache[keys[i]] = row
+            lg = np.stack([self.cache[k] for k in keys])
+            return lg, (np.exp(lg[:, 0]) / np.exp(lg).sum(1)).astype(np.float32)
+
+        def score_yes_no(self, ids, lengths, yes_id, no_id):
+            return self._score(ids, lengths, yes_id, no_id)
 
         def stage(self, ids, lengths):
             self.staged = (np.asarray(ids), np.asarray(lengths))
@@ -137,7 +150,7 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
     def broken_text_api(*a, **k):
         raise RuntimeError("text leg down")
     monkeypatch.setattr(bench, "text_api_docs_per_s", broken_text_api)
-    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=False, no_pipeline=False, hf_cuda=False, no_hf_cuda=True, no_sustained=False)
+    args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, no_cpu_baseline=False, no_text_api=False, no_pipeline=False, hf_cuda=False, no_hf_cuda=True, no_sustained=False, queries_per_step=qps)
     assert bench.run_engine(args) == 0
     line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(line) == 1
@@ -147,10 +160,11 @@ def test_engine_arm_json_assembly_with_a_stand_in_engine(monkeypatch, capsys):
         assert key in d, key
     assert d["api_text"] == {"unavailable": "RuntimeError: text leg down"}
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["dtype"] == "bf16" and d["vs_baseline"] is None
-    assert d["gpu_launches"] == 3 * 438 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1200
+    assert d["gpu_launches"] == 3 * 438 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1200 * qps
+    assert d["config"]["queries_per_step"] == qps and d["config"]["docs_per_step_per_gpu"] == 100 * qps
     r = d["roofline"]
-    assert r["bound"] == "tensor" and r["kernel"].startswith("gemm_tcgen05<bn256,epi2> M18400") and r["unit"] == "TFLOP/s" and r["frac"] > 0
-    assert abs(r["flop_per_launch"] - 2.0 * 18400 * 2048 * 512) < 1 and r["launches_per_step"] == 16 / 3
+    assert r["bound"] == "tensor" and r["kernel"].startswith(f"gemm_tcgen05<bn256,epi2> M{18400 * qps}") and r["unit"] == "TFLOP/s" and r["frac"] > 0
+    assert abs(r["flop_per_launch"] - 2.0 * 18400 * qps * 2048 * 512) < 1 and r["launches_per_step"] == 16 / 3
     assert r["hbm_kernels"][0]["kernel"] == "rmsnorm_kernel" and r["hbm_kernels"][0]["launches_per_step"] == 34 / 3
     assert "rmsnorm_small" in r["by_kernel_ms_per_step"]
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
