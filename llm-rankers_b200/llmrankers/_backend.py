@@ -58,6 +58,10 @@ class T5Backend:
              max_tokens: int = 0, max_docs: int = 0) -> "T5Backend":
         import b200rank as br
         dev = _device_index(device)
+        # tokens of one device pass: two 100-hit queries of ~184-token prompts share a pass in rerank_many (36.8 k tokens), so the public
+        # constructors size the workspaces for 64 k (8 GB for flan-t5-large, 31 GB for flan-t5-xxl, of 180); B200RANK_MAX_TOKENS overrides
+        if max_tokens <= 0:
+            max_tokens = int(os.environ.get("B200RANK_MAX_TOKENS", "65536"))
         key = (f"{model_name_or_path}|{tokenizer_name_or_path}|{max_tokens}|{max_docs}", dev)
         if key in _ENGINE_CACHE:
             return _ENGINE_CACHE[key]
