@@ -328,7 +328,7 @@ def workload_config(world, sample_docs=None, queries_per_step=1):
         "docs_per_step_per_gpu": HITS * queries_per_step if sample_docs is None else sample_docs,
         "global_docs_per_step": (HITS * queries_per_step if sample_docs is None else sample_docs) * world,
         "parallelism": f"dp{world} (queries sharded across ranks, weights NCCL-broadcast once at load, no collective in the loop)",
-        "pipeline": "two queries in flight per GPU (submit/wait): decoder pass of query i on a second stream overlaps the encoder GEMMs of query i+1",
+        "pipeline": "two device passes in flight per GPU (submit/wait): the decoder chain of pass i on a second stream overlaps the encoder GEMMs of pass i+1",
         "weights": f"seeded random init (numpy PCG64 seed {SEED}), bf16 on device",
         "l2": "no explicit flush: each step streams 1.6 GB of weights + ~3.5 GB of activations, far beyond the 126 MB L2",
         "algorithmic_gflop_per_doc": GF_PER_DOC,
